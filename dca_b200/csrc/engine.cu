@@ -1,0 +1,595 @@
+// The engine behind the C ABI: owns the arena layout (parameters, gradients, RMSprop and
+// BatchNorm state, fixed workspace) and sequences the kernels of one training / validation /
+// predict batch.  Replaces what Keras Model.fit / Model.predict execute for
+// dca/train.py:91-98, dca/network.py:92-141,366-393 (see include/dca_b200.h per entry point).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "dca_internal.cuh"
+#include "engine.h"
+
+namespace dca {
+
+std::atomic<long long> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+__global__ void add_double_kernel(double* p, double v) { *p += v; }
+__global__ void gather_sf_kernel(const float* __restrict__ sf, const int32_t* __restrict__ rows, int n,
+                                 float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = sf ? sf[rows ? rows[i] : i] : 1.0f;
+}
+__global__ void copy_strided_kernel(const float* __restrict__ in, int64_t ldi, float* __restrict__ out, int64_t ldo,
+                                    int M, int N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  const int r = (int)(i / N), c = (int)(i % N);
+  out[(int64_t)r * ldo + c] = in[(int64_t)r * ldi + c];
+}
+
+int validate(const dca_config* c) {
+  if (!c) { set_error("config is NULL"); return DCA_ERR_BAD_ARG; }
+  if (c->struct_bytes != (int32_t)sizeof(dca_config)) {
+    set_error("dca_config.struct_bytes=%d does not match library (%zu): header/library mismatch", c->struct_bytes,
+              sizeof(dca_config));
+    return DCA_ERR_BAD_ARG;
+  }
+  if (c->n_in <= 0 || c->n_out <= 0) { set_error("n_in/n_out must be positive (got %d, %d)", c->n_in, c->n_out); return DCA_ERR_BAD_ARG; }
+  if (c->n_hidden < 0 || c->n_hidden > DCA_MAX_HIDDEN) { set_error("n_hidden must be in [0,%d]", DCA_MAX_HIDDEN); return DCA_ERR_BAD_ARG; }
+  for (int i = 0; i < c->n_hidden; ++i)
+    if (c->hidden[i] <= 0) { set_error("hidden[%d] must be positive", i); return DCA_ERR_BAD_ARG; }
+  if (c->ae_type < 0 || c->ae_type > 3) { set_error("loss type not supported (ae_type=%d)", c->ae_type); return DCA_ERR_UNSUPPORTED; }
+  if (c->max_batch <= 0) { set_error("max_batch must be positive"); return DCA_ERR_BAD_ARG; }
+  if (c->x_dtype != DCA_F32 && c->x_dtype != DCA_BF16) { set_error("x_dtype must be DCA_F32 or DCA_BF16"); return DCA_ERR_BAD_ARG; }
+  if (c->gemm_path < 0 || c->gemm_path > 2) { set_error("unknown gemm_path %d", c->gemm_path); return DCA_ERR_BAD_ARG; }
+  return DCA_OK;
+}
+
+void add_tensor(std::vector<dca_tensor_info>& v, int64_t& off, const std::string& name, int rows, int cols) {
+  dca_tensor_info t;
+  memset(&t, 0, sizeof(t));
+  snprintf(t.name, sizeof(t.name), "%s", name.c_str());
+  t.offset = off; t.rows = rows; t.cols = cols;
+  off += (int64_t)rows * cols;
+  v.push_back(t);
+}
+
+std::string layer_name(int i, int n) {   // dca/network.py:102-111
+  const int center = n / 2;
+  if (i == center) return "center";
+  if (i < center) return "enc" + std::to_string(i);
+  return "dec" + std::to_string(i - center);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ layout
+int Engine::plan(const dca_config& c) {
+  cfg = c;
+  L = c.n_hidden;
+  has_pi = (c.ae_type == DCA_AE_ZINB_CONDDISP || c.ae_type == DCA_AE_ZINB);
+  cond = (c.ae_type == DCA_AE_ZINB_CONDDISP || c.ae_type == DCA_AE_NB_CONDDISP);
+  params.clear(); states.clear();
+  int64_t off = 0, soff = 0;
+  int prev = c.n_in;
+  maxh = 1;
+  for (int i = 0; i < L; ++i) {
+    const std::string nm = layer_name(i, L);
+    const int h = c.hidden[i];
+    lay[i].in = prev; lay[i].out = h;
+    lay[i].W = off; add_tensor(params, off, nm + "/kernel", prev, h);
+    lay[i].b = off; add_tensor(params, off, nm + "/bias", 1, h);
+    if (c.batchnorm) {
+      lay[i].beta = off; add_tensor(params, off, nm + "/bn_beta", 1, h);
+      lay[i].mm = soff; add_tensor(states, soff, nm + "/bn_moving_mean", 1, h);
+      lay[i].mv = soff; add_tensor(states, soff, nm + "/bn_moving_var", 1, h);
+    }
+    prev = h;
+    if (h > maxh) maxh = h;
+  }
+  K_head = prev;
+  const int G = c.n_out;
+  head_W[0] = off; add_tensor(params, off, "mean/kernel", prev, G);
+  head_b[0] = off; add_tensor(params, off, "mean/bias", 1, G);
+  head_W[1] = head_b[1] = head_W[2] = head_b[2] = theta_off = -1;
+  if (cond) {
+    head_W[1] = off; add_tensor(params, off, "dispersion/kernel", prev, G);
+    head_b[1] = off; add_tensor(params, off, "dispersion/bias", 1, G);
+  }
+  if (has_pi) {
+    head_W[2] = off; add_tensor(params, off, "pi/kernel", prev, G);
+    head_b[2] = off; add_tensor(params, off, "pi/bias", 1, G);
+  }
+  if (!cond) { theta_off = off; add_tensor(params, off, "dispersion/theta", 1, G); }
+  P = off; S = soff;
+
+  // ---- arena carve-up
+  const size_t B = (size_t)c.max_batch;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes); return at; };
+  o_params = take(sizeof(float) * (size_t)P);
+  o_grads = take(sizeof(float) * (size_t)(P + 2));
+  o_rms = take(sizeof(float) * (size_t)P);
+  o_state = take(sizeof(float) * (size_t)(S > 0 ? S : 1));
+  o_acc = take(sizeof(double) * 8);          // epoch acc[4], loss_sum, penalty
+  for (int i = 0; i < L; ++i) {
+    const size_t h = (size_t)c.hidden[i];
+    lay[i].o_a = take(sizeof(float) * B * h);
+    lay[i].o_xhat = take(sizeof(float) * B * h);
+    lay[i].o_h = take(sizeof(float) * B * h);
+    lay[i].o_mean = take(sizeof(float) * h);
+    lay[i].o_inv = take(sizeof(float) * h);
+  }
+  for (int k = 0; k < 3; ++k) o_head[k] = take(sizeof(float) * B * (size_t)G);
+  o_dh[0] = take(sizeof(float) * B * (size_t)maxh);
+  o_dh[1] = take(sizeof(float) * B * (size_t)maxh);
+  const size_t statw = (size_t)(maxh > G ? maxh : G);
+  o_dsum = take(sizeof(double) * statw);
+  o_dprod = take(sizeof(double) * statw);
+  o_scratch = take(sizeof(double) * (size_t)col_sums_scratch_elems((int)B, (int)statw));
+  o_theta = take(sizeof(float) * (size_t)G);
+  o_chain = take(sizeof(float) * (size_t)G);
+  o_dtheta = take(sizeof(float) * (size_t)G);
+  o_sfb = take(sizeof(float) * B);
+  loss_ws_bytes = loss_workspace_bytes((int)B, G);
+  o_lossws = take(loss_ws_bytes);
+  // staging for the host-buffer entry point
+  const size_t xb = (c.x_dtype == DCA_BF16) ? 2 : 4;
+  o_stage_x = take(xb * B * (size_t)c.n_in);
+  o_stage_y = take(sizeof(float) * B * (size_t)G);
+  o_stage_sf = take(sizeof(float) * B);
+  arena_bytes = o;
+  return DCA_OK;
+}
+
+void Engine::bind(void* base_) {
+  base = reinterpret_cast<char*>(base_);
+}
+
+// ------------------------------------------------------------------------------------ forward
+int Engine::gemm_auto(GemmArgs g, cudaStream_t s) {
+  // split-K so that skinny outputs still fill the 148 SMs
+  const long long tiles = (long long)cdiv(g.M, 64) * cdiv(g.N, 64);
+  int splits = 1;
+  if (g.epilogue == EPI_ACCUM && tiles < 296 && g.K >= 256) {
+    splits = (int)((296 + tiles - 1) / tiles);
+    const int maxs = g.K / 128;
+    if (splits > maxs) splits = maxs;
+    if (splits < 1) splits = 1;
+  }
+  g.splits = splits;
+  return gemm_generic(g, s);
+}
+
+int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, bool training, cudaStream_t s) {
+  const void* hin = X; int64_t ldin = ldx; int in_bf16 = (cfg.x_dtype == DCA_BF16); const int32_t* gather = rows;
+  for (int i = 0; i < L; ++i) {
+    Layer& l = lay[i];
+    float* a = f(l.o_a);
+    DCA_TRY(fill_rows_with_bias(a, l.out, Bn, l.out, pp(l.b), s));
+    GemmArgs g{};
+    g.A = hin; g.lda = ldin; g.a_bf16 = in_bf16; g.transA = 0; g.a_rows = gather;
+    g.B = pp(l.W); g.ldb = l.out; g.transB = 0;
+    g.C = a; g.ldc = l.out; g.M = Bn; g.N = l.out; g.K = l.in; g.epilogue = EPI_ACCUM;
+    DCA_TRY(gemm_auto(g, s));
+    if (cfg.batchnorm) {
+      if (training) {
+        DCA_TRY(col_sums(a, nullptr, l.out, Bn, l.out, d(o_dsum), d(o_dprod), d(o_scratch), s));
+        DCA_TRY(bn_train_finalize(d(o_dsum), d(o_dprod), Bn, l.out, cfg.bn_eps, cfg.bn_momentum, f(l.o_mean),
+                                  f(l.o_inv), st(l.mm), st(l.mv), s));
+      } else {
+        DCA_TRY(bn_infer_prepare(st(l.mm), st(l.mv), l.out, cfg.bn_eps, f(l.o_mean), f(l.o_inv), s));
+      }
+      DCA_TRY(bn_relu_fwd(a, l.out, Bn, l.out, f(l.o_mean), f(l.o_inv), pp(l.beta), training ? f(l.o_xhat) : nullptr,
+                          f(l.o_h), nullptr, s));
+    } else {
+      DCA_TRY(bias_relu_fwd(a, l.out, Bn, l.out, f(l.o_h), s));
+    }
+    hin = f(l.o_h); ldin = l.out; in_bf16 = 0; gather = nullptr;
+  }
+  head_in = hin; head_ld = ldin; head_bf16 = in_bf16; head_rows = gather;
+  return DCA_OK;
+}
+
+int Engine::heads_forward(int Bn, float* m_out, float* d_out, float* p_out, int64_t ld_out, const float* row_scale,
+                          cudaStream_t s) {
+  const int G = cfg.n_out;
+  struct H { int k; float* out; int epi; const float* rs; } hs[3] = {
+      {0, m_out, EPI_MEAN_ACT, row_scale}, {1, d_out, EPI_DISP_ACT, nullptr}, {2, p_out, EPI_SIGMOID, nullptr}};
+  for (auto& h : hs) {
+    if (head_W[h.k] < 0 || !h.out) continue;
+    GemmArgs g{};
+    g.A = head_in; g.lda = head_ld; g.a_bf16 = head_bf16; g.transA = 0; g.a_rows = head_rows;
+    g.B = pp(head_W[h.k]); g.ldb = G; g.transB = 0;
+    g.C = h.out; g.ldc = ld_out; g.M = Bn; g.N = G; g.K = K_head;
+    g.bias = pp(head_b[h.k]); g.row_scale = h.rs; g.epilogue = h.epi; g.splits = 1;
+    DCA_TRY(gemm_generic(g, s));
+  }
+  return DCA_OK;
+}
+
+int Engine::penalty(cudaStream_t s, bool& any) {
+  any = false;
+  auto coeff = [&](int i, float& l1, float& l2) {   // dca/network.py:113-122
+    const int center = L / 2;
+    const bool enc = (i >= 0 && i <= center);
+    l1 = (enc && cfg.l1_enc != 0.f) ? cfg.l1_enc : cfg.l1;
+    l2 = (enc && cfg.l2_enc != 0.f) ? cfg.l2_enc : cfg.l2;
+  };
+  for (int i = 0; i < L; ++i) {
+    float l1, l2; coeff(i, l1, l2);
+    if (l1 != 0.f || l2 != 0.f) any = true;
+  }
+  if (cfg.l1 != 0.f || cfg.l2 != 0.f) any = true;
+  if (!any) return DCA_OK;
+  DCA_CUDA_OK(cudaMemsetAsync(d(o_acc) + 5, 0, sizeof(double), s));
+  for (int i = 0; i < L; ++i) {
+    float l1, l2; coeff(i, l1, l2);
+    if (l1 == 0.f && l2 == 0.f) continue;
+    const int64_t n = (int64_t)lay[i].in * lay[i].out;
+    DCA_TRY(reg_penalty(pp(lay[i].W), n, l1, l2, d(o_acc) + 5, s));
+    DCA_TRY(add_reg_grad(pp(lay[i].W), gp(lay[i].W), n, l1, l2, s));
+  }
+  if (cfg.l1 != 0.f || cfg.l2 != 0.f) {
+    for (int k = 0; k < 3; ++k) {
+      if (head_W[k] < 0) continue;
+      const int64_t n = (int64_t)K_head * cfg.n_out;
+      DCA_TRY(reg_penalty(pp(head_W[k]), n, cfg.l1, cfg.l2, d(o_acc) + 5, s));
+      DCA_TRY(add_reg_grad(pp(head_W[k]), gp(head_W[k]), n, cfg.l1, cfg.l2, s));
+    }
+  }
+  return DCA_OK;
+}
+
+// ------------------------------------------------------------------------------------ train step
+int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows,
+                       int Bn, cudaStream_t s) {
+  if (!X || !Y) { set_error("dca_train_step: X and Y must not be NULL"); return DCA_ERR_BAD_ARG; }
+  if (Bn <= 0 || Bn > cfg.max_batch) { set_error("dca_train_step: batch %d outside (0, max_batch=%d]", Bn, cfg.max_batch); return DCA_ERR_BAD_ARG; }
+  const int G = cfg.n_out;
+  DCA_CUDA_OK(cudaMemsetAsync(gp(0), 0, sizeof(float) * (size_t)(P + 2), s));
+  bool any_pen = false;
+  DCA_TRY(penalty(s, any_pen));
+  DCA_TRY(forward(X, ldx, rows, Bn, true, s));
+  float* Mb = f(o_head[0]); float* Db = f(o_head[1]); float* Pb = f(o_head[2]);
+  DCA_TRY(heads_forward(Bn, Mb, cond ? Db : nullptr, has_pi ? Pb : nullptr, G, nullptr, s));
+  if (!cond) DCA_TRY(theta_prepare(pp(theta_off), G, f(o_theta), f(o_chain), s));
+
+  const float inv_n = 1.0f / ((float)Bn * (float)G);
+  LossArgs la{};
+  la.Y = Y; la.ldy = ldy; la.rows = rows; la.sf = sf;
+  la.m = Mb; la.d = cond ? Db : f(o_theta); la.pi = has_pi ? Pb : nullptr; la.ld = G;
+  la.B = Bn; la.G = G; la.ae_type = cfg.ae_type; la.ridge = cfg.ridge; la.inv_n = inv_n;
+  la.dzm = Mb; la.dzd = cond ? Db : nullptr; la.dzp = has_pi ? Pb : nullptr; la.grad_bf16 = 0;
+  la.dtheta = cond ? nullptr : f(o_dtheta);
+  la.loss_sum = d(o_acc) + 4; la.ws = base + o_lossws; la.ws_bytes = loss_ws_bytes;
+  DCA_TRY(zinb_loss_fwd_bwd(la, s));
+  DCA_TRY(loss_finalize(d(o_acc) + 4, any_pen ? d(o_acc) + 5 : nullptr, inv_n, Bn, gp(P), d(o_acc), s));
+  if (!cond) {
+    // dtheta currently holds sum over rows of dL/dtheta (not / N)
+    DCA_TRY(theta_grad_finish(f(o_dtheta), f(o_chain), G, inv_n, gp(theta_off), s));
+  }
+
+  // ---- head backward
+  float* dh = f(o_dh[0]); float* dh2 = f(o_dh[1]);
+  if (L > 0) DCA_CUDA_OK(cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)Bn * K_head, s));
+  float* dz[3] = {Mb, cond ? Db : nullptr, has_pi ? Pb : nullptr};
+  for (int k = 0; k < 3; ++k) {
+    if (head_W[k] < 0 || !dz[k]) continue;
+    GemmArgs g{};
+    g.A = head_in; g.lda = head_ld; g.a_bf16 = head_bf16; g.transA = 1; g.a_rows = head_rows;
+    g.B = dz[k]; g.ldb = G; g.transB = 0;
+    g.C = gp(head_W[k]); g.ldc = G; g.M = K_head; g.N = G; g.K = Bn; g.epilogue = EPI_ACCUM;
+    DCA_TRY(gemm_auto(g, s));
+    DCA_TRY(col_sums(dz[k], nullptr, G, Bn, G, d(o_dsum), nullptr, d(o_scratch), s));
+    DCA_TRY(col_sum_to_float(d(o_dsum), G, gp(head_b[k]), s));
+    if (L > 0) {
+      GemmArgs b{};
+      b.A = dz[k]; b.lda = G; b.a_bf16 = 0; b.transA = 0; b.a_rows = nullptr;
+      b.B = pp(head_W[k]); b.ldb = G; b.transB = 1;
+      b.C = dh; b.ldc = K_head; b.M = Bn; b.N = K_head; b.K = G; b.epilogue = EPI_ACCUM;
+      DCA_TRY(gemm_auto(b, s));
+    }
+  }
+  // ---- hidden stack backward
+  for (int i = L - 1; i >= 0; --i) {
+    Layer& l = lay[i];
+    DCA_TRY(relu_bwd(dh, f(l.o_h), l.out, Bn, l.out, s));
+    if (cfg.batchnorm) {
+      DCA_TRY(col_sums(dh, f(l.o_xhat), l.out, Bn, l.out, d(o_dsum), d(o_dprod), d(o_scratch), s));
+      DCA_TRY(bn_bwd_apply(dh, f(l.o_xhat), l.out, Bn, l.out, f(l.o_inv), d(o_dsum), d(o_dprod), gp(l.beta), s));
+    }
+    const void* ain = (i == 0) ? X : (const void*)f(lay[i - 1].o_h);
+    GemmArgs g{};
+    g.A = ain; g.lda = (i == 0) ? ldx : lay[i - 1].out; g.a_bf16 = (i == 0) ? (cfg.x_dtype == DCA_BF16) : 0;
+    g.transA = 1; g.a_rows = (i == 0) ? rows : nullptr;
+    g.B = dh; g.ldb = l.out; g.transB = 0;
+    g.C = gp(l.W); g.ldc = l.out; g.M = l.in; g.N = l.out; g.K = Bn; g.epilogue = EPI_ACCUM;
+    DCA_TRY(gemm_auto(g, s));
+    DCA_TRY(col_sums(dh, nullptr, l.out, Bn, l.out, d(o_dsum), nullptr, d(o_scratch), s));
+    DCA_TRY(col_sum_to_float(d(o_dsum), l.out, gp(l.b), s));
+    if (i > 0) {
+      GemmArgs b{};
+      b.A = dh; b.lda = l.out; b.transA = 0;
+      b.B = pp(l.W); b.ldb = l.out; b.transB = 1;
+      b.C = dh2; b.ldc = l.in; b.M = Bn; b.N = l.in; b.K = l.out; b.epilogue = EPI_STORE; b.splits = 1;
+      DCA_TRY(gemm_generic(b, s));
+      float* t = dh; dh = dh2; dh2 = t;
+    }
+  }
+  return DCA_OK;
+}
+
+int Engine::apply_update(float lr, float clip, float grad_scale, cudaStream_t s) {
+  DCA_TRY(rmsprop_update(pp(0), gp(0), f(o_rms), P, lr, clip, cfg.rms_rho, cfg.rms_eps, grad_scale, s));
+  return DCA_OK;
+}
+
+int Engine::eval_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows,
+                      int Bn, cudaStream_t s) {
+  if (!X || !Y) { set_error("dca_eval_step: X and Y must not be NULL"); return DCA_ERR_BAD_ARG; }
+  if (Bn <= 0 || Bn > cfg.max_batch) { set_error("dca_eval_step: batch %d outside (0, max_batch=%d]", Bn, cfg.max_batch); return DCA_ERR_BAD_ARG; }
+  const int G = cfg.n_out;
+  DCA_TRY(forward(X, ldx, rows, Bn, false, s));
+  float* Mb = f(o_head[0]); float* Db = f(o_head[1]); float* Pb = f(o_head[2]);
+  DCA_TRY(heads_forward(Bn, Mb, cond ? Db : nullptr, has_pi ? Pb : nullptr, G, nullptr, s));
+  if (!cond) DCA_TRY(theta_prepare(pp(theta_off), G, f(o_theta), f(o_chain), s));
+  LossArgs la{};
+  la.Y = Y; la.ldy = ldy; la.rows = rows; la.sf = sf;
+  la.m = Mb; la.d = cond ? Db : f(o_theta); la.pi = has_pi ? Pb : nullptr; la.ld = G;
+  la.B = Bn; la.G = G; la.ae_type = cfg.ae_type; la.ridge = cfg.ridge; la.inv_n = 1.f;
+  la.loss_sum = d(o_acc) + 2; la.ws = base + o_lossws; la.ws_bytes = loss_ws_bytes;
+  DCA_TRY(zinb_loss_fwd(la, s));
+  add_double_kernel<<<1, 1, 0, s>>>(d(o_acc) + 3, (double)Bn * (double)G);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int Engine::predict(const void* X, int64_t ldx, const float* sf, const int32_t* rows, int Bn, float* mean_out,
+                    float* disp_out, float* pi_out, int64_t ld_out, float* latent_out, cudaStream_t s) {
+  if (!X) { set_error("dca_predict: X must not be NULL"); return DCA_ERR_BAD_ARG; }
+  if (Bn <= 0 || Bn > cfg.max_batch) { set_error("dca_predict: batch %d outside (0, max_batch=%d]", Bn, cfg.max_batch); return DCA_ERR_BAD_ARG; }
+  const int G = cfg.n_out;
+  DCA_TRY(forward(X, ldx, rows, Bn, false, s));
+  if (latent_out) {
+    if (L == 0) { set_error("dca_predict: no hidden layer -> no latent output"); return DCA_ERR_BAD_ARG; }
+    const int c = L / 2;
+    copy_strided_kernel<<<cdiv((int64_t)Bn * lay[c].out, 256), 256, 0, s>>>(f(lay[c].o_a), lay[c].out, latent_out,
+                                                                            lay[c].out, Bn, lay[c].out);
+    DCA_LAUNCH_CHECK();
+  }
+  const bool want_heads = mean_out || (cond && disp_out) || (has_pi && pi_out);
+  if (want_heads) {
+    gather_sf_kernel<<<cdiv(Bn, 256), 256, 0, s>>>(sf, rows, Bn, f(o_sfb));
+    DCA_LAUNCH_CHECK();
+    DCA_TRY(heads_forward(Bn, mean_out, cond ? disp_out : nullptr, has_pi ? pi_out : nullptr, ld_out, f(o_sfb), s));
+  }
+  if (!cond && disp_out) {
+    DCA_TRY(theta_prepare(pp(theta_off), G, disp_out, f(o_chain), s));
+  }
+  return DCA_OK;
+}
+
+int Engine::init_params(uint64_t seed, cudaStream_t s) {
+  DCA_CUDA_OK(cudaMemsetAsync(pp(0), 0, sizeof(float) * (size_t)P, s));
+  DCA_CUDA_OK(cudaMemsetAsync(f(o_rms), 0, sizeof(float) * (size_t)P, s));
+  DCA_CUDA_OK(cudaMemsetAsync(gp(0), 0, sizeof(float) * (size_t)(P + 2), s));
+  DCA_CUDA_OK(cudaMemsetAsync(d(o_acc), 0, sizeof(double) * 8, s));
+  uint64_t sid = 0;
+  for (int i = 0; i < L; ++i)
+    DCA_TRY(glorot_fill(pp(lay[i].W), (int64_t)lay[i].in * lay[i].out, lay[i].in, lay[i].out, seed, sid++, s));
+  for (int k = 0; k < 3; ++k)
+    if (head_W[k] >= 0) DCA_TRY(glorot_fill(pp(head_W[k]), (int64_t)K_head * cfg.n_out, K_head, cfg.n_out, seed, 100 + k, s));
+  if (cfg.batchnorm)
+    for (int i = 0; i < L; ++i) {
+      DCA_TRY(fill_value(st(lay[i].mm), lay[i].out, 0.f, s));
+      DCA_TRY(fill_value(st(lay[i].mv), lay[i].out, 1.f, s));
+    }
+  return DCA_OK;
+}
+
+}  // namespace dca
+
+// ==================================================================================== C ABI
+using namespace dca;
+
+struct dca_handle { Engine e; void* owned = nullptr; int device = 0; };
+
+extern "C" int dca_version(void) { return DCA_B200_VERSION; }
+extern "C" const char* dca_last_error(void) { return g_err; }
+extern "C" int64_t dca_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" void dca_config_default(dca_config* c) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->struct_bytes = (int32_t)sizeof(dca_config);
+  c->n_hidden = 3; c->hidden[0] = 64; c->hidden[1] = 32; c->hidden[2] = 64;   // dca/network.py:47
+  c->ae_type = DCA_AE_ZINB_CONDDISP;
+  c->batchnorm = 1; c->max_batch = 32; c->x_dtype = DCA_F32; c->gemm_path = DCA_GEMM_AUTO;
+  c->bn_momentum = 0.99f; c->bn_eps = 1e-3f; c->rms_rho = 0.9f; c->rms_eps = 1e-7f;
+}
+
+extern "C" int dca_arena_bytes(const dca_config* cfg, size_t* bytes) {
+  DCA_TRY(validate(cfg));
+  if (!bytes) { set_error("dca_arena_bytes: bytes is NULL"); return DCA_ERR_BAD_ARG; }
+  Engine e;
+  DCA_TRY(e.plan(*cfg));
+  *bytes = e.arena_bytes;
+  return DCA_OK;
+}
+
+extern "C" int dca_create(const dca_config* cfg, void* arena, size_t arena_bytes, dca_handle** out) {
+  if (!out) { set_error("dca_create: out is NULL"); return DCA_ERR_BAD_ARG; }
+  *out = nullptr;
+  DCA_TRY(validate(cfg));
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    (void)cudaGetLastError();
+    set_error("dca_create: no CUDA device available (this library has no CPU fallback)");
+    return DCA_ERR_NO_DEVICE;
+  }
+  dca_handle* h = new dca_handle();
+  int st = h->e.plan(*cfg);
+  if (st != DCA_OK) { delete h; return st; }
+  if (cfg->gemm_path == DCA_GEMM_TCGEN05 && !h->e.tc_supported()) {
+    set_error("dca_create: gemm_path=TCGEN05 requested but the layer shapes do not qualify (%s)", h->e.tc_reason());
+    delete h; return DCA_ERR_UNSUPPORTED;
+  }
+  cudaGetDevice(&h->device);
+  if (arena) {
+    if (arena_bytes < h->e.arena_bytes) {
+      set_error("dca_create: arena too small (%zu < %zu)", arena_bytes, h->e.arena_bytes);
+      delete h; return DCA_ERR_BAD_ARG;
+    }
+    if (reinterpret_cast<uintptr_t>(arena) & 255) { set_error("dca_create: arena must be 256-byte aligned"); delete h; return DCA_ERR_BAD_ARG; }
+    h->e.bind(arena);
+  } else {
+    void* p = nullptr;
+    cudaError_t ce = cudaMalloc(&p, h->e.arena_bytes);
+    if (ce != cudaSuccess) { set_error("dca_create: cudaMalloc(%zu) failed: %s", h->e.arena_bytes, cudaGetErrorString(ce)); delete h; return DCA_ERR_CUDA; }
+    h->owned = p;
+    h->e.bind(p);
+  }
+  cudaError_t ce = cudaMemset(h->e.base, 0, h->e.arena_bytes);
+  if (ce != cudaSuccess) { set_error("dca_create: cudaMemset failed: %s", cudaGetErrorString(ce)); if (h->owned) cudaFree(h->owned); delete h; return DCA_ERR_CUDA; }
+  st = h->e.setup_tc();
+  if (st != DCA_OK) { if (h->owned) cudaFree(h->owned); delete h; return st; }
+  *out = h;
+  return DCA_OK;
+}
+
+extern "C" int dca_destroy(dca_handle* h) {
+  if (!h) return DCA_OK;
+  if (h->owned) cudaFree(h->owned);
+  delete h;
+  return DCA_OK;
+}
+
+#define DCA_NEED_HANDLE(h) \
+  if (!(h)) { set_error("%s: handle is NULL", __func__); return DCA_ERR_BAD_ARG; }
+
+extern "C" int dca_param_count(const dca_handle* h, int64_t* n, int32_t* nt) {
+  DCA_NEED_HANDLE(h);
+  if (n) *n = h->e.P;
+  if (nt) *nt = (int32_t)h->e.params.size();
+  return DCA_OK;
+}
+extern "C" int dca_param_info(const dca_handle* h, int32_t i, dca_tensor_info* info) {
+  DCA_NEED_HANDLE(h);
+  if (!info || i < 0 || i >= (int32_t)h->e.params.size()) { set_error("dca_param_info: index out of range"); return DCA_ERR_BAD_ARG; }
+  *info = h->e.params[i];
+  return DCA_OK;
+}
+extern "C" int dca_state_count(const dca_handle* h, int64_t* n, int32_t* nt) {
+  DCA_NEED_HANDLE(h);
+  if (n) *n = h->e.S;
+  if (nt) *nt = (int32_t)h->e.states.size();
+  return DCA_OK;
+}
+extern "C" int dca_state_info(const dca_handle* h, int32_t i, dca_tensor_info* info) {
+  DCA_NEED_HANDLE(h);
+  if (!info || i < 0 || i >= (int32_t)h->e.states.size()) { set_error("dca_state_info: index out of range"); return DCA_ERR_BAD_ARG; }
+  *info = h->e.states[i];
+  return DCA_OK;
+}
+extern "C" int dca_region(dca_handle* h, int32_t id, void** ptr, int64_t* count) {
+  DCA_NEED_HANDLE(h);
+  Engine& e = h->e;
+  void* p = nullptr; int64_t n = 0;
+  switch (id) {
+    case DCA_REGION_PARAMS: p = e.base + e.o_params; n = e.P; break;
+    case DCA_REGION_GRADS: p = e.base + e.o_grads; n = e.P + 2; break;
+    case DCA_REGION_RMS: p = e.base + e.o_rms; n = e.P; break;
+    case DCA_REGION_BN_STATE: p = e.base + e.o_state; n = e.S; break;
+    case DCA_REGION_EPOCH_ACC: p = e.base + e.o_acc; n = 4; break;
+    default: set_error("dca_region: unknown region %d", id); return DCA_ERR_BAD_ARG;
+  }
+  if (ptr) *ptr = p;
+  if (count) *count = n;
+  return DCA_OK;
+}
+
+extern "C" int dca_init_params(dca_handle* h, uint64_t seed, void* stream) {
+  DCA_NEED_HANDLE(h);
+  DCA_TRY(h->e.init_params(seed, (cudaStream_t)stream));
+  return h->e.refresh_shadows((cudaStream_t)stream);
+}
+extern "C" int dca_params_changed(dca_handle* h, void* stream) {
+  DCA_NEED_HANDLE(h);
+  return h->e.refresh_shadows((cudaStream_t)stream);
+}
+
+extern "C" int dca_train_step(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf,
+                              const int32_t* rows, int32_t batch, void* stream) {
+  DCA_NEED_HANDLE(h);
+  return h->e.train_step(X, ldx, Y, ldy, sf, rows, batch, (cudaStream_t)stream);
+}
+extern "C" int dca_apply_update(dca_handle* h, float lr, float clip, float grad_scale, void* stream) {
+  DCA_NEED_HANDLE(h);
+  DCA_TRY(h->e.apply_update(lr, clip, grad_scale, (cudaStream_t)stream));
+  return h->e.refresh_shadows((cudaStream_t)stream);
+}
+extern "C" int dca_eval_step(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf,
+                             const int32_t* rows, int32_t batch, void* stream) {
+  DCA_NEED_HANDLE(h);
+  return h->e.eval_step(X, ldx, Y, ldy, sf, rows, batch, (cudaStream_t)stream);
+}
+extern "C" int dca_predict(dca_handle* h, const void* X, int64_t ldx, const float* sf, const int32_t* rows,
+                           int32_t batch, float* mean_out, float* disp_out, float* pi_out, int64_t ld_out,
+                           float* latent_out, void* stream) {
+  DCA_NEED_HANDLE(h);
+  return h->e.predict(X, ldx, sf, rows, batch, mean_out, disp_out, pi_out, ld_out, latent_out, (cudaStream_t)stream);
+}
+
+extern "C" int dca_read_loss(dca_handle* h, float* loss_host, int32_t* nonfinite_host, void* stream) {
+  DCA_NEED_HANDLE(h);
+  float v[2] = {0.f, 0.f};
+  cudaStream_t s = (cudaStream_t)stream;
+  DCA_CUDA_OK(cudaMemcpyAsync(v, h->e.gp(h->e.P), sizeof(v), cudaMemcpyDeviceToHost, s));
+  DCA_CUDA_OK(cudaStreamSynchronize(s));
+  if (loss_host) *loss_host = v[0];
+  if (nonfinite_host) *nonfinite_host = v[1] != 0.f;
+  return DCA_OK;
+}
+extern "C" int dca_read_epoch_acc(dca_handle* h, double acc_host[4], int32_t reset, void* stream) {
+  DCA_NEED_HANDLE(h);
+  cudaStream_t s = (cudaStream_t)stream;
+  DCA_CUDA_OK(cudaMemcpyAsync(acc_host, h->e.d(h->e.o_acc), 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (reset) DCA_CUDA_OK(cudaMemsetAsync(h->e.d(h->e.o_acc), 0, 4 * sizeof(double), s));
+  DCA_CUDA_OK(cudaStreamSynchronize(s));
+  return DCA_OK;
+}
+
+extern "C" int dca_train_step_host(dca_handle* h, const void* x_host, const float* y_host, const float* sf_host,
+                                   int32_t batch, float lr, float clip, float* loss_host, void* stream) {
+  DCA_NEED_HANDLE(h);
+  Engine& e = h->e;
+  if (!x_host || !y_host) { set_error("dca_train_step_host: NULL host buffer"); return DCA_ERR_BAD_ARG; }
+  if (batch <= 0 || batch > e.cfg.max_batch) { set_error("dca_train_step_host: batch %d outside (0, max_batch=%d]", batch, e.cfg.max_batch); return DCA_ERR_BAD_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t xb = (e.cfg.x_dtype == DCA_BF16) ? 2 : 4;
+  DCA_CUDA_OK(cudaMemcpyAsync(e.base + e.o_stage_x, x_host, xb * (size_t)batch * e.cfg.n_in, cudaMemcpyHostToDevice, s));
+  DCA_CUDA_OK(cudaMemcpyAsync(e.base + e.o_stage_y, y_host, sizeof(float) * (size_t)batch * e.cfg.n_out, cudaMemcpyHostToDevice, s));
+  const float* sfd = nullptr;
+  if (sf_host) {
+    DCA_CUDA_OK(cudaMemcpyAsync(e.base + e.o_stage_sf, sf_host, sizeof(float) * (size_t)batch, cudaMemcpyHostToDevice, s));
+    sfd = e.f(e.o_stage_sf);
+  }
+  DCA_TRY(e.train_step(e.base + e.o_stage_x, e.cfg.n_in, e.f(e.o_stage_y), e.cfg.n_out, sfd, nullptr, batch, s));
+  DCA_TRY(e.apply_update(lr, clip, 1.0f, s));
+  DCA_TRY(e.refresh_shadows(s));
+  return dca_read_loss(h, loss_host, nullptr, stream);
+}

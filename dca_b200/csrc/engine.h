@@ -1,0 +1,69 @@
+// Engine: arena layout + kernel sequencing (see engine.cu).
+#pragma once
+#include <string>
+#include <vector>
+#include "dca_internal.cuh"
+
+namespace dca {
+
+struct Layer {
+  int in = 0, out = 0;
+  int64_t W = -1, b = -1, beta = -1;     // element offsets into params / grads
+  int64_t mm = -1, mv = -1;              // element offsets into the BN state region
+  size_t o_a = 0, o_xhat = 0, o_h = 0, o_mean = 0, o_inv = 0;   // byte offsets into the arena
+};
+
+struct TcState;   // tcgen05 path (dense_tc.cu)
+
+struct Engine {
+  dca_config cfg{};
+  int L = 0, maxh = 1, K_head = 0;
+  bool has_pi = false, cond = false;
+  int64_t P = 0, S = 0;
+  std::vector<dca_tensor_info> params, states;
+  Layer lay[DCA_MAX_HIDDEN];
+  int64_t head_W[3], head_b[3], theta_off = -1;
+  // arena
+  char* base = nullptr;
+  size_t arena_bytes = 0;
+  size_t o_params = 0, o_grads = 0, o_rms = 0, o_state = 0, o_acc = 0;
+  size_t o_head[3] = {0, 0, 0}, o_dh[2] = {0, 0}, o_dsum = 0, o_dprod = 0, o_scratch = 0;
+  size_t o_theta = 0, o_chain = 0, o_dtheta = 0, o_sfb = 0, o_lossws = 0, loss_ws_bytes = 0;
+  size_t o_stage_x = 0, o_stage_y = 0, o_stage_sf = 0;
+  // head input of the current forward (set by forward())
+  const void* head_in = nullptr; int64_t head_ld = 0; int head_bf16 = 0; const int32_t* head_rows = nullptr;
+  // tcgen05 path
+  TcState* tc = nullptr;
+  size_t o_tc = 0, tc_bytes = 0;
+
+  ~Engine();
+  int plan(const dca_config& c);
+  void bind(void* base_);
+  float* f(size_t byte_off) const { return reinterpret_cast<float*>(base + byte_off); }
+  double* d(size_t byte_off) const { return reinterpret_cast<double*>(base + byte_off); }
+  float* pp(int64_t elem) const { return reinterpret_cast<float*>(base + o_params) + elem; }
+  float* gp(int64_t elem) const { return reinterpret_cast<float*>(base + o_grads) + elem; }
+  float* st(int64_t elem) const { return reinterpret_cast<float*>(base + o_state) + elem; }
+
+  int gemm_auto(GemmArgs g, cudaStream_t s);
+  int forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, bool training, cudaStream_t s);
+  int heads_forward(int Bn, float* m_out, float* d_out, float* p_out, int64_t ld_out, const float* row_scale,
+                    cudaStream_t s);
+  int penalty(cudaStream_t s, bool& any);
+  int train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
+                 cudaStream_t s);
+  int apply_update(float lr, float clip, float grad_scale, cudaStream_t s);
+  int eval_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
+                cudaStream_t s);
+  int predict(const void* X, int64_t ldx, const float* sf, const int32_t* rows, int Bn, float* mean_out, float* disp_out,
+              float* pi_out, int64_t ld_out, float* latent_out, cudaStream_t s);
+  int init_params(uint64_t seed, cudaStream_t s);
+
+  // tcgen05 path hooks (dense_tc.cu)
+  bool tc_supported() const;
+  const char* tc_reason() const;
+  int setup_tc();
+  int refresh_shadows(cudaStream_t s);
+};
+
+}  // namespace dca

@@ -1,0 +1,334 @@
+// Small element-wise / column-reduction kernels of the hidden stack and the optimizer:
+//   BatchNormalization(center=True, scale=False) train / inference / backward  (dca/network.py:127-128)
+//   relu forward / backward                                                    (dca/network.py:135)
+//   ConstantDispersionLayer theta = clip(exp(theta_raw), 1e-3, 1e4)             (dca/layers.py:17-21)
+//   l1_l2 kernel regulariser gradient + penalty                                (dca/network.py:125)
+//   clipvalue + RMSprop                                                        (dca/train.py:54-57)
+//   Glorot-uniform initialiser                                                 (dca/network.py:124-126)
+#include "dca_internal.cuh"
+
+namespace dca {
+namespace {
+
+constexpr int kColChunks = 64;   // row chunks for column statistics
+
+__global__ void fill_rows_kernel(float* C, int64_t ldc, int M, int N, const float* __restrict__ bias) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  const int r = (int)(i / N), c = (int)(i % N);
+  C[(int64_t)r * ldc + c] = bias ? bias[c] : 0.f;
+}
+
+// partial column sums over a chunk of rows: block (32 cols, 8 row lanes)
+__global__ void col_sums_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t ld,
+                                        int M, int N, int rows_per_chunk, double* __restrict__ psum,
+                                        double* __restrict__ pprod) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(M, r0 + rows_per_chunk);
+  double t1 = 0.0, t2 = 0.0;
+  if (col < N) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float x = a[(int64_t)r * ld + col];
+      const float y = b ? b[(int64_t)r * ld + col] : x;
+      t1 += (double)x;
+      t2 += (double)x * (double)y;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = t1;
+  s2[threadIdx.y][threadIdx.x] = t2;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { t1 += s1[i][threadIdx.x]; t2 += s2[i][threadIdx.x]; }
+    psum[(int64_t)blockIdx.y * N + col] = t1;
+    pprod[(int64_t)blockIdx.y * N + col] = t2;
+  }
+}
+
+__global__ void col_sums_fold_kernel(const double* __restrict__ psum, const double* __restrict__ pprod, int chunks,
+                                     int N, double* __restrict__ out_sum, double* __restrict__ out_prod) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < chunks; ++k) { a += psum[(int64_t)k * N + c]; b += pprod[(int64_t)k * N + c]; }
+  out_sum[c] = a;
+  if (out_prod) out_prod[c] = b;
+}
+
+__global__ void bn_train_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq, int M, int N,
+                                         float eps, float momentum, float* __restrict__ mean,
+                                         float* __restrict__ inv_std, float* __restrict__ mmean,
+                                         float* __restrict__ mvar) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const double mu = sum[c] / (double)M;
+  double var = sq[c] / (double)M - mu * mu;          // biased batch variance (Keras non-fused BN)
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  inv_std[c] = (float)(1.0 / sqrt(var + (double)eps));
+  mmean[c] = momentum * mmean[c] + (1.0f - momentum) * (float)mu;
+  mvar[c] = momentum * mvar[c] + (1.0f - momentum) * (float)var;
+}
+
+__global__ void bn_relu_fwd_kernel(const float* __restrict__ a, int64_t ld, int M, int N,
+                                   const float* __restrict__ mean, const float* __restrict__ inv_std,
+                                   const float* __restrict__ beta, float* __restrict__ xhat,
+                                   float* __restrict__ h, __nv_bfloat16* __restrict__ hb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  const int r = (int)(i / N), c = (int)(i % N);
+  const float xh = (a[(int64_t)r * ld + c] - mean[c]) * inv_std[c];
+  if (xhat) xhat[i] = xh;
+  const float v = fmaxf(xh + beta[c], 0.f);
+  h[i] = v;
+  if (hb) hb[i] = __float2bfloat16_rn(v);
+}
+
+__global__ void bn_infer_prepare_kernel(const float* __restrict__ mm, const float* __restrict__ mv, int N, float eps,
+                                        float* __restrict__ mean, float* __restrict__ inv_std) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  mean[c] = mm[c];
+  inv_std[c] = rsqrtf(mv[c] + eps);
+}
+
+__global__ void relu_fwd_kernel(const float* __restrict__ a, int64_t ld, int M, int N, float* __restrict__ h) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  const int r = (int)(i / N), c = (int)(i % N);
+  h[i] = fmaxf(a[(int64_t)r * ld + c], 0.f);
+}
+
+__global__ void relu_bwd_kernel(float* __restrict__ dh, const float* __restrict__ h, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!(h[i] > 0.f)) dh[i] = 0.f;
+}
+
+__global__ void bn_bwd_apply_kernel(float* __restrict__ g, const float* __restrict__ xhat, int M, int N,
+                                    const float* __restrict__ inv_std, const double* __restrict__ sum_g,
+                                    const double* __restrict__ sum_gx, float* __restrict__ dbeta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  const int c = (int)(i % N);
+  const float mg = (float)(sum_g[c] / (double)M), mgx = (float)(sum_gx[c] / (double)M);
+  g[i] = inv_std[c] * (g[i] - mg - xhat[i] * mgx);
+  if (i < N && dbeta) dbeta[c] = (float)sum_g[c];
+}
+
+__global__ void double_to_float_kernel(const double* __restrict__ in, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+__global__ void theta_prepare_kernel(const float* __restrict__ raw, int G, float* __restrict__ theta,
+                                     float* __restrict__ chain) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const float e = expf(raw[g]);
+  const float t = fminf(fmaxf(e, 1e-3f), 1e4f);        // dca/layers.py:21
+  theta[g] = t;
+  chain[g] = (e >= 1e-3f && e <= 1e4f) ? t : 0.f;       // d theta / d raw, clip_by_value gradient
+}
+
+__global__ void theta_grad_finish_kernel(const float* __restrict__ dth, const float* __restrict__ chain, int G,
+                                         float scale, float* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) out[g] = dth[g] * chain[g] * scale;
+}
+
+__global__ void add_reg_grad_kernel(const float* __restrict__ w, float* __restrict__ g, int64_t n, float l1, float l2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = w[i];
+  const float sg = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
+  g[i] += l1 * sg + 2.f * l2 * v;
+}
+
+__global__ void reg_penalty_kernel(const float* __restrict__ w, int64_t n, float l1, float l2, double* acc) {
+  __shared__ double sm[8];
+  double t = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = w[i];
+    t += l1 * fabs(v) + l2 * v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += sm[i];
+    atomicAdd(acc, a);
+  }
+}
+
+__global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ r, int64_t n,
+                               float lr, float clip, float rho, float eps, float gs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] * gs;
+  if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);       // clipvalue
+  const float ri = rho * r[i] + (1.0f - rho) * gi * gi;
+  r[i] = ri;
+  p[i] -= lr * gi / (sqrtf(ri) + eps);                      // epsilon outside the sqrt (Keras RMSprop)
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void glorot_kernel(float* __restrict__ w, int64_t n, float limit, uint64_t seed, uint64_t sid) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t h = splitmix64(splitmix64(seed ^ (sid * 0xD1B54A32D192ED03ull)) + (uint64_t)i);
+  const float u = (float)(h >> 40) * (1.0f / 16777216.0f);   // [0,1)
+  w[i] = (2.0f * u - 1.0f) * limit;
+}
+
+__global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+inline int blocks_for(int64_t n, int t = 256) { return (int)((n + t - 1) / t); }
+
+}  // namespace
+
+int fill_rows_with_bias(float* C, int64_t ldc, int M, int N, const float* bias, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return DCA_OK;
+  fill_rows_kernel<<<blocks_for((int64_t)M * N), 256, 0, s>>>(C, ldc, M, N, bias);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int col_sums_scratch_elems(int M, int N) { (void)M; return 2 * kColChunks * N; }
+
+int col_sums(const float* a, const float* b, int64_t ld, int M, int N, double* out_sum, double* out_prod,
+             double* scratch, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return DCA_OK;
+  int rpc = cdiv(M, kColChunks);
+  if (rpc < 8) rpc = 8;
+  const int chunks = cdiv(M, rpc);
+  double* psum = scratch;
+  double* pprod = scratch + (size_t)kColChunks * N;
+  col_sums_partial_kernel<<<dim3(cdiv(N, 32), chunks), dim3(32, 8), 0, s>>>(a, b, ld, M, N, rpc, psum, pprod);
+  DCA_LAUNCH_CHECK();
+  col_sums_fold_kernel<<<cdiv(N, 128), 128, 0, s>>>(psum, pprod, chunks, N, out_sum, out_prod);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int bn_train_finalize(const double* sum, const double* sq, int M, int N, float eps, float momentum, float* mean,
+                      float* inv_std, float* moving_mean, float* moving_var, cudaStream_t s) {
+  bn_train_finalize_kernel<<<cdiv(N, 128), 128, 0, s>>>(sum, sq, M, N, eps, momentum, mean, inv_std, moving_mean,
+                                                        moving_var);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int bn_relu_fwd(const float* a, int64_t ld, int M, int N, const float* mean, const float* inv_std, const float* beta,
+                float* xhat, float* h, __nv_bfloat16* h_bf16, cudaStream_t s) {
+  bn_relu_fwd_kernel<<<blocks_for((int64_t)M * N), 256, 0, s>>>(a, ld, M, N, mean, inv_std, beta, xhat, h, h_bf16);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int bn_infer_prepare(const float* mm, const float* mv, int N, float eps, float* mean, float* inv_std, cudaStream_t s) {
+  bn_infer_prepare_kernel<<<cdiv(N, 128), 128, 0, s>>>(mm, mv, N, eps, mean, inv_std);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int bias_relu_fwd(const float* a, int64_t ld, int M, int N, float* h, cudaStream_t s) {
+  relu_fwd_kernel<<<blocks_for((int64_t)M * N), 256, 0, s>>>(a, ld, M, N, h);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int relu_bwd(float* dh, const float* h, int64_t ld, int M, int N, cudaStream_t s) {
+  (void)ld;
+  relu_bwd_kernel<<<blocks_for((int64_t)M * N), 256, 0, s>>>(dh, h, (int64_t)M * N);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int bn_bwd_apply(float* g, const float* xhat, int64_t ld, int M, int N, const float* inv_std, const double* sum_g,
+                 const double* sum_gx, float* dbeta, cudaStream_t s) {
+  (void)ld;
+  bn_bwd_apply_kernel<<<blocks_for((int64_t)M * N), 256, 0, s>>>(g, xhat, M, N, inv_std, sum_g, sum_gx, dbeta);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int col_sum_to_float(const double* sum, int N, float* out, cudaStream_t s) {
+  double_to_float_kernel<<<cdiv(N, 128), 128, 0, s>>>(sum, N, out);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int theta_prepare(const float* raw, int G, float* theta, float* chain, cudaStream_t s) {
+  theta_prepare_kernel<<<cdiv(G, 256), 256, 0, s>>>(raw, G, theta, chain);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int theta_grad_finish(const float* dth, const float* chain, int G, float scale, float* out, cudaStream_t s) {
+  theta_grad_finish_kernel<<<cdiv(G, 256), 256, 0, s>>>(dth, chain, G, scale, out);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int add_reg_grad(const float* w, float* g, int64_t n, float l1, float l2, cudaStream_t s) {
+  add_reg_grad_kernel<<<blocks_for(n), 256, 0, s>>>(w, g, n, l1, l2);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int reg_penalty(const float* w, int64_t n, float l1, float l2, double* acc, cudaStream_t s) {
+  int blocks = blocks_for(n);
+  if (blocks > 296) blocks = 296;
+  reg_penalty_kernel<<<blocks, 256, 0, s>>>(w, n, l1, l2, acc);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int rmsprop_update(float* params, const float* grads, float* rms, int64_t n, float lr, float clip, float rho,
+                   float eps, float grad_scale, cudaStream_t s) {
+  rmsprop_kernel<<<blocks_for(n), 256, 0, s>>>(params, grads, rms, n, lr, clip, rho, eps, grad_scale);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int glorot_fill(float* w, int64_t n, int fan_in, int fan_out, uint64_t seed, uint64_t sid, cudaStream_t s) {
+  const float limit = sqrtf(6.0f / (float)(fan_in + fan_out));
+  glorot_kernel<<<blocks_for(n), 256, 0, s>>>(w, n, limit, seed, sid);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int fill_value(float* p, int64_t n, float v, cudaStream_t s) {
+  if (n <= 0) return DCA_OK;
+  fill_kernel<<<blocks_for(n), 256, 0, s>>>(p, n, v);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int cast_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s) {
+  if (n <= 0) return DCA_OK;
+  cast_bf16_kernel<<<blocks_for(n), 256, 0, s>>>(in, out, n);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+}  // namespace dca

@@ -1,0 +1,296 @@
+// K3: ZINB / NB negative log-likelihood, forward + backward in ONE pass over the B x G head
+// outputs (replaces dca/loss.py:72-156 and the TF autodiff of it; see zinb_math.cuh).
+//
+// Layout: every tensor is row-major cells x genes.  A thread owns 4 consecutive genes (one
+// 128-bit load per tensor per row) and walks a strip of rows, so a warp touches 512 contiguous
+// bytes per tensor per row and the per-gene reduction needed by the constant-dispersion
+// variants stays in registers.  HBM traffic per element: y 4 B + nh*4 B in, nh*(4|2) B out.
+// The loss scalar is reduced thread -> warp shuffle -> shared memory -> one double per block,
+// and a second tiny kernel folds the block partials (deterministic, no float atomics).
+#include "dca_internal.cuh"
+#include "zinb_math.cuh"
+
+namespace dca {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kVec = 4;
+constexpr int kColsPerBlock = kThreads * kVec;   // 1024 genes per block
+constexpr int kMaxRowChunks = 128;
+
+struct Plan { int col_blocks, rows_per_block, row_chunks; };
+
+inline Plan make_plan(int B, int G) {
+  Plan p;
+  p.col_blocks = cdiv(G, kColsPerBlock);
+  int rpb = 16;
+  while (cdiv(B, rpb) > kMaxRowChunks) rpb *= 2;
+  p.rows_per_block = rpb;
+  p.row_chunks = cdiv(B, rpb);
+  return p;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 v;
+  v.x = *reinterpret_cast<uint32_t*>(&lo);
+  v.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = v;
+}
+__device__ __forceinline__ void st1(float* p, float a) { *p = a; }
+__device__ __forceinline__ void st1(__nv_bfloat16* p, float a) { *p = __float2bfloat16_rn(a); }
+
+__device__ __forceinline__ double block_reduce_sum(float v, double* smem /* >= 8 */) {
+  double d = (double)v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) smem[w] = d;
+  __syncthreads();
+  double t = 0.0;
+  if (w == 0) {
+    t = (l < (kThreads >> 5)) ? smem[l] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;   // valid in thread 0
+}
+
+// VEC == 4: aligned 128-bit path; VEC == 1: scalar fallback for ragged G / unaligned ld.
+template <bool HAS_PI, bool COND_DISP, typename GT, int VEC, bool BWD>
+__global__ void __launch_bounds__(kThreads)
+zinb_loss_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __restrict__ rows,
+                 const float* __restrict__ sf, const float* m, const float* d, const float* pi,
+                 int64_t ld, int B, int G, float ridge, float inv_n, int rows_per_block,
+                 GT* dzm, GT* dzd, GT* dzp, float* __restrict__ dth_partial,
+                 double* __restrict__ loss_partial) {
+  __shared__ double red[8];
+  const int col0 = (blockIdx.x * kThreads + threadIdx.x) * VEC;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(B, r0 + rows_per_block);
+  float lsum = 0.f;
+  float tacc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) tacc[j] = 0.f;
+
+  if (col0 < G) {
+    float thg[VEC];
+    if (!COND_DISP) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) thg[j] = (col0 + j < G) ? d[col0 + j] : 1.f;
+    }
+    for (int r = r0; r < r1; ++r) {
+      const int64_t yr = rows ? (int64_t)rows[r] : (int64_t)r;
+      const float s = sf ? sf[yr] : 1.0f;
+      const float* yp = Y + yr * ldy + col0;
+      const int64_t off = (int64_t)r * ld + col0;
+      float yv[VEC], mv[VEC], dv[VEC], pv[VEC];
+      if (VEC == 4) {
+        float4 t = ld4_stream(yp); yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3] = t.w;
+        t = ld4(m + off); mv[0] = t.x; mv[1] = t.y; mv[2] = t.z; mv[3] = t.w;
+        if (COND_DISP) { t = ld4(d + off); dv[0] = t.x; dv[1] = t.y; dv[2] = t.z; dv[3] = t.w; }
+        if (HAS_PI) { t = ld4(pi + off); pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w; }
+      } else {
+        yv[0] = yp[0]; mv[0] = m[off];
+        if (COND_DISP) dv[0] = d[off];
+        if (HAS_PI) pv[0] = pi[off];
+      }
+      float gm[VEC], gd[VEC], gp[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float th = COND_DISP ? dv[j] : thg[j];
+        const float p = HAS_PI ? pv[j] : 0.f;
+        if (BWD) {
+          zmath::Elem e = zmath::zinb_elem<HAS_PI, COND_DISP>(yv[j], mv[j], s, th, p, ridge);
+          lsum += e.loss;
+          gm[j] = e.gm * inv_n; gd[j] = e.gd * inv_n; gp[j] = e.gp * inv_n;
+          if (!COND_DISP) tacc[j] += e.gd;
+        } else {
+          lsum += zmath::zinb_elem_loss<HAS_PI>(yv[j], mv[j], s, th, p, ridge);
+        }
+      }
+      if (BWD) {
+        if (VEC == 4) {
+          st4(dzm + off, gm[0], gm[1], gm[2], gm[3]);
+          if (COND_DISP) st4(dzd + off, gd[0], gd[1], gd[2], gd[3]);
+          if (HAS_PI) st4(dzp + off, gp[0], gp[1], gp[2], gp[3]);
+        } else {
+          st1(dzm + off, gm[0]);
+          if (COND_DISP) st1(dzd + off, gd[0]);
+          if (HAS_PI) st1(dzp + off, gp[0]);
+        }
+      }
+    }
+    if (BWD && !COND_DISP) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        if (col0 + j < G) dth_partial[(int64_t)blockIdx.y * G + col0 + j] = tacc[j];
+    }
+  }
+  const double tot = block_reduce_sum(lsum, red);
+  if (threadIdx.x == 0) loss_partial[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+
+__global__ void fold_partials_kernel(const double* __restrict__ part, int n, double* out, int accumulate) {
+  __shared__ double sm[32];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += part[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (threadIdx.x == 0) *out = accumulate ? (*out + a) : a;
+  }
+}
+
+__global__ void fold_dtheta_kernel(const float* __restrict__ part, int chunks, int G, float* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  float a = 0.f;
+  for (int c = 0; c < chunks; ++c) a += part[(int64_t)c * G + g];
+  out[g] = a;
+}
+
+__global__ void loss_finalize_kernel(const double* loss_sum, const double* penalty, float inv_n, int batch,
+                                     float* loss_slot, double* epoch_acc) {
+  double l = (*loss_sum) * (double)inv_n;
+  if (l != l) l = INFINITY;                                   // _nan2inf, dca/loss.py:148
+  if (penalty) l += *penalty;
+  const float lf = (float)l;
+  loss_slot[0] = lf;
+  loss_slot[1] = (isfinite(lf)) ? 0.f : 1.f;
+  if (epoch_acc) { epoch_acc[0] += l * (double)batch; epoch_acc[1] += (double)batch; }
+}
+
+template <bool BWD>
+int launch(const LossArgs& a, cudaStream_t s) {
+  if (a.B <= 0 || a.G <= 0) { set_error("zinb_loss: empty batch (B=%d, G=%d)", a.B, a.G); return DCA_ERR_BAD_ARG; }
+  const bool has_pi = (a.ae_type == DCA_AE_ZINB_CONDDISP || a.ae_type == DCA_AE_ZINB);
+  const bool cond = (a.ae_type == DCA_AE_ZINB_CONDDISP || a.ae_type == DCA_AE_NB_CONDDISP);
+  if (!a.Y || !a.m || !a.d || (has_pi && !a.pi) || !a.loss_sum) { set_error("zinb_loss: null input"); return DCA_ERR_BAD_ARG; }
+  if (BWD && (!a.dzm || (cond && !a.dzd) || (has_pi && !a.dzp) || (!cond && !a.dtheta))) {
+    set_error("zinb_loss: null gradient output"); return DCA_ERR_BAD_ARG;
+  }
+  const Plan p = make_plan(a.B, a.G);
+  const size_t need = loss_workspace_bytes(a.B, a.G);
+  if (!a.ws || a.ws_bytes < need) { set_error("zinb_loss: workspace too small (%zu < %zu)", a.ws_bytes, need); return DCA_ERR_BAD_ARG; }
+  double* lpart = reinterpret_cast<double*>(a.ws);
+  float* tpart = reinterpret_cast<float*>(reinterpret_cast<char*>(a.ws) +
+                                         sizeof(double) * (size_t)kMaxRowChunks * (size_t)cdiv(a.G, kThreads));
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  bool vec = (a.G % 4 == 0) && (a.ld % 4 == 0) && (a.ldy % 4 == 0) && al16(a.Y) && al16(a.m) && al16(a.d) &&
+             (!has_pi || al16(a.pi));
+  if (BWD) vec = vec && al16(a.dzm) && (!cond || al16(a.dzd)) && (!has_pi || al16(a.dzp));
+  Plan q = p;
+  dim3 grid, block(kThreads);
+  if (vec) grid = dim3(p.col_blocks, p.row_chunks);
+  else { q.col_blocks = cdiv(a.G, kThreads); grid = dim3(q.col_blocks, p.row_chunks); }
+
+#define DCA_LOSS_LAUNCH(HP, CD, GT, V)                                                                 \
+  zinb_loss_kernel<HP, CD, GT, V, BWD><<<grid, block, 0, s>>>(                                          \
+      a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, a.G, a.ridge, a.inv_n, p.rows_per_block,      \
+      (GT*)a.dzm, (GT*)a.dzd, (GT*)a.dzp, tpart, lpart)
+#define DCA_LOSS_DISPATCH(GT, V)                                   \
+  do {                                                             \
+    if (has_pi && cond) DCA_LOSS_LAUNCH(true, true, GT, V);        \
+    else if (has_pi && !cond) DCA_LOSS_LAUNCH(true, false, GT, V); \
+    else if (!has_pi && cond) DCA_LOSS_LAUNCH(false, true, GT, V); \
+    else DCA_LOSS_LAUNCH(false, false, GT, V);                     \
+  } while (0)
+  if (BWD && a.grad_bf16) {
+    if (vec) DCA_LOSS_DISPATCH(__nv_bfloat16, 4); else DCA_LOSS_DISPATCH(__nv_bfloat16, 1);
+  } else {
+    if (vec) DCA_LOSS_DISPATCH(float, 4); else DCA_LOSS_DISPATCH(float, 1);
+  }
+#undef DCA_LOSS_DISPATCH
+#undef DCA_LOSS_LAUNCH
+  DCA_LAUNCH_CHECK();
+  fold_partials_kernel<<<1, 256, 0, s>>>(lpart, (int)(grid.x * grid.y), a.loss_sum, BWD ? 0 : 1);
+  DCA_LAUNCH_CHECK();
+  if (BWD && !cond) {
+    fold_dtheta_kernel<<<cdiv(a.G, 256), 256, 0, s>>>(tpart, p.row_chunks, a.G, a.dtheta);
+    DCA_LAUNCH_CHECK();
+  }
+  return DCA_OK;
+}
+
+}  // namespace
+
+size_t loss_workspace_bytes(int B, int G) {
+  (void)B;
+  const size_t colb_scalar = (size_t)cdiv(G, kThreads);
+  return sizeof(double) * kMaxRowChunks * colb_scalar + sizeof(float) * (size_t)kMaxRowChunks * (size_t)G + 256;
+}
+
+int zinb_loss_fwd_bwd(const LossArgs& a, cudaStream_t s) { return launch<true>(a, s); }
+int zinb_loss_fwd(const LossArgs& a, cudaStream_t s) { return launch<false>(a, s); }
+
+int loss_finalize(const double* loss_sum, const double* penalty, float inv_n, int batch, float* loss_slot,
+                  double* epoch_acc, cudaStream_t s) {
+  loss_finalize_kernel<<<1, 1, 0, s>>>(loss_sum, penalty, inv_n, batch, loss_slot, epoch_acc);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+}  // namespace dca
+
+// ------------------------------------------------------------------------------------ C ABI
+using namespace dca;
+
+extern "C" int dca_zinb_loss_workspace_bytes(int32_t batch, int32_t genes, size_t* bytes) {
+  if (!bytes || batch <= 0 || genes <= 0) { set_error("dca_zinb_loss_workspace_bytes: bad argument"); return DCA_ERR_BAD_ARG; }
+  *bytes = loss_workspace_bytes(batch, genes);
+  return DCA_OK;
+}
+
+extern "C" int dca_zinb_loss_fwd_bwd(const float* Y, int64_t ldy, const int32_t* rows, const float* sf,
+                                     const float* m, const float* d, const float* pi, int64_t ld,
+                                     int32_t batch, int32_t genes, int32_t ae_type, float ridge, float inv_n,
+                                     void* dzm, void* dzd, void* dzp, int32_t grad_dtype, float* dtheta,
+                                     double* loss_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  if (ae_type < 0 || ae_type > 3) { set_error("dca_zinb_loss_fwd_bwd: unknown ae_type %d", ae_type); return DCA_ERR_BAD_ARG; }
+  LossArgs a{Y, ldy, rows, sf, m, d, pi, ld, batch, genes, ae_type, ridge, inv_n, dzm, dzd, dzp,
+             grad_dtype == DCA_BF16 ? 1 : 0, dtheta, loss_sum, workspace, workspace_bytes};
+  return zinb_loss_fwd_bwd(a, (cudaStream_t)stream);
+}
+
+extern "C" int dca_zinb_loss_fwd(const float* Y, int64_t ldy, const int32_t* rows, const float* sf,
+                                 const float* m, const float* d, const float* pi, int64_t ld, int32_t batch,
+                                 int32_t genes, int32_t ae_type, float ridge, double* loss_sum, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (ae_type < 0 || ae_type > 3) { set_error("dca_zinb_loss_fwd: unknown ae_type %d", ae_type); return DCA_ERR_BAD_ARG; }
+  LossArgs a{Y, ldy, rows, sf, m, d, pi, ld, batch, genes, ae_type, ridge, 1.0f, nullptr, nullptr, nullptr,
+             0, nullptr, loss_sum, workspace, workspace_bytes};
+  return zinb_loss_fwd(a, (cudaStream_t)stream);
+}
+
+// Host mirror of the per-element device math (same source, compiled for the CPU) so the
+// arithmetic can be unit-tested against the oracle on a machine without a GPU.
+extern "C" int dca_zinb_elem_host(int32_t ae_type, float y, float m, float sf, float d, float pi, float ridge,
+                                  float out[4]) {
+  zmath::Elem e;
+  switch (ae_type) {
+    case DCA_AE_ZINB_CONDDISP: e = zmath::zinb_elem<true, true>(y, m, sf, d, pi, ridge); break;
+    case DCA_AE_ZINB: e = zmath::zinb_elem<true, false>(y, m, sf, d, pi, ridge); break;
+    case DCA_AE_NB_CONDDISP: e = zmath::zinb_elem<false, true>(y, m, sf, d, pi, ridge); break;
+    case DCA_AE_NB: e = zmath::zinb_elem<false, false>(y, m, sf, d, pi, ridge); break;
+    default: set_error("dca_zinb_elem_host: unknown ae_type %d", ae_type); return DCA_ERR_BAD_ARG;
+  }
+  out[0] = e.loss; out[1] = e.gm; out[2] = e.gd; out[3] = e.gp;
+  return DCA_OK;
+}

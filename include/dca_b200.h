@@ -1,0 +1,207 @@
+/* dca_b200.h -- C ABI of libdca_b200.so: the B200-native DCA training hot path.
+ *
+ * The reference (theislab/dca @ 6abd124) has no FFI: its boundary is the Python API, and the
+ * arithmetic runs inside Keras/TensorFlow.  Each entry point below names the reference call
+ * site(s) whose work it replaces (paths relative to the reference repository root).  The
+ * Python binding a maintainer would add is shown in INTEGRATION.md; ours is dca_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative dca_status; a thread-local message
+ *     is available from dca_last_error().
+ *   - all data pointers are DEVICE pointers unless the name ends in _host.
+ *   - the caller owns every data buffer; a handle owns only what lives in its arena
+ *     (parameters, gradients, optimizer state, BatchNorm state, fixed workspace).  No
+ *     allocation happens inside step / predict calls.
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*); no
+ *     hidden synchronisation except in the *_host entry points and dca_read_*.
+ *   - a handle is bound to the device that was current at dca_create and is not thread safe.
+ *   - matrices are row-major (cells x genes), leading dimensions in ELEMENTS.
+ */
+#ifndef DCA_B200_H
+#define DCA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCA_B200_VERSION 100          /* major*10000 + minor*100 + patch */
+#define DCA_MAX_HIDDEN 8
+#define DCA_NAME_LEN 48
+
+typedef enum dca_status {
+  DCA_OK = 0,
+  DCA_ERR_BAD_ARG = -1,
+  DCA_ERR_CUDA = -2,
+  DCA_ERR_UNSUPPORTED = -3,
+  DCA_ERR_NONFINITE = -4,
+  DCA_ERR_NO_DEVICE = -5
+} dca_status;
+
+/* dca/network.py:763-768 AE_types keys on the accelerated path */
+typedef enum dca_ae_type {
+  DCA_AE_ZINB_CONDDISP = 0,   /* 'zinb-conddisp' ZINBAutoencoder              dca/network.py:366-393 */
+  DCA_AE_ZINB = 1,            /* 'zinb'          ZINBConstantDispAutoencoder  dca/network.py:496-522 */
+  DCA_AE_NB_CONDDISP = 2,     /* 'nb-conddisp'   NBAutoencoder                dca/network.py:293-316 */
+  DCA_AE_NB = 3               /* 'nb'            NBConstantDispAutoencoder    dca/network.py:249-269 */
+} dca_ae_type;
+
+typedef enum dca_dtype { DCA_F32 = 0, DCA_BF16 = 1 } dca_dtype;
+
+typedef enum dca_gemm_path {
+  DCA_GEMM_AUTO = 0,          /* tcgen05 tiles whenever the shape qualifies, else generic */
+  DCA_GEMM_GENERIC = 1,       /* fp32 CUDA-core tiles for every layer (arbitrary shapes)  */
+  DCA_GEMM_TCGEN05 = 2        /* require the tcgen05 path; create fails if shape unsupported */
+} dca_gemm_path;
+
+typedef enum dca_region_id {
+  DCA_REGION_PARAMS = 0,      /* float[P]   trainable parameters, Keras layouts (see dca_param_info) */
+  DCA_REGION_GRADS = 1,       /* float[P+2] gradient of the mean loss; [P] = batch loss, [P+1] = non-finite flag */
+  DCA_REGION_RMS = 2,         /* float[P]   RMSprop accumulator */
+  DCA_REGION_BN_STATE = 3,    /* float[S]   BatchNorm moving_mean / moving_variance, see dca_state_info */
+  DCA_REGION_EPOCH_ACC = 4    /* double[4]  {sum(loss*batch), sum(batch), sum(val_loss_elem), n_val_elem} */
+} dca_region_id;
+
+/* Mirrors the constructor of dca/network.py:44-59 (Autoencoder.__init__) plus the optimizer
+ * constants of dca/train.py:54-57 and the Keras defaults they imply. */
+typedef struct dca_config {
+  int32_t struct_bytes;       /* sizeof(dca_config), ABI guard */
+  int32_t n_in;               /* input_size  (genes)           */
+  int32_t n_out;              /* output_size (genes)           */
+  int32_t n_hidden;           /* len(hidden_size), 0..DCA_MAX_HIDDEN */
+  int32_t hidden[DCA_MAX_HIDDEN];
+  int32_t ae_type;            /* dca_ae_type */
+  int32_t batchnorm;          /* BatchNormalization(center=True, scale=False) after each hidden Dense */
+  int32_t max_batch;          /* largest batch any step/predict call will pass */
+  int32_t x_dtype;            /* dca_dtype of the network input matrix X */
+  int32_t gemm_path;          /* dca_gemm_path */
+  float ridge;                /* ZINB ridge_lambda, dca/loss.py:139 */
+  float l1, l2, l1_enc, l2_enc;   /* kernel regularisers, dca/network.py:113-125 */
+  float bn_momentum, bn_eps;  /* 0.99, 1e-3 */
+  float rms_rho, rms_eps;     /* 0.9, 1e-7 */
+} dca_config;
+
+typedef struct dca_handle dca_handle;
+
+typedef struct dca_tensor_info {
+  char name[DCA_NAME_LEN];    /* e.g. "enc0/kernel", "center/bn_beta", "mean/bias", "dispersion/theta" */
+  int64_t offset;             /* element offset into the region */
+  int32_t rows, cols;         /* kernel: (in, out) as in Keras; vectors: rows = 1 */
+} dca_tensor_info;
+
+int dca_version(void);
+const char* dca_last_error(void);
+void dca_config_default(dca_config* cfg);
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* Bytes of device memory a handle needs. */
+int dca_arena_bytes(const dca_config* cfg, size_t* bytes);
+/* Build the engine.  `arena` is caller-allocated device memory of at least dca_arena_bytes
+ * (256-byte aligned), or NULL to let the library cudaMalloc it.
+ * Replaces: AE_types[type](...).build() + model.compile(...)  (dca/api.py:183-188,
+ * dca/network.py:92-156, dca/train.py:54-59). Parameters are zero until dca_init_params /
+ * a write through DCA_REGION_PARAMS. */
+int dca_create(const dca_config* cfg, void* arena, size_t arena_bytes, dca_handle** out);
+int dca_destroy(dca_handle* h);
+
+int dca_param_count(const dca_handle* h, int64_t* n_params, int32_t* n_tensors);
+int dca_param_info(const dca_handle* h, int32_t index, dca_tensor_info* info);
+int dca_state_count(const dca_handle* h, int64_t* n_state, int32_t* n_tensors);
+int dca_state_info(const dca_handle* h, int32_t index, dca_tensor_info* info);
+int dca_region(dca_handle* h, int32_t region_id, void** dev_ptr, int64_t* count);
+
+/* Glorot-uniform kernels, zero biases/beta/theta, moving_mean 0, moving_var 1, rms 0
+ * (Keras initialisers named at dca/network.py:124-126, dca/layers.py:17-20). */
+int dca_init_params(dca_handle* h, uint64_t seed, void* stream);
+/* Call after writing DCA_REGION_PARAMS directly (refreshes operand-layout shadow copies). */
+int dca_params_changed(dca_handle* h, void* stream);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* One training batch: forward (training-mode BatchNorm, moving statistics updated), loss,
+ * backward into DCA_REGION_GRADS (gradient of the batch-mean loss; grads[P] = loss).
+ * X: network input (dataset base pointer, dtype cfg.x_dtype, leading dim ldx);
+ * Y: raw counts float32 (leading dim ldy); sf: size factors, one per dataset row;
+ * rows: int32[batch] dataset row indices of this batch, or NULL for rows 0..batch-1.
+ * Replaces one iteration of Keras Model.fit's batch loop up to (excluding) the optimizer
+ * update: dca/train.py:91-98 executing dca/network.py:124-139,369-381 and dca/loss.py:122-148. */
+int dca_train_step(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy,
+                   const float* sf, const int32_t* rows, int32_t batch, void* stream);
+
+/* clip(g*grad_scale, +-clip) -> RMSprop (rho, eps from config) -> parameters.
+ * Replaces keras RMSprop(clipvalue=clip_grad[, lr]) applied by model.fit: dca/train.py:54-57.
+ * grad_scale = 1/world_size after a sum all-reduce of DCA_REGION_GRADS, else 1. */
+int dca_apply_update(dca_handle* h, float lr, float clip, float grad_scale, void* stream);
+
+/* Inference-mode forward + summed element loss, accumulated into DCA_REGION_EPOCH_ACC[2..3].
+ * Replaces the validation pass of Model.fit (validation_split, dca/train.py:96). */
+int dca_eval_step(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy,
+                  const float* sf, const int32_t* rows, int32_t batch, void* stream);
+
+/* Inference forward producing every output of the four Keras predict() passes in one:
+ * mean_out = MeanAct(.)*sf  (model.predict, dca/network.py:202-203),
+ * disp_out (B x G; for const-disp types G values, the per-gene theta)  (dca/network.py:400, 530),
+ * pi_out (dca/network.py:401), latent_out = 'center' Dense output before BN (dca/network.py:184-185,197).
+ * Any output pointer may be NULL.  ld_out is the leading dim of the B x G outputs. */
+int dca_predict(dca_handle* h, const void* X, int64_t ldx, const float* sf, const int32_t* rows,
+                int32_t batch, float* mean_out, float* disp_out, float* pi_out, int64_t ld_out,
+                float* latent_out, void* stream);
+
+/* Blocking helpers: copy the last batch loss / epoch accumulators to the host. */
+int dca_read_loss(dca_handle* h, float* loss_host, int32_t* nonfinite_host, void* stream);
+int dca_read_epoch_acc(dca_handle* h, double acc_host[4], int32_t reset, void* stream);
+
+/* End-to-end variant with HOST buffers (pinned recommended): copies the batch
+ * (x_host: batch x n_in of cfg.x_dtype, y_host: batch x n_out float, sf_host: batch float)
+ * to the device, runs dca_train_step + dca_apply_update, copies the loss back and waits. */
+int dca_train_step_host(dca_handle* h, const void* x_host, const float* y_host,
+                        const float* sf_host, int32_t batch, float lr, float clip,
+                        float* loss_host, void* stream);
+
+/* ---- stand-alone kernels (parity tests, profiling) -------------------------------------- */
+/* ZINB / NB negative log-likelihood forward + backward, one pass (dca/loss.py:72-156 and its
+ * autodiff).  Inputs are POST-activation head outputs: m = MeanAct(zm) (not yet multiplied by
+ * sf), d = DispAct(zd) (B x G) or, for const-disp types, theta (G values, ld ignored), pi.
+ * Outputs (may alias the inputs): gradients of the mean loss w.r.t. the PRE-activations
+ * dzm, dzd, dzp scaled by inv_n; for const-disp types dzd receives nothing and
+ * dtheta (G floats) receives d(loss)/d(theta) (before the exp/clip chain) summed over rows.
+ * loss_sum: device double, receives the SUM of element losses (not the mean).
+ * grad_dtype selects float32 or bfloat16 storage for dz*. */
+int dca_zinb_loss_fwd_bwd(const float* Y, int64_t ldy, const int32_t* rows, const float* sf,
+                          const float* m, const float* d, const float* pi, int64_t ld,
+                          int32_t batch, int32_t genes, int32_t ae_type, float ridge, float inv_n,
+                          void* dzm, void* dzd, void* dzp, int32_t grad_dtype,
+                          float* dtheta, double* loss_sum, void* workspace, size_t workspace_bytes,
+                          void* stream);
+int dca_zinb_loss_workspace_bytes(int32_t batch, int32_t genes, size_t* bytes);
+/* Forward only (validation): loss_sum += sum of element losses. */
+int dca_zinb_loss_fwd(const float* Y, int64_t ldy, const int32_t* rows, const float* sf,
+                      const float* m, const float* d, const float* pi, int64_t ld,
+                      int32_t batch, int32_t genes, int32_t ae_type, float ridge,
+                      double* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* HOST mirror of the per-element device arithmetic of the loss kernel (same source compiled for
+ * the CPU); a testing aid so the formulas can be checked against the oracle without a GPU.
+ * out = {element loss, dL/dzm, dL/dzd (or raw dL/dtheta for const-disp types), dL/dzp}, not / N. */
+int dca_zinb_elem_host(int32_t ae_type, float y, float m, float sf, float d, float pi, float ridge,
+                       float out[4]);
+
+/* Head Dense layers with fused output activations (dca/network.py:369-381, :38-39,
+ * dca/layers.py:85): H (B x K float32, ld ldh) times the Keras-layout kernels (K x G) plus bias,
+ * then MeanAct / DispAct / sigmoid.  Any of the three heads may be NULL.  row_scale (B floats,
+ * or NULL) multiplies the mean head (mean*sf, used by predict). */
+int dca_dense_heads_fwd(const float* H, int64_t ldh, int32_t batch, int32_t K, int32_t genes,
+                        const float* w_mean, const float* b_mean,
+                        const float* w_disp, const float* b_disp,
+                        const float* w_pi, const float* b_pi,
+                        const float* row_scale,
+                        float* m_out, float* d_out, float* pi_out, int64_t ld_out, void* stream);
+
+/* Number of kernels this library has launched in this process (all handles, all streams). */
+int64_t dca_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCA_B200_H */
