@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the DCA training hot path on B200 (contract: see the task statement / DESIGN.md).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path
+  python bench.py --impl reference --gpus N ...            # CPU arm: torch-CPU restatement of the
+                                                           # reference step (TensorFlow is not installable)
+
+A "step" is one training batch of the hot path: forward (Dense stack, BatchNorm, three-head
+output activations), ZINB loss + gradient, backward, gradient all-reduce (N > 1), clip + RMSprop.
+Metric: cells/sec = steps * batch * n_gpus / device time (CUDA events, max over ranks).
+Workload at N = 1: BASELINE.json configs[1] -- synthetic 10k cells x 2k genes, zinb-conddisp,
+hidden 64,32,64; every rank holds its own 10k-cell shard for N > 1 (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (cells per GPU, genes, ae_type, description)
+    "c2": (10000, 2000, "zinb-conddisp", "synthetic 10k cells x 2k genes ZINB-conddisp, hidden=64,32,64 (BASELINE configs[1])"),
+    "c3": (68000, 20000, "zinb-conddisp", "synthetic 68k cells x 20k genes ZINB-conddisp (BASELINE configs[2], PBMC shape)"),
+    "c5shard": (125000, 20000, "zinb-conddisp", "synthetic 125k cells x 20k genes per GPU (BASELINE configs[4] shard, 1M/8)"),
+}
+HIDDEN = (64, 32, 64)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("DCA_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=4096, help="cells per GPU per step")
+    ap.add_argument("--x-dtype", default="float32", choices=["float32", "bfloat16"])
+    ap.add_argument("--gemm-path", default="auto", choices=["auto", "generic", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the CPU baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def synth_on_device(n_cells, n_genes, device, seed, x_dtype=torch.float32, chunk=8192):
+    """SURVEY.md 8d generator: gene log-means N(-2,1.5), depth LogNormal(0,.35), Gamma(2)-Poisson,
+    20 % extra zeros.  Returns X = zscore(log1p(Y/sf)) (x_dtype), Y (fp32 raw counts), sf, zero fraction."""
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    logm = torch.randn(n_genes, generator=g, device=device) * 1.5 - 2.0
+    Y = torch.empty((n_cells, n_genes), dtype=torch.float32, device=device)
+    for s in range(0, n_cells, chunk):
+        e = min(s + chunk, n_cells)
+        depth = torch.exp(torch.randn(e - s, 1, generator=g, device=device) * 0.35)
+        scale = depth * torch.exp(logm)[None, :] / 2.0
+        lam = torch._standard_gamma(torch.full((e - s, n_genes), 2.0, device=device), generator=g) * scale
+        y = torch.poisson(lam, generator=g)
+        y[torch.rand(e - s, n_genes, generator=g, device=device) < 0.2] = 0
+        Y[s:e] = y
+    dead = (Y.sum(0) == 0).nonzero().flatten()            # reference asserts no all-zero genes (dca/api.py:163-164)
+    if dead.numel():
+        Y[torch.randint(0, n_cells, (dead.numel(),), generator=g, device=device), dead] = 1
+    n_counts = Y.sum(1)
+    empty = (n_counts == 0).nonzero().flatten()
+    if empty.numel():
+        Y[empty, torch.randint(0, n_genes, (empty.numel(),), generator=g, device=device)] = 1
+        n_counts = Y.sum(1)
+    sf = (n_counts / n_counts.median()).float()
+    # X = zscore(log1p(Y / sf)), per gene, ddof=1 -- dca/io.py:99-109
+    mean = torch.zeros(n_genes, dtype=torch.float64, device=device); sq = torch.zeros_like(mean)
+    for s in range(0, n_cells, chunk):
+        l = torch.log1p(Y[s:s + chunk] / sf[s:s + chunk, None]).double()
+        mean += l.sum(0); sq += (l * l).sum(0)
+    mean /= n_cells
+    var = (sq - n_cells * mean * mean) / (n_cells - 1)
+    std = var.clamp_min(1e-12).sqrt()
+    X = torch.empty((n_cells, n_genes), dtype=x_dtype, device=device)
+    for s in range(0, n_cells, chunk):
+        l = torch.log1p(Y[s:s + chunk] / sf[s:s + chunk, None]).double()
+        X[s:s + chunk] = ((l - mean) / std).to(x_dtype)
+    zero_frac = float((Y == 0).float().mean().item())
+    return X, Y, sf.contiguous(), zero_frac
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.p = None; self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_arm(n_genes, ae_type, batch, seconds, steps=None, warmup=1, seed=0):
+    """torch-CPU restatement of the reference training step, all host threads, on a bounded sample:
+    batches of `batch` cells drawn from a min(16384, 4*batch)-row slice of the same synthetic shape."""
+    from oracle import dca_oracle as O
+    from oracle.torch_ref import TorchRefNet
+    from tests.util import synth_counts
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n = min(16384, 4 * batch)
+    Y = synth_counts(n, n_genes, seed)
+    X, sf = O.normalize_inputs(Y)
+    p0 = O.init_params(n_genes, n_genes, HIDDEN, ae_type, True, seed=0, dtype=np.float32)
+    net = TorchRefNet(p0, HIDDEN, ae_type, True, dtype=torch.float32)
+    Xt, Yt, sft = torch.from_numpy(X), torch.from_numpy(Y), torch.from_numpy(sf)
+    rng = np.random.default_rng(0)
+
+    def one():
+        idx = torch.from_numpy(rng.permutation(n)[:batch])
+        return net.train_step(Xt[idx], Yt[idx], sft[idx])
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter(); done = 0
+    while True:
+        one(); done += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and done >= steps) or (steps is None and el >= seconds) or el > 20 * seconds:
+            break
+    return {"value": done * batch / el, "unit": "cells/sec", "cores": threads, "kind": "port",
+            "sample": "%d steps of batch %d on a %d-cell x %d-gene slice; torch-CPU fp32 restatement of the reference "
+                      "path (TensorFlow unavailable in image)" % (done, batch, n, n_genes),
+            "ms_per_step": 1e3 * el / done, "steps": done}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cells, genes, ae_type, desc = WORKLOADS[a.workload]
+    batch = a.batch
+    config = {"workload": desc, "ae_type": ae_type, "hidden": list(HIDDEN), "cells_per_gpu": cells, "genes": genes,
+              "batch_per_gpu": batch, "global_batch": batch * max(world, 1), "x_dtype": a.x_dtype,
+              "optimizer": "RMSprop(lr=1e-3, clipvalue=5)", "batchnorm": "per-rank batch statistics",
+              "parallelism": "dp%d" % max(world, 1),
+              "l2": "dataset (X+Y %.0f MB/GPU) and per-step head tensors exceed the 126 MB L2; no explicit flush"
+                    % (cells * genes * (4 + (2 if a.x_dtype == 'bfloat16' else 4)) / 1e6)}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_arm(genes, ae_type, batch, a.cpu_seconds, steps=a.steps, warmup=min(a.warmup, 2))
+        line = {"impl": "reference", "metric": "cells/sec (ZINB AE train step, host-timed, torch-CPU restatement of the reference)",
+                "value": r["value"], "unit": "cells/sec", "n_gpus": a.gpus, "steps": r["steps"], "warmup": min(a.warmup, 2),
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "cells/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line)); return
+
+    import torch.distributed as dist
+    from dca_b200.engine import DeviceEngine, launch_count
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    X, Y, sf, zero_frac = synth_on_device(cells, genes, dev, 1234 + rank, {"float32": torch.float32, "bfloat16": torch.bfloat16}[a.x_dtype])
+    n_train = int(cells * 0.9)                                  # validation_split=0.1 tail, dca/train.py:96
+    eng = DeviceEngine(genes, genes, HIDDEN, ae_type, True, max_batch=batch, x_dtype=a.x_dtype,
+                       gemm_path=a.gemm_path, device=dev, seed=0)
+    if world > 1:
+        dist.broadcast(eng.params, 0); eng.params_changed()
+    lr, clip, gscale = 1e-3, 5.0, 1.0 / world
+    total = a.steps + a.warmup
+    gperm = torch.Generator(device=dev); gperm.manual_seed(99 + rank)
+    need = total * batch
+    stream_idx = torch.cat([torch.randperm(n_train, generator=gperm, device=dev) for _ in range(need // n_train + 1)])[:need]
+    stream_idx = stream_idx.to(torch.int32).contiguous()
+
+    def step(i):
+        rows = stream_idx[i * batch:(i + 1) * batch]
+        eng.train_step(X, Y, sf, rows=rows)
+        if world > 1:
+            dist.all_reduce(eng.grads)
+        eng.apply_update(lr, clip, gscale)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(a.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(a.warmup, total):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = eng.read_loss()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    value = a.steps * batch * world / (ms * 1e-3)
+
+    # ---- profiled pass (separate from the timed region): per-phase device time, loss-kernel roofline
+    eng.profile(True)
+    for i in range(a.warmup, total):
+        step(i)
+    torch.cuda.synchronize(dev)
+    prof = eng.profile_read()
+    eng.profile(False)
+    peak, peak_src = measured_peaks()
+    nh = 3
+    loss_ms, loss_n = prof["loss_fwd_bwd"]
+    loss_bytes = batch * genes * (4 + 4 * nh + 4 * nh)          # y + m,d,pi in, dzm,dzd,dzp out (fp32), SURVEY 8d
+    ach = loss_bytes / (loss_ms / max(loss_n, 1) * 1e-3) / 1e9 if loss_ms > 0 else None
+    step_ms_prof = sum(v[0] for v in prof.values()) / max(a.steps, 1)
+    roofline = {"kernel": "zinb_loss_kernel (phase loss_fwd_bwd: K3 + partial folds)", "bound": "hbm", "achieved": ach,
+                "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": loss_bytes,
+                "share_of_step": (loss_ms / max(loss_n, 1)) / step_ms_prof if step_ms_prof > 0 else None}
+    phases = {k: (v[0] / max(v[1], 1)) for k, v in prof.items()}
+
+    # ---- end to end: host (pinned) buffers -> H2D -> step -> D2H loss, through the public API
+    e2e = None
+    if not a.no_e2e:
+        nb = min(8, max(2, n_train // batch))
+        xh = X[: nb * batch].cpu().pin_memory(); yh = Y[: nb * batch].cpu().pin_memory(); sfh = sf[: nb * batch].cpu().pin_memory()
+        k_e2e = max(3, min(a.steps, 20))
+        def e2e_step(i):
+            j = i % nb
+            xs, ys, ss = xh[j * batch:(j + 1) * batch], yh[j * batch:(j + 1) * batch], sfh[j * batch:(j + 1) * batch]
+            if world == 1:
+                return eng.train_step_host(xs, ys, ss, lr, clip)
+            xd = xs.to(dev, non_blocking=True); yd = ys.to(dev, non_blocking=True); sd = ss.to(dev, non_blocking=True)
+            eng.train_step(xd, yd, sd); dist.all_reduce(eng.grads); eng.apply_update(lr, clip, gscale)
+            return eng.read_loss()
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(k_e2e):
+            e2e_step(i)
+        f1.record(); barrier()
+        ems = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([ems], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ems = float(t.item())
+        xb = 2 if a.x_dtype == "bfloat16" else 4
+        e2e = {"value": k_e2e * batch * world / (ems * 1e-3), "unit": "cells/sec", "steps": k_e2e,
+               "h2d_bytes_per_step": batch * (genes * xb + genes * 4 + 4), "d2h_bytes_per_step": 8,
+               "api": "DeviceEngine.train_step_host -> dca_train_step_host (C ABI, pinned host buffers)" if world == 1
+                      else "pinned H2D + DeviceEngine.train_step/all_reduce/apply_update/read_loss"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_reference_arm(genes, ae_type, batch, a.cpu_seconds)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "cells/sec (ZINB AE train step: fwd + ZINB loss + bwd + allreduce + clip/RMSprop, device-timed)",
+                "value": value, "unit": "cells/sec", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if a.x_dtype == "float32" else "bf16-in/f32", "data": "synthetic (zero fraction %.3f)" % zero_frac,
+                "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu, "phase_ms": phases, "final_loss": final_loss,
+                "impl": "ours"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

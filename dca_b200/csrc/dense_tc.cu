@@ -4,7 +4,7 @@
 
 namespace dca {
 
-Engine::~Engine() {}
+Engine::~Engine() { for (auto e : prof.ev) cudaEventDestroy(e); }
 bool Engine::tc_supported() const { return false; }
 const char* Engine::tc_reason() const { return "tcgen05 kernels not built into this library version"; }
 int Engine::setup_tc() { return DCA_OK; }

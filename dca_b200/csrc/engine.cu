@@ -155,6 +155,31 @@ int Engine::plan(const dca_config& c) {
   return DCA_OK;
 }
 
+void Engine::mark(int phase, cudaStream_t s) {
+  if (!prof.on) return;
+  if (prof.n == prof.ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    prof.ev.push_back(e); prof.phase.push_back(-1);
+  }
+  prof.phase[prof.n] = phase;
+  cudaEventRecord(prof.ev[prof.n], s);
+  ++prof.n;
+}
+
+int Engine::prof_collect() {
+  if (prof.n == 0) return DCA_OK;
+  DCA_CUDA_OK(cudaEventSynchronize(prof.ev[prof.n - 1]));
+  for (size_t i = 0; i + 1 < prof.n; ++i) {
+    const int ph = prof.phase[i];
+    if (ph < 0 || ph >= DCA_N_PHASES) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, prof.ev[i], prof.ev[i + 1]) == cudaSuccess) { prof.ms[ph] += ms; prof.cnt[ph] += 1; }
+  }
+  prof.n = 0;
+  return DCA_OK;
+}
+
 void Engine::bind(void* base_) {
   base = reinterpret_cast<char*>(base_);
 }
@@ -262,11 +287,14 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
   const int G = cfg.n_out;
   DCA_CUDA_OK(cudaMemsetAsync(gp(0), 0, sizeof(float) * (size_t)(P + 2), s));
   bool any_pen = false;
+  mark(0, s);
   DCA_TRY(penalty(s, any_pen));
   DCA_TRY(forward(X, ldx, rows, Bn, true, s));
+  mark(1, s);
   float* Mb = f(o_head[0]); float* Db = f(o_head[1]); float* Pb = f(o_head[2]);
   DCA_TRY(heads_forward(Bn, Mb, cond ? Db : nullptr, has_pi ? Pb : nullptr, G, nullptr, s));
   if (!cond) DCA_TRY(theta_prepare(pp(theta_off), G, f(o_theta), f(o_chain), s));
+  mark(2, s);
 
   const float inv_n = 1.0f / ((float)Bn * (float)G);
   LossArgs la{};
@@ -284,6 +312,7 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
   }
 
   // ---- head backward
+  mark(3, s);
   float* dh = f(o_dh[0]); float* dh2 = f(o_dh[1]);
   if (L > 0) DCA_CUDA_OK(cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)Bn * K_head, s));
   float* dz[3] = {Mb, cond ? Db : nullptr, has_pi ? Pb : nullptr};
@@ -305,6 +334,7 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
     }
   }
   // ---- hidden stack backward
+  mark(4, s);
   for (int i = L - 1; i >= 0; --i) {
     Layer& l = lay[i];
     DCA_TRY(relu_bwd(dh, f(l.o_h), l.out, Bn, l.out, s));
@@ -330,11 +360,15 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
       float* t = dh; dh = dh2; dh2 = t;
     }
   }
+  mark(-1, s);
   return DCA_OK;
 }
 
 int Engine::apply_update(float lr, float clip, float grad_scale, cudaStream_t s) {
+  mark(5, s);
   DCA_TRY(rmsprop_update(pp(0), gp(0), f(o_rms), P, lr, clip, cfg.rms_rho, cfg.rms_eps, grad_scale, s));
+  DCA_TRY(refresh_shadows(s));
+  mark(-1, s);
   return DCA_OK;
 }
 
@@ -539,8 +573,7 @@ extern "C" int dca_train_step(dca_handle* h, const void* X, int64_t ldx, const f
 }
 extern "C" int dca_apply_update(dca_handle* h, float lr, float clip, float grad_scale, void* stream) {
   DCA_NEED_HANDLE(h);
-  DCA_TRY(h->e.apply_update(lr, clip, grad_scale, (cudaStream_t)stream));
-  return h->e.refresh_shadows((cudaStream_t)stream);
+  return h->e.apply_update(lr, clip, grad_scale, (cudaStream_t)stream);
 }
 extern "C" int dca_eval_step(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf,
                              const int32_t* rows, int32_t batch, void* stream) {
@@ -590,6 +623,22 @@ extern "C" int dca_train_step_host(dca_handle* h, const void* x_host, const floa
   }
   DCA_TRY(e.train_step(e.base + e.o_stage_x, e.cfg.n_in, e.f(e.o_stage_y), e.cfg.n_out, sfd, nullptr, batch, s));
   DCA_TRY(e.apply_update(lr, clip, 1.0f, s));
-  DCA_TRY(e.refresh_shadows(s));
   return dca_read_loss(h, loss_host, nullptr, stream);
+}
+
+extern "C" int dca_profile_enable(dca_handle* h, int32_t on) {
+  DCA_NEED_HANDLE(h);
+  if (!on && h->e.prof.on) DCA_TRY(h->e.prof_collect());
+  h->e.prof.on = on != 0;
+  return DCA_OK;
+}
+extern "C" int dca_profile_read(dca_handle* h, double ms[DCA_N_PHASES], int64_t counts[DCA_N_PHASES], int32_t reset) {
+  DCA_NEED_HANDLE(h);
+  DCA_TRY(h->e.prof_collect());
+  for (int i = 0; i < DCA_N_PHASES; ++i) {
+    if (ms) ms[i] = h->e.prof.ms[i];
+    if (counts) counts[i] = h->e.prof.cnt[i];
+    if (reset) { h->e.prof.ms[i] = 0; h->e.prof.cnt[i] = 0; }
+  }
+  return DCA_OK;
 }

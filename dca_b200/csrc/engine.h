@@ -32,6 +32,14 @@ struct Engine {
   size_t o_stage_x = 0, o_stage_y = 0, o_stage_sf = 0;
   // head input of the current forward (set by forward())
   const void* head_in = nullptr; int64_t head_ld = 0; int head_bf16 = 0; const int32_t* head_rows = nullptr;
+  // optional phase timing
+  struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> ev; std::vector<int> phase; size_t n = 0;
+    double ms[DCA_N_PHASES] = {0, 0, 0, 0, 0, 0}; long long cnt[DCA_N_PHASES] = {0, 0, 0, 0, 0, 0};
+  } prof;
+  void mark(int phase, cudaStream_t s);
+  int prof_collect();
   // tcgen05 path
   TcState* tc = nullptr;
   size_t o_tc = 0, tc_bytes = 0;

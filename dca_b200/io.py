@@ -1,0 +1,157 @@
+"""Data preparation and text I/O with the surface of dca/io.py:53-131.
+
+scanpy / anndata are not available in the image, so the four ``sc.pp`` calls the reference
+makes (dca/io.py:91-109, dca/api.py:163) are restated in NumPy (semantics in SURVEY.md A.1 /
+Appendix B); real AnnData objects are accepted when ``anndata`` is importable.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+
+import numpy as np
+import pandas as pd
+
+from .anndata_lite import AnnData, is_anndata
+
+
+def _dense(X):
+    return X.toarray() if hasattr(X, "toarray") else np.asarray(X)
+
+
+def read_text_or_h5ad(path: str):
+    """sc.read(path, first_column_names=True) -- dca/io.py:59."""
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".h5ad":
+        try:
+            import anndata  # type: ignore
+        except ImportError as e:
+            raise ImportError("reading .h5ad needs the anndata package, which is not installed") from e
+        return anndata.read_h5ad(path)
+    sep = "," if ext == ".csv" else "\t"
+    tab = pd.read_csv(path, sep=sep, index_col=0)
+    return AnnData(tab.values.astype(np.float32), obs=pd.DataFrame(index=tab.index.astype(str)),
+                   var=pd.DataFrame(index=tab.columns.astype(str)))
+
+
+def read_dataset(adata, transpose=False, test_split=False, copy=False, check_counts=True):
+    """dca/io.py:53-85."""
+    if is_anndata(adata):
+        if copy:
+            adata = adata.copy()
+    elif isinstance(adata, str):
+        adata = read_text_or_h5ad(adata)
+    else:
+        raise NotImplementedError
+
+    if check_counts:
+        # check if observations are unnormalized using first 10           (dca/io.py:63-70)
+        X_subset = _dense(adata.X[:10])
+        norm_error = 'Make sure that the dataset (adata.X) contains unnormalized count data.'
+        assert np.all(X_subset.astype(int) == X_subset), norm_error
+
+    if transpose:
+        adata = adata.transpose()
+
+    if test_split:
+        from sklearn.model_selection import train_test_split
+        train_idx, test_idx = train_test_split(np.arange(adata.n_obs), test_size=0.1, random_state=42)
+        spl = pd.Series(['train'] * adata.n_obs)
+        spl.iloc[test_idx] = 'test'
+        adata.obs['dca_split'] = spl.values
+    else:
+        adata.obs['dca_split'] = 'train'
+
+    adata.obs['dca_split'] = adata.obs['dca_split'].astype('category')
+    print('dca: Successfully preprocessed {} genes and {} cells.'.format(adata.n_vars, adata.n_obs))
+    return adata
+
+
+def filter_genes_mask(X, min_counts=1):
+    """sc.pp.filter_genes(X, min_counts=1) -> (mask, counts)   (dca/api.py:163)."""
+    counts = np.asarray(_dense(X).sum(axis=0)).reshape(-1)
+    return counts >= min_counts, counts
+
+
+def _subset(adata, rows=None, cols=None):
+    X = _dense(adata.X)
+    obs, var = adata.obs, adata.var
+    if cols is not None:
+        X = X[:, cols]; var = var[cols]
+    if rows is not None:
+        X = X[rows]; obs = obs[rows]
+    return AnnData(X, obs=obs, var=var, uns=dict(getattr(adata, "uns", {})))
+
+
+def normalize(adata, filter_min_counts=True, size_factors=True, normalize_input=True, logtrans_input=True):
+    """dca/io.py:88-111 with scanpy's arithmetic restated:
+    filter_genes/filter_cells(min_counts=1); raw copy; normalize_per_cell (each cell scaled to the
+    median total count; zero-count cells dropped as scanpy does); size_factors = n_counts/median;
+    log1p (natural); scale (zero mean, unit variance with ddof=1, no clipping)."""
+    if not isinstance(adata, AnnData):
+        # real anndata object: work on a lite copy carrying the same fields, results are written back below
+        lite = AnnData(_dense(adata.X), obs=adata.obs, var=adata.var, uns=dict(adata.uns))
+    else:
+        lite = adata
+
+    if filter_min_counts:
+        gmask, _ = filter_genes_mask(lite.X, 1)
+        if not gmask.all():
+            lite = _subset(lite, cols=gmask)
+        cmask = np.asarray(lite.X.sum(axis=1)).reshape(-1) >= 1
+        if not cmask.all():
+            lite = _subset(lite, rows=cmask)
+
+    if size_factors or normalize_input or logtrans_input:
+        lite.raw = lite.copy()
+    else:
+        lite.raw = lite
+
+    if size_factors:
+        n_counts = lite.X.sum(axis=1, dtype=np.float64)
+        keep = n_counts >= 1                         # normalize_per_cell filters cells with < 1 count
+        if not keep.all():
+            raw = lite.raw
+            lite = _subset(lite, rows=keep)
+            from .anndata_lite import _Raw
+            lite.raw = _Raw(raw.X[keep], raw.var)
+            n_counts = n_counts[keep]
+        med = np.median(n_counts)
+        lite.obs['n_counts'] = n_counts
+        lite.X = (lite.X / (n_counts / med)[:, None]).astype(np.float32)
+        lite.obs['size_factors'] = (n_counts / med).astype(np.float32)
+    else:
+        lite.obs['size_factors'] = np.float32(1.0)
+
+    if logtrans_input:
+        lite.X = np.log1p(lite.X)
+
+    if normalize_input:
+        mean = lite.X.mean(axis=0, dtype=np.float64)
+        var = lite.X.var(axis=0, ddof=1, dtype=np.float64) if lite.n_obs > 1 else np.ones(lite.n_vars)
+        std = np.sqrt(var)
+        std[std == 0] = 1.0
+        lite.X = ((lite.X - mean) / std).astype(np.float32)
+
+    lite.X = np.ascontiguousarray(lite.X, dtype=np.float32)
+    return lite
+
+
+def read_genelist(filename):
+    genelist = list(set(open(filename, 'rt').read().strip().split('\n')))
+    assert len(genelist) > 0, 'No genes detected in genelist file'
+    print('dca: Subset of {} genes will be denoised.'.format(len(genelist)))
+    return genelist
+
+
+def write_text_matrix(matrix, filename, rownames=None, colnames=None, transpose=False):
+    """dca/io.py:120-129: TSV, '%.6f'."""
+    if transpose:
+        matrix = matrix.T
+        rownames, colnames = colnames, rownames
+    pd.DataFrame(matrix, index=rownames, columns=colnames).to_csv(
+        filename, sep='\t', index=(rownames is not None), header=(colnames is not None), float_format='%.6f')
+
+
+def read_pickle(inputfile):
+    return pickle.load(open(inputfile, "rb"))

@@ -198,6 +198,14 @@ int dca_dense_heads_fwd(const float* H, int64_t ldh, int32_t batch, int32_t K, i
                         const float* row_scale,
                         float* m_out, float* d_out, float* pi_out, int64_t ld_out, void* stream);
 
+/* Optional per-phase device timing (CUDA events on the caller's stream around each phase of
+ * dca_train_step / dca_apply_update).  Off by default; bench.py turns it on for a separate
+ * profiled pass.  Phases: 0 hidden forward, 1 head Dense + activations, 2 ZINB loss fwd+bwd,
+ * 3 head backward, 4 hidden backward, 5 optimizer update. */
+#define DCA_N_PHASES 6
+int dca_profile_enable(dca_handle* h, int32_t on);
+int dca_profile_read(dca_handle* h, double ms[DCA_N_PHASES], int64_t counts[DCA_N_PHASES], int32_t reset);
+
 /* Number of kernels this library has launched in this process (all handles, all streams). */
 int64_t dca_launch_count(void);
 

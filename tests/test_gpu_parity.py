@@ -1,0 +1,313 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Needs a B200: -m gpu."""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+import torch
+
+from oracle import dca_oracle as O
+from tests.util import synth_counts, rel_err
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _lib():
+    from dca_b200 import _lib
+    return _lib
+
+
+def _t(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(DEV, dtype)
+
+
+def _problem(B, G, seed=0):
+    Y = synth_counts(B, G, seed)
+    X, sf = O.normalize_inputs(Y)
+    return X, Y, sf
+
+
+def _post_act(B, G, seed):
+    rng = np.random.default_rng(seed)
+    m = np.exp(rng.normal(0, 1.5, (B, G))).astype(np.float32)
+    d = np.exp(rng.normal(0, 1.5, (B, G))).astype(np.float32).clip(2e-4, 9e3)
+    pi = (1 / (1 + np.exp(-rng.normal(0, 2, (B, G))))).astype(np.float32)
+    return m, d, pi
+
+
+def _oracle_loss(ae_type, Y, sf, m, d, pi, ridge, rows=None):
+    Yb = Y[rows] if rows is not None else Y
+    sfb = sf[rows] if rows is not None else sf
+    m64, d64, pi64 = [a.astype(np.float64) for a in (m, d, pi)]
+    mu = m64 * sfb.astype(np.float64)[:, None]
+    has_pi = ae_type.startswith("zinb"); cond = ae_type.endswith("conddisp")
+    th = d64 if cond else np.broadcast_to(d64[0:1, :], mu.shape)
+    Yb = Yb.astype(np.float64)
+    if has_pi:
+        el = O.zinb_loss_elem(Yb, mu, th, pi64, ridge); dmu, dth, dpi = O.loss_partials(Yb, mu, th, pi64, ridge)
+    else:
+        el = O.nb_loss_elem(Yb, mu, th); dmu, dth, dpi = O.loss_partials(Yb, mu, th)
+    n = el.size
+    out = {"sum": el.sum(), "dzm": dmu * mu / n}
+    if cond:
+        out["dzd"] = dth * (1 - np.exp(-d64)) / n
+    else:
+        out["dtheta"] = dth.sum(0)
+    if has_pi:
+        out["dzp"] = dpi * pi64 * (1 - pi64) / n
+    return out
+
+
+@pytest.mark.parametrize("ae_type", O.AE_TYPES)
+@pytest.mark.parametrize("shape", [(37, 203), (64, 256), (200, 1028)])
+def test_loss_kernel_vs_oracle(ae_type, shape):
+    L = _lib(); lib = L.load()
+    B, G = shape
+    N = B + 13
+    Y = synth_counts(N, G, 1)
+    Y[0, :4] = [0, 17, 40, 3000]
+    sf = np.exp(np.random.default_rng(2).normal(0, 0.3, N)).astype(np.float32)
+    rows = np.random.default_rng(3).permutation(N)[:B].astype(np.int32)
+    m, d, pi = _post_act(B, G, 4)
+    cond = ae_type.endswith("conddisp"); has_pi = ae_type.startswith("zinb")
+    ref = _oracle_loss(ae_type, Y, sf, m, d, pi, 0.01, rows)
+    Yd, sfd, rd = _t(Y), _t(sf), torch.as_tensor(rows).to(DEV)
+    md, dd, pd = _t(m), (_t(d) if cond else _t(d[0])), _t(pi)
+    gm, gd, gp = torch.empty_like(md), torch.empty_like(md), torch.empty_like(md)
+    dth = torch.zeros(G, device=DEV)
+    loss = torch.zeros(1, dtype=torch.float64, device=DEV)
+    nb = C.c_size_t(); assert lib.dca_zinb_loss_workspace_bytes(B, G, C.byref(nb)) == 0
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=DEV)
+    st = lib.dca_zinb_loss_fwd_bwd(Yd.data_ptr(), G, rd.data_ptr(), sfd.data_ptr(), md.data_ptr(), dd.data_ptr(),
+                                   pd.data_ptr() if has_pi else None, G, B, G, L.AE_TYPE_IDS[ae_type], 0.01,
+                                   1.0 / (B * G), gm.data_ptr(), gd.data_ptr() if cond else None,
+                                   gp.data_ptr() if has_pi else None, L.F32, dth.data_ptr(), loss.data_ptr(),
+                                   ws.data_ptr(), nb.value, None)
+    L.check(st, "dca_zinb_loss_fwd_bwd")
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref["sum"]) <= 2e-5 * abs(ref["sum"])
+    assert rel_err(gm.cpu().numpy(), ref["dzm"]) < 3e-4
+    if cond:
+        assert rel_err(gd.cpu().numpy(), ref["dzd"]) < 3e-4
+    else:
+        assert rel_err(dth.cpu().numpy(), ref["dtheta"]) < 3e-4
+    if has_pi:
+        assert rel_err(gp.cpu().numpy(), ref["dzp"]) < 3e-4
+    # forward-only kernel accumulates
+    loss2 = torch.full((1,), 5.0, dtype=torch.float64, device=DEV)
+    L.check(lib.dca_zinb_loss_fwd(Yd.data_ptr(), G, rd.data_ptr(), sfd.data_ptr(), md.data_ptr(), dd.data_ptr(),
+                                  pd.data_ptr() if has_pi else None, G, B, G, L.AE_TYPE_IDS[ae_type], 0.01,
+                                  loss2.data_ptr(), ws.data_ptr(), nb.value, None))
+    torch.cuda.synchronize()
+    assert abs(loss2.item() - 5.0 - ref["sum"]) <= 2e-5 * abs(ref["sum"])
+
+
+def test_loss_kernel_inplace_and_bf16():
+    L = _lib(); lib = L.load()
+    B, G = 128, 512
+    Y = synth_counts(B, G, 5); sf = np.ones(B, np.float32)
+    m, d, pi = _post_act(B, G, 6)
+    ref = _oracle_loss("zinb-conddisp", Y, sf, m, d, pi, 0.0)
+    nb = C.c_size_t(); lib.dca_zinb_loss_workspace_bytes(B, G, C.byref(nb))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=DEV)
+    loss = torch.zeros(1, dtype=torch.float64, device=DEV)
+    Yd, sfd = _t(Y), _t(sf)
+    # in place: gradients overwrite the activations
+    md, dd, pd = _t(m), _t(d), _t(pi)
+    L.check(lib.dca_zinb_loss_fwd_bwd(Yd.data_ptr(), G, None, sfd.data_ptr(), md.data_ptr(), dd.data_ptr(), pd.data_ptr(),
+                                      G, B, G, 0, 0.0, 1.0 / (B * G), md.data_ptr(), dd.data_ptr(), pd.data_ptr(), L.F32,
+                                      None, loss.data_ptr(), ws.data_ptr(), nb.value, None))
+    torch.cuda.synchronize()
+    assert rel_err(md.cpu().numpy(), ref["dzm"]) < 3e-4 and rel_err(pd.cpu().numpy(), ref["dzp"]) < 3e-4
+    # bf16 gradient storage
+    md, dd, pd = _t(m), _t(d), _t(pi)
+    g = [torch.empty((B, G), dtype=torch.bfloat16, device=DEV) for _ in range(3)]
+    L.check(lib.dca_zinb_loss_fwd_bwd(Yd.data_ptr(), G, None, sfd.data_ptr(), md.data_ptr(), dd.data_ptr(), pd.data_ptr(),
+                                      G, B, G, 0, 0.0, 1.0 / (B * G), g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(),
+                                      L.BF16, None, loss.data_ptr(), ws.data_ptr(), nb.value, None))
+    torch.cuda.synchronize()
+    assert rel_err(g[0].float().cpu().numpy(), ref["dzm"]) < 6e-3      # bf16: 2^-8 relative
+    assert rel_err(g[1].float().cpu().numpy(), ref["dzd"]) < 6e-3
+
+
+def test_loss_kernel_golden_biochemists(golden_dir):
+    """KAT: summed NLL at R's MLE (reference fixtures data/biochemists-*.tsv) through the CUDA kernel."""
+    L = _lib(); lib = L.load()
+    bio = dict(np.load(os.path.join(golden_dir, "biochemists.npz")))
+    y = bio["y"].astype(np.float32).reshape(-1, 1); B = y.shape[0]
+    nb = C.c_size_t(); lib.dca_zinb_loss_workspace_bytes(B, 1, C.byref(nb))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=DEV)
+    loss = torch.zeros(1, dtype=torch.float64, device=DEV)
+    sf = _t(np.ones(B, np.float32)); Yd = _t(y)
+    g = [torch.empty((B, 1), device=DEV) for _ in range(3)]
+    # NB, per-gene theta (ae_type 'nb')
+    m = _t(bio["nb_pred"].reshape(-1, 1)); th = _t(np.array([float(bio["nb_theta"])]))
+    dth = torch.zeros(1, device=DEV)
+    L.check(lib.dca_zinb_loss_fwd_bwd(Yd.data_ptr(), 1, None, sf.data_ptr(), m.data_ptr(), th.data_ptr(), None, 1, B, 1, 3,
+                                      0.0, 1.0, g[0].data_ptr(), None, None, L.F32, dth.data_ptr(), loss.data_ptr(),
+                                      ws.data_ptr(), nb.value, None))
+    torch.cuda.synchronize()
+    assert abs(loss.item() - 1560.9583383552) < 2e-2
+    assert abs(dth.item()) < 2e-2                          # stationary in theta at the MLE
+    # ZINB
+    m = _t(bio["zinb_pred_count"].reshape(-1, 1)); p = _t(bio["zinb_pred_zero"].reshape(-1, 1))
+    th = _t(np.array([float(bio["zinb_theta"])]))
+    L.check(lib.dca_zinb_loss_fwd_bwd(Yd.data_ptr(), 1, None, sf.data_ptr(), m.data_ptr(), th.data_ptr(), p.data_ptr(), 1, B, 1,
+                                      1, 0.0, 1.0, g[0].data_ptr(), None, g[2].data_ptr(), L.F32, dth.data_ptr(),
+                                      loss.data_ptr(), ws.data_ptr(), nb.value, None))
+    torch.cuda.synchronize()
+    assert abs(loss.item() - 1549.9908867856) < 2e-2
+    design = bio["design"]
+    assert np.max(np.abs(design.T @ g[0].cpu().numpy().astype(np.float64))) < 5e-2   # d/d beta_count = 0
+    assert np.max(np.abs(design.T @ g[2].cpu().numpy().astype(np.float64))) < 5e-2   # d/d beta_zero = 0
+
+
+def test_heads_fwd_vs_oracle():
+    L = _lib(); lib = L.load()
+    B, K, G = 50, 64, 300
+    rng = np.random.default_rng(0)
+    H = rng.normal(0, 1, (B, K)).astype(np.float32)
+    W = [rng.normal(0, 0.3, (K, G)).astype(np.float32) for _ in range(3)]
+    b = [rng.normal(0, 0.5, G).astype(np.float32) for _ in range(3)]
+    sf = np.exp(rng.normal(0, 0.3, B)).astype(np.float32)
+    outs = [torch.empty((B, G), device=DEV) for _ in range(3)]
+    Hd, Wd, bd, sfd = _t(H), [_t(w) for w in W], [_t(x) for x in b], _t(sf)
+    L.check(lib.dca_dense_heads_fwd(Hd.data_ptr(), K, B, K, G, Wd[0].data_ptr(), bd[0].data_ptr(), Wd[1].data_ptr(),
+                                    bd[1].data_ptr(), Wd[2].data_ptr(), bd[2].data_ptr(), sfd.data_ptr(),
+                                    outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), G, None))
+    torch.cuda.synchronize()
+    H64 = H.astype(np.float64)
+    z = [H64 @ W[i].astype(np.float64) + b[i] for i in range(3)]
+    np.testing.assert_allclose(outs[0].cpu().numpy(), O.mean_act(z[0]) * sf[:, None], rtol=2e-4)
+    np.testing.assert_allclose(outs[1].cpu().numpy(), O.disp_act(z[1]), rtol=2e-4)
+    np.testing.assert_allclose(outs[2].cpu().numpy(), O.sigmoid(z[2]), rtol=2e-4, atol=1e-7)
+
+
+CASES = [("zinb-conddisp", True, (64, 32, 64)), ("zinb", True, (16, 8, 16)), ("nb-conddisp", False, (10, 2, 10)),
+         ("nb", True, (12,)), ("zinb-conddisp", True, ()), ("zinb-conddisp", False, (64, 32, 64))]
+
+
+def _make_pair(ae_type, batchnorm, hidden, B, G, seed=0, ridge=0.0, **eng_kw):
+    from dca_b200.engine import DeviceEngine
+    p0 = O.init_params(G, G, hidden, ae_type, batchnorm, seed=seed, dtype=np.float32)
+    rng = np.random.default_rng(seed + 1)
+    for k in p0:
+        if k.endswith(("/bias", "/bn_beta", "/theta")):
+            p0[k] = rng.normal(0, 0.2, p0[k].shape).astype(np.float32)
+    net = O.OracleNet(G, G, hidden, ae_type, batchnorm, ridge=ridge, dtype=np.float64, params=p0, **{
+        k: v for k, v in eng_kw.items() if k in ("l1", "l2", "l1_enc", "l2_enc")})
+    eng = DeviceEngine(G, G, hidden, ae_type, batchnorm, max_batch=B, ridge=ridge, seed=None, gemm_path="generic", **eng_kw)
+    eng.set_weights(p0)
+    return net, eng
+
+
+@pytest.mark.parametrize("ae_type,batchnorm,hidden", CASES)
+def test_train_step_vs_oracle(ae_type, batchnorm, hidden):
+    B, G = 96, 200
+    X, Y, sf = _problem(B + 20, G, 7)
+    rows = np.random.default_rng(0).permutation(B + 20)[:B].astype(np.int32)
+    net, eng = _make_pair(ae_type, batchnorm, hidden, B, G, ridge=0.02, l2=1e-4, l1_enc=1e-5)
+    Xd, Yd, sfd, rd = _t(X), _t(Y), _t(sf), torch.as_tensor(rows).to(DEV)
+    eng.train_step(Xd, Yd, sfd, rows=rd)
+    loss = eng.read_loss()
+    oloss, og = net.loss_and_grads(X[rows].astype(np.float64), Y[rows].astype(np.float64), sf[rows].astype(np.float64))
+    assert abs(loss - oloss) < 1e-4 * abs(oloss)
+    g = eng.grads.cpu().numpy()
+    for name, off, r, c in eng.param_info:
+        ref = og[name].reshape(-1)
+        got = g[off: off + r * c]
+        if name.endswith("/bias") and batchnorm and not name.startswith(("mean", "dispersion", "pi")):
+            assert np.max(np.abs(got)) < 1e-6          # exactly zero in exact arithmetic (BN removes it)
+            continue
+        assert rel_err(got, ref, 2e-3) < 2e-3, name
+    # update + BN moving statistics
+    net.rmsprop_step(og, lr=1e-3, clip=5.0)
+    eng.apply_update(1e-3, 5.0, 1.0)
+    w = eng.get_weights()
+    for k, v in net.params.items():
+        if k.endswith("/bias") and batchnorm and not k.startswith(("mean", "dispersion", "pi")):
+            continue                                      # noise/(sqrt(noise^2)+eps): not comparable
+        np.testing.assert_allclose(w[k], v, rtol=2e-3, atol=2e-4, err_msg=k)
+
+
+def test_trajectory_five_steps():
+    B, G = 64, 120
+    X, Y, sf = _problem(B, G, 9)
+    net, eng = _make_pair("zinb-conddisp", True, (64, 32, 64), B, G)
+    Xd, Yd, sfd = _t(X), _t(Y), _t(sf)
+    for _ in range(5):
+        eng.train_step(Xd, Yd, sfd)
+        eng.apply_update(1e-3, 5.0)
+        l_o = net.train_step(X.astype(np.float64), Y.astype(np.float64), sf.astype(np.float64))
+        assert abs(eng.read_loss() - l_o) < 5e-4 * abs(l_o)
+    acc = eng.read_epoch_acc()
+    assert acc[1] == 5 * B
+
+
+@pytest.mark.parametrize("ae_type", O.AE_TYPES)
+def test_predict_and_eval_vs_oracle(ae_type):
+    B, G = 80, 150
+    X, Y, sf = _problem(B, G, 11)
+    net, eng = _make_pair(ae_type, True, (64, 32, 64), B, G)
+    rng = np.random.default_rng(1)
+    w = eng.get_weights()
+    for k in list(w):
+        if k.endswith("moving_mean"): w[k] = rng.normal(0, 0.3, w[k].shape).astype(np.float32)
+        if k.endswith("moving_var"): w[k] = rng.uniform(0.5, 2.0, w[k].shape).astype(np.float32)
+    eng.set_weights(w)
+    for k in w: net.params[k] = w[k].astype(np.float64)
+    ref = net.predict(X.astype(np.float64), sf.astype(np.float64))
+    cond = ae_type.endswith("conddisp"); has_pi = ae_type.startswith("zinb")
+    mean = torch.empty((B, G), device=DEV); pi = torch.empty((B, G), device=DEV) if has_pi else None
+    disp = torch.empty((B, G) if cond else (G,), device=DEV); lat = torch.empty((B, 32), device=DEV)
+    eng.predict(_t(X), _t(sf), mean=mean, disp=disp, pi=pi, latent=lat)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(mean.cpu().numpy(), ref["mean"], rtol=5e-4)
+    np.testing.assert_allclose(disp.cpu().numpy(), ref["dispersion"], rtol=5e-4)
+    np.testing.assert_allclose(lat.cpu().numpy(), ref["latent"], rtol=5e-4, atol=1e-5)
+    if has_pi:
+        np.testing.assert_allclose(pi.cpu().numpy(), ref["pi"], rtol=5e-4, atol=1e-7)
+    eng.read_epoch_acc(reset=True)
+    eng.eval_step(_t(X), _t(Y), _t(sf))
+    acc = eng.read_epoch_acc()
+    oval = net.loss(X.astype(np.float64), Y.astype(np.float64), sf.astype(np.float64), training=False)
+    assert acc[3] == B * G and abs(acc[2] / acc[3] - oval) < 1e-4 * abs(oval)
+
+
+def test_engine_errors_are_loud():
+    from dca_b200.engine import DeviceEngine
+    with pytest.raises(NotImplementedError):
+        DeviceEngine(10, 10, (4,), "poisson")
+    eng = DeviceEngine(10, 10, (4, 2, 4), "zinb", max_batch=8)
+    X = torch.zeros((9, 10), device=DEV); Y = torch.zeros((9, 10), device=DEV); sf = torch.ones(9, device=DEV)
+    with pytest.raises(ValueError):
+        eng.train_step(X, Y, sf)                       # batch > max_batch
+    with pytest.raises(ValueError):
+        eng.train_step(X[:4].double(), Y[:4], sf[:4])  # wrong dtype
+
+
+def test_full_size_properties_c2():
+    """C2 shape (10k x 2k zinb-conddisp, batch 4096): size-independent properties."""
+    from dca_b200.engine import DeviceEngine
+    N, G, B = 10000, 2000, 4096
+    Y = synth_counts(N, G, 3); X, sf = O.normalize_inputs(Y)
+    eng = DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=1)
+    Xd, Yd, sfd = _t(X), _t(Y), _t(sf)
+    rows = torch.randperm(9000, device=DEV)[:B].to(torch.int32)
+    eng.train_step(Xd, Yd, sfd, rows=rows); l1 = eng.read_loss(); g1 = eng.grads.clone()
+    eng.train_step(Xd, Yd, sfd, rows=rows); l2 = eng.read_loss(); g2 = eng.grads.clone()
+    assert np.isfinite(l1) and abs(l1 - l2) < 1e-5 * abs(l1)                   # repeatable
+    assert torch.isfinite(g1).all()
+    assert (g1[:-2] - g2[:-2]).abs().max().item() <= 1e-4 * g1[:-2].abs().max().item() + 1e-12
+    # loss of the batch == mean of the losses of its two halves (checksum of checksums)
+    eng.read_epoch_acc(reset=True)
+    eng.eval_step(Xd, Yd, sfd, rows=rows); a = eng.read_epoch_acc()
+    eng.eval_step(Xd, Yd, sfd, rows=rows[: B // 2].contiguous()); eng.eval_step(Xd, Yd, sfd, rows=rows[B // 2:].contiguous())
+    b = eng.read_epoch_acc()
+    assert abs(a[2] - b[2]) < 1e-6 * abs(a[2]) and a[3] == b[3]
+    # a few steps reduce the loss
+    l0 = l1
+    for _ in range(10):
+        eng.train_step(Xd, Yd, sfd, rows=rows); eng.apply_update(1e-3, 5.0)
+    assert eng.read_loss() < l0

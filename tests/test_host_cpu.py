@@ -1,0 +1,136 @@
+"""Host-side logic that needs no GPU: C-ABI export table, data preparation, CLI, callbacks."""
+import ctypes as C
+import os
+import re
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import dca_oracle as O
+from tests.util import synth_counts
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dca_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "dca_b200.h")).read()
+    declared = set(re.findall(r"\b(dca_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"dca_handle"}
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libdca_b200.so does not export %s" % name
+    assert declared == set(_lib.PROTOTYPES), (declared ^ set(_lib.PROTOTYPES))
+    assert lib.dca_version() == 100
+
+
+def test_config_struct_matches_header_and_errors_are_reported():
+    from dca_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.default_config()
+    assert cfg.struct_bytes == C.sizeof(_lib.Config)
+    assert list(cfg.hidden)[:3] == [64, 32, 64] and abs(cfg.bn_momentum - 0.99) < 1e-7
+    n = C.c_size_t()
+    cfg.n_in = 0
+    assert lib.dca_arena_bytes(C.byref(cfg), C.byref(n)) == -1
+    assert b"n_in" in lib.dca_last_error()
+    cfg.n_in = cfg.n_out = 2000; cfg.max_batch = 4096
+    assert lib.dca_arena_bytes(C.byref(cfg), C.byref(n)) == 0 and n.value > 3 * 4096 * 2000 * 4
+    cfg.ae_type = 9
+    assert lib.dca_arena_bytes(C.byref(cfg), C.byref(n)) == -3
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dca_b200 import _lib
+    from dca_b200.engine import DeviceEngine
+    with pytest.raises(_lib.DcaError):
+        DeviceEngine(10, 10, (4, 2, 4), "zinb")
+
+
+def test_normalize_matches_oracle_restatement():
+    from dca_b200.anndata_lite import AnnData
+    from dca_b200 import io
+    Y = synth_counts(60, 25, 1)
+    ad = AnnData(Y.copy())
+    ad = io.read_dataset(ad, check_counts=True)
+    ad = io.normalize(ad, filter_min_counts=False)
+    X, sf = O.normalize_inputs(Y)
+    np.testing.assert_allclose(ad.X, X, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ad.obs["size_factors"].values, sf, rtol=1e-6)
+    np.testing.assert_array_equal(ad.raw.X, Y)
+    assert abs(ad.X.mean(0)).max() < 1e-5 and abs(ad.X.std(0, ddof=1) - 1).max() < 1e-4
+    assert set(ad.obs["dca_split"]) == {"train"}
+
+
+def test_read_dataset_checks_counts_and_splits(tmp_path):
+    from dca_b200.anndata_lite import AnnData
+    from dca_b200 import io
+    Y = synth_counts(40, 12, 2)
+    bad = AnnData(Y + 0.5)
+    with pytest.raises(AssertionError, match="unnormalized count data"):
+        io.read_dataset(bad)
+    ad = io.read_dataset(AnnData(Y), test_split=True)
+    assert (ad.obs["dca_split"] == "test").sum() == 4
+    # gene x cell TSV, transposed on read like the reference CLI does
+    df = pd.DataFrame(Y.T.astype(int), index=["g%d" % i for i in range(12)], columns=["c%d" % i for i in range(40)])
+    p = tmp_path / "counts.tsv"; df.to_csv(p, sep="\t")
+    ad2 = io.read_dataset(str(p), transpose=True)
+    assert ad2.shape == (40, 12) and list(ad2.var_names[:2]) == ["g0", "g1"]
+    with pytest.raises(NotImplementedError):
+        io.read_dataset(123)
+
+
+def test_write_text_matrix_format(tmp_path):
+    from dca_b200 import io
+    m = np.array([[1.0, 2.5], [3.25, 4.125], [5, 6]], np.float32)
+    f = tmp_path / "mean.tsv"
+    io.write_text_matrix(m, str(f), rownames=["c0", "c1", "c2"], colnames=["g0", "g1"], transpose=True)
+    lines = open(f).read().rstrip("\n").split("\n")
+    assert lines[0] == "\tc0\tc1\tc2" and lines[1] == "g0\t1.000000\t3.250000\t5.000000"
+
+
+def test_cli_flags_match_reference_defaults():
+    from dca_b200.__main__ import parse_args
+    a = parse_args(["in.tsv", "out"])
+    assert (a.type, a.batchsize, a.hiddensize, a.epochs, a.earlystop, a.reducelr) == ("nb-conddisp", 32, "64,32,64", 300, 15, 10)
+    assert a.sizefactors and a.norminput and a.loginput and a.batchnorm and a.checkcounts
+    assert not (a.transpose or a.testsplit or a.saveweights or a.hyper or a.debug or a.tensorboard)
+    assert a.gradclip == 5.0 and a.learningrate is None and a.optimizer == "RMSprop" and a.ridge == 0.0
+    b = parse_args(["in.tsv", "out", "--nosizefactors", "--nobatchnorm", "-t", "--type", "zinb", "-r", "0.01", "-s", "16,2,16"])
+    assert not b.sizefactors and not b.batchnorm and b.transpose and b.type == "zinb" and b.learningrate == 0.01
+
+
+def test_ae_types_registry_keys():
+    from dca_b200.network import AE_types
+    assert set(AE_types) == {'normal', 'poisson', 'nb', 'nb-conddisp', 'nb-shared', 'nb-fork', 'zinb', 'zinb-conddisp',
+                             'zinb-shared', 'zinb-fork', 'zinb-elempi'}
+    net = AE_types['poisson'](input_size=5)
+    with pytest.raises(NotImplementedError):
+        net.build()
+    import dca.api, dca.network            # alias package resolves
+    assert dca.network.AE_types is AE_types
+
+
+def test_plateau_and_early_stop_match_oracle_fit_logic():
+    from dca_b200.train import PlateauAndStop
+    vals = [5.0, 4.0, 4.0, 4.00005, 3.9, 3.95, 3.95, 3.95, 3.95]
+    c = PlateauAndStop(1e-3, reduce_lr=2, early_stop=3)
+    lrs, stopped = [], None
+    for e, v in enumerate(vals):
+        lrs.append(c.lr)
+        if c.on_epoch_end(e, v):
+            stopped = e; break
+    assert stopped == 7
+    assert lrs[:5] == [1e-3, 1e-3, 1e-3, 1e-3, 1e-4]
+
+
+def test_shard_bounds():
+    from dca_b200.dist import shard_bounds
+    assert shard_bounds(10, 0, 1) == (0, 10)
+    assert [shard_bounds(10, r, 4, equal=True) for r in range(4)] == [(0, 2), (2, 4), (4, 6), (6, 8)]
+    b = [shard_bounds(10, r, 4) for r in range(4)]
+    assert b[0][0] == 0 and b[-1][1] == 10 and all(b[i][1] == b[i + 1][0] for i in range(3))
