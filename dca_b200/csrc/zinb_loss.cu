@@ -67,15 +67,45 @@ __device__ __forceinline__ double block_reduce_sum(float v, double* smem /* >= 8
   return t;   // valid in thread 0
 }
 
+// per-row operands of one thread (VEC consecutive genes)
+template <int VEC>
+struct RowVals { float y[VEC], m[VEC], d[VEC], p[VEC]; float sf; };
+
+template <bool HAS_PI, bool COND_DISP, int VEC>
+__device__ __forceinline__ void load_row(RowVals<VEC>& v, const float* __restrict__ Y, int64_t ldy,
+                                         const int32_t* __restrict__ rows, const float* __restrict__ sf,
+                                         const float* m, const float* d, const float* pi, int64_t ld, int r, int col0) {
+  const int64_t yr = rows ? (int64_t)rows[r] : (int64_t)r;
+  v.sf = sf ? sf[yr] : 1.0f;
+  const float* yp = Y + yr * ldy + col0;
+  const int64_t off = (int64_t)r * ld + col0;
+  if (VEC == 4) {
+    float4 t = ld4_stream(yp); v.y[0] = t.x; v.y[1] = t.y; v.y[2] = t.z; v.y[3] = t.w;
+    t = ld4(m + off); v.m[0] = t.x; v.m[1] = t.y; v.m[2] = t.z; v.m[3] = t.w;
+    if (COND_DISP) { t = ld4(d + off); v.d[0] = t.x; v.d[1] = t.y; v.d[2] = t.z; v.d[3] = t.w; }
+    if (HAS_PI) { t = ld4(pi + off); v.p[0] = t.x; v.p[1] = t.y; v.p[2] = t.z; v.p[3] = t.w; }
+  } else {
+    v.y[0] = yp[0]; v.m[0] = m[off];
+    if (COND_DISP) v.d[0] = d[off];
+    if (HAS_PI) v.p[0] = pi[off];
+  }
+}
+
 // VEC == 4: aligned 128-bit path; VEC == 1: scalar fallback for ragged G / unaligned ld.
+// The next row's operands are fetched before the current row is evaluated (software prefetch),
+// so every warp keeps 4 x 512 B of loads in flight while the MUFU/FMA work proceeds.
 template <bool HAS_PI, bool COND_DISP, typename GT, int VEC, bool BWD>
 __global__ void __launch_bounds__(kThreads)
 zinb_loss_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __restrict__ rows,
                  const float* __restrict__ sf, const float* m, const float* d, const float* pi,
                  int64_t ld, int B, int G, float ridge, float inv_n, int rows_per_block,
                  GT* dzm, GT* dzd, GT* dzp, float* __restrict__ dth_partial,
-                 double* __restrict__ loss_partial) {
+                 double* __restrict__ loss_partial, const float* __restrict__ lf_global) {
   __shared__ double red[8];
+  __shared__ float lf[zmath::kLogFactN];
+  if (threadIdx.x < zmath::kLogFactN) lf[threadIdx.x] = lf_global[threadIdx.x];
+  __syncthreads();
+  using Ops = zmath::FastOps;
   const int col0 = (blockIdx.x * kThreads + threadIdx.x) * VEC;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(B, r0 + rows_per_block);
@@ -90,34 +120,23 @@ zinb_loss_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __rest
 #pragma unroll
       for (int j = 0; j < VEC; ++j) thg[j] = (col0 + j < G) ? d[col0 + j] : 1.f;
     }
+    RowVals<VEC> cur, nxt;
+    load_row<HAS_PI, COND_DISP, VEC>(cur, Y, ldy, rows, sf, m, d, pi, ld, r0, col0);
     for (int r = r0; r < r1; ++r) {
-      const int64_t yr = rows ? (int64_t)rows[r] : (int64_t)r;
-      const float s = sf ? sf[yr] : 1.0f;
-      const float* yp = Y + yr * ldy + col0;
+      if (r + 1 < r1) load_row<HAS_PI, COND_DISP, VEC>(nxt, Y, ldy, rows, sf, m, d, pi, ld, r + 1, col0);
       const int64_t off = (int64_t)r * ld + col0;
-      float yv[VEC], mv[VEC], dv[VEC], pv[VEC];
-      if (VEC == 4) {
-        float4 t = ld4_stream(yp); yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3] = t.w;
-        t = ld4(m + off); mv[0] = t.x; mv[1] = t.y; mv[2] = t.z; mv[3] = t.w;
-        if (COND_DISP) { t = ld4(d + off); dv[0] = t.x; dv[1] = t.y; dv[2] = t.z; dv[3] = t.w; }
-        if (HAS_PI) { t = ld4(pi + off); pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w; }
-      } else {
-        yv[0] = yp[0]; mv[0] = m[off];
-        if (COND_DISP) dv[0] = d[off];
-        if (HAS_PI) pv[0] = pi[off];
-      }
       float gm[VEC], gd[VEC], gp[VEC];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        const float th = COND_DISP ? dv[j] : thg[j];
-        const float p = HAS_PI ? pv[j] : 0.f;
+        const float th = COND_DISP ? cur.d[j] : thg[j];
+        const float p = HAS_PI ? cur.p[j] : 0.f;
         if (BWD) {
-          zmath::Elem e = zmath::zinb_elem<HAS_PI, COND_DISP>(yv[j], mv[j], s, th, p, ridge);
+          zmath::Elem e = zmath::zinb_elem<Ops, HAS_PI, COND_DISP>(cur.y[j], cur.m[j], cur.sf, th, p, ridge, lf);
           lsum += e.loss;
           gm[j] = e.gm * inv_n; gd[j] = e.gd * inv_n; gp[j] = e.gp * inv_n;
           if (!COND_DISP) tacc[j] += e.gd;
         } else {
-          lsum += zmath::zinb_elem_loss<HAS_PI>(yv[j], mv[j], s, th, p, ridge);
+          lsum += zmath::zinb_elem_loss<Ops, HAS_PI>(cur.y[j], cur.m[j], cur.sf, th, p, ridge, lf);
         }
       }
       if (BWD) {
@@ -131,6 +150,7 @@ zinb_loss_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __rest
           if (HAS_PI) st1(dzp + off, gp[0]);
         }
       }
+      cur = nxt;
     }
     if (BWD && !COND_DISP) {
 #pragma unroll
@@ -177,6 +197,24 @@ __global__ void loss_finalize_kernel(const double* loss_sum, const double* penal
   if (epoch_acc) { epoch_acc[0] += l * (double)batch; epoch_acc[1] += (double)batch; }
 }
 
+__device__ float g_log_fact[zmath::kLogFactN];
+
+// log(k!) table in device global memory, filled once per device on first use
+const float* log_fact_table_device() {
+  static thread_local int ready_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return nullptr; }
+  float* p = nullptr;
+  if (cudaGetSymbolAddress((void**)&p, g_log_fact) != cudaSuccess) { set_error("cudaGetSymbolAddress failed"); return nullptr; }
+  if (ready_dev != dev) {
+    float t[zmath::kLogFactN];
+    zmath::fill_log_fact(t);
+    if (cudaMemcpy(p, t, sizeof(t), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("log-factorial table upload failed"); return nullptr; }
+    ready_dev = dev;
+  }
+  return p;
+}
+
 template <bool BWD>
 int launch(const LossArgs& a, cudaStream_t s) {
   if (a.B <= 0 || a.G <= 0) { set_error("zinb_loss: empty batch (B=%d, G=%d)", a.B, a.G); return DCA_ERR_BAD_ARG; }
@@ -186,6 +224,8 @@ int launch(const LossArgs& a, cudaStream_t s) {
   if (BWD && (!a.dzm || (cond && !a.dzd) || (has_pi && !a.dzp) || (!cond && !a.dtheta))) {
     set_error("zinb_loss: null gradient output"); return DCA_ERR_BAD_ARG;
   }
+  const float* lf_dev = log_fact_table_device();
+  if (!lf_dev) return DCA_ERR_CUDA;
   const Plan p = make_plan(a.B, a.G);
   const size_t need = loss_workspace_bytes(a.B, a.G);
   if (!a.ws || a.ws_bytes < need) { set_error("zinb_loss: workspace too small (%zu < %zu)", a.ws_bytes, need); return DCA_ERR_BAD_ARG; }
@@ -204,7 +244,7 @@ int launch(const LossArgs& a, cudaStream_t s) {
 #define DCA_LOSS_LAUNCH(HP, CD, GT, V)                                                                 \
   zinb_loss_kernel<HP, CD, GT, V, BWD><<<grid, block, 0, s>>>(                                          \
       a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, a.G, a.ridge, a.inv_n, p.rows_per_block,      \
-      (GT*)a.dzm, (GT*)a.dzd, (GT*)a.dzp, tpart, lpart)
+      (GT*)a.dzm, (GT*)a.dzd, (GT*)a.dzp, tpart, lpart, lf_dev)
 #define DCA_LOSS_DISPATCH(GT, V)                                   \
   do {                                                             \
     if (has_pi && cond) DCA_LOSS_LAUNCH(true, true, GT, V);        \
@@ -284,11 +324,15 @@ extern "C" int dca_zinb_loss_fwd(const float* Y, int64_t ldy, const int32_t* row
 extern "C" int dca_zinb_elem_host(int32_t ae_type, float y, float m, float sf, float d, float pi, float ridge,
                                   float out[4]) {
   zmath::Elem e;
+  static float lf[zmath::kLogFactN];
+  static bool lf_ready = false;
+  if (!lf_ready) { zmath::fill_log_fact(lf); lf_ready = true; }
+  using P = zmath::PreciseOps;
   switch (ae_type) {
-    case DCA_AE_ZINB_CONDDISP: e = zmath::zinb_elem<true, true>(y, m, sf, d, pi, ridge); break;
-    case DCA_AE_ZINB: e = zmath::zinb_elem<true, false>(y, m, sf, d, pi, ridge); break;
-    case DCA_AE_NB_CONDDISP: e = zmath::zinb_elem<false, true>(y, m, sf, d, pi, ridge); break;
-    case DCA_AE_NB: e = zmath::zinb_elem<false, false>(y, m, sf, d, pi, ridge); break;
+    case DCA_AE_ZINB_CONDDISP: e = zmath::zinb_elem<P, true, true>(y, m, sf, d, pi, ridge, lf); break;
+    case DCA_AE_ZINB: e = zmath::zinb_elem<P, true, false>(y, m, sf, d, pi, ridge, lf); break;
+    case DCA_AE_NB_CONDDISP: e = zmath::zinb_elem<P, false, true>(y, m, sf, d, pi, ridge, lf); break;
+    case DCA_AE_NB: e = zmath::zinb_elem<P, false, false>(y, m, sf, d, pi, ridge, lf); break;
     default: set_error("dca_zinb_elem_host: unknown ae_type %d", ae_type); return DCA_ERR_BAD_ARG;
   }
   out[0] = e.loss; out[1] = e.gm; out[2] = e.gd; out[3] = e.gp;

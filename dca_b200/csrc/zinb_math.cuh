@@ -1,13 +1,20 @@
-// Device math for the ZINB / NB negative log-likelihood and its gradient.
+// Per-element arithmetic of the ZINB / NB negative log-likelihood and its gradient.
 //
-// Restates dca/loss.py:72-156 (reference formulas, every epsilon position kept where it is
-// representable in fp32) and the closed-form derivatives TF autodiff would produce
-// (SURVEY.md A.4), re-arranged so that fp32 does not cancel catastrophically:
-//   lgamma(theta)-lgamma(y+theta) = -sum_{k<y} log(theta+k)           (integer y, exact recurrence)
-//   psi(theta)-psi(y+theta)       = -sum_{k<y} 1/(theta+k)
-//   general (large / non-integer y): shifted Stirling / asymptotic digamma differences
-//   d/dtheta nb  = [log1p(x) - x/(1+x)] + y/(theta+mu) - (psi(y+theta)-psi(theta)),  x = mu/theta
-//   d/dmu * mu   = theta*(mu-y)/(theta+mu)
+// Restates dca/loss.py:72-156 (reference formulas; every epsilon kept where it is representable
+// in fp32) and the closed-form derivatives TF autodiff produces for them,
+// re-arranged so that fp32 does not cancel catastrophically and so that ONE reciprocal serves
+// the whole element.  With  te = theta+eps,  den = te+mu,  q = mu/den,  r = te/den = 1-q:
+//   log(1+mu/te) = -log r =: L1            (series in q for q < 1/8, else lg2)
+//   t2 (loss.py:88) = (theta+y) L1 + y (log te - log(mu+eps)) = theta L1 - y log((mu+eps)/den)
+//   zero_nb (loss.py:136) = r^theta = exp(-theta L1)
+//   d/dmu * mu      = theta (mu - y)/den                 (nb)   |  w theta q          (zero)
+//   d/dtheta        = [L1 - q] + y/den - (psi(y+te)-psi(te))  (nb)   |  w [L1 - q]   (zero)
+//   lgamma(te)-lgamma(y+te) = -sum_{k<y} log(te+k),  psi(te)-psi(y+te) = -sum_{k<y} 1/(te+k)
+//     (integer y <= 16: product recurrence; otherwise shifted Stirling / asymptotic digamma)
+//
+// The same source compiles for the host (PreciseOps: libm) -- exported as dca_zinb_elem_host so
+// the formulas are unit-tested against the oracle without a GPU -- and for the device
+// (FastOps: MUFU rcp / lg2 / ex2 approximations, ~1 ulp each).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -15,86 +22,93 @@
 namespace dca {
 namespace zmath {
 
-constexpr float kEps = 1e-10f;            // dca/loss.py:65
-constexpr float kHalfLog2Pi = 0.918938533204672742f;
-
 #define DCA_HD __host__ __device__ __forceinline__
 
-// log(k!) for k = 0..15
-DCA_HD float log_fact(int k) {
-  const float t[16] = {
-    0.0f, 0.0f, 0.693147180559945f, 1.791759469228055f, 3.178053830347946f, 4.787491742782046f,
-    6.579251212010101f, 8.525161361065415f, 10.60460290274525f, 12.80182748008147f,
-    15.10441257307552f, 17.50230784587389f, 19.98721449566189f, 22.55216385312342f,
-    25.19122118273868f, 27.89927138384089f};
-  return t[k];
+constexpr float kEps = 1e-10f;            // dca/loss.py:65
+constexpr float kHalfLog2Pi = 0.918938533204672742f;
+constexpr float kLn2 = 0.693147180559945f;
+constexpr float kLog2e = 1.442695040888963f;
+constexpr int kLogFactN = 64;             // table of log(k!) for k < 64 (shared memory on the device)
+
+struct PreciseOps {
+  static DCA_HD float rcp(float x) { return 1.0f / x; }
+  static DCA_HD float lg2(float x) { return log2f(x); }
+  static DCA_HD float ex2(float x) { return exp2f(x); }
+};
+
+#ifdef __CUDACC__
+struct FastOps {   // device only: one MUFU instruction each
+  static __device__ __forceinline__ float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  static __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  static __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+};
+#endif
+
+// log(k!) table filler (host: static table; device: copied into shared memory by the kernel)
+inline void fill_log_fact(float* t) {
+  double acc = 0.0;
+  t[0] = 0.f;
+  for (int k = 1; k < kLogFactN; ++k) { acc += log((double)k); t[k] = (float)acc; }
 }
 
 // lgamma(x) - [(x-0.5)log x - x + 0.5 log 2pi]  for x >= 8
+template <class Ops>
 DCA_HD float stirling_corr(float x) {
-  float r = 1.0f / x, r2 = r * r;
+  const float r = Ops::rcp(x), r2 = r * r;
   return r * (0.0833333333f + r2 * (-0.00277777778f + r2 * 0.000793650794f));
 }
 // psi(x) - log(x) for x >= 8
+template <class Ops>
 DCA_HD float digamma_corr(float x) {
-  float r = 1.0f / x, r2 = r * r;
+  const float r = Ops::rcp(x), r2 = r * r;
   return -0.5f * r - r2 * (0.0833333333f - r2 * (0.00833333333f - r2 * 0.00396825397f));
 }
 
-// prod_{k<8}(x+k) as log, and sum_{k<8} 1/(x+k), for 0 < x < 8
-DCA_HD void shift8(float x, float& logprod, float& recsum) {
+// log prod_{k<n}(x+k) and sum_{k<n} 1/(x+k) via the product / derivative recurrence,
+// flushed every 4 factors so the product cannot overflow (x <= 1e4+16)
+template <class Ops>
+DCA_HD void rising_log_and_recsum(float x, int n, float& logprod, float& recsum) {
   float P = 1.f, dP = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { float t = x + (float)k; dP = fmaf(dP, t, P); P *= t; }
-  logprod = logf(P); recsum = dP / P;
-  P = 1.f; dP = 0.f;
-#pragma unroll
-  for (int k = 4; k < 8; ++k) { float t = x + (float)k; dP = fmaf(dP, t, P); P *= t; }
-  logprod += logf(P); recsum += dP / P;
+  logprod = 0.f; recsum = 0.f;
+  for (int k = 0; k < n; ++k) {
+    const float t = x + (float)k;
+    dP = fmaf(dP, t, P);
+    P *= t;
+    if ((k & 3) == 3) { logprod += Ops::lg2(P); recsum = fmaf(dP, Ops::rcp(P), recsum); P = 1.f; dP = 0.f; }
+  }
+  if (n & 3) { logprod += Ops::lg2(P); recsum = fmaf(dP, Ops::rcp(P), recsum); }
+  logprod *= kLn2;
 }
 
 // lgamma(y+1), y >= 0   (only the loss VALUE needs it; it has no gradient)
-DCA_HD float lgamma_1p(float y) {
-  if (y < 15.5f && y == rintf(y)) return log_fact((int)y);
+template <class Ops>
+DCA_HD float lgamma_1p(float y, const float* lf_table) {
+  if (y < (float)kLogFactN - 0.5f && y == rintf(y)) return lf_table[(int)y];
   float x = y + 1.0f, shift = 0.f;
-  if (x < 8.f) { float s; shift8(x, shift, s); x += 8.f; }
-  return (x - 0.5f) * logf(x) - x + kHalfLog2Pi + stirling_corr(x) - shift;
+  if (x < 8.f) { float s; rising_log_and_recsum<Ops>(x, 8, shift, s); x += 8.f; }
+  return (x - 0.5f) * (kLn2 * Ops::lg2(x)) - x + kHalfLog2Pi + stirling_corr<Ops>(x) - shift;
 }
 
 // lg = lgamma(th+y) - lgamma(th),  dg = psi(th+y) - psi(th);   th > 0, y >= 0
+template <class Ops>
 DCA_HD void lgam_digam_diff(float th, float y, float& lg, float& dg) {
-  if (y <= 16.f && y == rintf(y)) {
-    const int n = (int)y;
-    float P = 1.f, dP = 0.f;
-    lg = 0.f; dg = 0.f;
-    for (int k = 0; k < n; ++k) {
-      float t = th + (float)k;
-      dP = fmaf(dP, t, P);
-      P *= t;
-      if ((k & 3) == 3) { lg += logf(P); dg += dP / P; P = 1.f; dP = 0.f; }
-    }
-    if (n & 3) { lg += logf(P); dg += dP / P; }
-    return;
-  }
+  if (y <= 16.f && y == rintf(y)) { rising_log_and_recsum<Ops>(th, (int)y, lg, dg); return; }
   float a = th, b = th + y, sh_lg = 0.f, sh_dg = 0.f;
-  if (a < 8.f) { float lp, rs; shift8(a, lp, rs); sh_lg += lp; sh_dg += rs; a += 8.f; }
-  if (b < 8.f) { float lp, rs; shift8(b, lp, rs); sh_lg -= lp; sh_dg -= rs; b += 8.f; }
-  const float lr = log1pf((b - a) / a);                 // log(b/a)
-  lg = (a - 0.5f) * lr + (b - a) * (logf(b) - 1.0f) + stirling_corr(b) - stirling_corr(a) + sh_lg;
-  dg = lr + digamma_corr(b) - digamma_corr(a) + sh_dg;
-}
-
-// f(x) = log1p(x) - x/(1+x) >= 0 without cancellation for small x;  L1 = log1p(x) given
-DCA_HD float log1p_minus_ratio(float x, float L1) {
-  if (x < 0.05f) {
-    float p = fmaf(x, -0.857142857f, 0.833333333f);
-    p = fmaf(x, p, -0.8f);
-    p = fmaf(x, p, 0.75f);
-    p = fmaf(x, p, -0.666666667f);
-    p = fmaf(x, p, 0.5f);
-    return x * x * p;
+  if (a < 8.f) { float lp, rs; rising_log_and_recsum<Ops>(a, 8, lp, rs); sh_lg += lp; sh_dg += rs; a += 8.f; }
+  if (b < 8.f) { float lp, rs; rising_log_and_recsum<Ops>(b, 8, lp, rs); sh_lg -= lp; sh_dg -= rs; b += 8.f; }
+  // log(b/a) = log1p((b-a)/a): series when the ratio is close to one
+  const float u = (b - a) * Ops::rcp(a);
+  float lr;
+  if (fabsf(u) < 0.125f) {
+    float p = fmaf(u, -0.1f, 0.111111111f);
+    p = fmaf(u, p, -0.125f); p = fmaf(u, p, 0.142857143f); p = fmaf(u, p, -0.166666667f);
+    p = fmaf(u, p, 0.2f); p = fmaf(u, p, -0.25f); p = fmaf(u, p, 0.333333333f); p = fmaf(u, p, -0.5f);
+    lr = fmaf(u * u, p, u);
+  } else {
+    lr = kLn2 * Ops::lg2(1.0f + u);
   }
-  return L1 - x / (1.0f + x);
+  lg = (a - 0.5f) * lr + (b - a) * (kLn2 * Ops::lg2(b) - 1.0f) + stirling_corr<Ops>(b) - stirling_corr<Ops>(a) + sh_lg;
+  dg = lr + digamma_corr<Ops>(b) - digamma_corr<Ops>(a) + sh_dg;
 }
 
 struct Elem {
@@ -104,58 +118,87 @@ struct Elem {
   float gp;     // dL/d zp
 };
 
+// Quantities shared by both branches of loss.py:138
+struct Shared { float mu, th, te, rden, q, L1, f; };
+
+template <class Ops>
+DCA_HD Shared shared_terms(float m, float sf, float th) {
+  Shared s;
+  s.mu = m * sf;                                            // dca/layers.py:85
+  s.th = fminf(th, 1e6f);                                   // dca/loss.py:85
+  s.te = s.th + kEps;                                       // dca/loss.py:87
+  s.rden = Ops::rcp(s.te + s.mu);
+  s.q = s.mu * s.rden;
+  if (s.q < 0.125f) {                                       // -log(1-q) = q + q^2/2 + q^3/3 + ...
+    const float q = s.q;
+    float p = fmaf(q, 0.0909090909f, 0.1f);
+    p = fmaf(q, p, 0.111111111f); p = fmaf(q, p, 0.125f); p = fmaf(q, p, 0.142857143f);
+    p = fmaf(q, p, 0.166666667f); p = fmaf(q, p, 0.2f); p = fmaf(q, p, 0.25f);
+    p = fmaf(q, p, 0.333333333f); p = fmaf(q, p, 0.5f);
+    s.f = q * q * p;                                        // L1 - q
+    s.L1 = q + s.f;
+  } else {
+    s.L1 = -kLn2 * Ops::lg2(s.te * s.rden);                 // log(1 + mu/(theta+eps))   loss.py:88
+    s.f = s.L1 - s.q;
+  }
+  return s;
+}
+
+// 1 - exp(-d) = sigmoid(zd) when d = softplus(zd)
+template <class Ops>
+DCA_HD float one_minus_exp_neg(float d) {
+  if (d < 0.125f) {
+    float p = fmaf(d, -0.000198412698f, 0.00138888889f);
+    p = fmaf(d, p, -0.00833333333f); p = fmaf(d, p, 0.0416666667f); p = fmaf(d, p, -0.166666667f);
+    p = fmaf(d, p, 0.5f);
+    return d - d * d * p;
+  }
+  return 1.0f - Ops::ex2(-d * kLog2e);
+}
+
 // y: raw count; m: MeanAct output (before *sf); sf: size factor; th: DispAct output or per-gene
-// theta; pi: sigmoid output.
-template <bool HAS_PI, bool COND_DISP>
-DCA_HD Elem zinb_elem(float y, float m, float sf, float th, float pi, float ridge) {
-  const float mu = m * sf;                                 // dca/layers.py:85
-  const bool m_pass = (m > 1e-5f) && (m < 1e6f);           // clip_by_value gradient mask (network.py:38)
-  const float d_in = th;
-  th = fminf(th, 1e6f);                                    // dca/loss.py:85
-  const float te = th + kEps;
-  const float x = mu / te;
-  const float L1 = log1pf(x);                              // log(1 + mu/(theta+eps))   loss.py:88
-  const float rden = 1.0f / (te + mu);
-  const float f = log1p_minus_ratio(x, L1);
+// theta; pi: sigmoid output; lf_table: log(k!) for k < kLogFactN.
+template <class Ops, bool HAS_PI, bool COND_DISP>
+DCA_HD Elem zinb_elem(float y, float m, float sf, float th, float pi, float ridge, const float* lf_table) {
+  const Shared s = shared_terms<Ops>(m, sf, th);
   Elem o;
   float dth, dpi = 0.f;
   if (HAS_PI && y < 1e-8f) {                               // loss.py:138  zero branch
-    const float z = expf(-th * L1);                        // pow(theta/(theta+mu+eps), theta)  loss.py:136
+    const float z = Ops::ex2(-s.th * s.L1 * kLog2e);          // pow(theta/(theta+mu+eps), theta)  loss.py:136
     const float omp = 1.0f - pi;
     const float D = pi + omp * z + kEps;                   // loss.py:137
-    const float rD = 1.0f / D;
-    o.loss = -logf(D);
+    const float rD = Ops::rcp(D);
+    o.loss = -kLn2 * Ops::lg2(D);
     const float w = omp * z * rD;
-    o.gm = w * th * mu * rden;
-    dth = w * f;                                           // -w*(log r + 1 - r)
-    dpi = -(1.0f - z) * rD;
+    o.gm = w * s.th * s.q;
+    dth = w * s.f;                                         // -w*(log r + 1 - r)
+    dpi = (z - 1.0f) * rD;
   } else {                                                 // NB branch  loss.py:87-88,130
     float lg, dg;
-    lgam_digam_diff(te, y, lg, dg);
-    const float t1 = lgamma_1p(y) - lg;
-    const float t2 = (th + y) * L1 + y * (logf(te) - logf(mu + kEps));
-    float nb = t1 + t2;
+    lgam_digam_diff<Ops>(s.te, y, lg, dg);
+    const float theta = s.th;
+    float nb = lgamma_1p<Ops>(y, lf_table) - lg + theta * s.L1 - y * (kLn2 * Ops::lg2((s.mu + kEps) * s.rden));
     if (nb != nb) nb = INFINITY;                           // _nan2inf  loss.py:105
-    o.gm = th * (mu - y) * rden;
-    dth = f + y * rden - dg;
+    o.gm = theta * (s.mu - y) * s.rden;
+    dth = s.f + y * s.rden - dg;
     if (HAS_PI) {
-      const float q = 1.0f - pi + kEps;
-      nb -= logf(q);                                       // loss.py:130
-      dpi = 1.0f / q;
+      const float qq = 1.0f - pi + kEps;
+      nb -= kLn2 * Ops::lg2(qq);                           // loss.py:130
+      dpi = Ops::rcp(qq);
     }
     o.loss = nb;
   }
+  const bool m_pass = (m > 1e-5f) && (m < 1e6f);           // clip_by_value gradient mask (network.py:38)
   o.gm = m_pass ? o.gm : 0.f;
   if (COND_DISP) {
-    const bool d_pass = (d_in > 1e-4f) && (d_in < 1e4f);   // DispAct clip mask (network.py:39)
-    o.gd = d_pass ? dth * (-expm1f(-d_in)) : 0.f;          // sigmoid(zd) = 1 - exp(-softplus(zd))
+    const bool d_pass = (th > 1e-4f) && (th < 1e4f);       // DispAct clip mask (network.py:39)
+    o.gd = d_pass ? dth * one_minus_exp_neg<Ops>(th) : 0.f;
   } else {
     o.gd = dth;
   }
   if (HAS_PI) {
-    const float s = pi * (1.0f - pi);
     o.loss = fmaf(ridge * pi, pi, o.loss);                 // loss.py:139-140
-    o.gp = (dpi + 2.0f * ridge * pi) * s;
+    o.gp = (dpi + 2.0f * ridge * pi) * (pi * (1.0f - pi));
   } else {
     o.gp = 0.f;
   }
@@ -163,22 +206,19 @@ DCA_HD Elem zinb_elem(float y, float m, float sf, float th, float pi, float ridg
 }
 
 // forward-only value
-template <bool HAS_PI>
-DCA_HD float zinb_elem_loss(float y, float m, float sf, float th, float pi, float ridge) {
-  const float mu = m * sf;
-  th = fminf(th, 1e6f);
-  const float te = th + kEps;
-  const float L1 = log1pf(mu / te);
+template <class Ops, bool HAS_PI>
+DCA_HD float zinb_elem_loss(float y, float m, float sf, float th, float pi, float ridge, const float* lf_table) {
+  const Shared s = shared_terms<Ops>(m, sf, th);
   float l;
   if (HAS_PI && y < 1e-8f) {
-    const float z = expf(-th * L1);
-    l = -logf(pi + (1.0f - pi) * z + kEps);
+    const float z = Ops::ex2(-s.th * s.L1 * kLog2e);
+    l = -kLn2 * Ops::lg2(pi + (1.0f - pi) * z + kEps);
   } else {
     float lg, dg;
-    lgam_digam_diff(te, y, lg, dg);
-    l = lgamma_1p(y) - lg + (th + y) * L1 + y * (logf(te) - logf(mu + kEps));
+    lgam_digam_diff<Ops>(s.te, y, lg, dg);
+    l = lgamma_1p<Ops>(y, lf_table) - lg + s.th * s.L1 - y * (kLn2 * Ops::lg2((s.mu + kEps) * s.rden));
     if (l != l) l = INFINITY;
-    if (HAS_PI) l -= logf(1.0f - pi + kEps);
+    if (HAS_PI) l -= kLn2 * Ops::lg2(1.0f - pi + kEps);
   }
   if (HAS_PI) l = fmaf(ridge * pi, pi, l);
   return l;
