@@ -17,15 +17,20 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kVec = 4;
 constexpr int kColsPerBlock = kThreads * kVec;   // 1024 genes per block
-constexpr int kMaxRowChunks = 128;
+constexpr int kTargetBlocks = 148 * 16;          // ~4 waves of 4 resident blocks per SM
+constexpr int kMaxBlocks = 8192;                 // bound of the per-block loss-partial buffer
 
 struct Plan { int col_blocks, rows_per_block, row_chunks; };
 
-inline Plan make_plan(int B, int G) {
+inline Plan make_plan(int B, int G, int cols_per_block) {
   Plan p;
-  p.col_blocks = cdiv(G, kColsPerBlock);
-  int rpb = 16;
-  while (cdiv(B, rpb) > kMaxRowChunks) rpb *= 2;
+  p.col_blocks = cdiv(G, cols_per_block);
+  int chunks = kTargetBlocks / p.col_blocks;
+  if (chunks < 1) chunks = 1;
+  if (chunks > B) chunks = B;
+  int rpb = cdiv(B, chunks);
+  if (rpb < 2 && B >= 2) rpb = 2;                // the software prefetch wants >= 2 rows per block
+  while ((long long)cdiv(B, rpb) * p.col_blocks > kMaxBlocks) ++rpb;
   p.rows_per_block = rpb;
   p.row_chunks = cdiv(B, rpb);
   return p;
@@ -155,8 +160,103 @@ zinb_loss_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __rest
     if (BWD && !COND_DISP) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j)
-        if (col0 + j < G) dth_partial[(int64_t)blockIdx.y * G + col0 + j] = tacc[j];
+        if (col0 + j < G) atomicAdd(dth_partial + col0 + j, tacc[j]);
     }
+  }
+  const double tot = block_reduce_sum(lsum, red);
+  if (threadIdx.x == 0) loss_partial[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+
+// ZINB models, 128-bit path, backward: the expensive NB branch (y > 0, ~10-20 % of a scRNA-seq
+// matrix) is warp-compacted through shared memory.  Every lane evaluates the cheap zero branch
+// for its own zero counts; the non-zero elements of the warp's 128-gene strip are queued in
+// shared memory (16 B items), evaluated densely (item i by lane i mod 32) and handed back.
+// Without this the NB branch runs once per vector slot with ~17 % of the lanes active.
+template <bool COND_DISP, typename GT>
+__global__ void __launch_bounds__(kThreads)
+zinb_loss_bwd_compact_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __restrict__ rows,
+                             const float* __restrict__ sf, const float* m, const float* d, const float* pi,
+                             int64_t ld, int B, int G, float ridge, float inv_n, int rows_per_block,
+                             GT* dzm, GT* dzd, GT* dzp, float* __restrict__ dth_acc,
+                             double* __restrict__ loss_partial, const float* __restrict__ lf_global) {
+  __shared__ double red[8];
+  __shared__ float lf[zmath::kLogFactN];
+  __shared__ float4 items[kThreads / 32][32 * kVec];                 // 16 KB
+  if (threadIdx.x < zmath::kLogFactN) lf[threadIdx.x] = lf_global[threadIdx.x];
+  __syncthreads();
+  using Ops = zmath::FastOps;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* q = items[warp];
+  const int col0 = (blockIdx.x * kThreads + threadIdx.x) * kVec;
+  const bool active = col0 < G;                                       // G % 4 == 0 on this path
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(B, r0 + rows_per_block);
+  float lsum = 0.f;
+  float tacc[kVec] = {0.f, 0.f, 0.f, 0.f};
+  float thg[kVec] = {1.f, 1.f, 1.f, 1.f};
+  if (!COND_DISP && active) {
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) thg[j] = d[col0 + j];
+  }
+  RowVals<kVec> cur, nxt;
+  if (active) load_row<true, COND_DISP, kVec>(cur, Y, ldy, rows, sf, m, d, pi, ld, r0, col0);
+  for (int r = r0; r < r1; ++r) {
+    if (active && r + 1 < r1) load_row<true, COND_DISP, kVec>(nxt, Y, ldy, rows, sf, m, d, pi, ld, r + 1, col0);
+    // ---- queue the non-zero counts of this warp's strip
+    int nz = 0;
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) nz |= (cur.y[j] < 1e-8f) ? 0 : (1 << j);           // loss.py:138
+    }
+    const int cnt = __popc(nz);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(kFull, incl, 31);
+    const float row_sf = __shfl_sync(kFull, active ? cur.sf : 1.0f, 0);                  // lane 0 is always active
+    int k = incl - cnt;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j)
+      if (nz & (1 << j)) q[k++] = make_float4(cur.y[j], cur.m[j], COND_DISP ? cur.d[j] : thg[j], cur.p[j]);
+    __syncwarp();
+    // ---- zero branch for my own zero counts (branch-free per element)
+    float gm[kVec], gd[kVec], gp[kVec];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      gm[j] = gd[j] = gp[j] = 0.f;
+      if (active && !(nz & (1 << j))) {
+        const zmath::Elem e = zmath::zinb_elem_zero<Ops, COND_DISP>(cur.m[j], cur.sf, COND_DISP ? cur.d[j] : thg[j], cur.p[j], ridge);
+        lsum += e.loss; gm[j] = e.gm; gd[j] = e.gd; gp[j] = e.gp;
+      }
+    }
+    // ---- dense NB pass over the queue
+    for (int i = lane; i < total; i += 32) {
+      const float4 it = q[i];
+      const zmath::Elem e = zmath::zinb_elem_nb<Ops, true, COND_DISP>(it.x, it.y, row_sf, it.z, it.w, ridge, lf);
+      q[i] = make_float4(e.loss, e.gm, e.gd, e.gp);
+    }
+    __syncwarp();
+    k = incl - cnt;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j)
+      if (nz & (1 << j)) { const float4 e = q[k++]; lsum += e.x; gm[j] = e.y; gd[j] = e.z; gp[j] = e.w; }
+    __syncwarp();
+    if (active) {
+      const int64_t off = (int64_t)r * ld + col0;
+      if (!COND_DISP) {
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) tacc[j] += gd[j];
+      }
+      st4(dzm + off, gm[0] * inv_n, gm[1] * inv_n, gm[2] * inv_n, gm[3] * inv_n);
+      if (COND_DISP) st4(dzd + off, gd[0] * inv_n, gd[1] * inv_n, gd[2] * inv_n, gd[3] * inv_n);
+      st4(dzp + off, gp[0] * inv_n, gp[1] * inv_n, gp[2] * inv_n, gp[3] * inv_n);
+    }
+    cur = nxt;
+  }
+  if (!COND_DISP && active) {
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) atomicAdd(dth_acc + col0 + j, tacc[j]);
   }
   const double tot = block_reduce_sum(lsum, red);
   if (threadIdx.x == 0) loss_partial[blockIdx.y * gridDim.x + blockIdx.x] = tot;
@@ -176,14 +276,6 @@ __global__ void fold_partials_kernel(const double* __restrict__ part, int n, dou
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (threadIdx.x == 0) *out = accumulate ? (*out + a) : a;
   }
-}
-
-__global__ void fold_dtheta_kernel(const float* __restrict__ part, int chunks, int G, float* __restrict__ out) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= G) return;
-  float a = 0.f;
-  for (int c = 0; c < chunks; ++c) a += part[(int64_t)c * G + g];
-  out[g] = a;
 }
 
 __global__ void loss_finalize_kernel(const double* loss_sum, const double* penalty, float inv_n, int batch,
@@ -226,21 +318,27 @@ int launch(const LossArgs& a, cudaStream_t s) {
   }
   const float* lf_dev = log_fact_table_device();
   if (!lf_dev) return DCA_ERR_CUDA;
-  const Plan p = make_plan(a.B, a.G);
   const size_t need = loss_workspace_bytes(a.B, a.G);
   if (!a.ws || a.ws_bytes < need) { set_error("zinb_loss: workspace too small (%zu < %zu)", a.ws_bytes, need); return DCA_ERR_BAD_ARG; }
   double* lpart = reinterpret_cast<double*>(a.ws);
-  float* tpart = reinterpret_cast<float*>(reinterpret_cast<char*>(a.ws) +
-                                         sizeof(double) * (size_t)kMaxRowChunks * (size_t)cdiv(a.G, kThreads));
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  bool vec = (a.G % 4 == 0) && (a.ld % 4 == 0) && (a.ldy % 4 == 0) && al16(a.Y) && al16(a.m) && al16(a.d) &&
+  bool vec = (a.G % 4 == 0) && (a.ld % 4 == 0) && (a.ldy % 4 == 0) && al16(a.Y) && al16(a.m) && (!cond || al16(a.d)) &&
              (!has_pi || al16(a.pi));
   if (BWD) vec = vec && al16(a.dzm) && (!cond || al16(a.dzd)) && (!has_pi || al16(a.dzp));
-  Plan q = p;
-  dim3 grid, block(kThreads);
-  if (vec) grid = dim3(p.col_blocks, p.row_chunks);
-  else { q.col_blocks = cdiv(a.G, kThreads); grid = dim3(q.col_blocks, p.row_chunks); }
+  const Plan p = make_plan(a.B, a.G, vec ? kColsPerBlock : kThreads);
+  dim3 grid(p.col_blocks, p.row_chunks), block(kThreads);
+  float* tpart = a.dtheta;                                            // const-disp: accumulated with atomics
+  if (BWD && !cond) DCA_CUDA_OK(cudaMemsetAsync(a.dtheta, 0, sizeof(float) * (size_t)a.G, s));
 
+  if (BWD && vec && has_pi) {
+#define DCA_COMPACT(CD, GT)                                                                                   \
+  zinb_loss_bwd_compact_kernel<CD, GT><<<grid, block, 0, s>>>(a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, a.G, \
+                                                              a.ridge, a.inv_n, p.rows_per_block, (GT*)a.dzm,  \
+                                                              (GT*)a.dzd, (GT*)a.dzp, tpart, lpart, lf_dev)
+    if (a.grad_bf16) { if (cond) DCA_COMPACT(true, __nv_bfloat16); else DCA_COMPACT(false, __nv_bfloat16); }
+    else             { if (cond) DCA_COMPACT(true, float); else DCA_COMPACT(false, float); }
+#undef DCA_COMPACT
+  } else {
 #define DCA_LOSS_LAUNCH(HP, CD, GT, V)                                                                 \
   zinb_loss_kernel<HP, CD, GT, V, BWD><<<grid, block, 0, s>>>(                                          \
       a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, a.G, a.ridge, a.inv_n, p.rows_per_block,      \
@@ -252,29 +350,25 @@ int launch(const LossArgs& a, cudaStream_t s) {
     else if (!has_pi && cond) DCA_LOSS_LAUNCH(false, true, GT, V); \
     else DCA_LOSS_LAUNCH(false, false, GT, V);                     \
   } while (0)
-  if (BWD && a.grad_bf16) {
-    if (vec) DCA_LOSS_DISPATCH(__nv_bfloat16, 4); else DCA_LOSS_DISPATCH(__nv_bfloat16, 1);
-  } else {
-    if (vec) DCA_LOSS_DISPATCH(float, 4); else DCA_LOSS_DISPATCH(float, 1);
-  }
+    if (BWD && a.grad_bf16) {
+      if (vec) DCA_LOSS_DISPATCH(__nv_bfloat16, 4); else DCA_LOSS_DISPATCH(__nv_bfloat16, 1);
+    } else {
+      if (vec) DCA_LOSS_DISPATCH(float, 4); else DCA_LOSS_DISPATCH(float, 1);
+    }
 #undef DCA_LOSS_DISPATCH
 #undef DCA_LOSS_LAUNCH
+  }
   DCA_LAUNCH_CHECK();
   fold_partials_kernel<<<1, 256, 0, s>>>(lpart, (int)(grid.x * grid.y), a.loss_sum, BWD ? 0 : 1);
   DCA_LAUNCH_CHECK();
-  if (BWD && !cond) {
-    fold_dtheta_kernel<<<cdiv(a.G, 256), 256, 0, s>>>(tpart, p.row_chunks, a.G, a.dtheta);
-    DCA_LAUNCH_CHECK();
-  }
   return DCA_OK;
 }
 
 }  // namespace
 
 size_t loss_workspace_bytes(int B, int G) {
-  (void)B;
-  const size_t colb_scalar = (size_t)cdiv(G, kThreads);
-  return sizeof(double) * kMaxRowChunks * colb_scalar + sizeof(float) * (size_t)kMaxRowChunks * (size_t)G + 256;
+  (void)B; (void)G;
+  return sizeof(double) * (size_t)kMaxBlocks + 256;
 }
 
 int zinb_loss_fwd_bwd(const LossArgs& a, cudaStream_t s) { return launch<true>(a, s); }

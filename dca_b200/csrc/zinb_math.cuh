@@ -156,38 +156,9 @@ DCA_HD float one_minus_exp_neg(float d) {
   return 1.0f - Ops::ex2(-d * kLog2e);
 }
 
-// y: raw count; m: MeanAct output (before *sf); sf: size factor; th: DispAct output or per-gene
-// theta; pi: sigmoid output; lf_table: log(k!) for k < kLogFactN.
+// Chain rule through the output activations + ridge, shared by both branches.
 template <class Ops, bool HAS_PI, bool COND_DISP>
-DCA_HD Elem zinb_elem(float y, float m, float sf, float th, float pi, float ridge, const float* lf_table) {
-  const Shared s = shared_terms<Ops>(m, sf, th);
-  Elem o;
-  float dth, dpi = 0.f;
-  if (HAS_PI && y < 1e-8f) {                               // loss.py:138  zero branch
-    const float z = Ops::ex2(-s.th * s.L1 * kLog2e);          // pow(theta/(theta+mu+eps), theta)  loss.py:136
-    const float omp = 1.0f - pi;
-    const float D = pi + omp * z + kEps;                   // loss.py:137
-    const float rD = Ops::rcp(D);
-    o.loss = -kLn2 * Ops::lg2(D);
-    const float w = omp * z * rD;
-    o.gm = w * s.th * s.q;
-    dth = w * s.f;                                         // -w*(log r + 1 - r)
-    dpi = (z - 1.0f) * rD;
-  } else {                                                 // NB branch  loss.py:87-88,130
-    float lg, dg;
-    lgam_digam_diff<Ops>(s.te, y, lg, dg);
-    const float theta = s.th;
-    float nb = lgamma_1p<Ops>(y, lf_table) - lg + theta * s.L1 - y * (kLn2 * Ops::lg2((s.mu + kEps) * s.rden));
-    if (nb != nb) nb = INFINITY;                           // _nan2inf  loss.py:105
-    o.gm = theta * (s.mu - y) * s.rden;
-    dth = s.f + y * s.rden - dg;
-    if (HAS_PI) {
-      const float qq = 1.0f - pi + kEps;
-      nb -= kLn2 * Ops::lg2(qq);                           // loss.py:130
-      dpi = Ops::rcp(qq);
-    }
-    o.loss = nb;
-  }
+DCA_HD void finish_elem(Elem& o, float dth, float dpi, float m, float th, float pi, float ridge) {
   const bool m_pass = (m > 1e-5f) && (m < 1e6f);           // clip_by_value gradient mask (network.py:38)
   o.gm = m_pass ? o.gm : 0.f;
   if (COND_DISP) {
@@ -202,7 +173,50 @@ DCA_HD Elem zinb_elem(float y, float m, float sf, float th, float pi, float ridg
   } else {
     o.gp = 0.f;
   }
+}
+
+// zero branch of loss.py:138 (y < 1e-8), ZINB models only
+template <class Ops, bool COND_DISP>
+DCA_HD Elem zinb_elem_zero(float m, float sf, float th, float pi, float ridge) {
+  const Shared s = shared_terms<Ops>(m, sf, th);
+  Elem o;
+  const float z = Ops::ex2(-s.th * s.L1 * kLog2e);         // pow(theta/(theta+mu+eps), theta)  loss.py:136
+  const float omp = 1.0f - pi;
+  const float D = pi + omp * z + kEps;                     // loss.py:137
+  const float rD = Ops::rcp(D);
+  o.loss = -kLn2 * Ops::lg2(D);
+  const float w = omp * z * rD;
+  o.gm = w * s.th * s.q;
+  finish_elem<Ops, true, COND_DISP>(o, w * s.f /* -w*(log r + 1 - r) */, (z - 1.0f) * rD, m, th, pi, ridge);
   return o;
+}
+
+// NB branch of loss.py:87-88,130 (all elements of NB models; y >= 1e-8 for ZINB models)
+template <class Ops, bool HAS_PI, bool COND_DISP>
+DCA_HD Elem zinb_elem_nb(float y, float m, float sf, float th, float pi, float ridge, const float* lf_table) {
+  const Shared s = shared_terms<Ops>(m, sf, th);
+  Elem o;
+  float lg, dg, dpi = 0.f;
+  lgam_digam_diff<Ops>(s.te, y, lg, dg);
+  float nb = lgamma_1p<Ops>(y, lf_table) - lg + s.th * s.L1 - y * (kLn2 * Ops::lg2((s.mu + kEps) * s.rden));
+  if (nb != nb) nb = INFINITY;                             // _nan2inf  loss.py:105
+  o.gm = s.th * (s.mu - y) * s.rden;
+  if (HAS_PI) {
+    const float qq = 1.0f - pi + kEps;
+    nb -= kLn2 * Ops::lg2(qq);                             // loss.py:130
+    dpi = Ops::rcp(qq);
+  }
+  o.loss = nb;
+  finish_elem<Ops, HAS_PI, COND_DISP>(o, s.f + y * s.rden - dg, dpi, m, th, pi, ridge);
+  return o;
+}
+
+// y: raw count; m: MeanAct output (before *sf); sf: size factor; th: DispAct output or per-gene
+// theta; pi: sigmoid output; lf_table: log(k!) for k < kLogFactN.
+template <class Ops, bool HAS_PI, bool COND_DISP>
+DCA_HD Elem zinb_elem(float y, float m, float sf, float th, float pi, float ridge, const float* lf_table) {
+  if (HAS_PI && y < 1e-8f) return zinb_elem_zero<Ops, COND_DISP>(m, sf, th, pi, ridge);   // loss.py:138
+  return zinb_elem_nb<Ops, HAS_PI, COND_DISP>(y, m, sf, th, pi, ridge, lf_table);
 }
 
 // forward-only value

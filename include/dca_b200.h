@@ -198,6 +198,21 @@ int dca_dense_heads_fwd(const float* H, int64_t ldh, int32_t batch, int32_t K, i
                         const float* row_scale,
                         float* m_out, float* d_out, float* pi_out, int64_t ld_out, void* stream);
 
+/* tcgen05 head layer, operands already in MMA layout: Hb = bf16 [batch x 64] (decoder output),
+ * WhT = bf16 [n_heads*genes x 64] (row = head_slot*genes + gene: the Keras kernels transposed and
+ * stacked), bias = float [n_heads*genes]; kind[i] in {2 MeanAct, 3 DispAct, 4 sigmoid} per head slot.
+ * Same arithmetic as dca_dense_heads_fwd with bf16-rounded operands and fp32 accumulation. */
+int dca_tc_heads_fwd(const void* Hb, int32_t batch, const void* WhT, const float* bias, int32_t genes,
+                     int32_t n_heads, const int32_t kind[3], const float* row_scale,
+                     float* out0, float* out1, float* out2, int64_t ld_out, void* stream);
+
+/* Single-tile tcgen05 probe used by the tests to pin the UMMA operand conventions: D[128 x N] =
+ * A . B with bf16 operands; a K-major operand is stored [MN x K], an MN-major one [K x MN].
+ * *_lbo / *_sbo < 0 select the library's defaults for that layout. */
+int dca_tc_probe(const void* A, int32_t a_rows, int32_t a_cols, const void* B, int32_t b_rows, int32_t b_cols,
+                 int32_t a_mn_major, int32_t b_mn_major, int32_t M, int32_t N, int32_t K,
+                 int32_t a_lbo, int32_t a_sbo, int32_t b_lbo, int32_t b_sbo, float* D, void* stream);
+
 /* Optional per-phase device timing (CUDA events on the caller's stream around each phase of
  * dca_train_step / dca_apply_update).  Off by default; bench.py turns it on for a separate
  * profiled pass.  Phases: 0 hidden forward, 1 head Dense + activations, 2 ZINB loss fwd+bwd,
