@@ -1,0 +1,339 @@
+// One tcgen05 kernel for the three gene-wide Dense products whose reduction or output dimension is
+// the gene axis (all with a 64-wide partner dimension):
+//
+//   encoder forward  (K1)  A1[B x 64]  += X[B x G] . W1[G x 64]                      DO_B
+//   head backward    (K4)  dWh[64 x G] += H3^T . dZ,  dH3[B x 64] += dZ . Wh^T,  db = colsum(dZ)   DO_A + DO_B + COLSUM
+//   encoder backward (K5)  dW1[G x 64] += X^T . dA1                                   DO_A
+//
+// "Z" is the cells x genes bf16 operand (X or dZ).  A 128-cell x 128-gene tile of Z is brought into
+// shared memory ONCE by TMA (two SWIZZLE_128B boxes of 64 genes) and feeds both products:
+//   (b) as a K-major  A operand (M = 128 cells, K = genes) against W  [64 x genes]  (K-major B), and
+//   (a) as an MN-major A operand (M = 128 genes, K = cells) against H [cells x 64] (MN-major B),
+// i.e. the same bytes with two different UMMA descriptors, so Z is read from HBM once per step for
+// both gradients.  Accumulators live in TMEM: one 128x64 fp32 tile per gene block
+// of the item for (a), a double-buffered 128x64 tile per cell block for (b).  (b) leaves through a
+// swizzled staging tile and a TMA reduce-add (split over gene ranges); (a) is added to the gradient
+// buffer by the epilogue warps at the end of the item; the per-gene column sums (bias gradient) are
+// taken from the shared-memory tile by four otherwise idle warps.
+//
+// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue, 8-11 column sums.
+#include "engine.h"
+#include "tc_common.cuh"
+
+namespace dca {
+namespace tc {
+namespace gg {
+
+constexpr int kThreads = 384;
+constexpr int kZStages = 3;
+constexpr uint32_t kZBytes = 128 * 128 * 2;          // 2 boxes x [128 cells x 64 genes] bf16
+constexpr uint32_t kWBytes = 64 * 128 * 2;           // 2 boxes x [64 feats x 64 genes] bf16
+constexpr uint32_t kHBytes = 128 * 64 * 2;           // [128 cells x 64 feats] bf16
+constexpr uint32_t kOutBytes = 2 * 128 * 32 * 4;     // two [128 x 32] fp32 staging tiles
+constexpr int kMaxGb = 4;                            // gene blocks (of 128) per item: 4 x 64 TMEM columns
+constexpr uint32_t kTmemCols = 512;
+
+struct Params {
+  int B, G, n_heads;
+  int n_cb, n_gb;                 // cell blocks (128), gene blocks per head (128)
+  int gb_per_item, cb_per_item;
+  int gene_ranges, cell_splits;   // per head
+  int total_items;
+  float* dW[3]; int64_t dW_ld; int dW_transposed;   // (a): transposed -> dW[f*ld + g] (Keras [64 x G]); else dW[g*ld + f]
+  float* db[3];                                     // column sums of Z per head (COLSUM)
+};
+
+template <bool DO_A, bool DO_B, bool COLSUM>
+__global__ void __launch_bounds__(kThreads, 1)
+gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_constant__ CUtensorMap map_z1,
+                 const __grid_constant__ CUtensorMap map_z2, const __grid_constant__ CUtensorMap map_h,
+                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_o, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr uint32_t kStage = kZBytes + (DO_B ? kWBytes : 0);
+  uint8_t* s_z = smem;                                          // [kZStages][Z | W]
+  uint8_t* s_h = s_z + kZStages * kStage;                       // [2][H]
+  uint8_t* s_o = s_h + (DO_A ? 2 * kHBytes : 0);                // staging for (b)
+  __shared__ uint64_t z_full[kZStages], z_empty[kZStages], h_full[2], h_empty[2], dh_full[2], dh_empty[2], dw_full, dw_empty;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kZStages; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 1 + (COLSUM ? 4 : 0)); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); mbar_init(&dh_full[i], 1); mbar_init(&dh_empty[i], 4); }
+    mbar_init(&dw_full, 1); mbar_init(&dw_empty, 4);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_z0); tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_o);
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tm_dw = tmem;                 // kMaxGb x 64 columns
+  const uint32_t tm_dh = tmem + kMaxGb * 64;   // 2 x 64 columns
+
+  struct Item { int head, gb0, gb1, cb0, cb1; };
+  auto decode = [&](int it) {
+    Item x;
+    const int cs = it % p.cell_splits; const int r = it / p.cell_splits;
+    const int gr = r % p.gene_ranges; x.head = r / p.gene_ranges;
+    x.gb0 = gr * p.gb_per_item; x.gb1 = min(p.n_gb, x.gb0 + p.gb_per_item);
+    x.cb0 = cs * p.cb_per_item; x.cb1 = min(p.n_cb, x.cb0 + p.cb_per_item);
+    return x;
+  };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t zi = 0, hi = 0;
+      for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
+        const Item x = decode(it);
+        const CUtensorMap* mz = x.head == 0 ? &map_z0 : (x.head == 1 ? &map_z1 : &map_z2);
+        for (int cb = x.cb0; cb < x.cb1; ++cb) {
+          if (DO_A) {
+            const uint32_t hs = hi & 1, hp = (hi >> 1) & 1; ++hi;
+            mbar_wait(&h_empty[hs], hp ^ 1);
+            mbar_expect_tx(&h_full[hs], kHBytes);
+            tma_load_2d(s_h + hs * kHBytes, &map_h, 0, cb * 128, &h_full[hs]);
+          }
+          for (int gb = x.gb0; gb < x.gb1; ++gb) {
+            const uint32_t st = zi % kZStages, ph = (zi / kZStages) & 1; ++zi;
+            mbar_wait(&z_empty[st], ph ^ 1);
+            uint8_t* dst = s_z + st * kStage;
+            mbar_expect_tx(&z_full[st], kStage);
+            tma_load_2d(dst, mz, gb * 128, cb * 128, &z_full[st]);
+            tma_load_2d(dst + kZBytes / 2, mz, gb * 128 + 64, cb * 128, &z_full[st]);
+            if (DO_B) {
+              tma_load_2d(dst + kZBytes, &map_w, x.head * p.G + gb * 128, 0, &z_full[st]);
+              tma_load_2d(dst + kZBytes + kWBytes / 2, &map_w, x.head * p.G + gb * 128 + 64, 0, &z_full[st]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_b = make_idesc_bf16(128, 64, 0, 0);     // Z K-major  x W K-major
+      constexpr uint32_t idesc_a = make_idesc_bf16(128, 64, 1, 1);     // Z MN-major x H MN-major
+      uint32_t zi = 0, hi = 0, di = 0, wi = 0;
+      for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++wi) {
+        const Item x = decode(it);
+        if (DO_A) { mbar_wait(&dw_empty, (wi & 1) ^ 1); tcgen05_fence_after(); }
+        for (int cb = x.cb0; cb < x.cb1; ++cb) {
+          uint32_t hs = 0, ds = 0;
+          if (DO_A) { hs = hi & 1; const uint32_t hp = (hi >> 1) & 1; ++hi; mbar_wait(&h_full[hs], hp); }
+          if (DO_B) { ds = di & 1; const uint32_t dp = (di >> 1) & 1; ++di; mbar_wait(&dh_empty[ds], dp ^ 1); }
+          for (int gb = x.gb0; gb < x.gb1; ++gb) {
+            const uint32_t st = zi % kZStages, ph = (zi / kZStages) & 1; ++zi;
+            mbar_wait(&z_full[st], ph);
+            tcgen05_fence_after();
+            const uint32_t zb = smem_u32(s_z + st * kStage);
+            if (DO_B) {
+              const uint32_t wb = zb + kZBytes;
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tm_dh + ds * 64, make_smem_desc(zb + h * (kZBytes / 2) + k * 32, 0, 1024),
+                            make_smem_desc(wb + h * (kWBytes / 2) + k * 32, 0, 1024), idesc_b,
+                            (gb > x.gb0 || h > 0 || k > 0) ? 1u : 0u);
+            }
+            if (DO_A) {
+              const uint32_t hb = smem_u32(s_h + hs * kHBytes);
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma_bf16(tm_dw + (gb - x.gb0) * 64, make_smem_desc(zb + k * 2048, kZBytes / 2, 1024),
+                          make_smem_desc(hb + k * 2048, 0, 1024), idesc_a, (cb > x.cb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&z_empty[st]);
+          }
+          if (DO_A) umma_commit(&h_empty[hs]);
+          if (DO_B) umma_commit(&dh_full[ds]);
+        }
+        if (DO_A) umma_commit(&dw_full);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================== epilogue
+    const int quarter = warp & 3;
+    uint32_t di = 0, wi = 0;
+    for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++wi) {
+      const Item x = decode(it);
+      if (DO_B) {
+        for (int cb = x.cb0; cb < x.cb1; ++cb) {
+          const uint32_t ds = di & 1, dp = (di >> 1) & 1; ++di;
+          mbar_wait(&dh_full[ds], dp);
+          tcgen05_fence_after();
+          if (warp == 4 && lane == 0) bulk_wait_read<0>();          // previous reduce has read the staging tiles
+          named_barrier_sync(3, 128);
+          const int row = quarter * 32 + lane;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tm_dh + ((uint32_t)(quarter * 32) << 16) + ds * 64 + c * 32, v);
+            tmem_ld_wait();
+            uint8_t* tile = s_o + c * (kOutBytes / 2);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(tile + row * 128 + ((q ^ (row & 7)) << 4)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          }
+          tcgen05_fence_before();
+          fence_proxy_async_smem();
+          named_barrier_sync(3, 128);
+          if (lane == 0) mbar_arrive(&dh_empty[ds]);
+          if (warp == 4 && lane == 0) {
+            tma_reduce_add_2d(&map_o, 0, cb * 128, s_o);
+            tma_reduce_add_2d(&map_o, 32, cb * 128, s_o + kOutBytes / 2);
+            bulk_commit();
+          }
+        }
+      }
+      if (DO_A) {
+        mbar_wait(&dw_full, wi & 1);
+        tcgen05_fence_after();
+        float* dst = p.dW[x.head];
+        for (int gb = x.gb0; gb < x.gb1; ++gb) {
+          const int g = gb * 128 + quarter * 32 + lane;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tm_dw + ((uint32_t)(quarter * 32) << 16) + (gb - x.gb0) * 64 + c * 32, v);
+            tmem_ld_wait();
+            if (g < p.G) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int f = c * 32 + j;
+                float* a = p.dW_transposed ? dst + (int64_t)f * p.dW_ld + g : dst + (int64_t)g * p.dW_ld + f;
+                atomicAdd(a, __uint_as_float(v[j]));
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dw_empty);
+      }
+    }
+    if (DO_B && warp == 4 && lane == 0) bulk_wait<0>();
+  } else if (COLSUM && warp >= 8) {
+    // ===================================================== column sums of Z from the smem tile
+    const int t = threadIdx.x - 256;            // 0..127
+    const int pr = t & 63, half = t >> 6;       // gene pair within the 128-gene tile, row parity
+    uint32_t zi = 0;
+    for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
+      const Item x = decode(it);
+      float acc[kMaxGb][2];
+#pragma unroll
+      for (int i = 0; i < kMaxGb; ++i) acc[i][0] = acc[i][1] = 0.f;
+      for (int cb = x.cb0; cb < x.cb1; ++cb) {
+        for (int gb = x.gb0; gb < x.gb1; ++gb) {
+          const uint32_t st = zi % kZStages, ph = (zi / kZStages) & 1; ++zi;
+          mbar_wait(&z_full[st], ph);
+          const uint8_t* box = s_z + st * kStage + (pr >> 5) * (kZBytes / 2);   // 64-gene box holding this pair
+          const int cg = (pr & 31) * 2;                                          // gene offset inside the box (even)
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+          for (int r = half; r < 128; r += 2) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(box + r * 128 + ((((cg >> 3) ^ (r & 7))) << 4) + (cg & 7) * 2);
+            s0 += __uint_as_float(w << 16);
+            s1 += __uint_as_float(w & 0xffff0000u);
+          }
+          acc[gb - x.gb0][0] += s0; acc[gb - x.gb0][1] += s1;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&z_empty[st]);
+        }
+      }
+      float* db = p.db[x.head];
+      if (db) {
+        for (int gb = x.gb0; gb < x.gb1; ++gb) {
+          const int g = gb * 128 + pr * 2;
+          if (g < p.G) atomicAdd(db + g, acc[gb - x.gb0][0]);
+          if (g + 1 < p.G) atomicAdd(db + g + 1, acc[gb - x.gb0][1]);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+}
+
+template <bool DO_A, bool DO_B, bool COLSUM>
+constexpr uint32_t smem_bytes() {
+  return kZStages * (kZBytes + (DO_B ? kWBytes : 0)) + (DO_A ? 2 * kHBytes : 0) + (DO_B ? kOutBytes : 0) + 1024;
+}
+
+}  // namespace gg
+
+// Z: bf16 [B x G] per head (ldz elements); H: bf16 [B x 64]; W: bf16 [64 x n_heads*G] (Keras layout, heads packed along
+// columns); out_b: fp32 [B x 64] (+=).  mode: 1 = DO_B (K1), 2 = DO_A (K5), 3 = DO_A|DO_B|COLSUM (K4).
+int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, int G, int n_heads,
+                 const __nv_bfloat16* H, const __nv_bfloat16* W, float* out_b, float* const dW[3], int64_t dW_ld,
+                 int dW_transposed, float* const db[3], int sm_count, cudaStream_t s) {
+  using namespace gg;
+  if (ldz % 8 != 0) { set_error("gene_gemm_tc: ldz must be a multiple of 8 (16-byte TMA stride)"); return DCA_ERR_BAD_ARG; }
+  const bool do_a = mode & 2, do_b = mode & 1;
+  CUtensorMap mz[3], mh, mw, mo;
+  for (int i = 0; i < 3; ++i) DCA_TRY(make_tensor_map_2d(&mz[i], Z[i < n_heads ? i : 0], 2, 1, (uint64_t)B, (uint64_t)G, (uint64_t)ldz, 128, 64, 1));
+  if (do_a) DCA_TRY(make_tensor_map_2d(&mh, H, 2, 1, (uint64_t)B, 64, 64, 128, 64, 1)); else mh = mz[0];
+  if (do_b) {
+    DCA_TRY(make_tensor_map_2d(&mw, W, 2, 1, 64, (uint64_t)n_heads * G, (uint64_t)n_heads * G, 64, 64, 1));
+    DCA_TRY(make_tensor_map_2d(&mo, out_b, 4, 0, (uint64_t)B, 64, 64, 128, 32, 1));
+  } else { mw = mz[0]; mo = mz[0]; }
+  Params p{};
+  p.B = B; p.G = G; p.n_heads = n_heads;
+  p.n_cb = cdiv(B, 128); p.n_gb = cdiv(G, 128);
+  const int total_gb = p.n_gb * n_heads;
+  if (do_a) {
+    // gene ranges limited by TMEM (kMaxGb accumulators); split cells to fill the SMs
+    int gpi = cdiv(total_gb, sm_count); if (gpi < 1) gpi = 1; if (gpi > kMaxGb) gpi = kMaxGb;
+    p.gb_per_item = gpi; p.gene_ranges = cdiv(p.n_gb, gpi);
+    int splits = sm_count / (p.gene_ranges * n_heads); if (splits < 1) splits = 1; if (splits > p.n_cb) splits = p.n_cb;
+    p.cb_per_item = cdiv(p.n_cb, splits); p.cell_splits = cdiv(p.n_cb, p.cb_per_item);
+  } else {
+    // (b) only: one cell block per item, genes split so that items ~ SM count
+    p.cb_per_item = 1; p.cell_splits = p.n_cb;
+    int gsplits = sm_count / p.n_cb; if (gsplits < 1) gsplits = 1; if (gsplits > p.n_gb) gsplits = p.n_gb;
+    p.gb_per_item = cdiv(p.n_gb, gsplits); p.gene_ranges = cdiv(p.n_gb, p.gb_per_item);
+  }
+  p.total_items = p.gene_ranges * p.cell_splits * n_heads;
+  for (int i = 0; i < 3; ++i) { p.dW[i] = dW ? dW[i] : nullptr; p.db[i] = db ? db[i] : nullptr; }
+  p.dW_ld = dW_ld; p.dW_transposed = dW_transposed;
+  const int grid = p.total_items < sm_count ? p.total_items : sm_count;
+#define DCA_GG_LAUNCH(A, Bb, Cc)                                                                                       \
+  do {                                                                                                                 \
+    static bool attr = false;                                                                                          \
+    constexpr uint32_t sm = smem_bytes<A, Bb, Cc>();                                                                   \
+    if (!attr) { DCA_CUDA_OK(cudaFuncSetAttribute(gene_gemm_kernel<A, Bb, Cc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr = true; } \
+    gene_gemm_kernel<A, Bb, Cc><<<grid, kThreads, sm, s>>>(mz[0], mz[1], mz[2], mh, mw, mo, p);                         \
+  } while (0)
+  if (mode == 1) DCA_GG_LAUNCH(false, true, false);
+  else if (mode == 2) DCA_GG_LAUNCH(true, false, false);
+  else if (mode == 3) DCA_GG_LAUNCH(true, true, true);
+  else { set_error("gene_gemm_tc: bad mode %d", mode); return DCA_ERR_BAD_ARG; }
+#undef DCA_GG_LAUNCH
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+}  // namespace tc
+}  // namespace dca
+
+// ------------------------------------------------------------------------------------ C ABI (tests / profiling)
+using namespace dca;
+extern "C" int dca_tc_gene_gemm(int32_t mode, const void* Z0, const void* Z1, const void* Z2, int64_t ldz, int32_t batch,
+                                int32_t genes, int32_t n_heads, const void* H, const void* W, float* out_b, float* dW0,
+                                float* dW1, float* dW2, int64_t dW_ld, int32_t dW_transposed, float* db0, float* db1,
+                                float* db2, void* stream) {
+  if (!Z0 || batch <= 0 || genes <= 0 || n_heads < 1 || n_heads > 3) { set_error("dca_tc_gene_gemm: bad argument"); return DCA_ERR_BAD_ARG; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const __nv_bfloat16* Z[3] = {(const __nv_bfloat16*)Z0, (const __nv_bfloat16*)Z1, (const __nv_bfloat16*)Z2};
+  float* dW[3] = {dW0, dW1, dW2};
+  float* db[3] = {db0, db1, db2};
+  return tc::gene_gemm_tc(mode, Z, ldz, batch, genes, n_heads, (const __nv_bfloat16*)H, (const __nv_bfloat16*)W, out_b, dW,
+                          dW_ld, dW_transposed, db, sms, (cudaStream_t)stream);
+}

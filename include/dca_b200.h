@@ -206,6 +206,17 @@ int dca_tc_heads_fwd(const void* Hb, int32_t batch, const void* WhT, const float
                      int32_t n_heads, const int32_t kind[3], const float* row_scale,
                      float* out0, float* out1, float* out2, int64_t ld_out, void* stream);
 
+/* The gene-wide tcgen05 product kernel (one smem tile of Z = X or dZ feeds both products):
+ * mode 1: out_b[B x 64] += Z . W^T (W = bf16 [64 x n_heads*genes])                 -- encoder forward
+ * mode 2: dW += Z^T . H (H = bf16 [B x 64])                                       -- encoder backward
+ * mode 3: both, plus db = column sums of Z                                        -- head backward
+ * Z0..Z2: bf16 [B x genes] per head (leading dim ldz); dW per head: float, dW[f*dW_ld + g] when
+ * dW_transposed (Keras [64 x genes]) else dW[g*dW_ld + f].  All outputs are accumulated (+=). */
+int dca_tc_gene_gemm(int32_t mode, const void* Z0, const void* Z1, const void* Z2, int64_t ldz, int32_t batch,
+                     int32_t genes, int32_t n_heads, const void* H, const void* W, float* out_b,
+                     float* dW0, float* dW1, float* dW2, int64_t dW_ld, int32_t dW_transposed,
+                     float* db0, float* db1, float* db2, void* stream);
+
 /* Single-tile tcgen05 probe used by the tests to pin the UMMA operand conventions: D[128 x N] =
  * A . B with bf16 operands; a K-major operand is stored [MN x K], an MN-major one [K x MN].
  * *_lbo / *_sbo < 0 select the library's defaults for that layout. */

@@ -81,3 +81,65 @@ def test_tc_heads_fwd(B, G, nh):
         got = outs[i].cpu().numpy()
         assert np.all(np.isfinite(got)), "head %d has non-finite / unwritten outputs" % i
         np.testing.assert_allclose(got, ref, rtol=3e-5, atol=1e-7, err_msg="head kind %d" % kind)
+
+
+def _gg(mode, Z, H, W, B, G, nh, out_b=None, dW=None, dW_ld=0, transposed=0, db=None):
+    L = _L(); lib = L.load()
+    z = [Z[i].data_ptr() if i < nh else None for i in range(3)]
+    dWp = [dW[i].data_ptr() if (dW is not None and i < nh) else None for i in range(3)]
+    dbp = [db[i].data_ptr() if (db is not None and i < nh) else None for i in range(3)]
+    st = lib.dca_tc_gene_gemm(mode, z[0], z[1], z[2], Z[0].stride(0), B, G, nh, None if H is None else H.data_ptr(),
+                              None if W is None else W.data_ptr(), None if out_b is None else out_b.data_ptr(),
+                              dWp[0], dWp[1], dWp[2], dW_ld, transposed, dbp[0], dbp[1], dbp[2], None)
+    L.check(st, "dca_tc_gene_gemm")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("B,G", [(128, 128), (4096, 2000), (300, 1000), (77, 264)])
+def test_tc_encoder_forward_mode1(B, G):
+    """K1: A1 += X . W1 (bf16 operands), output pre-filled with the bias."""
+    rng = np.random.default_rng(B * 3 + G)
+    X = _bf(rng.normal(0, 1, (B, G)))
+    W1 = rng.normal(0, 0.05, (G, 64)).astype(np.float32)
+    W1T = _bf(W1.T)                                       # [64 x G], K(gene)-major
+    bias = rng.normal(0, 0.3, 64).astype(np.float32)
+    out = torch.as_tensor(np.tile(bias, (B, 1))).to(DEV).contiguous()
+    _gg(1, [X], None, W1T, B, G, 1, out_b=out)
+    ref = X.double().cpu().numpy() @ W1T.double().cpu().numpy().T + bias
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("B,G", [(128, 128), (4096, 2000), (300, 1000), (77, 264)])
+def test_tc_encoder_backward_mode2(B, G):
+    """K5: dW1[G x 64] += X^T . dA1."""
+    rng = np.random.default_rng(B * 5 + G)
+    X = _bf(rng.normal(0, 1, (B, G)))
+    dA = _bf(rng.normal(0, 1e-3, (B, 64)))
+    dW = torch.zeros((G, 64), device=DEV)
+    _gg(2, [X], dA, None, B, G, 1, dW=[dW], dW_ld=64, transposed=0)
+    ref = X.double().cpu().numpy().T @ dA.double().cpu().numpy()
+    assert np.max(np.abs(dW.cpu().numpy() - ref)) < 2e-5 * np.max(np.abs(ref)) + 1e-12
+
+
+@pytest.mark.parametrize("B,G,nh", [(128, 128, 1), (4096, 2000, 3), (300, 1000, 2), (77, 264, 3)])
+def test_tc_head_backward_mode3(B, G, nh):
+    """K4: dWh (Keras [64 x G]) += H^T . dZ, dH += dZ . Wh^T, db = colsum(dZ), one pass over dZ."""
+    rng = np.random.default_rng(B * 7 + G + nh)
+    dZ = [_bf(rng.normal(0, 1e-3, (B, G))) for _ in range(nh)]
+    H = _bf(np.maximum(rng.normal(0, 1, (B, 64)), 0))
+    Wk = [rng.normal(0, 0.2, (64, G)).astype(np.float32) for _ in range(nh)]
+    Wp = _bf(np.concatenate(Wk, 1))                       # [64 x nh*G]
+    dH = torch.zeros((B, 64), device=DEV)
+    dW = [torch.zeros((64, G), device=DEV) for _ in range(nh)]
+    db = [torch.zeros(G, device=DEV) for _ in range(nh)]
+    _gg(3, dZ, H, Wp, B, G, nh, out_b=dH, dW=dW, dW_ld=G, transposed=1, db=db)
+    Hd = H.double().cpu().numpy(); Wd = Wp.double().cpu().numpy()
+    ref_dH = np.zeros((B, 64))
+    for i in range(nh):
+        z = dZ[i].double().cpu().numpy()
+        ref_dH += z @ Wd[:, i * G:(i + 1) * G].T
+        ref_dW = Hd.T @ z
+        assert np.max(np.abs(dW[i].cpu().numpy() - ref_dW)) < 3e-5 * np.max(np.abs(ref_dW)) + 1e-12, "dW head %d" % i
+        ref_db = z.sum(0)
+        assert np.max(np.abs(db[i].cpu().numpy() - ref_db)) < 3e-5 * np.max(np.abs(ref_db)) + 1e-9, "db head %d" % i
+    assert np.max(np.abs(dH.cpu().numpy() - ref_dH)) < 3e-5 * np.max(np.abs(ref_dH)) + 1e-12
