@@ -75,7 +75,7 @@ int bn_relu_fwd(const float* a, int64_t ld, int M, int N, const float* mean, con
                 const float* beta, float* xhat, float* h, __nv_bfloat16* h_bf16, cudaStream_t s);
 int bn_infer_prepare(const float* moving_mean, const float* moving_var, int N, float eps,
                      float* mean, float* inv_std, cudaStream_t s);
-int bias_relu_fwd(const float* a, int64_t ld, int M, int N, float* h, cudaStream_t s);
+int bias_relu_fwd(const float* a, int64_t ld, int M, int N, float* h, __nv_bfloat16* h_bf16, cudaStream_t s);
 // g = dh * (h > 0), in place on dh
 int relu_bwd(float* dh, const float* h, int64_t ld, int M, int N, cudaStream_t s);
 // da = inv*(g - mean(g) - xhat*mean(g*xhat)); dbeta = sum(g);  sums provided in double
@@ -91,6 +91,21 @@ int rmsprop_update(float* params, const float* grads, float* rms, int64_t n, flo
 int glorot_fill(float* w, int64_t n, int fan_in, int fan_out, uint64_t seed, uint64_t stream_id, cudaStream_t s);
 int fill_value(float* p, int64_t n, float v, cudaStream_t s);
 int cast_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
+int pack_head_shadows(const float* W, const float* b, int G, int slot, int nslots, __nv_bfloat16* whT,
+                      __nv_bfloat16* whkm, float* biasp, cudaStream_t s);
+int transpose_w1_shadow(const float* W, int n_in, __nv_bfloat16* wt, cudaStream_t s);
+int gather_rows_bf16(const void* X, int x_bf16, int64_t ldx, const int32_t* rows, int M, int n, __nv_bfloat16* out,
+                     cudaStream_t s);
+
+// ---------------------------------------------------------------- tcgen05 kernels (dense_tc.cu, gene_gemm_tc.cu)
+namespace tc {
+int heads_fwd_tc(const __nv_bfloat16* Hb, int B, const __nv_bfloat16* WhT, const float* bias, int G, int n_heads,
+                 const int kind[3], const float* row_scale, float* const out[3], int64_t ld_out, int sm_count,
+                 cudaStream_t s);
+int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, int G, int n_heads,
+                 const __nv_bfloat16* H, const __nv_bfloat16* W, float* out_b, float* const dW[3], int64_t dW_ld,
+                 int dW_transposed, float* const db[3], int sm_count, cudaStream_t s);
+}  // namespace tc
 
 // ---------------------------------------------------------------- ZINB loss (zinb_loss.cu)
 struct LossArgs {

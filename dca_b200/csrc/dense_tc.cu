@@ -300,12 +300,7 @@ int heads_fwd_tc(const __nv_bfloat16* Hb, int B, const __nv_bfloat16* WhT, const
 
 }  // namespace tc
 
-// ------------------------------------------------------------------------------------ engine hooks
 Engine::~Engine() { for (auto e : prof.ev) cudaEventDestroy(e); }
-bool Engine::tc_supported() const { return false; }
-const char* Engine::tc_reason() const { return "tcgen05 path not wired into the engine yet"; }
-int Engine::setup_tc() { return DCA_OK; }
-int Engine::refresh_shadows(cudaStream_t) { return DCA_OK; }
 
 }  // namespace dca
 

@@ -146,6 +146,26 @@ int Engine::plan(const dca_config& c) {
   o_sfb = take(sizeof(float) * B);
   loss_ws_bytes = loss_workspace_bytes((int)B, G);
   o_lossws = take(loss_ws_bytes);
+  // tcgen05 path (flagship shape): gene-wide layers with a 64-wide partner dimension
+  n_slots = 0;
+  slot_head[0] = 0; slot_kind[0] = EPI_MEAN_ACT; n_slots = 1;
+  if (cond) { slot_head[n_slots] = 1; slot_kind[n_slots] = EPI_DISP_ACT; ++n_slots; }
+  if (has_pi) { slot_head[n_slots] = 2; slot_kind[n_slots] = EPI_SIGMOID; ++n_slots; }
+  const bool want_tc = c.gemm_path != DCA_GEMM_GENERIC;
+  tc_heads = want_tc && L >= 1 && K_head == 64 && (G % 8 == 0);
+  tc_enc = want_tc && L >= 1 && c.hidden[0] == 64 && (c.n_in % 8 == 0);
+  if (tc_heads) {
+    o_whT = take(2 * (size_t)n_slots * G * 64);
+    o_whkm = take(2 * (size_t)n_slots * G * 64);
+    o_biasp = take(sizeof(float) * (size_t)n_slots * G);
+    o_h3b = take(2 * B * 64);
+    for (int k = 0; k < n_slots; ++k) o_dzb[k] = take(2 * B * (size_t)G);
+  }
+  if (tc_enc) {
+    o_w1t = take(2 * (size_t)c.n_in * 64);
+    o_da1b = take(2 * B * 64);
+    o_xb = take(2 * B * (size_t)c.n_in);
+  }
   // staging for the host-buffer entry point
   const size_t xb = (c.x_dtype == DCA_BF16) ? 2 : 4;
   o_stage_x = take(xb * B * (size_t)c.n_in);
@@ -201,15 +221,31 @@ int Engine::gemm_auto(GemmArgs g, cudaStream_t s) {
 
 int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, bool training, cudaStream_t s) {
   const void* hin = X; int64_t ldin = ldx; int in_bf16 = (cfg.x_dtype == DCA_BF16); const int32_t* gather = rows;
+  // tcgen05 encoder: needs a contiguous bf16 batch (gathered / converted once, reused by the backward pass)
+  cur_xb = nullptr;
+  if (tc_enc) {
+    const bool direct = in_bf16 && !rows && (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    const bool can_gather = (ldx % (in_bf16 ? 8 : 4) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    if (direct) { cur_xb = reinterpret_cast<const __nv_bfloat16*>(X); cur_ldxb = ldx; }
+    else if (can_gather) {
+      DCA_TRY(gather_rows_bf16(X, in_bf16, ldx, rows, Bn, cfg.n_in, bf(o_xb), s));
+      cur_xb = bf(o_xb); cur_ldxb = cfg.n_in;
+    }
+  }
   for (int i = 0; i < L; ++i) {
     Layer& l = lay[i];
     float* a = f(l.o_a);
     DCA_TRY(fill_rows_with_bias(a, l.out, Bn, l.out, pp(l.b), s));
+    if (i == 0 && cur_xb) {
+      const __nv_bfloat16* Z[3] = {cur_xb, cur_xb, cur_xb};
+      DCA_TRY(tc::gene_gemm_tc(1, Z, cur_ldxb, Bn, cfg.n_in, 1, nullptr, bf(o_w1t), a, nullptr, 0, 0, nullptr, sm_count, s));
+    } else {
     GemmArgs g{};
     g.A = hin; g.lda = ldin; g.a_bf16 = in_bf16; g.transA = 0; g.a_rows = gather;
     g.B = pp(l.W); g.ldb = l.out; g.transB = 0;
     g.C = a; g.ldc = l.out; g.M = Bn; g.N = l.out; g.K = l.in; g.epilogue = EPI_ACCUM;
     DCA_TRY(gemm_auto(g, s));
+    }
     if (cfg.batchnorm) {
       if (training) {
         DCA_TRY(col_sums(a, nullptr, l.out, Bn, l.out, d(o_dsum), d(o_dprod), d(o_scratch), s));
@@ -219,9 +255,9 @@ int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, boo
         DCA_TRY(bn_infer_prepare(st(l.mm), st(l.mv), l.out, cfg.bn_eps, f(l.o_mean), f(l.o_inv), s));
       }
       DCA_TRY(bn_relu_fwd(a, l.out, Bn, l.out, f(l.o_mean), f(l.o_inv), pp(l.beta), training ? f(l.o_xhat) : nullptr,
-                          f(l.o_h), nullptr, s));
+                          f(l.o_h), (tc_heads && i == L - 1) ? bf(o_h3b) : nullptr, s));
     } else {
-      DCA_TRY(bias_relu_fwd(a, l.out, Bn, l.out, f(l.o_h), s));
+      DCA_TRY(bias_relu_fwd(a, l.out, Bn, l.out, f(l.o_h), (tc_heads && i == L - 1) ? bf(o_h3b) : nullptr, s));
     }
     hin = f(l.o_h); ldin = l.out; in_bf16 = 0; gather = nullptr;
   }
@@ -232,6 +268,17 @@ int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, boo
 int Engine::heads_forward(int Bn, float* m_out, float* d_out, float* p_out, int64_t ld_out, const float* row_scale,
                           cudaStream_t s) {
   const int G = cfg.n_out;
+  if (tc_heads && (ld_out % 4 == 0)) {
+    float* outs_by_head[3] = {m_out, d_out, p_out};
+    bool all = true;
+    for (int k = 0; k < n_slots; ++k) all = all && outs_by_head[slot_head[k]] && ((reinterpret_cast<uintptr_t>(outs_by_head[slot_head[k]]) & 15) == 0);
+    if (all) {
+      float* outs[3] = {nullptr, nullptr, nullptr};
+      for (int k = 0; k < n_slots; ++k) outs[k] = outs_by_head[slot_head[k]];
+      for (int k = n_slots; k < 3; ++k) outs[k] = outs[0];
+      return tc::heads_fwd_tc(bf(o_h3b), Bn, bf(o_whT), f(o_biasp), G, n_slots, slot_kind, row_scale, outs, ld_out, sm_count, s);
+    }
+  }
   struct H { int k; float* out; int epi; const float* rs; } hs[3] = {
       {0, m_out, EPI_MEAN_ACT, row_scale}, {1, d_out, EPI_DISP_ACT, nullptr}, {2, p_out, EPI_SIGMOID, nullptr}};
   for (auto& h : hs) {
@@ -302,6 +349,11 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
   la.m = Mb; la.d = cond ? Db : f(o_theta); la.pi = has_pi ? Pb : nullptr; la.ld = G;
   la.B = Bn; la.G = G; la.ae_type = cfg.ae_type; la.ridge = cfg.ridge; la.inv_n = inv_n;
   la.dzm = Mb; la.dzd = cond ? Db : nullptr; la.dzp = has_pi ? Pb : nullptr; la.grad_bf16 = 0;
+  if (tc_heads) {          // bf16 gradients for the tcgen05 head-backward kernel, packed-slot order
+    void* slot_buf[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < n_slots; ++k) slot_buf[slot_head[k]] = bf(o_dzb[k]);
+    la.dzm = slot_buf[0]; la.dzd = cond ? slot_buf[1] : nullptr; la.dzp = has_pi ? slot_buf[2] : nullptr; la.grad_bf16 = 1;
+  }
   la.dtheta = cond ? nullptr : f(o_dtheta);
   la.loss_sum = d(o_acc) + 4; la.ws = base + o_lossws; la.ws_bytes = loss_ws_bytes;
   DCA_TRY(zinb_loss_fwd_bwd(la, s));
@@ -316,6 +368,14 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
   float* dh = f(o_dh[0]); float* dh2 = f(o_dh[1]);
   if (L > 0) DCA_CUDA_OK(cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)Bn * K_head, s));
   float* dz[3] = {Mb, cond ? Db : nullptr, has_pi ? Pb : nullptr};
+  if (tc_heads) {
+    const __nv_bfloat16* Z[3]; float* dWp[3]; float* dbp[3];
+    for (int k = 0; k < 3; ++k) {
+      const int kk = k < n_slots ? k : 0;
+      Z[k] = bf(o_dzb[kk]); dWp[k] = gp(head_W[slot_head[kk]]); dbp[k] = gp(head_b[slot_head[kk]]);
+    }
+    DCA_TRY(tc::gene_gemm_tc(3, Z, G, Bn, G, n_slots, bf(o_h3b), bf(o_whkm), dh, dWp, G, 1, dbp, sm_count, s));
+  } else
   for (int k = 0; k < 3; ++k) {
     if (head_W[k] < 0 || !dz[k]) continue;
     GemmArgs g{};
@@ -341,6 +401,15 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
     if (cfg.batchnorm) {
       DCA_TRY(col_sums(dh, f(l.o_xhat), l.out, Bn, l.out, d(o_dsum), d(o_dprod), d(o_scratch), s));
       DCA_TRY(bn_bwd_apply(dh, f(l.o_xhat), l.out, Bn, l.out, f(l.o_inv), d(o_dsum), d(o_dprod), gp(l.beta), s));
+    }
+    if (i == 0 && cur_xb) {
+      DCA_TRY(cast_to_bf16(dh, bf(o_da1b), (int64_t)Bn * l.out, s));
+      const __nv_bfloat16* Z[3] = {cur_xb, cur_xb, cur_xb};
+      float* dWp[3] = {gp(l.W), gp(l.W), gp(l.W)};
+      DCA_TRY(tc::gene_gemm_tc(2, Z, cur_ldxb, Bn, cfg.n_in, 1, bf(o_da1b), nullptr, nullptr, dWp, l.out, 0, nullptr, sm_count, s));
+      DCA_TRY(col_sums(dh, nullptr, l.out, Bn, l.out, d(o_dsum), nullptr, d(o_scratch), s));
+      DCA_TRY(col_sum_to_float(d(o_dsum), l.out, gp(l.b), s));
+      continue;
     }
     const void* ain = (i == 0) ? X : (const void*)f(lay[i - 1].o_h);
     GemmArgs g{};
@@ -414,6 +483,31 @@ int Engine::predict(const void* X, int64_t ldx, const float* sf, const int32_t* 
   if (!cond && disp_out) {
     DCA_TRY(theta_prepare(pp(theta_off), G, disp_out, f(o_chain), s));
   }
+  return DCA_OK;
+}
+
+bool Engine::tc_supported() const { return tc_heads && tc_enc; }
+const char* Engine::tc_reason() const {
+  return "tcgen05 path needs hidden_size[0] == hidden_size[-1] == 64, n_in % 8 == 0 and n_out % 8 == 0";
+}
+int Engine::setup_tc() {
+  int dev = 0;
+  DCA_CUDA_OK(cudaGetDevice(&dev));
+  DCA_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (tc_heads || tc_enc) {
+    int major = 0;
+    DCA_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) { set_error("libdca_b200 is built for sm_100a only (device compute capability %d.x)", major); return DCA_ERR_UNSUPPORTED; }
+  }
+  return DCA_OK;
+}
+// Re-derive the bf16 operand-layout copies of the weights from the fp32 master parameters.
+int Engine::refresh_shadows(cudaStream_t s) {
+  if (tc_heads)
+    for (int k = 0; k < n_slots; ++k)
+      DCA_TRY(pack_head_shadows(pp(head_W[slot_head[k]]), pp(head_b[slot_head[k]]), cfg.n_out, k, n_slots, bf(o_whT),
+                                bf(o_whkm), f(o_biasp), s));
+  if (tc_enc) DCA_TRY(transpose_w1_shadow(pp(lay[0].W), cfg.n_in, bf(o_w1t), s));
   return DCA_OK;
 }
 

@@ -94,11 +94,75 @@ __global__ void bn_infer_prepare_kernel(const float* __restrict__ mm, const floa
   inv_std[c] = rsqrtf(mv[c] + eps);
 }
 
-__global__ void relu_fwd_kernel(const float* __restrict__ a, int64_t ld, int M, int N, float* __restrict__ h) {
+__global__ void relu_fwd_kernel(const float* __restrict__ a, int64_t ld, int M, int N, float* __restrict__ h,
+                                __nv_bfloat16* __restrict__ hb) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * N) return;
   const int r = (int)(i / N), c = (int)(i % N);
-  h[i] = fmaxf(a[(int64_t)r * ld + c], 0.f);
+  const float v = fmaxf(a[(int64_t)r * ld + c], 0.f);
+  h[i] = v;
+  if (hb) hb[i] = __float2bfloat16_rn(v);
+}
+
+// Operand-layout shadows of the head weights for the tcgen05 kernels (one 64-gene x 64-k tile per block):
+//   whT [(slot*G + g) * 64 + k]        bf16  K-major B operand of the head forward kernel
+//   whkm[k * (nslots*G) + slot*G + g]  bf16  Keras layout, heads packed along columns (head backward)
+//   biasp[slot*G + g]
+__global__ void pack_heads_kernel(const float* __restrict__ W, const float* __restrict__ b, int G, int slot, int nslots,
+                                  __nv_bfloat16* __restrict__ whT, __nv_bfloat16* __restrict__ whkm,
+                                  float* __restrict__ biasp) {
+  __shared__ float t[64][65];
+  const int g0 = blockIdx.x * 64, tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 256 threads
+  for (int k = ty; k < 64; k += 4) {
+    const int g = g0 + tx;
+    const float v = (g < G) ? W[(int64_t)k * G + g] : 0.f;
+    t[k][tx] = v;
+    if (g < G) whkm[(int64_t)k * nslots * G + (int64_t)slot * G + g] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  for (int gi = ty; gi < 64; gi += 4) {
+    const int g = g0 + gi;
+    if (g < G) whT[((int64_t)slot * G + g) * 64 + tx] = __float2bfloat16_rn(t[tx][gi]);
+  }
+  if (threadIdx.x < 64 && g0 + threadIdx.x < G) biasp[(int64_t)slot * G + g0 + threadIdx.x] = b[g0 + threadIdx.x];
+}
+
+// W1 [n_in x 64] (Keras) -> W1T [64 x n_in] bf16 (gene-contiguous K-major operand of the encoder forward)
+__global__ void transpose_w1_kernel(const float* __restrict__ W, int n_in, __nv_bfloat16* __restrict__ wt) {
+  __shared__ float t[64][65];
+  const int g0 = blockIdx.x * 64, tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int gi = ty; gi < 64; gi += 4) {
+    const int g = g0 + gi;
+    t[gi][tx] = (g < n_in) ? W[(int64_t)g * 64 + tx] : 0.f;
+  }
+  __syncthreads();
+  for (int f = ty; f < 64; f += 4) {
+    const int g = g0 + tx;
+    if (g < n_in) wt[(int64_t)f * n_in + g] = __float2bfloat16_rn(t[tx][f]);
+  }
+}
+
+// out[r][0..n) = bf16(X[rows[r]][0..n)), 8 elements per thread (n % 8 == 0, 16-byte aligned rows)
+template <typename T>
+__global__ void gather_rows_bf16_kernel(const T* __restrict__ X, int64_t ldx, const int32_t* __restrict__ rows, int M,
+                                        int n, __nv_bfloat16* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = n / 8;
+  if (i >= (int64_t)M * per_row) return;
+  const int r = (int)(i / per_row), c = (int)(i % per_row) * 8;
+  const int64_t sr = rows ? (int64_t)rows[r] : (int64_t)r;
+  uint4 o;
+  if (sizeof(T) == 2) {
+    o = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(X) + sr * ldx + c);
+  } else {
+    const float* s = reinterpret_cast<const float*>(X) + sr * ldx + c;
+    const float4 a = *reinterpret_cast<const float4*>(s), bq = *reinterpret_cast<const float4*>(s + 4);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(bq.x, bq.y), p3 = __floats2bfloat162_rn(bq.z, bq.w);
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+  }
+  *reinterpret_cast<uint4*>(out + (int64_t)r * n + c) = o;
 }
 
 __global__ void relu_bwd_kernel(float* __restrict__ dh, const float* __restrict__ h, int64_t n) {
@@ -250,8 +314,8 @@ int bn_infer_prepare(const float* mm, const float* mv, int N, float eps, float* 
   return DCA_OK;
 }
 
-int bias_relu_fwd(const float* a, int64_t ld, int M, int N, float* h, cudaStream_t s) {
-  relu_fwd_kernel<<<blocks_for((int64_t)M * N), 256, 0, s>>>(a, ld, M, N, h);
+int bias_relu_fwd(const float* a, int64_t ld, int M, int N, float* h, __nv_bfloat16* h_bf16, cudaStream_t s) {
+  relu_fwd_kernel<<<blocks_for((int64_t)M * N), 256, 0, s>>>(a, ld, M, N, h, h_bf16);
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }
@@ -320,6 +384,28 @@ int glorot_fill(float* w, int64_t n, int fan_in, int fan_out, uint64_t seed, uin
 int fill_value(float* p, int64_t n, float v, cudaStream_t s) {
   if (n <= 0) return DCA_OK;
   fill_kernel<<<blocks_for(n), 256, 0, s>>>(p, n, v);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int pack_head_shadows(const float* W, const float* b, int G, int slot, int nslots, __nv_bfloat16* whT,
+                      __nv_bfloat16* whkm, float* biasp, cudaStream_t s) {
+  pack_heads_kernel<<<cdiv(G, 64), 256, 0, s>>>(W, b, G, slot, nslots, whT, whkm, biasp);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int transpose_w1_shadow(const float* W, int n_in, __nv_bfloat16* wt, cudaStream_t s) {
+  transpose_w1_kernel<<<cdiv(n_in, 64), 256, 0, s>>>(W, n_in, wt);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int gather_rows_bf16(const void* X, int x_bf16, int64_t ldx, const int32_t* rows, int M, int n, __nv_bfloat16* out,
+                     cudaStream_t s) {
+  const int64_t tot = (int64_t)M * (n / 8);
+  if (x_bf16) gather_rows_bf16_kernel<__nv_bfloat16><<<blocks_for(tot), 256, 0, s>>>((const __nv_bfloat16*)X, ldx, rows, M, n, out);
+  else gather_rows_bf16_kernel<float><<<blocks_for(tot), 256, 0, s>>>((const float*)X, ldx, rows, M, n, out);
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }

@@ -311,3 +311,72 @@ def test_full_size_properties_c2():
     for _ in range(10):
         eng.train_step(Xd, Yd, sfd, rows=rows); eng.apply_update(1e-3, 5.0)
     assert eng.read_loss() < l0
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 path (bf16 operands, fp32 accumulation) inside the engine
+TC_CASES = [("zinb-conddisp", True), ("zinb", True), ("nb-conddisp", False), ("nb", True)]
+
+
+def _make_pair_tc(ae_type, batchnorm, B, G, seed=0):
+    from dca_b200.engine import DeviceEngine
+    hidden = (64, 32, 64)
+    p0 = O.init_params(G, G, hidden, ae_type, batchnorm, seed=seed, dtype=np.float32)
+    rng = np.random.default_rng(seed + 1)
+    for k in p0:
+        if k.endswith(("/bias", "/bn_beta", "/theta")):
+            p0[k] = rng.normal(0, 0.2, p0[k].shape).astype(np.float32)
+    net = O.OracleNet(G, G, hidden, ae_type, batchnorm, dtype=np.float64, params=p0)
+    eng = DeviceEngine(G, G, hidden, ae_type, batchnorm, max_batch=B, seed=None, gemm_path="tcgen05")
+    eng.set_weights(p0)
+    return net, eng
+
+
+@pytest.mark.parametrize("ae_type,batchnorm", TC_CASES)
+def test_tc_train_step_vs_oracle(ae_type, batchnorm):
+    """Whole step through the tcgen05 kernels vs the fp64 oracle.  Tolerance: bf16 operand rounding
+    (2^-9 relative per operand) -> loss 2e-3 relative, gradients 3 % of the per-tensor maximum."""
+    B, G = 300, 264
+    X, Y, sf = _problem(B + 40, G, 21)
+    rows = np.random.default_rng(1).permutation(B + 40)[:B].astype(np.int32)
+    net, eng = _make_pair_tc(ae_type, batchnorm, B, G)
+    Xd, Yd, sfd, rd = _t(X), _t(Y), _t(sf), torch.as_tensor(rows).to(DEV)
+    eng.train_step(Xd, Yd, sfd, rows=rd)
+    loss = eng.read_loss()
+    oloss, og = net.loss_and_grads(X[rows].astype(np.float64), Y[rows].astype(np.float64), sf[rows].astype(np.float64))
+    assert abs(loss - oloss) < 2e-3 * abs(oloss), (loss, oloss)
+    g = eng.grads.cpu().numpy()
+    for name, off, r, c in eng.param_info:
+        ref = og[name].reshape(-1); got = g[off: off + r * c]
+        if name.endswith("/bias") and batchnorm and not name.startswith(("mean", "dispersion", "pi")):
+            continue
+        err = np.max(np.abs(got - ref)) / (np.max(np.abs(ref)) + 1e-30)
+        assert err < 3e-2, "%s: %.3g" % (name, err)
+    # bf16 X storage takes the same path without the conversion copy
+    from dca_b200.engine import DeviceEngine
+    eng2 = DeviceEngine(G, G, (64, 32, 64), ae_type, batchnorm, max_batch=B, seed=None, gemm_path="tcgen05", x_dtype="bfloat16")
+    eng2.set_weights(eng.get_weights())
+    eng2.train_step(_t(X[rows], torch.bfloat16), _t(Y[rows]), _t(sf[rows]))
+    assert abs(eng2.read_loss() - oloss) < 4e-3 * abs(oloss)
+
+
+def test_tc_trajectory_and_predict():
+    B, G = 256, 200
+    X, Y, sf = _problem(B, G, 23)
+    net, eng = _make_pair_tc("zinb-conddisp", True, B, G)
+    Xd, Yd, sfd = _t(X), _t(Y), _t(sf)
+    for _ in range(8):
+        eng.train_step(Xd, Yd, sfd); eng.apply_update(1e-3, 5.0)
+        l_o = net.train_step(X.astype(np.float64), Y.astype(np.float64), sf.astype(np.float64))
+        assert abs(eng.read_loss() - l_o) < 1e-2 * abs(l_o)
+    ref = net.predict(X.astype(np.float64), sf.astype(np.float64))
+    mean = torch.empty((B, G), device=DEV); disp = torch.empty((B, G), device=DEV); pi = torch.empty((B, G), device=DEV)
+    lat = torch.empty((B, 32), device=DEV)
+    eng.predict(Xd, sfd, mean=mean, disp=disp, pi=pi, latent=lat)
+    torch.cuda.synchronize()
+    for got, key in ((mean, "mean"), (disp, "dispersion"), (pi, "pi")):
+        r = ref[key]; gnp = got.cpu().numpy()
+        assert np.median(np.abs(gnp - r) / (np.abs(r) + 1e-6)) < 2e-2, key
+    with pytest.raises(Exception):
+        from dca_b200.engine import DeviceEngine
+        DeviceEngine(100, 100, (10, 2, 10), "zinb", max_batch=8, gemm_path="tcgen05")   # shape does not qualify
