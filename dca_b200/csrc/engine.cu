@@ -146,6 +146,9 @@ int Engine::plan(const dca_config& c) {
   o_sfb = take(sizeof(float) * B);
   loss_ws_bytes = loss_workspace_bytes((int)B, G);
   o_lossws = take(loss_ws_bytes);
+  mid_ok = mid_supported(c.hidden, L);
+  o_bar = take(256);
+  o_midpart = take(sizeof(double) * mid_partial_doubles());
   // tcgen05 path (flagship shape): gene-wide layers with a 64-wide partner dimension
   n_slots = 0;
   slot_head[0] = 0; slot_kind[0] = EPI_MEAN_ACT; n_slots = 1;
@@ -232,7 +235,8 @@ int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, boo
       cur_xb = bf(o_xb); cur_ldxb = cfg.n_in;
     }
   }
-  for (int i = 0; i < L; ++i) {
+  const bool fused = use_mid(Bn);
+  for (int i = 0; i < (fused ? 1 : L); ++i) {
     Layer& l = lay[i];
     float* a = f(l.o_a);
     DCA_TRY(fill_rows_with_bias(a, l.out, Bn, l.out, pp(l.b), s));
@@ -246,6 +250,7 @@ int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, boo
     g.C = a; g.ldc = l.out; g.M = Bn; g.N = l.out; g.K = l.in; g.epilogue = EPI_ACCUM;
     DCA_TRY(gemm_auto(g, s));
     }
+    if (fused) break;                 // BN / relu / inner layers: one fused launch below
     if (cfg.batchnorm) {
       if (training) {
         DCA_TRY(col_sums(a, nullptr, l.out, Bn, l.out, d(o_dsum), d(o_dprod), d(o_scratch), s));
@@ -261,8 +266,31 @@ int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, boo
     }
     hin = f(l.o_h); ldin = l.out; in_bf16 = 0; gather = nullptr;
   }
+  if (fused) {
+    mid::Params mp;
+    mid_params(mp, Bn, training);
+    DCA_TRY(mid_forward(mp, s));
+    hin = f(lay[L - 1].o_h); ldin = lay[L - 1].out; in_bf16 = 0; gather = nullptr;
+  }
   head_in = hin; head_ld = ldin; head_bf16 = in_bf16; head_rows = gather;
   return DCA_OK;
+}
+
+void Engine::mid_params(mid::Params& p, int Bn, bool training) {
+  memset(&p, 0, sizeof(p));
+  p.L = L; p.B = Bn; p.training = training ? 1 : 0; p.batchnorm = cfg.batchnorm; p.center = L / 2;
+  for (int i = 0; i < L; ++i) {
+    Layer& l = lay[i];
+    p.w[i] = l.out; p.W[i] = pp(l.W); p.b[i] = pp(l.b);
+    p.beta[i] = cfg.batchnorm ? pp(l.beta) : nullptr;
+    p.mm[i] = cfg.batchnorm ? st(l.mm) : nullptr; p.mv[i] = cfg.batchnorm ? st(l.mv) : nullptr;
+    p.mean[i] = f(l.o_mean); p.inv[i] = f(l.o_inv); p.xhat[i] = f(l.o_xhat); p.h[i] = f(l.o_h);
+    p.gW[i] = gp(l.W); p.gb[i] = gp(l.b); p.gbeta[i] = cfg.batchnorm ? gp(l.beta) : nullptr;
+  }
+  p.a0 = f(lay[0].o_a); p.a_center = f(lay[L / 2].o_a);
+  p.h_last_bf16 = tc_heads ? bf(o_h3b) : nullptr;
+  p.partial = d(o_midpart); p.bar = reinterpret_cast<unsigned*>(base + o_bar);
+  p.eps = cfg.bn_eps; p.momentum = cfg.bn_momentum;
 }
 
 int Engine::heads_forward(int Bn, float* m_out, float* d_out, float* p_out, int64_t ld_out, const float* row_scale,
@@ -395,6 +423,24 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
   }
   // ---- hidden stack backward
   mark(4, s);
+  if (L > 0 && use_mid(Bn)) {
+    mid::Params mp;
+    mid_params(mp, Bn, true);
+    mp.dh_last = dh; mp.da0 = dh2; mp.da0_bf16 = cur_xb ? bf(o_da1b) : nullptr;
+    DCA_TRY(mid_backward(mp, s));
+    Layer& l = lay[0];
+    if (cur_xb) {
+      const __nv_bfloat16* Z[3] = {cur_xb, cur_xb, cur_xb};
+      float* dWp[3] = {gp(l.W), gp(l.W), gp(l.W)};
+      DCA_TRY(tc::gene_gemm_tc(2, Z, cur_ldxb, Bn, cfg.n_in, 1, bf(o_da1b), nullptr, nullptr, dWp, l.out, 0, nullptr, sm_count, s));
+    } else {
+      GemmArgs g{};
+      g.A = X; g.lda = ldx; g.a_bf16 = (cfg.x_dtype == DCA_BF16); g.transA = 1; g.a_rows = rows;
+      g.B = dh2; g.ldb = l.out; g.transB = 0;
+      g.C = gp(l.W); g.ldc = l.out; g.M = l.in; g.N = l.out; g.K = Bn; g.epilogue = EPI_ACCUM;
+      DCA_TRY(gemm_auto(g, s));
+    }
+  } else
   for (int i = L - 1; i >= 0; --i) {
     Layer& l = lay[i];
     DCA_TRY(relu_bwd(dh, f(l.o_h), l.out, Bn, l.out, s));

@@ -3,6 +3,7 @@
 #include <string>
 #include <vector>
 #include "dca_internal.cuh"
+#include "mid_stack.h"
 
 namespace dca {
 
@@ -39,6 +40,10 @@ struct Engine {
   } prof;
   void mark(int phase, cudaStream_t s);
   int prof_collect();
+  // fused hidden stack (mid_stack.cu)
+  bool mid_ok = false; size_t o_bar = 0, o_midpart = 0;
+  bool use_mid(int Bn) const { return mid_ok && Bn <= mid::kMaxRows * mid::kMaxCtas; }
+  void mid_params(mid::Params& p, int Bn, bool training);
   // tcgen05 path: flags + operand-layout shadows / bf16 activations in the arena
   bool tc_heads = false, tc_enc = false;
   int sm_count = 148, n_slots = 1;

@@ -1,0 +1,314 @@
+// Fused hidden stack ("K7"): everything between the first Dense layer's pre-activation and the last
+// hidden activation, forward and backward, in ONE launch each (dca/network.py:124-139 for every hidden
+// layer: [Dense ->] BatchNormalization(center, no scale) -> relu).  The tensors are tiny (B x <=64), the
+// work is latency-bound, and training-mode BatchNorm needs full-batch column statistics before it can
+// normalise -- so the kernel runs as <= 64 co-resident CTAs that own a strip of rows each, keep the
+// strip in shared memory across layers, and meet at a grid-wide barrier once per BatchNorm layer.
+//
+//   forward : a_0 (given, bias included) -> BN/relu -> [Dense -> BN/relu]* -> h_last (fp32 + bf16)
+//             saves x_hat_i, h_i (training) for the backward pass, the pre-BN 'center' output (latent,
+//             dca/network.py:184-185) and updates the moving statistics (momentum 0.99).
+//   backward: dh_last -> for each layer: relu mask, BN backward (two column sums -> barrier), bias / beta /
+//             kernel gradients of the inner layers (atomicAdd into the flat gradient buffer), dh of the
+//             previous layer; ends with da_0 (fp32 + bf16) for the first layer's weight gradient.
+#include "dca_internal.cuh"
+#include "mid_stack.h"
+
+namespace dca {
+namespace mid {
+
+constexpr int kThreads = 256;
+
+// Self-resetting sense-reversal barrier over the whole (co-resident) grid.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n, unsigned& gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned arrived = atomicAdd(&bar[0], 1u);
+    if (arrived == n - 1) {
+      bar[0] = 0;
+      __threadfence();
+      atomicAdd(&bar[1], 1u);
+    } else {
+      while (*reinterpret_cast<volatile unsigned*>(&bar[1]) == gen) { __nanosleep(20); }
+    }
+    __threadfence();
+  }
+  ++gen;
+  __syncthreads();
+}
+
+// column sums over this CTA's rows of s1 = sum(x) and s2 = sum(x*y) (double), x,y in smem [rows][kMaxW]
+__device__ __forceinline__ void cta_col_sums(float (*x)[kMaxW + 1], float (*y)[kMaxW + 1], int rows, int w,
+                                             double* out /* [2][kMaxW] global */, double (*red)[kMaxW]) {
+  // 256 threads: 4 row-groups x 64 columns
+  const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < w)
+    for (int r = g; r < rows; r += 4) { const double a = x[r][c]; s1 += a; s2 += a * (double)y[r][c]; }
+  red[g][c] = s1; red[4 + g][c] = s2;
+  __syncthreads();
+  if (threadIdx.x < 64 && c < w) {
+    out[c] = red[0][c] + red[1][c] + red[2][c] + red[3][c];
+    out[kMaxW + c] = red[4][c] + red[5][c] + red[6][c] + red[7][c];
+  }
+}
+
+__device__ __forceinline__ void fold_partials(const double* partial, int n_ctas, int w, double* tot /* smem [2][kMaxW] */) {
+  if (threadIdx.x < 2 * kMaxW) {
+    const int c = threadIdx.x & 63, k = threadIdx.x >> 6;
+    double s = 0.0;
+    if (c < w)
+      for (int i = 0; i < n_ctas; ++i) s += partial[(size_t)i * 2 * kMaxW + k * kMaxW + c];
+    tot[k * kMaxW + c] = s;
+  }
+  __syncthreads();
+}
+
+// out[r][c] = sum_k in[r][k] * W[k][c] (+ bias[c]); W in smem as [w_in][kMaxW+1]
+__device__ __forceinline__ void strip_gemm(float (*in)[kMaxW + 1], float (*Ws)[kMaxW + 1], const float* bias,
+                                           int rows, int w_in, int w_out, float (*out)[kMaxW + 1]) {
+  const int c = threadIdx.x & 63, g = threadIdx.x >> 6;      // 4 row groups
+  if (c < w_out) {
+    for (int r0 = g * 4; r0 < rows; r0 += 16) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < w_in; ++k) {
+        const float wv = Ws[k][c];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(in[r0 + j][k], wv, acc[j]);   // rows beyond `rows` hold zeros
+      }
+      const float bv = bias ? bias[c] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (r0 + j < rows) out[r0 + j][c] = acc[j] + bv;
+    }
+  }
+}
+
+typedef float Strip[kMaxW + 1];
+constexpr size_t kStripFloats = (size_t)(kMaxRows + 4) * (kMaxW + 1);
+constexpr size_t kWsFloats = (size_t)kMaxW * (kMaxW + 1);
+constexpr size_t kSmemBytes = sizeof(double) * (8 * kMaxW + 2 * kMaxW) + sizeof(float) * (2 * kStripFloats + kWsFloats + 2 * kMaxW) + 16;
+
+__global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p) {
+  extern __shared__ __align__(16) unsigned char smem_mid[];
+  double (*red)[kMaxW] = reinterpret_cast<double (*)[kMaxW]>(smem_mid);
+  double* tot = reinterpret_cast<double*>(smem_mid) + 8 * kMaxW;
+  float* fbase = reinterpret_cast<float*>(tot + 2 * kMaxW);
+  Strip* cur = reinterpret_cast<Strip*>(fbase);                       // current layer pre-activation / activation strip
+  Strip* nxt = reinterpret_cast<Strip*>(fbase + kStripFloats);
+  Strip* Ws = reinterpret_cast<Strip*>(fbase + 2 * kStripFloats);
+  float* s_mean = fbase + 2 * kStripFloats + kWsFloats;
+  float* s_inv = s_mean + kMaxW;
+  __shared__ unsigned s_gen;
+  if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile unsigned*>(&p.bar[1]);
+  __syncthreads();
+  unsigned gen = s_gen;
+
+  const int row0 = blockIdx.x * p.rows_per_cta;
+  const int rows = max(0, min(p.rows_per_cta, p.B - row0));
+  for (int i = threadIdx.x; i < (int)kStripFloats; i += kThreads) { (&cur[0][0])[i] = 0.f; (&nxt[0][0])[i] = 0.f; }
+  __syncthreads();
+  // load a_0 strip
+  for (int i = threadIdx.x; i < rows * p.w[0]; i += kThreads) {
+    const int r = i / p.w[0], c = i % p.w[0];
+    cur[r][c] = p.a0[(size_t)(row0 + r) * p.w[0] + c];
+  }
+  __syncthreads();
+  Strip* a = cur;
+  Strip* o = nxt;
+  for (int l = 0; l < p.L; ++l) {
+    const int w = p.w[l];
+    if (l > 0) {
+      const int win = p.w[l - 1];
+      for (int i = threadIdx.x; i < win * w; i += kThreads) Ws[i / w][i % w] = p.W[l][i];
+      __syncthreads();
+      strip_gemm(a, Ws, p.b[l], rows, win, w, o);
+      __syncthreads();
+      Strip* t = a; a = o; o = t;
+    }
+    if (l == p.center && p.a_center && !(l == 0 && p.a_center == p.a0))
+      for (int i = threadIdx.x; i < rows * w; i += kThreads) p.a_center[(size_t)(row0 + i / w) * w + i % w] = a[i / w][i % w];
+    if (p.batchnorm) {
+      if (p.training) {
+        double* part = p.partial + (size_t)(l & 1) * kMaxCtas * 2 * kMaxW;       // double-buffered across layers
+        cta_col_sums(a, a, rows, w, part + (size_t)blockIdx.x * 2 * kMaxW, red);
+        grid_barrier(p.bar, gridDim.x, gen);
+        fold_partials(part, gridDim.x, w, tot);
+        if (threadIdx.x < w) {
+          const int c = threadIdx.x;
+          const double mu = tot[c] / (double)p.B;
+          double var = tot[kMaxW + c] / (double)p.B - mu * mu;      // biased batch variance
+          if (var < 0.0) var = 0.0;
+          s_mean[c] = (float)mu;
+          s_inv[c] = (float)(1.0 / sqrt(var + (double)p.eps));
+          if (blockIdx.x == 0) {
+            p.mean[l][c] = s_mean[c]; p.inv[l][c] = s_inv[c];
+            p.mm[l][c] = p.momentum * p.mm[l][c] + (1.0f - p.momentum) * (float)mu;
+            p.mv[l][c] = p.momentum * p.mv[l][c] + (1.0f - p.momentum) * (float)var;
+          }
+        }
+        __syncthreads();
+      } else {
+        if (threadIdx.x < w) { s_mean[threadIdx.x] = p.mm[l][threadIdx.x]; s_inv[threadIdx.x] = rsqrtf(p.mv[l][threadIdx.x] + p.eps); }
+        __syncthreads();
+      }
+    }
+    const bool last = (l == p.L - 1);
+    for (int i = threadIdx.x; i < rows * w; i += kThreads) {
+      const int r = i / w, c = i % w;
+      float v = a[r][c];
+      if (p.batchnorm) {
+        const float xh = (v - s_mean[c]) * s_inv[c];
+        if (p.training) p.xhat[l][(size_t)(row0 + r) * w + c] = xh;
+        v = xh + p.beta[l][c];
+      }
+      v = fmaxf(v, 0.f);
+      a[r][c] = v;
+      p.h[l][(size_t)(row0 + r) * w + c] = v;
+      if (last && p.h_last_bf16) p.h_last_bf16[(size_t)(row0 + r) * w + c] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params p) {
+  extern __shared__ __align__(16) unsigned char smem_mid[];
+  double (*red)[kMaxW] = reinterpret_cast<double (*)[kMaxW]>(smem_mid);
+  double* tot = reinterpret_cast<double*>(smem_mid) + 8 * kMaxW;
+  float* fbase = reinterpret_cast<float*>(tot + 2 * kMaxW);
+  Strip* g = reinterpret_cast<Strip*>(fbase);                         // gradient strip of the current layer
+  Strip* xh = reinterpret_cast<Strip*>(fbase + kStripFloats);         // x_hat strip / previous activation strip
+  Strip* Ws = reinterpret_cast<Strip*>(fbase + 2 * kStripFloats);
+  __shared__ unsigned s_gen;
+  if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile unsigned*>(&p.bar[1]);
+  __syncthreads();
+  unsigned gen = s_gen;
+
+  const int row0 = blockIdx.x * p.rows_per_cta;
+  const int rows = max(0, min(p.rows_per_cta, p.B - row0));
+  for (int i = threadIdx.x; i < (int)kStripFloats; i += kThreads) { (&g[0][0])[i] = 0.f; (&xh[0][0])[i] = 0.f; }
+  __syncthreads();
+  {
+    const int w = p.w[p.L - 1];
+    for (int i = threadIdx.x; i < rows * w; i += kThreads) g[i / w][i % w] = p.dh_last[(size_t)(row0 + i / w) * w + i % w];
+  }
+  __syncthreads();
+  for (int l = p.L - 1; l >= 0; --l) {
+    const int w = p.w[l];
+    // relu mask (+ load x_hat)
+    for (int i = threadIdx.x; i < rows * w; i += kThreads) {
+      const int r = i / w, c = i % w;
+      const size_t gi = (size_t)(row0 + r) * w + c;
+      if (!(p.h[l][gi] > 0.f)) g[r][c] = 0.f;
+      if (p.batchnorm) xh[r][c] = p.xhat[l][gi];
+    }
+    __syncthreads();
+    if (p.batchnorm) {
+      double* part = p.partial + (size_t)(l & 1) * kMaxCtas * 2 * kMaxW;
+      cta_col_sums(g, xh, rows, w, part + (size_t)blockIdx.x * 2 * kMaxW, red);
+      grid_barrier(p.bar, gridDim.x, gen);
+      fold_partials(part, gridDim.x, w, tot);
+      if (blockIdx.x == 0 && threadIdx.x < w) p.gbeta[l][threadIdx.x] = (float)tot[threadIdx.x];   // d beta = sum(g)
+      for (int i = threadIdx.x; i < rows * w; i += kThreads) {
+        const int r = i / w, c = i % w;
+        const float mg = (float)(tot[c] / (double)p.B), mgx = (float)(tot[kMaxW + c] / (double)p.B);
+        g[r][c] = p.inv[l][c] * (g[r][c] - mg - xh[r][c] * mgx);
+      }
+      __syncthreads();
+    }
+    // bias gradient: column sums of da over my rows
+    {
+      const int c = threadIdx.x & 63, q = threadIdx.x >> 6;
+      float s = 0.f;
+      if (c < w) for (int r = q; r < rows; r += 4) s += g[r][c];
+      red[q][c] = (double)s;
+      __syncthreads();
+      if (threadIdx.x < w) atomicAdd(&p.gb[l][threadIdx.x], (float)(red[0][c] + red[1][c] + red[2][c] + red[3][c]));
+      __syncthreads();
+    }
+    if (l == 0) {
+      for (int i = threadIdx.x; i < rows * w; i += kThreads) {
+        const int r = i / w, c = i % w;
+        const size_t gi = (size_t)(row0 + r) * w + c;
+        if (p.da0) p.da0[gi] = g[r][c];
+        if (p.da0_bf16) p.da0_bf16[gi] = __float2bfloat16_rn(g[r][c]);
+      }
+      break;
+    }
+    // ---- inner layer l >= 1: dW_l += h_{l-1}^T . da ;  dh_{l-1} = da . W_l^T
+    const int win = p.w[l - 1];
+    for (int i = threadIdx.x; i < rows * win; i += kThreads) xh[i / win][i % win] = p.h[l - 1][(size_t)(row0 + i / win) * win + i % win];
+    for (int i = threadIdx.x; i < win * w; i += kThreads) Ws[i / w][i % w] = p.W[l][i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < win * w; i += kThreads) {          // dW[k][c] = sum_r h[r][k] * da[r][c]
+      const int k = i / w, c = i % w;
+      float s = 0.f;
+      for (int r = 0; r < rows; ++r) s = fmaf(xh[r][k], g[r][c], s);
+      atomicAdd(&p.gW[l][i], s);
+    }
+    __syncthreads();
+    // dh_{l-1}[r][k] = sum_c da[r][c] * W[k][c]  -> write into xh, then swap roles
+    for (int i = threadIdx.x; i < rows * win; i += kThreads) {
+      const int r = i / win, k = i % win;
+      float s = 0.f;
+      for (int c = 0; c < w; ++c) s = fmaf(g[r][c], Ws[k][c], s);
+      xh[r][k] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)kStripFloats; i += kThreads) (&g[0][0])[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * win; i += kThreads) g[i / win][i % win] = xh[i / win][i % win];
+    __syncthreads();
+  }
+}
+
+}  // namespace mid
+
+bool mid_supported(const int* widths, int L) {
+  if (L < 1) return false;
+  for (int i = 0; i < L; ++i) if (widths[i] > mid::kMaxW) return false;
+  return true;
+}
+
+static int mid_fill(mid::Params& p, int B) {
+  int ctas = cdiv(B, mid::kMaxRows);
+  if (ctas > mid::kMaxCtas) { set_error("mid_stack: batch %d exceeds %d rows", B, mid::kMaxRows * mid::kMaxCtas); return DCA_ERR_UNSUPPORTED; }
+  // spread rows evenly, at least 16 rows per CTA so tiny batches do not pay for 64 barriers participants
+  int rpc = cdiv(B, ctas);
+  if (rpc < 16) rpc = 16;
+  rpc = (rpc + 3) & ~3;
+  if (rpc > mid::kMaxRows) rpc = mid::kMaxRows;
+  p.rows_per_cta = rpc; p.n_ctas = cdiv(B, rpc);
+  return DCA_OK;
+}
+
+size_t mid_partial_doubles() { return (size_t)2 * mid::kMaxCtas * 2 * mid::kMaxW; }
+
+static int mid_attr() {
+  static bool done = false;
+  if (!done) {
+    DCA_CUDA_OK(cudaFuncSetAttribute(mid::mid_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid::kSmemBytes));
+    DCA_CUDA_OK(cudaFuncSetAttribute(mid::mid_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid::kSmemBytes));
+    done = true;
+  }
+  return DCA_OK;
+}
+
+int mid_forward(mid::Params& p, cudaStream_t s) {
+  DCA_TRY(mid_fill(p, p.B));
+  DCA_TRY(mid_attr());
+  mid::mid_forward_kernel<<<p.n_ctas, mid::kThreads, mid::kSmemBytes, s>>>(p);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int mid_backward(mid::Params& p, cudaStream_t s) {
+  DCA_TRY(mid_fill(p, p.B));
+  DCA_TRY(mid_attr());
+  mid::mid_backward_kernel<<<p.n_ctas, mid::kThreads, mid::kSmemBytes, s>>>(p);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+}  // namespace dca

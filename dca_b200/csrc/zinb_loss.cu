@@ -173,7 +173,7 @@ zinb_loss_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __rest
 // shared memory (16 B items), evaluated densely (item i by lane i mod 32) and handed back.
 // Without this the NB branch runs once per vector slot with ~17 % of the lanes active.
 template <bool COND_DISP, typename GT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 zinb_loss_bwd_compact_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __restrict__ rows,
                              const float* __restrict__ sf, const float* m, const float* d, const float* pi,
                              int64_t ld, int B, int G, float ridge, float inv_n, int rows_per_block,
@@ -203,22 +203,25 @@ zinb_loss_bwd_compact_kernel(const float* __restrict__ Y, int64_t ldy, const int
   if (active) load_row<true, COND_DISP, kVec>(cur, Y, ldy, rows, sf, m, d, pi, ld, r0, col0);
   for (int r = r0; r < r1; ++r) {
     if (active && r + 1 < r1) load_row<true, COND_DISP, kVec>(nxt, Y, ldy, rows, sf, m, d, pi, ld, r + 1, col0);
-    // ---- queue the non-zero counts of this warp's strip
+    // ---- queue the non-zero counts of this warp's strip (ballot compaction: items ordered by j, then lane)
+    unsigned bal[kVec];
     int nz = 0;
-    if (active) {
 #pragma unroll
-      for (int j = 0; j < kVec; ++j) nz |= (cur.y[j] < 1e-8f) ? 0 : (1 << j);           // loss.py:138
+    for (int j = 0; j < kVec; ++j) {
+      const bool is_nz = active && !(cur.y[j] < 1e-8f);                                  // loss.py:138
+      bal[j] = __ballot_sync(kFull, is_nz);
+      nz |= is_nz ? (1 << j) : 0;
     }
-    const int cnt = __popc(nz);
-    int incl = cnt;
+    const unsigned lt = (1u << lane) - 1u;
+    int pos[kVec];
+    int base = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-    const int total = __shfl_sync(kFull, incl, 31);
-    const float row_sf = __shfl_sync(kFull, active ? cur.sf : 1.0f, 0);                  // lane 0 is always active
-    int k = incl - cnt;
+    for (int j = 0; j < kVec; ++j) { pos[j] = base + __popc(bal[j] & lt); base += __popc(bal[j]); }
+    const int total = base;
+    const float row_sf = __shfl_sync(kFull, active ? cur.sf : 1.0f, 0);                  // lane 0 of an active warp is active
 #pragma unroll
     for (int j = 0; j < kVec; ++j)
-      if (nz & (1 << j)) q[k++] = make_float4(cur.y[j], cur.m[j], COND_DISP ? cur.d[j] : thg[j], cur.p[j]);
+      if (nz & (1 << j)) q[pos[j]] = make_float4(cur.y[j], cur.m[j], COND_DISP ? cur.d[j] : thg[j], cur.p[j]);
     __syncwarp();
     // ---- zero branch for my own zero counts (branch-free per element)
     float gm[kVec], gd[kVec], gp[kVec];
@@ -237,10 +240,9 @@ zinb_loss_bwd_compact_kernel(const float* __restrict__ Y, int64_t ldy, const int
       q[i] = make_float4(e.loss, e.gm, e.gd, e.gp);
     }
     __syncwarp();
-    k = incl - cnt;
 #pragma unroll
     for (int j = 0; j < kVec; ++j)
-      if (nz & (1 << j)) { const float4 e = q[k++]; lsum += e.x; gm[j] = e.y; gd[j] = e.z; gp[j] = e.w; }
+      if (nz & (1 << j)) { const float4 e = q[pos[j]]; lsum += e.x; gm[j] = e.y; gd[j] = e.z; gp[j] = e.w; }
     __syncwarp();
     if (active) {
       const int64_t off = (int64_t)r * ld + col0;

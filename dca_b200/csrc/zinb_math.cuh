@@ -4,7 +4,7 @@
 // in fp32) and the closed-form derivatives TF autodiff produces for them,
 // re-arranged so that fp32 does not cancel catastrophically and so that ONE reciprocal serves
 // the whole element.  With  te = theta+eps,  den = te+mu,  q = mu/den,  r = te/den = 1-q:
-//   log(1+mu/te) = -log r =: L1            (series in q for q < 1/8, else lg2)
+//   log(1+mu/te) = -log r =: L1            (series in q for q < 1/16, else lg2)
 //   t2 (loss.py:88) = (theta+y) L1 + y (log te - log(mu+eps)) = theta L1 - y log((mu+eps)/den)
 //   zero_nb (loss.py:136) = r^theta = exp(-theta L1)
 //   d/dmu * mu      = theta (mu - y)/den                 (nb)   |  w theta q          (zero)
@@ -129,10 +129,9 @@ DCA_HD Shared shared_terms(float m, float sf, float th) {
   s.te = s.th + kEps;                                       // dca/loss.py:87
   s.rden = Ops::rcp(s.te + s.mu);
   s.q = s.mu * s.rden;
-  if (s.q < 0.125f) {                                       // -log(1-q) = q + q^2/2 + q^3/3 + ...
+  if (s.q < 0.0625f) {                                      // -log(1-q) = q + q^2/2 + q^3/3 + ... (q^9/9 < 2e-11 q)
     const float q = s.q;
-    float p = fmaf(q, 0.0909090909f, 0.1f);
-    p = fmaf(q, p, 0.111111111f); p = fmaf(q, p, 0.125f); p = fmaf(q, p, 0.142857143f);
+    float p = fmaf(q, 0.125f, 0.142857143f);
     p = fmaf(q, p, 0.166666667f); p = fmaf(q, p, 0.2f); p = fmaf(q, p, 0.25f);
     p = fmaf(q, p, 0.333333333f); p = fmaf(q, p, 0.5f);
     s.f = q * q * p;                                        // L1 - q
@@ -147,9 +146,8 @@ DCA_HD Shared shared_terms(float m, float sf, float th) {
 // 1 - exp(-d) = sigmoid(zd) when d = softplus(zd)
 template <class Ops>
 DCA_HD float one_minus_exp_neg(float d) {
-  if (d < 0.125f) {
-    float p = fmaf(d, -0.000198412698f, 0.00138888889f);
-    p = fmaf(d, p, -0.00833333333f); p = fmaf(d, p, 0.0416666667f); p = fmaf(d, p, -0.166666667f);
+  if (d < 0.03125f) {                         // d - d^2/2 + d^3/6 - d^4/24; next term d^5/120 < 1e-8 d
+    float p = fmaf(d, 0.0416666667f, -0.166666667f);
     p = fmaf(d, p, 0.5f);
     return d - d * d * p;
   }

@@ -50,6 +50,16 @@ LOSS_EPS = 1e-10           # dca/loss.py:65
 AE_TYPES = ("zinb-conddisp", "zinb", "nb-conddisp", "nb")
 
 
+def bf16_round(a):
+    """Round-to-nearest-even to bfloat16 precision (8-bit mantissa), returned in a's dtype.
+    Used by the "same-rounding" oracle that mirrors where the tcgen05 path rounds its GEMM operands."""
+    a = np.asarray(a)
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    out = ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
+    return out.astype(a.dtype).reshape(a.shape)
+
+
 # ----------------------------------------------------------------------------
 # Activations (dca/network.py:38-39, 369)
 # ----------------------------------------------------------------------------
@@ -324,6 +334,9 @@ class OracleNet:
     rms: Dict[str, np.ndarray] = field(default_factory=dict)
     bn_momentum: float = KERAS_DEFAULTS["bn_momentum"]
     bn_eps: float = KERAS_DEFAULTS["bn_eps"]
+    # same-rounding emulation of the tcgen05 path: GEMM operands of the gene-wide layers are rounded
+    # to bf16 (X, first kernel, last hidden activation, head kernels, dZ, dA of the first layer)
+    emulate_bf16: bool = False
 
     def __post_init__(self):
         assert self.ae_type in AE_TYPES
@@ -348,8 +361,12 @@ class OracleNet:
         h = np.asarray(X, dt)
         c = {"h_in": [h]} if cache is not None else None
         latent = None
+        rnd = bf16_round if self.emulate_bf16 else (lambda t: t)
         for i, nm in enumerate(self.names):
-            a = h @ self.params[nm + "/kernel"] + self.params[nm + "/bias"]
+            if i == 0:
+                a = rnd(h) @ rnd(self.params[nm + "/kernel"]) + self.params[nm + "/bias"]
+            else:
+                a = h @ self.params[nm + "/kernel"] + self.params[nm + "/bias"]
             if nm == "center":
                 latent = a                                  # dca/network.py:184-185 (pre-BN)
             if self.batchnorm:
@@ -373,7 +390,7 @@ class OracleNet:
         out = {"latent": latent, "decoded": h}
         z = {}
         for nm in self.heads:
-            z[nm] = h @ self.params[nm + "/kernel"] + self.params[nm + "/bias"]
+            z[nm] = rnd(h) @ rnd(self.params[nm + "/kernel"]) + self.params[nm + "/bias"]
         out["z"] = z
         out["mean_norm"] = mean_act(z["mean"])
         sfc = np.asarray(sf, dt).reshape(-1, 1)
@@ -422,15 +439,16 @@ class OracleNet:
                                     self.ridge)
         loss = hg["loss"] + self.penalty()
         g: Dict[str, np.ndarray] = {}
+        rnd = bf16_round if self.emulate_bf16 else (lambda t: t)
         h_last = cache["h_in"][-1]
         dh = np.zeros_like(h_last)
         for nm, key in (("mean", "dzm"), ("dispersion", "dzd"), ("pi", "dzp")):
             if nm in z:
-                dz = hg[key]
+                dz = rnd(hg[key])
                 W = self.params[nm + "/kernel"]
-                g[nm + "/kernel"] = h_last.T @ dz + self.l1 * np.sign(W) + 2 * self.l2 * W
+                g[nm + "/kernel"] = rnd(h_last).T @ dz + self.l1 * np.sign(W) + 2 * self.l2 * W
                 g[nm + "/bias"] = dz.sum(axis=0)
-                dh = dh + dz @ W.T
+                dh = dh + dz @ rnd(W).T
         if "dtheta_raw" in hg:
             g["dispersion/theta"] = hg["dtheta_raw"]
         for i in reversed(range(len(self.names))):
@@ -445,7 +463,10 @@ class OracleNet:
                 da = dpre
             W = self.params[nm + "/kernel"]
             l1, l2 = self._reg(i)
-            g[nm + "/kernel"] = cache["h_in"][i].T @ da + l1 * np.sign(W) + 2 * l2 * W
+            if i == 0:
+                g[nm + "/kernel"] = rnd(cache["h_in"][i]).T @ rnd(da) + l1 * np.sign(W) + 2 * l2 * W
+            else:
+                g[nm + "/kernel"] = cache["h_in"][i].T @ da + l1 * np.sign(W) + 2 * l2 * W
             g[nm + "/bias"] = da.sum(axis=0)
             dh = da @ W.T
         if update_bn and self.batchnorm:

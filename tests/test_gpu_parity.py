@@ -326,7 +326,7 @@ def _make_pair_tc(ae_type, batchnorm, B, G, seed=0):
     for k in p0:
         if k.endswith(("/bias", "/bn_beta", "/theta")):
             p0[k] = rng.normal(0, 0.2, p0[k].shape).astype(np.float32)
-    net = O.OracleNet(G, G, hidden, ae_type, batchnorm, dtype=np.float64, params=p0)
+    net = O.OracleNet(G, G, hidden, ae_type, batchnorm, dtype=np.float64, params=p0, emulate_bf16=True)
     eng = DeviceEngine(G, G, hidden, ae_type, batchnorm, max_batch=B, seed=None, gemm_path="tcgen05")
     eng.set_weights(p0)
     return net, eng
@@ -334,8 +334,10 @@ def _make_pair_tc(ae_type, batchnorm, B, G, seed=0):
 
 @pytest.mark.parametrize("ae_type,batchnorm", TC_CASES)
 def test_tc_train_step_vs_oracle(ae_type, batchnorm):
-    """Whole step through the tcgen05 kernels vs the fp64 oracle.  Tolerance: bf16 operand rounding
-    (2^-9 relative per operand) -> loss 2e-3 relative, gradients 3 % of the per-tensor maximum."""
+    """Whole step through the tcgen05 kernels vs the SAME-ROUNDING fp64 oracle (GEMM operands of the
+    gene-wide layers rounded to bf16 exactly where the kernels round them, everything else exact).
+    ReLU-mask flips make the exact-oracle comparison discontinuous (a 2^-9 perturbation of W1 moves
+    single columns of dW1 by ~10 % at batch 300), so parity of the bf16 path is defined against this."""
     B, G = 300, 264
     X, Y, sf = _problem(B + 40, G, 21)
     rows = np.random.default_rng(1).permutation(B + 40)[:B].astype(np.int32)
@@ -344,14 +346,16 @@ def test_tc_train_step_vs_oracle(ae_type, batchnorm):
     eng.train_step(Xd, Yd, sfd, rows=rd)
     loss = eng.read_loss()
     oloss, og = net.loss_and_grads(X[rows].astype(np.float64), Y[rows].astype(np.float64), sf[rows].astype(np.float64))
-    assert abs(loss - oloss) < 2e-3 * abs(oloss), (loss, oloss)
+    assert abs(loss - oloss) < 5e-5 * abs(oloss), (loss, oloss)
+    exact = O.OracleNet(G, G, (64, 32, 64), ae_type, batchnorm, dtype=np.float64, params=net.params)
+    assert abs(loss - exact.loss(X[rows].astype(np.float64), Y[rows].astype(np.float64), sf[rows].astype(np.float64), training=True)) < 5e-3 * abs(oloss)
     g = eng.grads.cpu().numpy()
     for name, off, r, c in eng.param_info:
         ref = og[name].reshape(-1); got = g[off: off + r * c]
         if name.endswith("/bias") and batchnorm and not name.startswith(("mean", "dispersion", "pi")):
             continue
         err = np.max(np.abs(got - ref)) / (np.max(np.abs(ref)) + 1e-30)
-        assert err < 3e-2, "%s: %.3g" % (name, err)
+        assert err < 2e-3, "%s: %.3g" % (name, err)
     # bf16 X storage takes the same path without the conversion copy
     from dca_b200.engine import DeviceEngine
     eng2 = DeviceEngine(G, G, (64, 32, 64), ae_type, batchnorm, max_batch=B, seed=None, gemm_path="tcgen05", x_dtype="bfloat16")
