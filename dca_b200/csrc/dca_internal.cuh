@@ -93,6 +93,8 @@ int fill_value(float* p, int64_t n, float v, cudaStream_t s);
 int cast_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
 int pack_head_shadows(const float* W, const float* b, int G, int slot, int nslots, __nv_bfloat16* whT,
                       __nv_bfloat16* whkm, float* biasp, cudaStream_t s);
+int refresh_all_shadows(const float* const W[3], const float* const b[3], int n_slots, int G, __nv_bfloat16* whT,
+                        __nv_bfloat16* whkm, float* biasp, const float* W1, int n_in, __nv_bfloat16* w1t, cudaStream_t s);
 int transpose_w1_shadow(const float* W, int n_in, __nv_bfloat16* wt, cudaStream_t s);
 int gather_rows_bf16(const void* X, int x_bf16, int64_t ldx, const int32_t* rows, int M, int n, __nv_bfloat16* out,
                      cudaStream_t s);

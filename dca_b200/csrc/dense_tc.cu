@@ -117,12 +117,12 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 namespace k2 {
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kStages = 2, kAccStages = 2;
-constexpr int kEpiWarps = 8, kEpiWarp0 = 4;
-constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;            // 384
+constexpr int kEpiWarps = 16, kEpiWarp0 = 4;                     // 4 TMEM lane quarters x 4 column groups of 64
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;            // 640
 constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;  // 16 KB, 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kChunkBytes = 32 * 32 * 4;                     // one warp's 32x32 fp32 staging tile
-constexpr uint32_t kOutBytes = kEpiWarps * 2 * kChunkBytes;       // double buffered per warp
+constexpr uint32_t kOutBytes = kEpiWarps * kChunkBytes;           // one staging tile per warp
 constexpr uint32_t kSmemBytes = kStages * kStageBytes + kOutBytes + kAccStages * BN * 4 + 1024;
 
 struct Params {
@@ -134,13 +134,12 @@ struct Params {
 };
 
 __device__ __forceinline__ float act_mean(float z) { return fminf(fmaxf(ex2f(z * 1.442695041f), 1e-5f), 1e6f); }
+// softplus(z) = max(z,0) + log1p(exp(-|z|)), branch-free; log1p by series when exp(-|z|) is small
 __device__ __forceinline__ float act_disp(float z) {
-  float sp;
-  if (z > 15.f) sp = z;
-  else {
-    const float e = ex2f(z * 1.442695041f);
-    sp = (e < 1e-3f) ? e * (1.0f - 0.5f * e) : 0.693147181f * lg2f(1.0f + e);
-  }
+  const float e = ex2f(-fabsf(z) * 1.442695041f);                       // (0, 1]
+  const float l_series = e * fmaf(e, fmaf(e, 0.333333333f, -0.5f), 1.0f);
+  const float l_log = 0.693147181f * lg2f(1.0f + e);
+  const float sp = fmaxf(z, 0.f) + (e < 0.01f ? l_series : l_log);
   return fminf(fmaxf(sp, 1e-4f), 1e4f);
 }
 __device__ __forceinline__ float act_sigmoid(float z) { return rcpf(1.0f + ex2f(-z * 1.442695041f)); }
@@ -206,19 +205,21 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
       }
     }
   } else if (warp >= kEpiWarp0) {
-    const int ew = warp - kEpiWarp0;               // 0..7
+    const int ew = warp - kEpiWarp0;               // 0..15
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                      // column half of the tile
-    uint8_t* my_out = s_out + (size_t)ew * 2 * kChunkBytes;
-    int it = 0, obuf = 0;
+    const int cgrp = ew >> 2;                      // 64-column group of the tile
+    uint8_t* ob = s_out + (size_t)ew * kChunkBytes;
+    int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int hs, nt, mt; decode(t, hs, nt, mt);
       const int as = it % kAccStages; const uint32_t aph = (it / kAccStages) & 1;
-      // bias of this tile -> smem (256 epilogue threads, one column each)
+      // bias of this tile -> smem (first 256 epilogue threads, one column each)
       {
-        const int c = (warp - kEpiWarp0) * 32 + lane;
-        const int g = nt * BN + c;
-        s_bias[as * BN + c] = (g < p.G) ? p.bias[(size_t)hs * p.G + g] : 0.f;
+        const int c = ew * 32 + lane;
+        if (c < BN) {
+          const int g = nt * BN + c;
+          s_bias[as * BN + c] = (g < p.G) ? p.bias[(size_t)hs * p.G + g] : 0.f;
+        }
       }
       named_barrier_sync(1, kEpiWarps * 32);
       mbar_wait(&tfull_bar[as], aph);
@@ -227,39 +228,42 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
       const float rs = (p.row_scale && row < p.B) ? p.row_scale[row] : 1.0f;
       const int kind = p.kind[hs];
       const CUtensorMap* mo = hs == 0 ? &map_o0 : (hs == 1 ? &map_o1 : &map_o2);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col0 = half * 128 + c * 32;
-        if (nt * BN + col0 >= p.G) break;                            // whole chunk outside the head
+      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + cgrp * 64);
+      const bool have[2] = {nt * BN + cgrp * 64 < p.G, nt * BN + cgrp * 64 + 32 < p.G};
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + col0), v);
-        tmem_ld_wait();
-        uint8_t* ob = my_out + (size_t)obuf * kChunkBytes;
-        if (lane == 0) bulk_wait_read<1>();                          // the store that last used this buffer has drained
+        if (have[c]) { tmem_ld_32x32(tbase + c * 32, v); tmem_ld_wait(); }
+        if (c == 1) {                                       // accumulator fully read: release it to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (!have[c]) continue;
+        const int col0 = cgrp * 64 + c * 32;
+        if (lane == 0) bulk_wait_read<0>();                 // previous store has finished reading the staging tile
         __syncwarp();
         const float* bz = s_bias + as * BN + col0;
+        auto emit = [&](auto act) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float o[4];
+          for (int q = 0; q < 8; ++q) {
+            float o[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float z = __uint_as_float(v[q * 4 + j]) + bz[q * 4 + j];
-            o[j] = (kind == EPI_MEAN_ACT) ? act_mean(z) * rs : ((kind == EPI_DISP_ACT) ? act_disp(z) : act_sigmoid(z));
+            for (int j = 0; j < 4; ++j) o[j] = act(__uint_as_float(v[q * 4 + j]) + bz[q * 4 + j]);
+            // 128-byte rows, 16-byte chunks XOR-swizzled with the row index (matches SWIZZLE_128B)
+            *reinterpret_cast<float4*>(ob + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
           }
-          // 128-byte rows, 16-byte chunks XOR-swizzled with the row index (matches SWIZZLE_128B)
-          *reinterpret_cast<float4*>(ob + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
-        }
+        };
+        if (kind == EPI_MEAN_ACT) emit([rs](float z) { return act_mean(z) * rs; });
+        else if (kind == EPI_DISP_ACT) emit([](float z) { return act_disp(z); });
+        else emit([](float z) { return act_sigmoid(z); });
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           tma_store_2d(mo, nt * BN + col0, mt * BM + quarter * 32, ob);
           bulk_commit();
         }
-        obuf ^= 1;
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
     if (lane == 0) bulk_wait<0>();
   }

@@ -549,12 +549,12 @@ int Engine::setup_tc() {
 }
 // Re-derive the bf16 operand-layout copies of the weights from the fp32 master parameters.
 int Engine::refresh_shadows(cudaStream_t s) {
-  if (tc_heads)
-    for (int k = 0; k < n_slots; ++k)
-      DCA_TRY(pack_head_shadows(pp(head_W[slot_head[k]]), pp(head_b[slot_head[k]]), cfg.n_out, k, n_slots, bf(o_whT),
-                                bf(o_whkm), f(o_biasp), s));
-  if (tc_enc) DCA_TRY(transpose_w1_shadow(pp(lay[0].W), cfg.n_in, bf(o_w1t), s));
-  return DCA_OK;
+  if (!tc_heads && !tc_enc) return DCA_OK;
+  const float* W[3] = {nullptr, nullptr, nullptr}; const float* b[3] = {nullptr, nullptr, nullptr};
+  for (int k = 0; k < n_slots; ++k) { W[k] = pp(head_W[slot_head[k]]); b[k] = pp(head_b[slot_head[k]]); }
+  return refresh_all_shadows(W, b, n_slots, cfg.n_out, tc_heads ? bf(o_whT) : nullptr, tc_heads ? bf(o_whkm) : nullptr,
+                             tc_heads ? f(o_biasp) : nullptr, tc_enc ? pp(lay[0].W) : nullptr, cfg.n_in,
+                             tc_enc ? bf(o_w1t) : nullptr, s);
 }
 
 int Engine::init_params(uint64_t seed, cudaStream_t s) {

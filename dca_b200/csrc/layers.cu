@@ -388,6 +388,58 @@ int fill_value(float* p, int64_t n, float v, cudaStream_t s) {
   return DCA_OK;
 }
 
+// all operand shadows in ONE launch: blocks [0, n_slots*gt) pack head tiles, the rest transpose W1
+struct ShadowJob {
+  const float* W[3]; const float* b[3]; int n_slots, G, gt;
+  __nv_bfloat16* whT; __nv_bfloat16* whkm; float* biasp;
+  const float* W1; int n_in; __nv_bfloat16* w1t;
+};
+__global__ void refresh_shadows_kernel(const ShadowJob j) {
+  __shared__ float t[64][65];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int head_blocks = j.whT ? j.n_slots * j.gt : 0;
+  if ((int)blockIdx.x < head_blocks) {
+    const int slot = blockIdx.x / j.gt, g0 = (blockIdx.x % j.gt) * 64, G = j.G;
+    const float* W = j.W[slot];
+    for (int k = ty; k < 64; k += 4) {
+      const int g = g0 + tx;
+      const float v = (g < G) ? W[(int64_t)k * G + g] : 0.f;
+      t[k][tx] = v;
+      if (g < G) j.whkm[(int64_t)k * j.n_slots * G + (int64_t)slot * G + g] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    for (int gi = ty; gi < 64; gi += 4) {
+      const int g = g0 + gi;
+      if (g < G) j.whT[((int64_t)slot * G + g) * 64 + tx] = __float2bfloat16_rn(t[tx][gi]);
+    }
+    if (threadIdx.x < 64 && g0 + threadIdx.x < G) j.biasp[(int64_t)slot * G + g0 + threadIdx.x] = j.b[slot][g0 + threadIdx.x];
+  } else {
+    const int g0 = (blockIdx.x - head_blocks) * 64;
+    for (int gi = ty; gi < 64; gi += 4) {
+      const int g = g0 + gi;
+      t[gi][tx] = (g < j.n_in) ? j.W1[(int64_t)g * 64 + tx] : 0.f;
+    }
+    __syncthreads();
+    for (int f = ty; f < 64; f += 4) {
+      const int g = g0 + tx;
+      if (g < j.n_in) j.w1t[(int64_t)f * j.n_in + g] = __float2bfloat16_rn(t[tx][f]);
+    }
+  }
+}
+
+int refresh_all_shadows(const float* const W[3], const float* const b[3], int n_slots, int G, __nv_bfloat16* whT,
+                        __nv_bfloat16* whkm, float* biasp, const float* W1, int n_in, __nv_bfloat16* w1t, cudaStream_t s) {
+  ShadowJob j{};
+  for (int i = 0; i < 3; ++i) { j.W[i] = W ? W[i] : nullptr; j.b[i] = b ? b[i] : nullptr; }
+  j.n_slots = n_slots; j.G = G; j.gt = cdiv(G, 64); j.whT = whT; j.whkm = whkm; j.biasp = biasp;
+  j.W1 = W1; j.n_in = n_in; j.w1t = w1t;
+  const int blocks = (whT ? n_slots * j.gt : 0) + (w1t ? cdiv(n_in, 64) : 0);
+  if (blocks == 0) return DCA_OK;
+  refresh_shadows_kernel<<<blocks, 256, 0, s>>>(j);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
 int pack_head_shadows(const float* W, const float* b, int G, int slot, int nslots, __nv_bfloat16* whT,
                       __nv_bfloat16* whkm, float* biasp, cudaStream_t s) {
   pack_heads_kernel<<<cdiv(G, 64), 256, 0, s>>>(W, b, G, slot, nslots, whT, whkm, biasp);
