@@ -267,13 +267,16 @@ def main():
     eng.profile(False)
     peak, peak_src = measured_peaks()
     nh = 3
+    einfo = eng.info()
     loss_ms, loss_n = prof["loss_fwd_bwd"]
-    loss_bytes = batch * genes * (4 + 4 * nh + 4 * nh)          # y + m,d,pi in, dzm,dzd,dzp out (fp32), SURVEY 8d
+    # y (4 B) + m, d, pi in (fp32) + dzm, dzd, dzp out (fp32 generic path | bf16 tcgen05 path) -- SURVEY 8d
+    loss_bytes = batch * genes * (4 + 4 * nh + einfo["grad_bytes"] * nh)
     ach = loss_bytes / (loss_ms / max(loss_n, 1) * 1e-3) / 1e9 if loss_ms > 0 else None
     step_ms_prof = sum(v[0] for v in prof.values()) / max(a.steps, 1)
     roofline = {"kernel": "zinb_loss_kernel (phase loss_fwd_bwd: K3 + partial folds)", "bound": "hbm", "achieved": ach,
                 "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": loss_bytes,
+                "bytes_per_element": 4 + 4 * nh + einfo["grad_bytes"] * nh, "engine": einfo,
                 "share_of_step": (loss_ms / max(loss_n, 1)) / step_ms_prof if step_ms_prof > 0 else None}
     phases = {k: (v[0] / max(v[1], 1)) for k, v in prof.items()}
 

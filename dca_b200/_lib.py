@@ -80,6 +80,7 @@ PROTOTYPES = {
                                _vp, _vp]),
     "dca_profile_enable": (C.c_int, [_vp, _i32]),
     "dca_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double * 6), C.POINTER(C.c_int64 * 6), _i32]),
+    "dca_engine_info": (C.c_int, [_vp, C.POINTER(_i32 * 8)]),
     "dca_launch_count": (C.c_int64, []),
 }
 

@@ -30,7 +30,8 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n, unsigned
       __threadfence();
       atomicAdd(&bar[1], 1u);
     } else {
-      while (*reinterpret_cast<volatile unsigned*>(&bar[1]) == gen) { __nanosleep(20); }
+      unsigned cur;
+      do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&bar[1]) : "memory"); } while (cur == gen);
     }
     __threadfence();
   }
@@ -48,19 +49,24 @@ __device__ __forceinline__ void cta_col_sums(float (*x)[kMaxW + 1], float (*y)[k
     for (int r = g; r < rows; r += 4) { const double a = x[r][c]; s1 += a; s2 += a * (double)y[r][c]; }
   red[g][c] = s1; red[4 + g][c] = s2;
   __syncthreads();
+  // partial layout: [stat k][column c][cta]  (so that the fold reads contiguous CTAs per column)
   if (threadIdx.x < 64 && c < w) {
-    out[c] = red[0][c] + red[1][c] + red[2][c] + red[3][c];
-    out[kMaxW + c] = red[4][c] + red[5][c] + red[6][c] + red[7][c];
+    out[(size_t)c * kMaxCtas] = red[0][c] + red[1][c] + red[2][c] + red[3][c];
+    out[(size_t)(kMaxW + c) * kMaxCtas] = red[4][c] + red[5][c] + red[6][c] + red[7][c];
   }
 }
 
+// tot[k][c] = sum over CTAs; one warp per (k, c) pair at a time, lanes over CTAs (kMaxCtas = 64 -> 2 loads per lane)
 __device__ __forceinline__ void fold_partials(const double* partial, int n_ctas, int w, double* tot /* smem [2][kMaxW] */) {
-  if (threadIdx.x < 2 * kMaxW) {
-    const int c = threadIdx.x & 63, k = threadIdx.x >> 6;
-    double s = 0.0;
-    if (c < w)
-      for (int i = 0; i < n_ctas; ++i) s += partial[(size_t)i * 2 * kMaxW + k * kMaxW + c];
-    tot[k * kMaxW + c] = s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pair = warp; pair < 2 * kMaxW; pair += kThreads / 32) {
+    const int c = pair & 63;
+    if (c >= w) continue;
+    const double* src = partial + (size_t)pair * kMaxCtas;
+    double s = (lane < n_ctas ? src[lane] : 0.0) + (lane + 32 < n_ctas ? src[lane + 32] : 0.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) tot[pair] = s;
   }
   __syncthreads();
 }
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
     if (p.batchnorm) {
       if (p.training) {
         double* part = p.partial + (size_t)(l & 1) * kMaxCtas * 2 * kMaxW;       // double-buffered across layers
-        cta_col_sums(a, a, rows, w, part + (size_t)blockIdx.x * 2 * kMaxW, red);
+        cta_col_sums(a, a, rows, w, part + blockIdx.x, red);
         grid_barrier(p.bar, gridDim.x, gen);
         fold_partials(part, gridDim.x, w, tot);
         if (threadIdx.x < w) {
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
     __syncthreads();
     if (p.batchnorm) {
       double* part = p.partial + (size_t)(l & 1) * kMaxCtas * 2 * kMaxW;
-      cta_col_sums(g, xh, rows, w, part + (size_t)blockIdx.x * 2 * kMaxW, red);
+      cta_col_sums(g, xh, rows, w, part + blockIdx.x, red);
       grid_barrier(p.bar, gridDim.x, gen);
       fold_partials(part, gridDim.x, w, tot);
       if (blockIdx.x == 0 && threadIdx.x < w) p.gbeta[l][threadIdx.x] = (float)tot[threadIdx.x];   // d beta = sum(g)

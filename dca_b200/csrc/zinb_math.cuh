@@ -64,20 +64,30 @@ DCA_HD float digamma_corr(float x) {
   return -0.5f * r - r2 * (0.0833333333f - r2 * (0.00833333333f - r2 * 0.00396825397f));
 }
 
-// log prod_{k<n}(x+k) and sum_{k<n} 1/(x+k) via the product / derivative recurrence,
-// flushed every 4 factors so the product cannot overflow (x <= 1e4+16)
+// log prod_{k<n}(x+k) and sum_{k<n} 1/(x+k): factors are multiplied four at a time (the product of four
+// factors <= (1e4+16)^4 cannot overflow), one lg2 + one rcp per group:
+//   1/t0+1/t1+1/t2+1/t3 = ((t0+t1) t2 t3 + t0 t1 (t2+t3)) / (t0 t1 t2 t3)
 template <class Ops>
 DCA_HD void rising_log_and_recsum(float x, int n, float& logprod, float& recsum) {
-  float P = 1.f, dP = 0.f;
-  logprod = 0.f; recsum = 0.f;
-  for (int k = 0; k < n; ++k) {
-    const float t = x + (float)k;
-    dP = fmaf(dP, t, P);
-    P *= t;
-    if ((k & 3) == 3) { logprod += Ops::lg2(P); recsum = fmaf(dP, Ops::rcp(P), recsum); P = 1.f; dP = 0.f; }
+  float lg = 0.f, rs = 0.f;
+  int k = 0;
+  for (; k + 4 <= n; k += 4) {
+    const float t0 = x + (float)k, t1 = t0 + 1.0f, t2 = t0 + 2.0f, t3 = t0 + 3.0f;
+    const float a = t0 * t1, b = t2 * t3, P = a * b;
+    lg += Ops::lg2(P);
+    rs = fmaf(fmaf(t0 + t1, b, a * (t2 + t3)), Ops::rcp(P), rs);
   }
-  if (n & 3) { logprod += Ops::lg2(P); recsum = fmaf(dP, Ops::rcp(P), recsum); }
-  logprod *= kLn2;
+  const int rem = n - k;
+  if (rem > 0) {
+    const float t0 = x + (float)k, t1 = t0 + 1.0f, t2 = t0 + 2.0f;
+    float P = t0, num = 1.0f;
+    if (rem >= 2) { num = t0 + t1; P = t0 * t1; }
+    if (rem == 3) { num = fmaf(num, t2, P); P *= t2; }
+    lg += Ops::lg2(P);
+    rs = fmaf(num, Ops::rcp(P), rs);
+  }
+  logprod = lg * kLn2;
+  recsum = rs;
 }
 
 // lgamma(y+1), y >= 0   (only the loss VALUE needs it; it has no gradient)
@@ -166,8 +176,11 @@ DCA_HD void finish_elem(Elem& o, float dth, float dpi, float m, float th, float 
     o.gd = dth;
   }
   if (HAS_PI) {
-    o.loss = fmaf(ridge * pi, pi, o.loss);                 // loss.py:139-140
-    o.gp = (dpi + 2.0f * ridge * pi) * (pi * (1.0f - pi));
+    if (ridge != 0.f) {                                    // loss.py:139-140 (uniform branch; ridge defaults to 0)
+      o.loss = fmaf(ridge * pi, pi, o.loss);
+      dpi = fmaf(2.0f * ridge, pi, dpi);
+    }
+    o.gp = dpi * (pi * (1.0f - pi));
   } else {
     o.gp = 0.f;
   }

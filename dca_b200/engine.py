@@ -231,6 +231,12 @@ class DeviceEngine:
         check(self.lib.dca_profile_read(self.handle, C.byref(ms), C.byref(cnt), int(reset)), "dca_profile_read")
         return {p: (ms[i], int(cnt[i])) for i, p in enumerate(self.PHASES)}
 
+    def info(self):
+        a = (C.c_int32 * 8)()
+        check(self.lib.dca_engine_info(self.handle, C.byref(a)), "dca_engine_info")
+        return {"tc_heads": bool(a[0]), "tc_encoder": bool(a[1]), "fused_hidden": bool(a[2]), "head_slots": a[3],
+                "sm_count": a[4], "grad_bytes": a[5]}
+
     @property
     def latent_dim(self):
         return self.hidden[len(self.hidden) // 2] if self.hidden else 0
