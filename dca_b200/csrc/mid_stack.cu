@@ -18,20 +18,26 @@ namespace dca {
 namespace mid {
 
 constexpr int kThreads = 256;
+constexpr int kGenWord = 32;       // generation counter lives 128 bytes after the arrival counter
 
 // Self-resetting sense-reversal barrier over the whole (co-resident) grid.
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n, unsigned& gen) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
+    // bar[0] = arrival count, bar[kGenWord] = generation (separate 128-byte lines: pollers do not slow arrivals)
     const unsigned arrived = atomicAdd(&bar[0], 1u);
     if (arrived == n - 1) {
       bar[0] = 0;
       __threadfence();
-      atomicAdd(&bar[1], 1u);
+      atomicAdd(&bar[kGenWord], 1u);
     } else {
       unsigned cur;
-      do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&bar[1]) : "memory"); } while (cur == gen);
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&bar[kGenWord]) : "memory");
+        if (cur != gen) break;
+        __nanosleep(40);
+      }
     }
     __threadfence();
   }
@@ -56,18 +62,20 @@ __device__ __forceinline__ void cta_col_sums(float (*x)[kMaxW + 1], float (*y)[k
   }
 }
 
-// tot[k][c] = sum over CTAs; one warp per (k, c) pair at a time, lanes over CTAs (kMaxCtas = 64 -> 2 loads per lane)
+// tot[k][c] = sum over CTAs in a fixed order (deterministic).  Thread t owns pair t/2 and half t%2 of the
+// CTA axis: 32 independent, contiguous 8-byte loads in flight per thread, then one shuffle to join the halves.
 __device__ __forceinline__ void fold_partials(const double* partial, int n_ctas, int w, double* tot /* smem [2][kMaxW] */) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int pair = warp; pair < 2 * kMaxW; pair += kThreads / 32) {
-    const int c = pair & 63;
-    if (c >= w) continue;
-    const double* src = partial + (size_t)pair * kMaxCtas;
-    double s = (lane < n_ctas ? src[lane] : 0.0) + (lane + 32 < n_ctas ? src[lane + 32] : 0.0);
+  const int pair = threadIdx.x >> 1, half = threadIdx.x & 1;       // 256 threads -> 128 pairs x 2 halves
+  const int c = pair & 63;
+  double v[32];
+  const double* src = partial + (size_t)pair * kMaxCtas + half * 32;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) tot[pair] = s;
-  }
+  for (int i = 0; i < 32; ++i) v[i] = (c < w && half * 32 + i < n_ctas) ? src[i] : 0.0;
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += v[i];
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (half == 0) tot[pair] = s;
   __syncthreads();
 }
 
@@ -107,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
   float* s_mean = fbase + 2 * kStripFloats + kWsFloats;
   float* s_inv = s_mean + kMaxW;
   __shared__ unsigned s_gen;
-  if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile unsigned*>(&p.bar[1]);
+  if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile unsigned*>(&p.bar[kGenWord]);
   __syncthreads();
   unsigned gen = s_gen;
 
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
   Strip* xh = reinterpret_cast<Strip*>(fbase + kStripFloats);         // x_hat strip / previous activation strip
   Strip* Ws = reinterpret_cast<Strip*>(fbase + 2 * kStripFloats);
   __shared__ unsigned s_gen;
-  if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile unsigned*>(&p.bar[1]);
+  if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile unsigned*>(&p.bar[kGenWord]);
   __syncthreads();
   unsigned gen = s_gen;
 
