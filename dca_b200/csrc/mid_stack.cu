@@ -123,11 +123,11 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
   const int rows = max(0, min(p.rows_per_cta, p.B - row0));
   for (int i = threadIdx.x; i < (int)kStripFloats; i += kThreads) { (&cur[0][0])[i] = 0.f; (&nxt[0][0])[i] = 0.f; }
   __syncthreads();
+  // thread -> (column tc, row lane tr): no integer divisions in the element loops (widths <= 64)
+  const int tc = threadIdx.x & 63, tr = threadIdx.x >> 6;
   // load a_0 strip
-  for (int i = threadIdx.x; i < rows * p.w[0]; i += kThreads) {
-    const int r = i / p.w[0], c = i % p.w[0];
-    cur[r][c] = p.a0[(size_t)(row0 + r) * p.w[0] + c];
-  }
+  if (tc < p.w[0])
+    for (int r = tr; r < rows; r += 4) cur[r][tc] = p.a0[(size_t)(row0 + r) * p.w[0] + tc];
   __syncthreads();
   Strip* a = cur;
   Strip* o = nxt;
@@ -135,14 +135,15 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
     const int w = p.w[l];
     if (l > 0) {
       const int win = p.w[l - 1];
-      for (int i = threadIdx.x; i < win * w; i += kThreads) Ws[i / w][i % w] = p.W[l][i];
+      if (tc < w)
+        for (int k = tr; k < win; k += 4) Ws[k][tc] = p.W[l][(size_t)k * w + tc];
       __syncthreads();
       strip_gemm(a, Ws, p.b[l], rows, win, w, o);
       __syncthreads();
       Strip* t = a; a = o; o = t;
     }
-    if (l == p.center && p.a_center && !(l == 0 && p.a_center == p.a0))
-      for (int i = threadIdx.x; i < rows * w; i += kThreads) p.a_center[(size_t)(row0 + i / w) * w + i % w] = a[i / w][i % w];
+    if (l == p.center && p.a_center && !(l == 0 && p.a_center == p.a0) && tc < w)
+      for (int r = tr; r < rows; r += 4) p.a_center[(size_t)(row0 + r) * w + tc] = a[r][tc];
     if (p.batchnorm) {
       if (p.training) {
         double* part = p.partial + (size_t)(l & 1) * kMaxCtas * 2 * kMaxW;       // double-buffered across layers
@@ -169,18 +170,22 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
       }
     }
     const bool last = (l == p.L - 1);
-    for (int i = threadIdx.x; i < rows * w; i += kThreads) {
-      const int r = i / w, c = i % w;
-      float v = a[r][c];
-      if (p.batchnorm) {
-        const float xh = (v - s_mean[c]) * s_inv[c];
-        if (p.training) p.xhat[l][(size_t)(row0 + r) * w + c] = xh;
-        v = xh + p.beta[l][c];
+    if (tc < w) {
+      const float mean_c = p.batchnorm ? s_mean[tc] : 0.f, inv_c = p.batchnorm ? s_inv[tc] : 1.f;
+      const float beta_c = p.batchnorm ? p.beta[l][tc] : 0.f;
+      for (int r = tr; r < rows; r += 4) {
+        const size_t gi = (size_t)(row0 + r) * w + tc;
+        float v = a[r][tc];
+        if (p.batchnorm) {
+          const float xh = (v - mean_c) * inv_c;
+          if (p.training) p.xhat[l][gi] = xh;
+          v = xh + beta_c;
+        }
+        v = fmaxf(v, 0.f);
+        a[r][tc] = v;
+        p.h[l][gi] = v;
+        if (last && p.h_last_bf16) p.h_last_bf16[gi] = __float2bfloat16_rn(v);
       }
-      v = fmaxf(v, 0.f);
-      a[r][c] = v;
-      p.h[l][(size_t)(row0 + r) * w + c] = v;
-      if (last && p.h_last_bf16) p.h_last_bf16[(size_t)(row0 + r) * w + c] = __float2bfloat16_rn(v);
     }
     __syncthreads();
   }
@@ -202,21 +207,27 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
   const int row0 = blockIdx.x * p.rows_per_cta;
   const int rows = max(0, min(p.rows_per_cta, p.B - row0));
   for (int i = threadIdx.x; i < (int)kStripFloats; i += kThreads) { (&g[0][0])[i] = 0.f; (&xh[0][0])[i] = 0.f; }
+  for (int i = threadIdx.x; i < (int)kWsFloats; i += kThreads) (&Ws[0][0])[i] = 0.f;
   __syncthreads();
+  const int tc = threadIdx.x & 63, tr = threadIdx.x >> 6;
+  float* s_mg = reinterpret_cast<float*>(Ws);          // per-column means of the BN backward (Ws is free at that point)
   {
     const int w = p.w[p.L - 1];
-    for (int i = threadIdx.x; i < rows * w; i += kThreads) g[i / w][i % w] = p.dh_last[(size_t)(row0 + i / w) * w + i % w];
+    if (tc < w)
+      for (int r = tr; r < rows; r += 4) g[r][tc] = p.dh_last[(size_t)(row0 + r) * w + tc];
   }
   __syncthreads();
   for (int l = p.L - 1; l >= 0; --l) {
     const int w = p.w[l];
     // relu mask (+ load x_hat)
-    for (int i = threadIdx.x; i < rows * w; i += kThreads) {
-      const int r = i / w, c = i % w;
-      const size_t gi = (size_t)(row0 + r) * w + c;
-      if (!(p.h[l][gi] > 0.f)) g[r][c] = 0.f;
-      if (p.batchnorm) xh[r][c] = p.xhat[l][gi];
-    }
+    if (tc < w)
+      for (int r = tr; r < rows; r += 4) {
+        const size_t gi = (size_t)(row0 + r) * w + tc;
+        const float hv = p.h[l][gi];
+        const float xv = p.batchnorm ? p.xhat[l][gi] : 0.f;
+        if (!(hv > 0.f)) g[r][tc] = 0.f;
+        xh[r][tc] = xv;
+      }
     __syncthreads();
     if (p.batchnorm) {
       double* part = p.partial + (size_t)(l & 1) * kMaxCtas * 2 * kMaxW;
@@ -224,10 +235,15 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
       grid_barrier(p.bar, gridDim.x, gen);
       fold_partials(part, gridDim.x, w, tot);
       if (blockIdx.x == 0 && threadIdx.x < w) p.gbeta[l][threadIdx.x] = (float)tot[threadIdx.x];   // d beta = sum(g)
-      for (int i = threadIdx.x; i < rows * w; i += kThreads) {
-        const int r = i / w, c = i % w;
-        const float mg = (float)(tot[c] / (double)p.B), mgx = (float)(tot[kMaxW + c] / (double)p.B);
-        g[r][c] = p.inv[l][c] * (g[r][c] - mg - xh[r][c] * mgx);
+      if (threadIdx.x < w) {
+        s_mg[threadIdx.x] = (float)(tot[threadIdx.x] / (double)p.B);
+        s_mg[kMaxW + threadIdx.x] = (float)(tot[kMaxW + threadIdx.x] / (double)p.B);
+        s_mg[2 * kMaxW + threadIdx.x] = p.inv[l][threadIdx.x];
+      }
+      __syncthreads();
+      if (tc < w) {
+        const float mg = s_mg[tc], mgx = s_mg[kMaxW + tc], inv_c = s_mg[2 * kMaxW + tc];
+        for (int r = tr; r < rows; r += 4) g[r][tc] = inv_c * (g[r][tc] - mg - xh[r][tc] * mgx);
       }
       __syncthreads();
     }
@@ -242,37 +258,40 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
       __syncthreads();
     }
     if (l == 0) {
-      for (int i = threadIdx.x; i < rows * w; i += kThreads) {
-        const int r = i / w, c = i % w;
-        const size_t gi = (size_t)(row0 + r) * w + c;
-        if (p.da0) p.da0[gi] = g[r][c];
-        if (p.da0_bf16) p.da0_bf16[gi] = __float2bfloat16_rn(g[r][c]);
-      }
+      if (tc < w)
+        for (int r = tr; r < rows; r += 4) {
+          const size_t gi = (size_t)(row0 + r) * w + tc;
+          if (p.da0) p.da0[gi] = g[r][tc];
+          if (p.da0_bf16) p.da0_bf16[gi] = __float2bfloat16_rn(g[r][tc]);
+        }
       break;
     }
     // ---- inner layer l >= 1: dW_l += h_{l-1}^T . da ;  dh_{l-1} = da . W_l^T
     const int win = p.w[l - 1];
-    for (int i = threadIdx.x; i < rows * win; i += kThreads) xh[i / win][i % win] = p.h[l - 1][(size_t)(row0 + i / win) * win + i % win];
-    for (int i = threadIdx.x; i < win * w; i += kThreads) Ws[i / w][i % w] = p.W[l][i];
+    if (tc < win)
+      for (int r = tr; r < rows; r += 4) xh[r][tc] = p.h[l - 1][(size_t)(row0 + r) * win + tc];
+    if (tc < w)
+      for (int k = tr; k < win; k += 4) Ws[k][tc] = p.W[l][(size_t)k * w + tc];
     __syncthreads();
-    for (int i = threadIdx.x; i < win * w; i += kThreads) {          // dW[k][c] = sum_r h[r][k] * da[r][c]
-      const int k = i / w, c = i % w;
-      float s = 0.f;
-      for (int r = 0; r < rows; ++r) s = fmaf(xh[r][k], g[r][c], s);
-      atomicAdd(&p.gW[l][i], s);
-    }
+    if (tc < w)
+      for (int k = tr; k < win; k += 4) {                             // dW[k][c] = sum_r h[r][k] * da[r][c]
+        float s0 = 0.f, s1 = 0.f;
+        for (int r = 0; r < rows; r += 2) { s0 = fmaf(xh[r][k], g[r][tc], s0); s1 = fmaf(xh[r + 1][k], g[r + 1][tc], s1); }
+        atomicAdd(&p.gW[l][(size_t)k * w + tc], s0 + s1);             // rows beyond `rows` hold zeros
+      }
     __syncthreads();
     // dh_{l-1}[r][k] = sum_c da[r][c] * W[k][c]  -> write into xh, then swap roles
-    for (int i = threadIdx.x; i < rows * win; i += kThreads) {
-      const int r = i / win, k = i % win;
-      float s = 0.f;
-      for (int c = 0; c < w; ++c) s = fmaf(g[r][c], Ws[k][c], s);
-      xh[r][k] = s;
-    }
+    if (tc < win)
+      for (int r = tr; r < rows; r += 4) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int c = 0; c < w; c += 2) { s0 = fmaf(g[r][c], Ws[tc][c], s0); s1 = fmaf(g[r][c + 1], Ws[tc][c + 1], s1); }
+        xh[r][tc] = s0 + s1;                                          // padded columns of g / Ws are zero
+      }
     __syncthreads();
     for (int i = threadIdx.x; i < (int)kStripFloats; i += kThreads) (&g[0][0])[i] = 0.f;
     __syncthreads();
-    for (int i = threadIdx.x; i < rows * win; i += kThreads) g[i / win][i % win] = xh[i / win][i % win];
+    if (tc < win)
+      for (int r = tr; r < rows; r += 4) g[r][tc] = xh[r][tc];
     __syncthreads();
   }
 }
