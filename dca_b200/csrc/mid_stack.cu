@@ -19,6 +19,9 @@ namespace mid {
 
 constexpr int kThreads = 256;
 constexpr int kGenWord = 32;       // generation counter lives 128 bytes after the arrival counter
+constexpr int kStripStride = kMaxW + 4;   // activation strips: rows 16-byte aligned (float4 broadcasts along k)
+typedef float Strip[kStripStride];        // lanes always differ in the COLUMN of a strip -> no bank conflicts
+typedef float WRow[kMaxW + 1];            // weights: lanes differ in the ROW -> odd stride
 
 // Self-resetting sense-reversal barrier over the whole (co-resident) grid.
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n, unsigned& gen) {
@@ -46,7 +49,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n, unsigned
 }
 
 // column sums over this CTA's rows of s1 = sum(x) and s2 = sum(x*y) (double), x,y in smem [rows][kMaxW]
-__device__ __forceinline__ void cta_col_sums(float (*x)[kMaxW + 1], float (*y)[kMaxW + 1], int rows, int w,
+__device__ __forceinline__ void cta_col_sums(Strip* x, Strip* y, int rows, int w,
                                              double* out /* [2][kMaxW] global */, double (*red)[kMaxW]) {
   // 256 threads: 4 row-groups x 64 columns
   const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
@@ -79,19 +82,22 @@ __device__ __forceinline__ void fold_partials(const double* partial, int n_ctas,
   __syncthreads();
 }
 
-// out[r][c] = sum_k in[r][k] * W[k][c] (+ bias[c]); W in smem as [w_in][kMaxW+1]
-__device__ __forceinline__ void strip_gemm(float (*in)[kMaxW + 1], float (*Ws)[kMaxW + 1], const float* bias,
-                                           int rows, int w_in, int w_out, float (*out)[kMaxW + 1]) {
+// out[r][c] = sum_k in[r][k] * W[k][c] (+ bias[c]).  Thread = column c, 4 rows at a time; k in groups of 4 with
+// one 128-bit broadcast load per row: 8 shared loads per 16 FMA.  Padded rows / columns of `in` are zero.
+__device__ __forceinline__ void strip_gemm(Strip* in, WRow* Ws, const float* bias, int rows, int w_in, int w_out, Strip* out) {
   const int c = threadIdx.x & 63, g = threadIdx.x >> 6;      // 4 row groups
   if (c < w_out) {
+    const float bv = bias ? bias[c] : 0.f;
     for (int r0 = g * 4; r0 < rows; r0 += 16) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int k = 0; k < w_in; ++k) {
-        const float wv = Ws[k][c];
+      for (int k = 0; k < w_in; k += 4) {
+        const float w0 = Ws[k][c], w1 = Ws[k + 1][c], w2 = Ws[k + 2][c], w3 = Ws[k + 3][c];   // rows >= w_in are zero
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = fmaf(in[r0 + j][k], wv, acc[j]);   // rows beyond `rows` hold zeros
+        for (int j = 0; j < 4; ++j) {
+          const float4 x = *reinterpret_cast<const float4*>(&in[r0 + j][k]);
+          acc[j] = fmaf(x.x, w0, fmaf(x.y, w1, fmaf(x.z, w2, fmaf(x.w, w3, acc[j]))));
+        }
       }
-      const float bv = bias ? bias[c] : 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (r0 + j < rows) out[r0 + j][c] = acc[j] + bv;
@@ -99,8 +105,7 @@ __device__ __forceinline__ void strip_gemm(float (*in)[kMaxW + 1], float (*Ws)[k
   }
 }
 
-typedef float Strip[kMaxW + 1];
-constexpr size_t kStripFloats = (size_t)(kMaxRows + 4) * (kMaxW + 1);
+constexpr size_t kStripFloats = (size_t)(kMaxRows + 4) * kStripStride;
 constexpr size_t kWsFloats = (size_t)kMaxW * (kMaxW + 1);
 constexpr size_t kSmemBytes = sizeof(double) * (8 * kMaxW + 2 * kMaxW) + sizeof(float) * (2 * kStripFloats + kWsFloats + 2 * kMaxW) + 16;
 
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
   float* fbase = reinterpret_cast<float*>(tot + 2 * kMaxW);
   Strip* cur = reinterpret_cast<Strip*>(fbase);                       // current layer pre-activation / activation strip
   Strip* nxt = reinterpret_cast<Strip*>(fbase + kStripFloats);
-  Strip* Ws = reinterpret_cast<Strip*>(fbase + 2 * kStripFloats);
+  WRow* Ws = reinterpret_cast<WRow*>(fbase + 2 * kStripFloats);
   float* s_mean = fbase + 2 * kStripFloats + kWsFloats;
   float* s_inv = s_mean + kMaxW;
   __shared__ unsigned s_gen;
@@ -122,6 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
   const int row0 = blockIdx.x * p.rows_per_cta;
   const int rows = max(0, min(p.rows_per_cta, p.B - row0));
   for (int i = threadIdx.x; i < (int)kStripFloats; i += kThreads) { (&cur[0][0])[i] = 0.f; (&nxt[0][0])[i] = 0.f; }
+  for (int i = threadIdx.x; i < (int)kWsFloats; i += kThreads) (&Ws[0][0])[i] = 0.f;
   __syncthreads();
   // thread -> (column tc, row lane tr): no integer divisions in the element loops (widths <= 64)
   const int tc = threadIdx.x & 63, tr = threadIdx.x >> 6;
@@ -135,8 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
     const int w = p.w[l];
     if (l > 0) {
       const int win = p.w[l - 1];
-      if (tc < w)
-        for (int k = tr; k < win; k += 4) Ws[k][tc] = p.W[l][(size_t)k * w + tc];
+      for (int k = tr; k < kMaxW; k += 4) Ws[k][tc] = (k < win && tc < w) ? p.W[l][(size_t)k * w + tc] : 0.f;
       __syncthreads();
       strip_gemm(a, Ws, p.b[l], rows, win, w, o);
       __syncthreads();
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
   float* fbase = reinterpret_cast<float*>(tot + 2 * kMaxW);
   Strip* g = reinterpret_cast<Strip*>(fbase);                         // gradient strip of the current layer
   Strip* xh = reinterpret_cast<Strip*>(fbase + kStripFloats);         // x_hat strip / previous activation strip
-  Strip* Ws = reinterpret_cast<Strip*>(fbase + 2 * kStripFloats);
+  WRow* Ws = reinterpret_cast<WRow*>(fbase + 2 * kStripFloats);
   __shared__ unsigned s_gen;
   if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile unsigned*>(&p.bar[kGenWord]);
   __syncthreads();
@@ -270,23 +275,49 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
     const int win = p.w[l - 1];
     if (tc < win)
       for (int r = tr; r < rows; r += 4) xh[r][tc] = p.h[l - 1][(size_t)(row0 + r) * win + tc];
-    if (tc < w)
-      for (int k = tr; k < win; k += 4) Ws[k][tc] = p.W[l][(size_t)k * w + tc];
+    for (int k = tr; k < kMaxW; k += 4) Ws[k][tc] = (k < win && tc < w) ? p.W[l][(size_t)k * w + tc] : 0.f;
     __syncthreads();
+    // dW[k][c] = sum_r h[r][k] * da[r][c]: thread = column c and a group of 4 consecutive k (128-bit broadcast of h)
     if (tc < w)
-      for (int k = tr; k < win; k += 4) {                             // dW[k][c] = sum_r h[r][k] * da[r][c]
-        float s0 = 0.f, s1 = 0.f;
-        for (int r = 0; r < rows; r += 2) { s0 = fmaf(xh[r][k], g[r][tc], s0); s1 = fmaf(xh[r + 1][k], g[r + 1][tc], s1); }
-        atomicAdd(&p.gW[l][(size_t)k * w + tc], s0 + s1);             // rows beyond `rows` hold zeros
+      for (int k0 = tr * 4; k0 < win; k0 += 16) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < rows; ++r) {
+          const float gv = g[r][tc];
+          const float4 hv = *reinterpret_cast<const float4*>(&xh[r][k0]);
+          s[0] = fmaf(hv.x, gv, s[0]); s[1] = fmaf(hv.y, gv, s[1]); s[2] = fmaf(hv.z, gv, s[2]); s[3] = fmaf(hv.w, gv, s[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (k0 + j < win) atomicAdd(&p.gW[l][(size_t)(k0 + j) * w + tc], s[j]);
       }
     __syncthreads();
-    // dh_{l-1}[r][k] = sum_c da[r][c] * W[k][c]  -> write into xh, then swap roles
-    if (tc < win)
-      for (int r = tr; r < rows; r += 4) {
-        float s0 = 0.f, s1 = 0.f;
-        for (int c = 0; c < w; c += 2) { s0 = fmaf(g[r][c], Ws[tc][c], s0); s1 = fmaf(g[r][c + 1], Ws[tc][c + 1], s1); }
-        xh[r][tc] = s0 + s1;                                          // padded columns of g / Ws are zero
+    // dh_{l-1}[r][k] = sum_c da[r][c] * W[k][c]: thread = k (= tc), 4 rows at a time, c in groups of 4
+    float dhv[4][4];                                                   // [row group][row in group]
+    if (tc < win) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r0 = tr * 4 + q * 16;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r0 < rows)
+          for (int c = 0; c < w; c += 4) {                             // padded columns of g / Ws are zero
+            const float w0 = Ws[tc][c], w1 = Ws[tc][c + 1], w2 = Ws[tc][c + 2], w3 = Ws[tc][c + 3];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 x = *reinterpret_cast<const float4*>(&g[r0 + j][c]);
+              acc[j] = fmaf(x.x, w0, fmaf(x.y, w1, fmaf(x.z, w2, fmaf(x.w, w3, acc[j]))));
+            }
+          }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dhv[q][j] = acc[j];
       }
+    }
+    __syncthreads();                                                   // all reads of xh (as h_{l-1}) and g are done
+    if (tc < win) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const int r = tr * 4 + q * 16 + j; if (r < rows) xh[r][tc] = dhv[q][j]; }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < (int)kStripFloats; i += kThreads) (&g[0][0])[i] = 0.f;
     __syncthreads();
