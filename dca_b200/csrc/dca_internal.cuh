@@ -118,6 +118,8 @@ struct LossArgs {
   float* dtheta;            // const-disp: [G] summed d/dtheta
   double* loss_sum;         // device scalar, overwritten (fwd_bwd) or accumulated (fwd)
   void* ws; size_t ws_bytes;
+  // optional fused finalize (engine): loss_slot[0] = loss_sum*inv_n (+penalty), [1] = non-finite flag, epoch acc update
+  float* fin_loss_slot = nullptr; double* fin_epoch_acc = nullptr; const double* fin_penalty = nullptr; int fin_batch = 0;
 };
 size_t loss_workspace_bytes(int B, int G);
 int zinb_loss_fwd_bwd(const LossArgs& a, cudaStream_t s);

@@ -384,8 +384,8 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
   }
   la.dtheta = cond ? nullptr : f(o_dtheta);
   la.loss_sum = d(o_acc) + 4; la.ws = base + o_lossws; la.ws_bytes = loss_ws_bytes;
+  la.fin_loss_slot = gp(P); la.fin_epoch_acc = d(o_acc); la.fin_penalty = any_pen ? d(o_acc) + 5 : nullptr; la.fin_batch = Bn;
   DCA_TRY(zinb_loss_fwd_bwd(la, s));
-  DCA_TRY(loss_finalize(d(o_acc) + 4, any_pen ? d(o_acc) + 5 : nullptr, inv_n, Bn, gp(P), d(o_acc), s));
   if (!cond) {
     // dtheta currently holds sum over rows of dL/dtheta (not / N)
     DCA_TRY(theta_grad_finish(f(o_dtheta), f(o_chain), G, inv_n, gp(theta_off), s));

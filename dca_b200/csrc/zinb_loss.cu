@@ -9,6 +9,8 @@
 // and a second tiny kernel folds the block partials (deterministic, no float atomics).
 #include "dca_internal.cuh"
 #include "zinb_math.cuh"
+#include "tc_common.cuh"
+#include <cstdlib>
 
 namespace dca {
 
@@ -18,11 +20,11 @@ constexpr int kThreads = 256;
 constexpr int kVec = 4;
 constexpr int kColsPerBlock = kThreads * kVec;   // 1024 genes per block
 constexpr int kTargetBlocks = 148 * 16;          // ~4 waves of 4 resident blocks per SM
-constexpr int kMaxBlocks = 8192;                 // bound of the per-block loss-partial buffer
+constexpr int kMaxBlocks = 65536;                // bound of the per-block loss-partial buffer
 
 struct Plan { int col_blocks, rows_per_block, row_chunks; };
 
-inline Plan make_plan(int B, int G, int cols_per_block) {
+inline Plan make_plan(int B, int G, int cols_per_block, int max_rpb = 1 << 30) {
   Plan p;
   p.col_blocks = cdiv(G, cols_per_block);
   int chunks = kTargetBlocks / p.col_blocks;
@@ -30,7 +32,8 @@ inline Plan make_plan(int B, int G, int cols_per_block) {
   if (chunks > B) chunks = B;
   int rpb = cdiv(B, chunks);
   if (rpb < 2 && B >= 2) rpb = 2;                // the software prefetch wants >= 2 rows per block
-  while ((long long)cdiv(B, rpb) * p.col_blocks > kMaxBlocks) ++rpb;
+  if (rpb > max_rpb) rpb = max_rpb;
+  while ((long long)cdiv(B, rpb) * p.col_blocks > kMaxBlocks && rpb < max_rpb) ++rpb;
   p.rows_per_block = rpb;
   p.row_chunks = cdiv(B, rpb);
   return p;
@@ -264,7 +267,176 @@ zinb_loss_bwd_compact_kernel(const float* __restrict__ Y, int64_t ldy, const int
   if (threadIdx.x == 0) loss_partial[blockIdx.y * gridDim.x + blockIdx.x] = tot;
 }
 
-__global__ void fold_partials_kernel(const double* __restrict__ part, int n, double* out, int accumulate) {
+// Same arithmetic, operands STAGED THROUGH SHARED MEMORY: one producer warp streams the block's rows with bulk
+// async copies (cp.async.bulk global->shared, one 16-byte-aligned row segment per tensor, completion on an
+// mbarrier) into a 3-deep ring, eight consumer warps read their 128-bit vectors from the ring.  The gather of
+// the count rows (rows[]) is free -- the producer simply points the copy at row rows[r] -- and the consumers
+// carry no address arithmetic or load latency, only the math, the warp compaction and the coalesced stores.
+constexpr int kStageRows = 3;
+constexpr int kMaxRowsPerBlock = 64;
+constexpr int kStagedThreads = kThreads + 32;      // 8 consumer warps + 1 producer warp
+
+template <bool COND_DISP, typename GT>
+__global__ void __launch_bounds__(kStagedThreads, 3)
+zinb_loss_bwd_staged_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __restrict__ rows,
+                            const float* __restrict__ sf, const float* m, const float* d, const float* pi,
+                            int64_t ld, int B, int G, float ridge, float inv_n, int rows_per_block,
+                            GT* dzm, GT* dzd, GT* dzp, float* __restrict__ dth_acc,
+                            double* __restrict__ loss_partial, const float* __restrict__ lf_global) {
+  extern __shared__ __align__(128) unsigned char smem_loss[];
+  constexpr int kArrays = COND_DISP ? 4 : 3;                           // y, m, [d], pi
+  constexpr uint32_t kArrBytes = kColsPerBlock * 4;                    // one row segment of one tensor
+  constexpr uint32_t kStageBytes = kArrays * kArrBytes;
+  float4* items = reinterpret_cast<float4*>(smem_loss + kStageRows * kStageBytes);   // [8 warps][128]
+  __shared__ double red[8];
+  __shared__ float lf[zmath::kLogFactN];
+  __shared__ float s_sf[kMaxRowsPerBlock];
+  __shared__ int s_row[kMaxRowsPerBlock];
+  __shared__ uint64_t full_bar[kStageRows], empty_bar[kStageRows];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * kColsPerBlock;
+  const int ncols = min(kColsPerBlock, G - c0);                        // multiple of 4 on this path
+  const int r0 = blockIdx.y * rows_per_block;
+  const int nrows = min(rows_per_block, B - r0);
+  if (threadIdx.x < zmath::kLogFactN) lf[threadIdx.x] = lf_global[threadIdx.x];
+  if (threadIdx.x < nrows) {
+    const int yr = rows ? rows[r0 + threadIdx.x] : (r0 + threadIdx.x);
+    s_row[threadIdx.x] = yr;
+    s_sf[threadIdx.x] = sf ? sf[yr] : 1.0f;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStageRows; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], kThreads / 32); }
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == kThreads / 32) {
+    // ===================================================== producer
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)ncols * 4u;
+      for (int i = 0; i < nrows; ++i) {
+        const int st = i % kStageRows; const uint32_t ph = (i / kStageRows) & 1;
+        tc::mbar_wait(&empty_bar[st], ph ^ 1);
+        unsigned char* dst = smem_loss + (size_t)st * kStageBytes;
+        tc::mbar_expect_tx(&full_bar[st], bytes * kArrays);
+        const int64_t off = (int64_t)(r0 + i) * ld + c0;
+        auto bulk = [&](unsigned char* to, const float* from) {
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(tc::smem_u32(to)), "l"(reinterpret_cast<uint64_t>(from)), "r"(bytes), "r"(tc::smem_u32(&full_bar[st])) : "memory");
+        };
+        bulk(dst, Y + (int64_t)s_row[i] * ldy + c0);
+        bulk(dst + kArrBytes, m + off);
+        if (COND_DISP) bulk(dst + 2 * kArrBytes, d + off);
+        bulk(dst + (kArrays - 1) * kArrBytes, pi + off);
+      }
+    }
+    return;
+  }
+
+  // ======================================================= consumers
+  using Ops = zmath::FastOps;
+  constexpr unsigned kFull = 0xffffffffu;
+  float4* q = items + warp * (32 * kVec);
+  const int col = threadIdx.x * kVec;                                  // column inside the block tile
+  const bool active = col < ncols;
+  float lsum = 0.f;
+  float tacc[kVec] = {0.f, 0.f, 0.f, 0.f};
+  float thg[kVec] = {1.f, 1.f, 1.f, 1.f};
+  if (!COND_DISP && active) {
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) thg[j] = d[c0 + col + j];
+  }
+  const unsigned lt = (1u << lane) - 1u;
+  GT* om = dzm + (int64_t)r0 * ld + c0 + col;
+  GT* od = COND_DISP ? dzd + (int64_t)r0 * ld + c0 + col : nullptr;
+  GT* op = dzp + (int64_t)r0 * ld + c0 + col;
+  for (int i = 0; i < nrows; ++i) {
+    const int st = i % kStageRows; const uint32_t ph = (i / kStageRows) & 1;
+    const unsigned char* src = smem_loss + (size_t)st * kStageBytes + (size_t)threadIdx.x * 16;
+    tc::mbar_wait(&full_bar[st], ph);
+    float4 vy = make_float4(0.f, 0.f, 0.f, 0.f), vm = vy, vd = vy, vp = vy;
+    if (active) {
+      vy = *reinterpret_cast<const float4*>(src);
+      vm = *reinterpret_cast<const float4*>(src + kArrBytes);
+      if (COND_DISP) vd = *reinterpret_cast<const float4*>(src + 2 * kArrBytes);
+      vp = *reinterpret_cast<const float4*>(src + (kArrays - 1) * kArrBytes);
+    }
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&empty_bar[st]);                    // operands are in registers: free the slot
+    const float y[kVec] = {vy.x, vy.y, vy.z, vy.w}, mm[kVec] = {vm.x, vm.y, vm.z, vm.w};
+    const float dd[kVec] = {COND_DISP ? vd.x : thg[0], COND_DISP ? vd.y : thg[1], COND_DISP ? vd.z : thg[2], COND_DISP ? vd.w : thg[3]};
+    const float pp[kVec] = {vp.x, vp.y, vp.z, vp.w};
+    const float row_sf = s_sf[i];
+    // ---- queue the non-zero counts of this warp's strip (ballot compaction: items ordered by j, then lane)
+    unsigned bal[kVec];
+    int nz = 0, pos[kVec], base = 0;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const bool is_nz = active && !(y[j] < 1e-8f);                    // loss.py:138
+      bal[j] = __ballot_sync(kFull, is_nz);
+      nz |= is_nz ? (1 << j) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) { pos[j] = base + __popc(bal[j] & lt); base += __popc(bal[j]); }
+    const int total = base;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j)
+      if (nz & (1 << j)) q[pos[j]] = make_float4(y[j], mm[j], dd[j], pp[j]);
+    __syncwarp();
+    // ---- zero branch for my own zero counts
+    float gm[kVec], gd[kVec], gp[kVec];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      gm[j] = gd[j] = gp[j] = 0.f;
+      if (active && !(nz & (1 << j))) {
+        const zmath::Elem e = zmath::zinb_elem_zero<Ops, COND_DISP>(mm[j], row_sf, dd[j], pp[j], ridge);
+        lsum += e.loss; gm[j] = e.gm; gd[j] = e.gd; gp[j] = e.gp;
+      }
+    }
+    // ---- dense NB pass over the queue
+    for (int k = lane; k < total; k += 32) {
+      const float4 it = q[k];
+      const zmath::Elem e = zmath::zinb_elem_nb<Ops, true, COND_DISP>(it.x, it.y, row_sf, it.z, it.w, ridge, lf);
+      q[k] = make_float4(e.loss, e.gm, e.gd, e.gp);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kVec; ++j)
+      if (nz & (1 << j)) { const float4 e = q[pos[j]]; lsum += e.x; gm[j] = e.y; gd[j] = e.z; gp[j] = e.w; }
+    __syncwarp();
+    if (active) {
+      if (!COND_DISP) {
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) tacc[j] += gd[j];
+      }
+      st4(om, gm[0] * inv_n, gm[1] * inv_n, gm[2] * inv_n, gm[3] * inv_n);
+      if (COND_DISP) st4(od, gd[0] * inv_n, gd[1] * inv_n, gd[2] * inv_n, gd[3] * inv_n);
+      st4(op, gp[0] * inv_n, gp[1] * inv_n, gp[2] * inv_n, gp[3] * inv_n);
+    }
+    om += ld; op += ld;
+    if (COND_DISP) od += ld;
+  }
+  if (!COND_DISP && active) {
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) atomicAdd(dth_acc + c0 + col + j, tacc[j]);
+  }
+  // block reduction over the 8 consumer warps (the producer warp has returned: named barrier on 256 threads)
+  double dsum = (double)lsum;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(kFull, dsum, o);
+  if (lane == 0) red[warp] = dsum;
+  tc::named_barrier_sync(1, kThreads);
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) t += red[w];
+    loss_partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+__global__ void fold_partials_kernel(const double* __restrict__ part, int n, double* out, int accumulate,
+                                     const double* penalty, float inv_n, int batch, float* loss_slot, double* epoch_acc) {
   __shared__ double sm[32];
   double a = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) a += part[i];
@@ -276,7 +448,18 @@ __global__ void fold_partials_kernel(const double* __restrict__ part, int n, dou
     a = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (threadIdx.x == 0) *out = accumulate ? (*out + a) : a;
+    if (threadIdx.x == 0) {
+      *out = accumulate ? (*out + a) : a;
+      if (loss_slot) {                                            // fused finalize (see loss_finalize_kernel)
+        double l = a * (double)inv_n;
+        if (l != l) l = INFINITY;                                 // _nan2inf, dca/loss.py:148
+        if (penalty) l += *penalty;
+        const float lf = (float)l;
+        loss_slot[0] = lf;
+        loss_slot[1] = (isfinite(lf)) ? 0.f : 1.f;
+        if (epoch_acc) { epoch_acc[0] += l * (double)batch; epoch_acc[1] += (double)batch; }
+      }
+    }
   }
 }
 
@@ -332,7 +515,24 @@ int launch(const LossArgs& a, cudaStream_t s) {
   float* tpart = a.dtheta;                                            // const-disp: accumulated with atomics
   if (BWD && !cond) DCA_CUDA_OK(cudaMemsetAsync(a.dtheta, 0, sizeof(float) * (size_t)a.G, s));
 
-  if (BWD && vec && has_pi) {
+  static const bool use_compact = [] { const char* e = getenv("DCA_LOSS_KERNEL"); return e && e[0] == 'c'; }();
+  const Plan ps = make_plan(a.B, a.G, kColsPerBlock, kMaxRowsPerBlock);
+  const bool staged_ok = BWD && vec && has_pi && !use_compact && (long long)ps.row_chunks * ps.col_blocks <= kMaxBlocks &&
+                         ps.row_chunks <= 65535;
+  if (staged_ok) {
+    grid = dim3(ps.col_blocks, ps.row_chunks);
+#define DCA_STAGED(CD, GT)                                                                                         \
+  do {                                                                                                             \
+    constexpr size_t sm = (size_t)kStageRows * (CD ? 4 : 3) * kColsPerBlock * 4 + (size_t)(kThreads / 32) * 32 * kVec * 16; \
+    static bool attr = false;                                                                                      \
+    if (!attr) { DCA_CUDA_OK(cudaFuncSetAttribute(zinb_loss_bwd_staged_kernel<CD, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr = true; } \
+    zinb_loss_bwd_staged_kernel<CD, GT><<<grid, kStagedThreads, sm, s>>>(a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, \
+        a.G, a.ridge, a.inv_n, ps.rows_per_block, (GT*)a.dzm, (GT*)a.dzd, (GT*)a.dzp, tpart, lpart, lf_dev);        \
+  } while (0)
+    if (a.grad_bf16) { if (cond) DCA_STAGED(true, __nv_bfloat16); else DCA_STAGED(false, __nv_bfloat16); }
+    else             { if (cond) DCA_STAGED(true, float); else DCA_STAGED(false, float); }
+#undef DCA_STAGED
+  } else if (BWD && vec && has_pi) {
 #define DCA_COMPACT(CD, GT)                                                                                   \
   zinb_loss_bwd_compact_kernel<CD, GT><<<grid, block, 0, s>>>(a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, a.G, \
                                                               a.ridge, a.inv_n, p.rows_per_block, (GT*)a.dzm,  \
@@ -361,7 +561,8 @@ int launch(const LossArgs& a, cudaStream_t s) {
 #undef DCA_LOSS_LAUNCH
   }
   DCA_LAUNCH_CHECK();
-  fold_partials_kernel<<<1, 256, 0, s>>>(lpart, (int)(grid.x * grid.y), a.loss_sum, BWD ? 0 : 1);
+  fold_partials_kernel<<<1, 256, 0, s>>>(lpart, (int)(grid.x * grid.y), a.loss_sum, BWD ? 0 : 1, a.fin_penalty, a.inv_n,
+                                         a.fin_batch, BWD ? a.fin_loss_slot : nullptr, a.fin_epoch_acc);
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }
