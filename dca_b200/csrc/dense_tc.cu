@@ -304,7 +304,10 @@ int heads_fwd_tc(const __nv_bfloat16* Hb, int B, const __nv_bfloat16* WhT, const
 
 }  // namespace tc
 
-Engine::~Engine() { for (auto e : prof.ev) cudaEventDestroy(e); }
+Engine::~Engine() {
+  for (auto e : prof.ev) cudaEventDestroy(e);
+  for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+}
 
 }  // namespace dca
 

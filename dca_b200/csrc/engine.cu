@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "dca_internal.cuh"
@@ -146,6 +147,7 @@ int Engine::plan(const dca_config& c) {
   o_sfb = take(sizeof(float) * B);
   loss_ws_bytes = loss_workspace_bytes((int)B, G);
   o_lossws = take(loss_ws_bytes);
+  o_rowsbuf = take(sizeof(int32_t) * B);
   mid_ok = mid_supported(c.hidden, L);
   o_bar = take(256);
   o_midpart = take(sizeof(double) * mid_partial_doubles());
@@ -359,6 +361,49 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
                        int Bn, cudaStream_t s) {
   if (!X || !Y) { set_error("dca_train_step: X and Y must not be NULL"); return DCA_ERR_BAD_ARG; }
   if (Bn <= 0 || Bn > cfg.max_batch) { set_error("dca_train_step: batch %d outside (0, max_batch=%d]", Bn, cfg.max_batch); return DCA_ERR_BAD_ARG; }
+  if (!graphs_enabled || prof.on) return train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s);
+  // ---- CUDA-graph replay: the launch sequence only depends on (pointers, leading dims, batch); the batch's row
+  // indices are copied into a fixed buffer so that the captured kernels read them from a stable address.
+  StepGraph* g = nullptr;
+  for (auto& c : graphs)
+    if (c.X == X && c.ldx == ldx && c.Y == Y && c.ldy == ldy && c.sf == sf && c.Bn == Bn && c.has_rows == (rows != nullptr)) { g = &c; break; }
+  if (!g) {
+    if (graphs.size() >= 16) { for (auto& c : graphs) if (c.exec) cudaGraphExecDestroy(c.exec); graphs.clear(); }
+    graphs.push_back(StepGraph{X, ldx, Y, ldy, sf, Bn, rows != nullptr, nullptr, 0, 0});
+    g = &graphs.back();
+  }
+  int32_t* rbuf = reinterpret_cast<int32_t*>(base + o_rowsbuf);
+  if (!g->exec && g->seen >= 1 && g->seen < 1000) {
+    // capture on the second call with this key (the first, direct call has done every one-time initialisation)
+    const long long l0 = g_launches.load();
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int st = train_step_body(X, ldx, Y, ldy, sf, rows ? rbuf : nullptr, Bn, s);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (st == DCA_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
+        g->launches = g_launches.load() - l0;
+        g_launches.store(l0);                      // the capture itself launched nothing
+      } else {
+        g->exec = nullptr; g->seen = 1000;         // not capturable: stay on the direct path for this key
+        (void)cudaGetLastError();
+      }
+      if (graph) cudaGraphDestroy(graph);
+    } else {
+      (void)cudaGetLastError(); g->seen = 1000;
+    }
+  }
+  if (g->exec) {
+    if (rows) DCA_CUDA_OK(cudaMemcpyAsync(rbuf, rows, sizeof(int32_t) * (size_t)Bn, cudaMemcpyDeviceToDevice, s));
+    DCA_CUDA_OK(cudaGraphLaunch(g->exec, s));
+    count_launch((int)g->launches);
+    return DCA_OK;
+  }
+  if (g->seen < 1000) ++g->seen;
+  return train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s);
+}
+
+int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows,
+                            int Bn, cudaStream_t s) {
   const int G = cfg.n_out;
   DCA_CUDA_OK(cudaMemsetAsync(gp(0), 0, sizeof(float) * (size_t)(P + 2), s));
   bool any_pen = false;
@@ -537,6 +582,7 @@ const char* Engine::tc_reason() const {
   return "tcgen05 path needs hidden_size[0] == hidden_size[-1] == 64, n_in % 8 == 0 and n_out % 8 == 0";
 }
 int Engine::setup_tc() {
+  if (const char* e = getenv("DCA_GRAPH")) graphs_enabled = !(e[0] == '0');
   int dev = 0;
   DCA_CUDA_OK(cudaGetDevice(&dev));
   DCA_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));

@@ -32,6 +32,16 @@ struct Engine {
   size_t o_stage_x = 0, o_stage_y = 0, o_stage_sf = 0;
   // head input of the current forward (set by forward())
   const void* head_in = nullptr; int64_t head_ld = 0; int head_bf16 = 0; const int32_t* head_rows = nullptr;
+  // CUDA-graph replay of the training step (captured from the same launch sequence on the 2nd call with a key)
+  struct StepGraph {
+    const void* X; int64_t ldx; const void* Y; int64_t ldy; const void* sf; int Bn; int has_rows;
+    cudaGraphExec_t exec; long long launches; int seen;
+  };
+  std::vector<StepGraph> graphs;
+  bool graphs_enabled = true;
+  size_t o_rowsbuf = 0;
+  int train_step_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
+                      cudaStream_t s);
   // optional phase timing
   struct Prof {
     bool on = false;

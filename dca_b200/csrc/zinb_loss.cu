@@ -479,10 +479,13 @@ __device__ float g_log_fact[zmath::kLogFactN];
 // log(k!) table in device global memory, filled once per device on first use
 const float* log_fact_table_device() {
   static thread_local int ready_dev = -1;
+  static thread_local float* cached = nullptr;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return nullptr; }
+  if (ready_dev == dev && cached) return cached;       // (also keeps stream capture free of non-stream API calls)
   float* p = nullptr;
   if (cudaGetSymbolAddress((void**)&p, g_log_fact) != cudaSuccess) { set_error("cudaGetSymbolAddress failed"); return nullptr; }
+  cached = p;
   if (ready_dev != dev) {
     float t[zmath::kLogFactN];
     zmath::fill_log_fact(t);
