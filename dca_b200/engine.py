@@ -235,7 +235,7 @@ class DeviceEngine:
         a = (C.c_int32 * 8)()
         check(self.lib.dca_engine_info(self.handle, C.byref(a)), "dca_engine_info")
         return {"tc_heads": bool(a[0]), "tc_encoder": bool(a[1]), "fused_hidden": bool(a[2]), "head_slots": a[3],
-                "sm_count": a[4], "grad_bytes": a[5]}
+                "sm_count": a[4], "grad_bytes": a[5], "step_graphs": a[6], "graphs_enabled": bool(a[7])}
 
     @property
     def latent_dim(self):

@@ -233,7 +233,8 @@ int dca_profile_enable(dca_handle* h, int32_t on);
 int dca_profile_read(dca_handle* h, double ms[DCA_N_PHASES], int64_t counts[DCA_N_PHASES], int32_t reset);
 
 /* Which code paths an engine selected: info = {tcgen05 heads (K2/K4), tcgen05 encoder (K1/K5),
- * fused hidden stack, head slots, SM count, bytes per loss-gradient element (4 fp32 | 2 bf16), 0, 0}. */
+ * fused hidden stack, head slots, SM count, bytes per loss-gradient element (4 fp32 | 2 bf16),
+ * instantiated step graphs, graphs enabled}. */
 int dca_engine_info(const dca_handle* h, int32_t info[8]);
 
 /* Number of kernels this library has launched in this process (all handles, all streams). */
