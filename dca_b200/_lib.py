@@ -65,6 +65,10 @@ PROTOTYPES = {
     "dca_read_loss": (C.c_int, [_vp, C.POINTER(_f), C.POINTER(_i32), _vp]),
     "dca_read_epoch_acc": (C.c_int, [_vp, C.POINTER(C.c_double * 4), _i32, _vp]),
     "dca_train_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _f, _f, C.POINTER(_f), _vp]),
+    "dca_set_input_transform": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "dca_stream_begin": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "dca_stream_step": (C.c_int, [_vp, _i64, _i64, _vp]),
+    "dca_stream_end": (C.c_int, [_vp, _vp]),
     "dca_zinb_loss_fwd_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f, _f,
                                         _vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "dca_zinb_loss_workspace_bytes": (C.c_int, [_i32, _i32, C.POINTER(_sz)]),

@@ -91,6 +91,8 @@ int rmsprop_update(float* params, const float* grads, float* rms, int64_t n, flo
 int glorot_fill(float* w, int64_t n, int fan_in, int fan_out, uint64_t seed, uint64_t stream_id, cudaStream_t s);
 int fill_value(float* p, int64_t n, float v, cudaStream_t s);
 int cast_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
+int expand_counts(const uint16_t* cnt, const float* sf_in, int M, int n, const float* mean, const float* inv_std, int use_sf,
+                  int use_log1p, float* Yout, void* Xout, int x_bf16, float* sf_out, cudaStream_t s);
 int pack_head_shadows(const float* W, const float* b, int G, int slot, int nslots, __nv_bfloat16* whT,
                       __nv_bfloat16* whkm, float* biasp, cudaStream_t s);
 int refresh_all_shadows(const float* const W[3], const float* const b[3], int n_slots, int G, __nv_bfloat16* whT,

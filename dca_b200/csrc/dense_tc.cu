@@ -307,6 +307,8 @@ int heads_fwd_tc(const __nv_bfloat16* Hb, int B, const __nv_bfloat16* WhT, const
 Engine::~Engine() {
   for (auto e : prof.ev) cudaEventDestroy(e);
   for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (hs.copy) cudaStreamDestroy(hs.copy);
+  for (int k = 0; k < 2; ++k) { if (hs.h2d_done[k]) cudaEventDestroy(hs.h2d_done[k]); if (hs.buf_free[k]) cudaEventDestroy(hs.buf_free[k]); }
 }
 
 }  // namespace dca

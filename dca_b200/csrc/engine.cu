@@ -171,6 +171,9 @@ int Engine::plan(const dca_config& c) {
     o_da1b = take(2 * B * 64);
     o_xb = take(2 * B * (size_t)c.n_in);
   }
+  // double-buffered staging of raw uint16 counts streamed from the host + the input transform
+  for (int k = 0; k < 2; ++k) { o_cnt[k] = take(sizeof(uint16_t) * B * (size_t)c.n_in); o_sfst[k] = take(sizeof(float) * B); }
+  o_gmean = take(sizeof(float) * (size_t)c.n_in); o_ginv = take(sizeof(float) * (size_t)c.n_in);
   // staging for the host-buffer entry point
   const size_t xb = (c.x_dtype == DCA_BF16) ? 2 : 4;
   o_stage_x = take(xb * B * (size_t)c.n_in);
@@ -225,7 +228,7 @@ int Engine::gemm_auto(GemmArgs g, cudaStream_t s) {
 }
 
 int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, bool training, cudaStream_t s) {
-  const void* hin = X; int64_t ldin = ldx; int in_bf16 = (cfg.x_dtype == DCA_BF16); const int32_t* gather = rows;
+  const void* hin = X; int64_t ldin = ldx; int in_bf16 = x_override_bf16 ? 1 : (cfg.x_dtype == DCA_BF16); const int32_t* gather = rows;
   // tcgen05 encoder: needs a contiguous bf16 batch (gathered / converted once, reused by the backward pass)
   cur_xb = nullptr;
   if (tc_enc) {
@@ -480,7 +483,7 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
       DCA_TRY(tc::gene_gemm_tc(2, Z, cur_ldxb, Bn, cfg.n_in, 1, bf(o_da1b), nullptr, nullptr, dWp, l.out, 0, nullptr, sm_count, s));
     } else {
       GemmArgs g{};
-      g.A = X; g.lda = ldx; g.a_bf16 = (cfg.x_dtype == DCA_BF16); g.transA = 1; g.a_rows = rows;
+      g.A = X; g.lda = ldx; g.a_bf16 = x_override_bf16 ? 1 : (cfg.x_dtype == DCA_BF16); g.transA = 1; g.a_rows = rows;
       g.B = dh2; g.ldb = l.out; g.transB = 0;
       g.C = gp(l.W); g.ldc = l.out; g.M = l.in; g.N = l.out; g.K = Bn; g.epilogue = EPI_ACCUM;
       DCA_TRY(gemm_auto(g, s));
@@ -504,7 +507,7 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
     }
     const void* ain = (i == 0) ? X : (const void*)f(lay[i - 1].o_h);
     GemmArgs g{};
-    g.A = ain; g.lda = (i == 0) ? ldx : lay[i - 1].out; g.a_bf16 = (i == 0) ? (cfg.x_dtype == DCA_BF16) : 0;
+    g.A = ain; g.lda = (i == 0) ? ldx : lay[i - 1].out; g.a_bf16 = (i == 0) ? (x_override_bf16 ? 1 : (cfg.x_dtype == DCA_BF16)) : 0;
     g.transA = 1; g.a_rows = (i == 0) ? rows : nullptr;
     g.B = dh; g.ldb = l.out; g.transB = 0;
     g.C = gp(l.W); g.ldc = l.out; g.M = l.in; g.N = l.out; g.K = Bn; g.epilogue = EPI_ACCUM;
@@ -837,5 +840,96 @@ extern "C" int dca_engine_info(const dca_handle* h, int32_t info[8]) {
   info[5] = e.tc_heads ? 2 : 4;
   int ng = 0; for (auto& g : e.graphs) if (g.exec) ++ng;
   info[6] = ng; info[7] = e.graphs_enabled;
+  return DCA_OK;
+}
+
+// ------------------------------------------------------------------------------------ streaming from host counts
+// copy batch `i` of the host dataset into staging buffer `b` on the copy stream
+int Engine::stream_prefetch(int64_t i, int b) {
+  const int64_t r0 = i * hs.batch;
+  const int64_t nb = (hs.n_rows - r0 < hs.batch) ? (hs.n_rows - r0) : hs.batch;
+  DCA_CUDA_OK(cudaStreamWaitEvent(hs.copy, hs.buf_free[b], 0));          // staging buffer b has been consumed
+  DCA_CUDA_OK(cudaMemcpy2DAsync(base + o_cnt[b], sizeof(uint16_t) * (size_t)cfg.n_in, hs.counts + r0 * hs.ld,
+                                sizeof(uint16_t) * (size_t)hs.ld, sizeof(uint16_t) * (size_t)cfg.n_in, (size_t)nb,
+                                cudaMemcpyHostToDevice, hs.copy));
+  if (hs.sf) DCA_CUDA_OK(cudaMemcpyAsync(base + o_sfst[b], hs.sf + r0, sizeof(float) * (size_t)nb, cudaMemcpyHostToDevice, hs.copy));
+  DCA_CUDA_OK(cudaEventRecord(hs.h2d_done[b], hs.copy));
+  hs.pref_idx = i;
+  return DCA_OK;
+}
+
+extern "C" int dca_set_input_transform(dca_handle* h, const float* gene_mean_host, const float* gene_inv_std_host,
+                                       int32_t use_size_factors, int32_t use_log1p, void* stream) {
+  DCA_NEED_HANDLE(h);
+  Engine& e = h->e;
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((gene_mean_host == nullptr) != (gene_inv_std_host == nullptr)) { set_error("dca_set_input_transform: give both mean and inv_std or neither"); return DCA_ERR_BAD_ARG; }
+  if (gene_mean_host) {
+    DCA_CUDA_OK(cudaMemcpyAsync(e.base + e.o_gmean, gene_mean_host, sizeof(float) * (size_t)e.cfg.n_in, cudaMemcpyHostToDevice, s));
+    DCA_CUDA_OK(cudaMemcpyAsync(e.base + e.o_ginv, gene_inv_std_host, sizeof(float) * (size_t)e.cfg.n_in, cudaMemcpyHostToDevice, s));
+    DCA_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  e.tf_set = gene_mean_host ? 2 : 1; e.tf_use_sf = use_size_factors != 0; e.tf_use_log1p = use_log1p != 0;
+  return DCA_OK;
+}
+
+extern "C" int dca_stream_begin(dca_handle* h, const uint16_t* counts_host, int64_t ld_counts, const float* sf_host,
+                                int64_t n_rows, int32_t batch, void* stream) {
+  DCA_NEED_HANDLE(h);
+  Engine& e = h->e;
+  if (!counts_host || n_rows <= 0 || batch <= 0 || batch > e.cfg.max_batch || ld_counts < e.cfg.n_in) { set_error("dca_stream_begin: bad argument"); return DCA_ERR_BAD_ARG; }
+  if (e.cfg.n_in != e.cfg.n_out) { set_error("dca_stream_begin: needs n_in == n_out"); return DCA_ERR_UNSUPPORTED; }
+  if (e.cfg.n_in % 8 != 0) { set_error("dca_stream_begin: n_in must be a multiple of 8"); return DCA_ERR_UNSUPPORTED; }
+  if (!e.tf_set) { set_error("dca_stream_begin: call dca_set_input_transform first"); return DCA_ERR_BAD_ARG; }
+  auto& hs = e.hs;
+  if (!hs.copy) {
+    DCA_CUDA_OK(cudaStreamCreateWithFlags(&hs.copy, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.h2d_done[k], cudaEventDisableTiming));
+      DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.buf_free[k], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int k = 0; k < 2; ++k) DCA_CUDA_OK(cudaEventRecord(hs.buf_free[k], s));   // both staging buffers start free
+  hs.counts = counts_host; hs.ld = ld_counts; hs.sf = sf_host; hs.n_rows = n_rows; hs.batch = batch;
+  hs.pref_idx = -1; hs.step_no = 0; hs.active = true;
+  return DCA_OK;
+}
+
+extern "C" int dca_stream_step(dca_handle* h, int64_t i, int64_t next, void* stream) {
+  DCA_NEED_HANDLE(h);
+  Engine& e = h->e; auto& hs = e.hs;
+  if (!hs.active) { set_error("dca_stream_step: no active stream (dca_stream_begin)"); return DCA_ERR_BAD_ARG; }
+  if (i < 0 || i * (int64_t)hs.batch >= hs.n_rows || next * (int64_t)hs.batch >= hs.n_rows) {
+    set_error("dca_stream_step: batch index out of range (%lld, next %lld)", (long long)i, (long long)next); return DCA_ERR_BAD_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int b = (int)(hs.step_no & 1);
+  if (hs.pref_idx != i) DCA_TRY(e.stream_prefetch(i, b));           // not prefetched by the previous step: fetch now
+  const int64_t r0 = i * hs.batch;
+  const int nb = (int)((hs.n_rows - r0 < hs.batch) ? (hs.n_rows - r0) : hs.batch);
+  DCA_CUDA_OK(cudaStreamWaitEvent(s, hs.h2d_done[b], 0));
+  const bool to_xb = e.tc_enc;                      // bf16 batch straight into the tcgen05 encoder's input buffer
+  void* xdst = to_xb ? (void*)e.bf(e.o_xb) : (void*)(e.base + e.o_stage_x);
+  const int x_bf16 = to_xb ? 1 : (e.cfg.x_dtype == DCA_BF16);
+  DCA_TRY(expand_counts(reinterpret_cast<const uint16_t*>(e.base + e.o_cnt[b]), hs.sf ? e.f(e.o_sfst[b]) : nullptr, nb, e.cfg.n_in,
+                        e.tf_set == 2 ? e.f(e.o_gmean) : nullptr, e.tf_set == 2 ? e.f(e.o_ginv) : nullptr, e.tf_use_sf && hs.sf,
+                        e.tf_use_log1p, e.f(e.o_stage_y), xdst, x_bf16, e.f(e.o_stage_sf), s));
+  DCA_CUDA_OK(cudaEventRecord(hs.buf_free[b], s));
+  ++hs.step_no;
+  hs.pref_idx = -1;
+  if (next >= 0) DCA_TRY(e.stream_prefetch(next, b ^ 1));           // next batch's copy overlaps this batch's compute
+  e.x_override_bf16 = to_xb ? 1 : 0;
+  const int st = e.train_step(xdst, e.cfg.n_in, e.f(e.o_stage_y), e.cfg.n_out, e.f(e.o_stage_sf), nullptr, nb, s);
+  e.x_override_bf16 = 0;
+  return st;
+}
+
+extern "C" int dca_stream_end(dca_handle* h, void* stream) {
+  DCA_NEED_HANDLE(h);
+  auto& hs = h->e.hs;
+  if (hs.copy) DCA_CUDA_OK(cudaStreamSynchronize(hs.copy));
+  DCA_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  hs.active = false; hs.counts = nullptr;
   return DCA_OK;
 }

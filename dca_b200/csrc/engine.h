@@ -42,6 +42,15 @@ struct Engine {
   size_t o_rowsbuf = 0;
   int train_step_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
                       cudaStream_t s);
+  // streaming from host counts
+  size_t o_cnt[2] = {0, 0}, o_sfst[2] = {0, 0}, o_gmean = 0, o_ginv = 0;
+  int tf_use_sf = 1, tf_use_log1p = 1, tf_set = 0, x_override_bf16 = 0;
+  struct HostStream {
+    const uint16_t* counts = nullptr; int64_t ld = 0; const float* sf = nullptr; int64_t n_rows = 0; int batch = 0;
+    cudaStream_t copy = nullptr; cudaEvent_t h2d_done[2] = {nullptr, nullptr}, buf_free[2] = {nullptr, nullptr};
+    int64_t pref_idx = -1, step_no = 0; bool active = false;
+  } hs;
+  int stream_prefetch(int64_t i, int buf);
   // optional phase timing
   struct Prof {
     bool on = false;

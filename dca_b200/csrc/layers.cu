@@ -265,6 +265,45 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
   if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
 
+// uint16 counts -> Y (fp32 target) and X = ((log1p)(y/sf) - mean_g) * inv_std_g (network input), 8 genes per thread
+template <typename XT>
+__global__ void expand_counts_kernel(const uint16_t* __restrict__ cnt, const float* __restrict__ sf_in, int M, int n,
+                                     const float* __restrict__ mean, const float* __restrict__ inv_std, int use_sf,
+                                     int use_log1p, float* __restrict__ Yout, XT* __restrict__ Xout, float* __restrict__ sf_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = n / 8;
+  if (i >= (int64_t)M * per_row) return;
+  const int r = (int)(i / per_row), c = (int)(i % per_row) * 8;
+  const float s = sf_in ? sf_in[r] : 1.0f;
+  if (c == 0 && sf_out) sf_out[r] = s;
+  const uint4 raw = *reinterpret_cast<const uint4*>(cnt + (int64_t)r * n + c);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  float y[8], x[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { y[2 * k] = (float)(w[k] & 0xffffu); y[2 * k + 1] = (float)(w[k] >> 16); }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v = use_sf ? y[k] / s : y[k];                   // sc.pp.normalize_per_cell   dca/io.py:99-100
+    if (use_log1p) v = log1pf(v);                         // sc.pp.log1p                dca/io.py:105-106
+    x[k] = mean ? (v - mean[c + k]) * inv_std[c + k] : v; // sc.pp.scale                dca/io.py:108-109
+  }
+  float* yo = Yout + (int64_t)r * n + c;
+  *reinterpret_cast<float4*>(yo) = make_float4(y[0], y[1], y[2], y[3]);
+  *reinterpret_cast<float4*>(yo + 4) = make_float4(y[4], y[5], y[6], y[7]);
+  if (sizeof(XT) == 2) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(x[0], x[1]), p1 = __floats2bfloat162_rn(x[2], x[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(x[4], x[5]), p3 = __floats2bfloat162_rn(x[6], x[7]);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(Xout) + (int64_t)r * n + c) = o;
+  } else {
+    float* xo = reinterpret_cast<float*>(Xout) + (int64_t)r * n + c;
+    *reinterpret_cast<float4*>(xo) = make_float4(x[0], x[1], x[2], x[3]);
+    *reinterpret_cast<float4*>(xo + 4) = make_float4(x[4], x[5], x[6], x[7]);
+  }
+}
+
 inline int blocks_for(int64_t n, int t = 256) { return (int)((n + t - 1) / t); }
 
 }  // namespace
@@ -458,6 +497,15 @@ int gather_rows_bf16(const void* X, int x_bf16, int64_t ldx, const int32_t* rows
   const int64_t tot = (int64_t)M * (n / 8);
   if (x_bf16) gather_rows_bf16_kernel<__nv_bfloat16><<<blocks_for(tot), 256, 0, s>>>((const __nv_bfloat16*)X, ldx, rows, M, n, out);
   else gather_rows_bf16_kernel<float><<<blocks_for(tot), 256, 0, s>>>((const float*)X, ldx, rows, M, n, out);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int expand_counts(const uint16_t* cnt, const float* sf_in, int M, int n, const float* mean, const float* inv_std, int use_sf,
+                  int use_log1p, float* Yout, void* Xout, int x_bf16, float* sf_out, cudaStream_t s) {
+  const int64_t tot = (int64_t)M * (n / 8);
+  if (x_bf16) expand_counts_kernel<__nv_bfloat16><<<blocks_for(tot), 256, 0, s>>>(cnt, sf_in, M, n, mean, inv_std, use_sf, use_log1p, Yout, (__nv_bfloat16*)Xout, sf_out);
+  else expand_counts_kernel<float><<<blocks_for(tot), 256, 0, s>>>(cnt, sf_in, M, n, mean, inv_std, use_sf, use_log1p, Yout, (float*)Xout, sf_out);
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }

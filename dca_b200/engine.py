@@ -220,6 +220,40 @@ class DeviceEngine:
                                            C.byref(out), self._stream()), "dca_train_step_host")
         return out.value
 
+    # ------------------------------------------------------------------ streaming from host counts
+    def set_input_transform(self, gene_mean=None, gene_std=None, use_size_factors=True, use_log1p=True):
+        """On-device restatement of io.normalize for streamed batches: X = ((log1p)(y/sf) - mean)/std."""
+        if gene_mean is None:
+            check(self.lib.dca_set_input_transform(self.handle, None, None, int(use_size_factors), int(use_log1p), self._stream()),
+                  "dca_set_input_transform")
+            return
+        mean = np.ascontiguousarray(gene_mean, dtype=np.float32)
+        std = np.asarray(gene_std, dtype=np.float64).copy(); std[std == 0] = 1.0
+        inv = np.ascontiguousarray(1.0 / std, dtype=np.float32)
+        if mean.size != self.n_in or inv.size != self.n_in:
+            raise ValueError("gene_mean / gene_std must have %d entries" % self.n_in)
+        check(self.lib.dca_set_input_transform(self.handle, mean.ctypes.data, inv.ctypes.data, int(use_size_factors),
+                                               int(use_log1p), self._stream()), "dca_set_input_transform")
+
+    def stream_begin(self, counts_u16: torch.Tensor, sf: Optional[torch.Tensor], batch: int):
+        """counts_u16: HOST uint16 tensor [n_rows x n_in] (pin it), sf: HOST float32 [n_rows] or None."""
+        if counts_u16.dtype != torch.uint16 or counts_u16.dim() != 2 or counts_u16.shape[1] != self.n_in or counts_u16.stride(1) != 1:
+            raise ValueError("counts must be a uint16 (rows, %d) row-major host tensor" % self.n_in)
+        if counts_u16.is_cuda or (sf is not None and sf.is_cuda):
+            raise ValueError("stream_begin takes HOST tensors")
+        self._stream_keep = (counts_u16, sf)
+        check(self.lib.dca_stream_begin(self.handle, counts_u16.data_ptr(), counts_u16.stride(0),
+                                        None if sf is None else sf.data_ptr(), counts_u16.shape[0], batch, self._stream()),
+              "dca_stream_begin")
+
+    def stream_step(self, batch_index: int, next_batch_index: int = -1):
+        """Forward + loss + backward of host batch `batch_index`; the copy of `next_batch_index` overlaps it."""
+        check(self.lib.dca_stream_step(self.handle, batch_index, next_batch_index, self._stream()), "dca_stream_step")
+
+    def stream_end(self):
+        check(self.lib.dca_stream_end(self.handle, self._stream()), "dca_stream_end")
+        self._stream_keep = None
+
     PHASES = ("hidden_fwd", "heads_fwd", "loss_fwd_bwd", "heads_bwd", "hidden_bwd", "update")
 
     def profile(self, on: bool):

@@ -159,6 +159,22 @@ int dca_train_step_host(dca_handle* h, const void* x_host, const float* y_host,
                         const float* sf_host, int32_t batch, float lr, float clip,
                         float* loss_host, void* stream);
 
+/* ---- streaming from host memory (out-of-core / end-to-end path) ----------------------------- */
+/* On-device restatement of dca/io.py:99-109 for one batch: X = ((log1p)(y / sf) - mean_g) * inv_std_g.
+ * gene_mean_host / gene_inv_std_host: float[n_in] HOST arrays (copied), or NULL for no centring/scaling. */
+int dca_set_input_transform(dca_handle* h, const float* gene_mean_host, const float* gene_inv_std_host,
+                            int32_t use_size_factors, int32_t use_log1p, void* stream);
+/* Train from a HOST-resident raw count matrix (uint16 counts [n_rows x n_in], leading dim ld_counts, pinned
+ * memory recommended; size factors float[n_rows]).  dca_stream_step(i, next) waits for batch i (rows
+ * [i*batch, min(n_rows,(i+1)*batch))) to arrive, starts the copy of batch `next` on an internal copy stream
+ * (double-buffered staging), expands the counts on the device into the fp32 target Y and the normalised
+ * network input X, and runs dca_train_step on them; the caller then all-reduces / calls dca_apply_update
+ * exactly as for the resident path.  Requires n_in == n_out. */
+int dca_stream_begin(dca_handle* h, const uint16_t* counts_host, int64_t ld_counts, const float* sf_host,
+                     int64_t n_rows, int32_t batch, void* stream);
+int dca_stream_step(dca_handle* h, int64_t batch_index, int64_t next_batch_index /* -1: none */, void* stream);
+int dca_stream_end(dca_handle* h, void* stream);
+
 /* ---- stand-alone kernels (parity tests, profiling) -------------------------------------- */
 /* ZINB / NB negative log-likelihood forward + backward, one pass (dca/loss.py:72-156 and its
  * autodiff).  Inputs are POST-activation head outputs: m = MeanAct(zm) (not yet multiplied by

@@ -384,3 +384,27 @@ def test_tc_trajectory_and_predict():
     with pytest.raises(Exception):
         from dca_b200.engine import DeviceEngine
         DeviceEngine(100, 100, (10, 2, 10), "zinb", max_batch=8, gemm_path="tcgen05")   # shape does not qualify
+
+
+def test_stream_from_host_counts_matches_resident_path():
+    """dca_stream_step (uint16 counts from pinned host memory, on-device normalisation) == dca_train_step on the
+    host-normalised matrix (dca/io.py:99-109 restated on the device)."""
+    from dca_b200.engine import DeviceEngine
+    N, G, B = 700, 264, 256
+    Y = synth_counts(N, G, 31); X, sf = O.normalize_inputs(Y)
+    l = np.log1p(Y / sf[:, None].astype(np.float32)).astype(np.float32)
+    mean = l.mean(0, dtype=np.float64); std = np.sqrt(l.var(0, ddof=1, dtype=np.float64))
+    for gemm_path, tol in (("tcgen05", 2e-3), ("generic", 2e-5)):
+        e1 = DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=3, gemm_path=gemm_path)
+        e2 = DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=3, gemm_path=gemm_path)
+        e2.set_input_transform(mean, std, True, True)
+        cnt = torch.from_numpy(Y.astype(np.uint16)).pin_memory(); sfh = torch.from_numpy(sf).pin_memory()
+        e2.stream_begin(cnt, sfh, B)
+        nb = (N + B - 1) // B
+        for i in range(nb):
+            s, e = i * B, min(N, (i + 1) * B)
+            e1.train_step(_t(X[s:e]), _t(Y[s:e]), _t(sf[s:e])); e1.apply_update(1e-3, 5.0)
+            e2.stream_step(i, i + 1 if i + 1 < nb else -1); e2.apply_update(1e-3, 5.0)
+            l1, l2 = e1.read_loss(), e2.read_loss()
+            assert abs(l1 - l2) < tol * abs(l1), (gemm_path, i, l1, l2)
+        e2.stream_end()
