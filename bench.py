@@ -88,7 +88,7 @@ def synth_on_device(n_cells, n_genes, device, seed, x_dtype=torch.float32, chunk
         l = torch.log1p(Y[s:s + chunk] / sf[s:s + chunk, None]).double()
         X[s:s + chunk] = ((l - mean) / std).to(x_dtype)
     zero_frac = float((Y == 0).float().mean().item())
-    return X, Y, sf.contiguous(), zero_frac
+    return X, Y, sf.contiguous(), zero_frac, mean.float().cpu().numpy(), std.float().cpu().numpy()
 
 
 class ClockSampler:
@@ -254,7 +254,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    X, Y, sf, zero_frac = synth_on_device(cells, genes, dev, 1234 + rank, {"float32": torch.float32, "bfloat16": torch.bfloat16}[a.x_dtype])
+    X, Y, sf, zero_frac, gmean, gstd = synth_on_device(cells, genes, dev, 1234 + rank, {"float32": torch.float32, "bfloat16": torch.bfloat16}[a.x_dtype])
     n_train = int(cells * 0.9)                                  # validation_split=0.1 tail, dca/train.py:96
     eng = DeviceEngine(genes, genes, HIDDEN, ae_type, True, max_batch=batch, x_dtype=a.x_dtype,
                        gemm_path=a.gemm_path, device=dev, seed=0)
@@ -324,37 +324,45 @@ def main():
     phases = {k: (v[0] / max(v[1], 1)) for k, v in prof.items()}
     roofline["loss_kernel_fp32_io"] = loss_kernel_standalone(eng, X, Y, sf, stream_idx[:batch], genes, batch, peak)
 
-    # ---- end to end: host (pinned) buffers -> H2D -> step -> D2H loss, through the public API
+    # ---- end to end through the public streaming API: the raw counts live in pinned HOST memory (uint16, what a
+    # count matrix is), every step copies its batch host->device (double-buffered, overlapping the previous step's
+    # compute), the device expands / normalises it (dca/io.py:99-109 restated), runs the full training step, and
+    # the step's loss is read back device->host.
     e2e = None
     if not a.no_e2e:
-        nb = min(8, max(2, n_train // batch))
-        xh = X[: nb * batch].cpu().pin_memory(); yh = Y[: nb * batch].cpu().pin_memory(); sfh = sf[: nb * batch].cpu().pin_memory()
-        k_e2e = max(3, min(a.steps, 20))
-        def e2e_step(i):
-            j = i % nb
-            xs, ys, ss = xh[j * batch:(j + 1) * batch], yh[j * batch:(j + 1) * batch], sfh[j * batch:(j + 1) * batch]
-            if world == 1:
-                return eng.train_step_host(xs, ys, ss, lr, clip)
-            xd = xs.to(dev, non_blocking=True); yd = ys.to(dev, non_blocking=True); sd = ss.to(dev, non_blocking=True)
-            eng.train_step(xd, yd, sd); dist.all_reduce(eng.grads); eng.apply_update(lr, clip, gscale)
-            return eng.read_loss()
-        for i in range(3):
-            e2e_step(i)
+        nb = max(2, min(8, cells // batch))
+        assert float(Y[: nb * batch].max().item()) < 65536
+        cnt_h = torch.from_numpy(Y[: nb * batch].cpu().numpy().astype(np.uint16)).pin_memory()
+        sf_h = sf[: nb * batch].cpu().pin_memory()
+        loss_h = torch.zeros(64, dtype=torch.float32).pin_memory()
+        eng.set_input_transform(gmean, gstd, True, True)
+        k_e2e = max(3, min(a.steps, 40))
+        P = eng.n_params
+
+        def e2e_run(k):
+            eng.stream_begin(cnt_h, sf_h, batch)
+            for i in range(k):
+                eng.stream_step(i % nb, (i + 1) % nb if i + 1 < k else -1)
+                if world > 1:
+                    dist.all_reduce(eng.grads)
+                eng.apply_update(lr, clip, gscale)
+                loss_h[i % 64: i % 64 + 1].copy_(eng.grads[P:P + 1], non_blocking=True)     # the step's result, D2H
+            eng.stream_end()
+
+        e2e_run(3)
         barrier()
-        t0 = time.perf_counter()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for i in range(k_e2e):
-            e2e_step(i)
+        e2e_run(k_e2e)
         f1.record(); barrier()
         ems = f0.elapsed_time(f1)
         if world > 1:
             t = torch.tensor([ems], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ems = float(t.item())
-        xb = 2 if a.x_dtype == "bfloat16" else 4
         e2e = {"value": k_e2e * batch * world / (ems * 1e-3), "unit": "cells/sec", "steps": k_e2e,
-               "h2d_bytes_per_step": batch * (genes * xb + genes * 4 + 4), "d2h_bytes_per_step": 8,
-               "api": "DeviceEngine.train_step_host -> dca_train_step_host (C ABI, pinned host buffers)" if world == 1
-                      else "pinned H2D + DeviceEngine.train_step/all_reduce/apply_update/read_loss"}
+               "h2d_bytes_per_step": batch * (genes * 2 + 4), "d2h_bytes_per_step": 4,
+               "host_format": "uint16 raw counts + float32 size factors in pinned memory; X is derived on the device",
+               "api": "DeviceEngine.stream_begin / stream_step / apply_update (C ABI dca_stream_*), loss read back per step",
+               "last_loss": float(loss_h[(k_e2e - 1) % 64])}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
