@@ -349,6 +349,13 @@ def main():
                 loss_h[i % 64: i % 64 + 1].copy_(eng.grads[P:P + 1], non_blocking=True)     # the step's result, D2H
             eng.stream_end()
 
+        # context: raw pinned host->device copy bandwidth of this box (64 MiB, best of 5)
+        probe_h = torch.empty(64 << 20, dtype=torch.uint8).pin_memory(); probe_d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        h2d_best = 0.0
+        for _ in range(5):
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(); probe_d.copy_(probe_h, non_blocking=True); p1.record(); torch.cuda.synchronize(dev)
+            h2d_best = max(h2d_best, (64 << 20) / (p0.elapsed_time(p1) * 1e-3) / 1e9)
         e2e_run(3)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -362,7 +369,8 @@ def main():
                "h2d_bytes_per_step": batch * (genes * 2 + 4), "d2h_bytes_per_step": 4,
                "host_format": "uint16 raw counts + float32 size factors in pinned memory; X is derived on the device",
                "api": "DeviceEngine.stream_begin / stream_step / apply_update (C ABI dca_stream_*), loss read back per step",
-               "last_loss": float(loss_h[(k_e2e - 1) % 64])}
+               "last_loss": float(loss_h[(k_e2e - 1) % 64]), "h2d_gbs_measured": h2d_best,
+               "ms_per_step": ems / k_e2e}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -849,9 +849,13 @@ int Engine::stream_prefetch(int64_t i, int b) {
   const int64_t r0 = i * hs.batch;
   const int64_t nb = (hs.n_rows - r0 < hs.batch) ? (hs.n_rows - r0) : hs.batch;
   DCA_CUDA_OK(cudaStreamWaitEvent(hs.copy, hs.buf_free[b], 0));          // staging buffer b has been consumed
-  DCA_CUDA_OK(cudaMemcpy2DAsync(base + o_cnt[b], sizeof(uint16_t) * (size_t)cfg.n_in, hs.counts + r0 * hs.ld,
-                                sizeof(uint16_t) * (size_t)hs.ld, sizeof(uint16_t) * (size_t)cfg.n_in, (size_t)nb,
+  if (hs.ld == cfg.n_in)        // contiguous rows: one linear copy (faster than the pitched path)
+    DCA_CUDA_OK(cudaMemcpyAsync(base + o_cnt[b], hs.counts + r0 * hs.ld, sizeof(uint16_t) * (size_t)cfg.n_in * (size_t)nb,
                                 cudaMemcpyHostToDevice, hs.copy));
+  else
+    DCA_CUDA_OK(cudaMemcpy2DAsync(base + o_cnt[b], sizeof(uint16_t) * (size_t)cfg.n_in, hs.counts + r0 * hs.ld,
+                                  sizeof(uint16_t) * (size_t)hs.ld, sizeof(uint16_t) * (size_t)cfg.n_in, (size_t)nb,
+                                  cudaMemcpyHostToDevice, hs.copy));
   if (hs.sf) DCA_CUDA_OK(cudaMemcpyAsync(base + o_sfst[b], hs.sf + r0, sizeof(float) * (size_t)nb, cudaMemcpyHostToDevice, hs.copy));
   DCA_CUDA_OK(cudaEventRecord(hs.h2d_done[b], hs.copy));
   hs.pref_idx = i;
