@@ -269,9 +269,10 @@ def main():
 
     def step(i):
         rows = stream_idx[i * batch:(i + 1) * batch]
-        eng.train_step(X, Y, sf, rows=rows)
         if world > 1:
-            dist.all_reduce(eng.grads)
+            eng.train_step_allreduce(X, Y, sf, rows=rows)     # head-gradient all-reduce overlaps the backward tail
+        else:
+            eng.train_step(X, Y, sf, rows=rows)
         eng.apply_update(lr, clip, gscale)
 
     def barrier():

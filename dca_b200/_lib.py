@@ -59,6 +59,8 @@ PROTOTYPES = {
     "dca_init_params": (C.c_int, [_vp, C.c_uint64, _vp]),
     "dca_params_changed": (C.c_int, [_vp, _vp]),
     "dca_train_step": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
+    "dca_train_step_phase": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp]),
+    "dca_grad_buckets": (C.c_int, [_vp, C.POINTER(_i64)]),
     "dca_apply_update": (C.c_int, [_vp, _f, _f, _f, _vp]),
     "dca_eval_step": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
     "dca_predict": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),

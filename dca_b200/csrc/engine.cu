@@ -361,18 +361,19 @@ int Engine::penalty(cudaStream_t s, bool& any) {
 
 // ------------------------------------------------------------------------------------ train step
 int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows,
-                       int Bn, cudaStream_t s) {
+                       int Bn, cudaStream_t s, int phase) {
+  if (phase < 0 || phase > 2) { set_error("dca_train_step: phase must be 0, 1 or 2"); return DCA_ERR_BAD_ARG; }
   if (!X || !Y) { set_error("dca_train_step: X and Y must not be NULL"); return DCA_ERR_BAD_ARG; }
   if (Bn <= 0 || Bn > cfg.max_batch) { set_error("dca_train_step: batch %d outside (0, max_batch=%d]", Bn, cfg.max_batch); return DCA_ERR_BAD_ARG; }
-  if (!graphs_enabled || prof.on) return train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s);
+  if (!graphs_enabled || prof.on) return train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, phase);
   // ---- CUDA-graph replay: the launch sequence only depends on (pointers, leading dims, batch); the batch's row
   // indices are copied into a fixed buffer so that the captured kernels read them from a stable address.
   StepGraph* g = nullptr;
   for (auto& c : graphs)
-    if (c.X == X && c.ldx == ldx && c.Y == Y && c.ldy == ldy && c.sf == sf && c.Bn == Bn && c.has_rows == (rows != nullptr)) { g = &c; break; }
+    if (c.X == X && c.ldx == ldx && c.Y == Y && c.ldy == ldy && c.sf == sf && c.Bn == Bn && c.has_rows == (rows != nullptr) && c.phase == phase) { g = &c; break; }
   if (!g) {
     if (graphs.size() >= 16) { for (auto& c : graphs) if (c.exec) cudaGraphExecDestroy(c.exec); graphs.clear(); }
-    graphs.push_back(StepGraph{X, ldx, Y, ldy, sf, Bn, rows != nullptr, nullptr, 0, 0});
+    graphs.push_back(StepGraph{X, ldx, Y, ldy, sf, Bn, rows != nullptr, phase, nullptr, 0, 0});
     g = &graphs.back();
   }
   int32_t* rbuf = reinterpret_cast<int32_t*>(base + o_rowsbuf);
@@ -380,7 +381,7 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
     // capture on the second call with this key (the first, direct call has done every one-time initialisation)
     const long long l0 = g_launches.load();
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      const int st = train_step_body(X, ldx, Y, ldy, sf, rows ? rbuf : nullptr, Bn, s);
+      const int st = train_step_body(X, ldx, Y, ldy, sf, rows ? rbuf : nullptr, Bn, s, phase);
       cudaGraph_t graph = nullptr;
       const cudaError_t ce = cudaStreamEndCapture(s, &graph);
       if (st == DCA_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
@@ -396,18 +397,22 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
     }
   }
   if (g->exec) {
-    if (rows) DCA_CUDA_OK(cudaMemcpyAsync(rbuf, rows, sizeof(int32_t) * (size_t)Bn, cudaMemcpyDeviceToDevice, s));
+    if (rows && phase != 2) DCA_CUDA_OK(cudaMemcpyAsync(rbuf, rows, sizeof(int32_t) * (size_t)Bn, cudaMemcpyDeviceToDevice, s));
     DCA_CUDA_OK(cudaGraphLaunch(g->exec, s));
     count_launch((int)g->launches);
     return DCA_OK;
   }
   if (g->seen < 1000) ++g->seen;
-  return train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s);
+  return train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, phase);
 }
 
+// phase 0: whole step; 1: forward + loss + head backward (the head gradients -- 98 % of the parameters -- are then
+// final, so their all-reduce can overlap phase 2); 2: hidden-stack / encoder backward.
 int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows,
-                            int Bn, cudaStream_t s) {
+                            int Bn, cudaStream_t s, int phase) {
   const int G = cfg.n_out;
+  float* dh = f(o_dh[0]); float* dh2 = f(o_dh[1]);
+  if (phase != 2) {
   DCA_CUDA_OK(cudaMemsetAsync(gp(0), 0, sizeof(float) * (size_t)(P + 2), s));
   bool any_pen = false;
   mark(0, s);
@@ -441,7 +446,6 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
 
   // ---- head backward
   mark(3, s);
-  float* dh = f(o_dh[0]); float* dh2 = f(o_dh[1]);
   if (L > 0) DCA_CUDA_OK(cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)Bn * K_head, s));
   float* dz[3] = {Mb, cond ? Db : nullptr, has_pi ? Pb : nullptr};
   if (tc_heads) {
@@ -469,6 +473,8 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
       DCA_TRY(gemm_auto(b, s));
     }
   }
+  }  // phase != 2
+  if (phase == 1) { mark(-1, s); return DCA_OK; }
   // ---- hidden stack backward
   mark(4, s);
   if (L > 0 && use_mid(Bn)) {
@@ -758,7 +764,19 @@ extern "C" int dca_params_changed(dca_handle* h, void* stream) {
 extern "C" int dca_train_step(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf,
                               const int32_t* rows, int32_t batch, void* stream) {
   DCA_NEED_HANDLE(h);
-  return h->e.train_step(X, ldx, Y, ldy, sf, rows, batch, (cudaStream_t)stream);
+  return h->e.train_step(X, ldx, Y, ldy, sf, rows, batch, (cudaStream_t)stream, 0);
+}
+extern "C" int dca_train_step_phase(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf,
+                                    const int32_t* rows, int32_t batch, int32_t phase, void* stream) {
+  DCA_NEED_HANDLE(h);
+  if (phase != 1 && phase != 2) { set_error("dca_train_step_phase: phase must be 1 or 2"); return DCA_ERR_BAD_ARG; }
+  return h->e.train_step(X, ldx, Y, ldy, sf, rows, batch, (cudaStream_t)stream, phase);
+}
+extern "C" int dca_grad_buckets(const dca_handle* h, int64_t* head_bucket_offset) {
+  DCA_NEED_HANDLE(h);
+  if (!head_bucket_offset) { set_error("dca_grad_buckets: NULL"); return DCA_ERR_BAD_ARG; }
+  *head_bucket_offset = h->e.head_W[0];      // grads[offset : P+2] are final after phase 1
+  return DCA_OK;
 }
 extern "C" int dca_apply_update(dca_handle* h, float lr, float clip, float grad_scale, void* stream) {
   DCA_NEED_HANDLE(h);
@@ -810,7 +828,7 @@ extern "C" int dca_train_step_host(dca_handle* h, const void* x_host, const floa
     DCA_CUDA_OK(cudaMemcpyAsync(e.base + e.o_stage_sf, sf_host, sizeof(float) * (size_t)batch, cudaMemcpyHostToDevice, s));
     sfd = e.f(e.o_stage_sf);
   }
-  DCA_TRY(e.train_step(e.base + e.o_stage_x, e.cfg.n_in, e.f(e.o_stage_y), e.cfg.n_out, sfd, nullptr, batch, s));
+  DCA_TRY(e.train_step(e.base + e.o_stage_x, e.cfg.n_in, e.f(e.o_stage_y), e.cfg.n_out, sfd, nullptr, batch, s, 0));
   DCA_TRY(e.apply_update(lr, clip, 1.0f, s));
   return dca_read_loss(h, loss_host, nullptr, stream);
 }
@@ -924,7 +942,7 @@ extern "C" int dca_stream_step(dca_handle* h, int64_t i, int64_t next, void* str
   hs.pref_idx = -1;
   if (next >= 0) DCA_TRY(e.stream_prefetch(next, b ^ 1));           // next batch's copy overlaps this batch's compute
   e.x_override_bf16 = to_xb ? 1 : 0;
-  const int st = e.train_step(xdst, e.cfg.n_in, e.f(e.o_stage_y), e.cfg.n_out, e.f(e.o_stage_sf), nullptr, nb, s);
+  const int st = e.train_step(xdst, e.cfg.n_in, e.f(e.o_stage_y), e.cfg.n_out, e.f(e.o_stage_sf), nullptr, nb, s, 0);
   e.x_override_bf16 = 0;
   return st;
 }

@@ -34,14 +34,14 @@ struct Engine {
   const void* head_in = nullptr; int64_t head_ld = 0; int head_bf16 = 0; const int32_t* head_rows = nullptr;
   // CUDA-graph replay of the training step (captured from the same launch sequence on the 2nd call with a key)
   struct StepGraph {
-    const void* X; int64_t ldx; const void* Y; int64_t ldy; const void* sf; int Bn; int has_rows;
+    const void* X; int64_t ldx; const void* Y; int64_t ldy; const void* sf; int Bn; int has_rows; int phase;
     cudaGraphExec_t exec; long long launches; int seen;
   };
   std::vector<StepGraph> graphs;
   bool graphs_enabled = true;
   size_t o_rowsbuf = 0;
   int train_step_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
-                      cudaStream_t s);
+                      cudaStream_t s, int phase);
   // streaming from host counts
   size_t o_cnt[2] = {0, 0}, o_sfst[2] = {0, 0}, o_gmean = 0, o_ginv = 0;
   int tf_use_sf = 1, tf_use_log1p = 1, tf_set = 0, x_override_bf16 = 0;
@@ -87,7 +87,7 @@ struct Engine {
                     cudaStream_t s);
   int penalty(cudaStream_t s, bool& any);
   int train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
-                 cudaStream_t s);
+                 cudaStream_t s, int phase = 0);
   int apply_update(float lr, float clip, float grad_scale, cudaStream_t s);
   int eval_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
                 cudaStream_t s);

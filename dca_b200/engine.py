@@ -71,6 +71,9 @@ class DeviceEngine:
         self.bn_state = self._region(_lib.REGION_BN_STATE, torch.float32)
         self.epoch_acc = self._region(_lib.REGION_EPOCH_ACC, torch.float64)
         self.n_params = self.params.numel()
+        hb = C.c_int64()
+        check(self.lib.dca_grad_buckets(self.handle, C.byref(hb)), "dca_grad_buckets")
+        self.head_bucket = int(hb.value)
         self.param_info = self._infos(self.lib.dca_param_count, self.lib.dca_param_info)
         self.state_info = self._infos(self.lib.dca_state_count, self.lib.dca_state_info)
         if seed is not None:
@@ -175,11 +178,27 @@ class DeviceEngine:
             raise ValueError("batch %d > max_batch %d" % (batch, self.max_batch))
         return int(batch)
 
-    def train_step(self, X, Y, sf, rows=None, batch=None):
-        """Forward + loss + backward into ``self.grads`` (no update)."""
+    def train_step(self, X, Y, sf, rows=None, batch=None, phase=0):
+        """Forward + loss + backward into ``self.grads`` (no update).  phase 1 / 2 run the two halves
+        (see dca_train_step_phase): after phase 1 ``self.grads[self.head_bucket:]`` is final."""
         b = self._check_inputs(X, Y, sf, rows, batch)
-        check(self.lib.dca_train_step(self.handle, _ptr(X), X.stride(0), _ptr(Y), Y.stride(0), _ptr(sf), _ptr(rows),
-                                      b, self._stream()), "dca_train_step")
+        if phase == 0:
+            check(self.lib.dca_train_step(self.handle, _ptr(X), X.stride(0), _ptr(Y), Y.stride(0), _ptr(sf), _ptr(rows),
+                                          b, self._stream()), "dca_train_step")
+        else:
+            check(self.lib.dca_train_step_phase(self.handle, _ptr(X), X.stride(0), _ptr(Y), Y.stride(0), _ptr(sf),
+                                                _ptr(rows), b, phase, self._stream()), "dca_train_step_phase")
+
+    def train_step_allreduce(self, X, Y, sf, rows=None):
+        """Data-parallel step: the all-reduce of the head-gradient bucket overlaps the hidden-stack backward."""
+        import torch.distributed as dist
+        self.train_step(X, Y, sf, rows=rows, phase=1)
+        w1 = dist.all_reduce(self.grads[self.head_bucket:], async_op=True)
+        self.train_step(X, Y, sf, rows=rows, phase=2)
+        w2 = dist.all_reduce(self.grads[:self.head_bucket], async_op=True) if self.head_bucket > 0 else None
+        w1.wait()
+        if w2 is not None:
+            w2.wait()
 
     def apply_update(self, lr: float, clip: float = 5.0, grad_scale: float = 1.0):
         check(self.lib.dca_apply_update(self.handle, lr, clip, grad_scale, self._stream()), "dca_apply_update")

@@ -131,9 +131,10 @@ def train(adata, network, output_dir=None, optimizer='RMSprop', learning_rate=No
         eng.read_epoch_acc(reset=True)
         for s in range(steps):
             rows = order_d[s * batch_size: min((s + 1) * batch_size, n_tr)]
-            eng.train_step(Xd, Yd, sfd, rows=rows)
             if world > 1:
-                D.all_reduce_sum_(eng.grads)
+                eng.train_step_allreduce(Xd, Yd, sfd, rows=rows)     # NCCL all-reduce overlapped with the backward tail
+            else:
+                eng.train_step(Xd, Yd, sfd, rows=rows)
             eng.apply_update(ctl.lr, clip_grad, gscale)
         # validation pass: inference-mode BN over the held-out tail
         for s in range(n_tr, n_tr + n_va, batch_size):

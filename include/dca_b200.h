@@ -129,6 +129,14 @@ int dca_params_changed(dca_handle* h, void* stream);
 int dca_train_step(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy,
                    const float* sf, const int32_t* rows, int32_t batch, void* stream);
 
+/* The same step in two halves, for overlapping the gradient all-reduce with the tail of the backward pass:
+ * phase 1 = forward + loss + head backward (afterwards grads[head_bucket_offset : P+2] -- the head kernels and
+ * biases, ~98 % of the parameters, plus the loss slot -- are final), phase 2 = hidden-stack / encoder backward
+ * (fills grads[0 : head_bucket_offset]).  Same arguments for both calls. */
+int dca_train_step_phase(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy,
+                         const float* sf, const int32_t* rows, int32_t batch, int32_t phase, void* stream);
+int dca_grad_buckets(const dca_handle* h, int64_t* head_bucket_offset);
+
 /* clip(g*grad_scale, +-clip) -> RMSprop (rho, eps from config) -> parameters.
  * Replaces keras RMSprop(clipvalue=clip_grad[, lr]) applied by model.fit: dca/train.py:54-57.
  * grad_scale = 1/world_size after a sum all-reduce of DCA_REGION_GRADS, else 1. */

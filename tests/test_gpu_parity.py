@@ -408,3 +408,24 @@ def test_stream_from_host_counts_matches_resident_path():
             l1, l2 = e1.read_loss(), e2.read_loss()
             assert abs(l1 - l2) < tol * abs(l1), (gemm_path, i, l1, l2)
         e2.stream_end()
+
+
+@pytest.mark.parametrize("gemm_path", ["generic", "tcgen05"])
+def test_two_phase_step_equals_single_call(gemm_path):
+    """dca_train_step_phase(1) + (2) == dca_train_step; after phase 1 the head bucket of the gradient is final."""
+    from dca_b200.engine import DeviceEngine
+    B, G = 256, 264
+    X, Y, sf = _problem(B, G, 41)
+    e1 = DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=5, gemm_path=gemm_path)
+    e2 = DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=5, gemm_path=gemm_path)
+    Xd, Yd, sfd = _t(X), _t(Y), _t(sf)
+    for _ in range(3):                       # 3 rounds: direct call, graph capture, graph replay
+        e1.train_step(Xd, Yd, sfd)
+        e2.train_step(Xd, Yd, sfd, phase=1)
+        head_after_1 = e2.grads[e2.head_bucket:].clone()
+        e2.train_step(Xd, Yd, sfd, phase=2)
+        torch.cuda.synchronize()
+        assert torch.equal(head_after_1, e2.grads[e2.head_bucket:])
+        g1, g2 = e1.grads.cpu().numpy(), e2.grads.cpu().numpy()
+        assert np.max(np.abs(g1 - g2)) <= 1e-5 * np.max(np.abs(g1)) + 1e-12     # atomics: summation order only
+        e1.apply_update(1e-3, 5.0); e2.apply_update(1e-3, 5.0)
