@@ -267,6 +267,12 @@ def main():
     stream_idx = torch.cat([torch.randperm(n_train, generator=gperm, device=dev) for _ in range(need // n_train + 1)])[:need]
     stream_idx = stream_idx.to(torch.int32).contiguous()
 
+    # Everything below runs on a NON-default stream: the legacy default stream serialises against the engine's
+    # internal copy stream (no H2D/compute overlap) and cannot be captured into a CUDA graph.
+    torch.cuda.synchronize(dev)
+    side = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(side)
+
     def step(i):
         rows = stream_idx[i * batch:(i + 1) * batch]
         if world > 1:

@@ -388,11 +388,15 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
         g->launches = g_launches.load() - l0;
         g_launches.store(l0);                      // the capture itself launched nothing
       } else {
+        if (getenv("DCA_GRAPH_DEBUG"))
+          fprintf(stderr, "[dca_b200] graph capture failed: body status %d (%s), end-capture %s\n", st, g_err,
+                  cudaGetErrorString(ce));
         g->exec = nullptr; g->seen = 1000;         // not capturable: stay on the direct path for this key
         (void)cudaGetLastError();
       }
       if (graph) cudaGraphDestroy(graph);
     } else {
+      if (getenv("DCA_GRAPH_DEBUG")) fprintf(stderr, "[dca_b200] cudaStreamBeginCapture failed: %s\n", cudaGetErrorString(cudaGetLastError()));
       (void)cudaGetLastError(); g->seen = 1000;
     }
   }
@@ -941,6 +945,8 @@ extern "C" int dca_stream_step(dca_handle* h, int64_t i, int64_t next, void* str
   ++hs.step_no;
   hs.pref_idx = -1;
   if (next >= 0) DCA_TRY(e.stream_prefetch(next, b ^ 1));           // next batch's copy overlaps this batch's compute
+  static const int diag = [] { const char* v = getenv("DCA_STREAM_DIAG"); return v ? atoi(v) : 0; }();
+  if (diag == 1) return DCA_OK;                     // diagnosis: copies + expansion only
   e.x_override_bf16 = to_xb ? 1 : 0;
   const int st = e.train_step(xdst, e.cfg.n_in, e.f(e.o_stage_y), e.cfg.n_out, e.f(e.o_stage_sf), nullptr, nb, s, 0);
   e.x_override_bf16 = 0;

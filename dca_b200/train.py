@@ -117,12 +117,29 @@ def train(adata, network, output_dir=None, optimizer='RMSprop', learning_rate=No
     lr = KERAS_DEFAULTS["rms_lr"] if learning_rate is None else float(learning_rate)
     ctl = PlateauAndStop(lr, reduce_lr, early_stop, verbose)
     hist = History()
-    best_val = np.inf
     if verbose:
         print(network.summary())
 
     steps = (n_tr + batch_size - 1) // batch_size
     gscale = 1.0 / world
+    # run on a non-default stream (CUDA-graph replay of the step needs a capturable stream)
+    torch.cuda.synchronize(dev)
+    prev_stream = torch.cuda.current_stream(dev)
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
+    try:
+        hist = _fit_loop(eng, network, Xd, Yd, sfd, n_tr, n_va, steps, batch_size, epochs, ctl, clip_grad, gscale, world, rank,
+                         dev, hist, verbose, save_weights, output_dir)
+    finally:
+        torch.cuda.synchronize(dev)
+        torch.cuda.set_stream(prev_stream)
+    if not hist.history["val_loss"]:
+        del hist.history["val_loss"]
+    return hist
+
+
+def _fit_loop(eng, network, Xd, Yd, sfd, n_tr, n_va, steps, batch_size, epochs, ctl, clip_grad, gscale, world, rank, dev, hist,
+              verbose, save_weights, output_dir):
+    best_val = np.inf
     for epoch in range(epochs):
         # Keras: np.random.shuffle(index_array) with the global NumPy RNG (seeded in api.dca / CLI)
         order = np.arange(n_tr)
@@ -168,8 +185,6 @@ def train(adata, network, output_dir=None, optimizer='RMSprop', learning_rate=No
                 network.save_weights(os.path.join(output_dir, "weights.npz"))
         if ctl.on_epoch_end(epoch, val):
             break
-    if not hist.history["val_loss"]:
-        del hist.history["val_loss"]
     return hist
 
 
