@@ -365,7 +365,9 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
   if (phase < 0 || phase > 2) { set_error("dca_train_step: phase must be 0, 1 or 2"); return DCA_ERR_BAD_ARG; }
   if (!X || !Y) { set_error("dca_train_step: X and Y must not be NULL"); return DCA_ERR_BAD_ARG; }
   if (Bn <= 0 || Bn > cfg.max_batch) { set_error("dca_train_step: batch %d outside (0, max_batch=%d]", Bn, cfg.max_batch); return DCA_ERR_BAD_ARG; }
-  if (!graphs_enabled || prof.on) return train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, phase);
+  // the legacy default stream (handle 0) cannot be captured: stay on the direct path there
+  if (!graphs_enabled || prof.on || s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread)
+    return train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, phase);
   // ---- CUDA-graph replay: the launch sequence only depends on (pointers, leading dims, batch); the batch's row
   // indices are copied into a fixed buffer so that the captured kernels read them from a stable address.
   StepGraph* g = nullptr;
