@@ -323,8 +323,17 @@ def main():
     loss_bytes = batch * genes * (4 + 4 * nh + einfo["grad_bytes"] * nh)
     ach = loss_bytes / (loss_ms / max(loss_n, 1) * 1e-3) / 1e9 if loss_ms > 0 else None
     step_ms_prof = sum(v[0] for v in prof.values()) / max(a.steps, 1)
-    roofline = {"kernel": "zinb_loss_kernel (phase loss_fwd_bwd: K3 + partial folds)", "bound": "hbm", "achieved": ach,
-                "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            tj = json.load(f).get(a.workload)
+        if tj and batch == 4096:
+            traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]; traffic_src = tj["source"]
+    except Exception:
+        pass
+    roofline = {"kernel": "zinb_loss_bwd_staged_kernel (phase loss_fwd_bwd: K3 + partial fold)", "bound": "hbm", "achieved": ach,
+                "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": loss_bytes,
                 "bytes_per_element": 4 + 4 * nh + einfo["grad_bytes"] * nh, "engine": einfo,
                 "share_of_step": (loss_ms / max(loss_n, 1)) / step_ms_prof if step_ms_prof > 0 else None}
