@@ -13,10 +13,10 @@
 // both gradients.  Accumulators live in TMEM: one 128x64 fp32 tile per gene block
 // of the item for (a), a double-buffered 128x64 tile per cell block for (b).  (b) leaves through a
 // swizzled staging tile and a TMA reduce-add (split over gene ranges); (a) is added to the gradient
-// buffer by the epilogue warps at the end of the item; the per-gene column sums (bias gradient) are
-// taken from the shared-memory tile by four otherwise idle warps.
+// buffer by the epilogue warps at the end of the item; the per-gene column sums (bias gradient) are one
+// more tcgen05 product of the same tile with a constant ones operand (Z^T . 1, N = 16).
 //
-// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue, 8-11 column sums.
+// Warp roles (256 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue.
 #include "engine.h"
 #include "tc_common.cuh"
 
@@ -24,7 +24,7 @@ namespace dca {
 namespace tc {
 namespace gg {
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 256;
 constexpr int kZStages = 3;
 constexpr uint32_t kZBytes = 128 * 128 * 2;          // 2 boxes x [128 cells x 64 genes] bf16
 constexpr uint32_t kWBytes = 64 * 128 * 2;           // 2 boxes x [64 feats x 64 genes] bf16
@@ -54,24 +54,30 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
   uint8_t* s_z = smem;                                          // [kZStages][Z | W]
   uint8_t* s_h = s_z + kZStages * kStage;                       // [2][H]
   uint8_t* s_o = s_h + (DO_A ? 2 * kHBytes : 0);                // staging for (b)
+  uint8_t* s_ones = s_o + (DO_B ? kOutBytes : 0);               // [16 x 64] bf16 ones (K-major B operand of the column sums)
   __shared__ uint64_t z_full[kZStages], z_empty[kZStages], h_full[2], h_empty[2], dh_full[2], dh_empty[2], dw_full, dw_empty;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kZStages; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 1 + (COLSUM ? 4 : 0)); }
+    for (int i = 0; i < kZStages; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); mbar_init(&dh_full[i], 1); mbar_init(&dh_empty[i], 4); }
     mbar_init(&dw_full, 1); mbar_init(&dw_empty, 4);
     fence_barrier_init();
     tma_prefetch_desc(&map_z0); tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_o);
   }
   if (warp == 2) tmem_alloc(&tmem_base_s, kTmemCols);
+  if (COLSUM) {   // bf16 1.0 = 0x3F80; every element equal, so the swizzle pattern does not matter
+    for (int i = threadIdx.x; i < 2048 / 4; i += kThreads) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t tm_dw = tmem;                 // kMaxGb x 64 columns
   const uint32_t tm_dh = tmem + kMaxGb * 64;   // 2 x 64 columns
+  const uint32_t tm_cs = tm_dh + 2 * 64;       // kMaxGb x 16 columns: column sums (every column of a block is the same)
 
   struct Item { int head, gb0, gb1, cb0, cb1; };
   auto decode = [&](int it) {
@@ -117,6 +123,7 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc_b = make_idesc_bf16(128, 64, 0, 0);     // Z K-major  x W K-major
       constexpr uint32_t idesc_a = make_idesc_bf16(128, 64, 1, 1);     // Z MN-major x H MN-major
+      constexpr uint32_t idesc_c = make_idesc_bf16(128, 16, 1, 0);     // Z MN-major x ones K-major -> column sums
       uint32_t zi = 0, hi = 0, di = 0, wi = 0;
       for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++wi) {
         const Item x = decode(it);
@@ -146,6 +153,13 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
               for (int k = 0; k < 8; ++k)
                 umma_bf16(tm_dw + (gb - x.gb0) * 64, make_smem_desc(zb + k * 2048, kZBytes / 2, 1024),
                           make_smem_desc(hb + k * 2048, 0, 1024), idesc_a, (cb > x.cb0 || k > 0) ? 1u : 0u);
+              if (COLSUM) {   // db[g] += sum over the tile's 128 cells of Z[cell][g]  (Z^T . 1 on the tensor core)
+                const uint32_t ob = smem_u32(s_ones);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  umma_bf16(tm_cs + (gb - x.gb0) * 16, make_smem_desc(zb + k * 2048, kZBytes / 2, 1024),
+                            make_smem_desc(ob + (k & 3) * 32, 0, 1024), idesc_c, (cb > x.cb0 || k > 0) ? 1u : 0u);
+              }
             }
             umma_commit(&z_empty[st]);
           }
@@ -196,6 +210,12 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
         float* dst = p.dW[x.head];
         for (int gb = x.gb0; gb < x.gb1; ++gb) {
           const int g = gb * 128 + quarter * 32 + lane;
+          if (COLSUM) {
+            uint32_t v[32];
+            tmem_ld_32x32(tm_cs + ((uint32_t)(quarter * 32) << 16) + (gb - x.gb0) * 16, v);
+            tmem_ld_wait();
+            if (g < p.G && p.db[x.head]) atomicAdd(p.db[x.head] + g, __uint_as_float(v[0]));
+          }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
@@ -217,43 +237,6 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
       }
     }
     if (DO_B && warp == 4 && lane == 0) bulk_wait<0>();
-  } else if (COLSUM && warp >= 8) {
-    // ===================================================== column sums of Z from the smem tile
-    const int t = threadIdx.x - 256;            // 0..127
-    const int pr = t & 63, half = t >> 6;       // gene pair within the 128-gene tile, row parity
-    uint32_t zi = 0;
-    for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
-      const Item x = decode(it);
-      float acc[kMaxGb][2];
-#pragma unroll
-      for (int i = 0; i < kMaxGb; ++i) acc[i][0] = acc[i][1] = 0.f;
-      for (int cb = x.cb0; cb < x.cb1; ++cb) {
-        for (int gb = x.gb0; gb < x.gb1; ++gb) {
-          const uint32_t st = zi % kZStages, ph = (zi / kZStages) & 1; ++zi;
-          mbar_wait(&z_full[st], ph);
-          const uint8_t* box = s_z + st * kStage + (pr >> 5) * (kZBytes / 2);   // 64-gene box holding this pair
-          const int cg = (pr & 31) * 2;                                          // gene offset inside the box (even)
-          float s0 = 0.f, s1 = 0.f;
-#pragma unroll 4
-          for (int r = half; r < 128; r += 2) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(box + r * 128 + ((((cg >> 3) ^ (r & 7))) << 4) + (cg & 7) * 2);
-            s0 += __uint_as_float(w << 16);
-            s1 += __uint_as_float(w & 0xffff0000u);
-          }
-          acc[gb - x.gb0][0] += s0; acc[gb - x.gb0][1] += s1;
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&z_empty[st]);
-        }
-      }
-      float* db = p.db[x.head];
-      if (db) {
-        for (int gb = x.gb0; gb < x.gb1; ++gb) {
-          const int g = gb * 128 + pr * 2;
-          if (g < p.G) atomicAdd(db + g, acc[gb - x.gb0][0]);
-          if (g + 1 < p.G) atomicAdd(db + g + 1, acc[gb - x.gb0][1]);
-        }
-      }
-    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -262,7 +245,7 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
 
 template <bool DO_A, bool DO_B, bool COLSUM>
 constexpr uint32_t smem_bytes() {
-  return kZStages * (kZBytes + (DO_B ? kWBytes : 0)) + (DO_A ? 2 * kHBytes : 0) + (DO_B ? kOutBytes : 0) + 1024;
+  return kZStages * (kZBytes + (DO_B ? kWBytes : 0)) + (DO_A ? 2 * kHBytes : 0) + (DO_B ? kOutBytes : 0) + (COLSUM ? 2048 : 0) + 1024;
 }
 
 }  // namespace gg
@@ -285,18 +268,28 @@ int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, 
   Params p{};
   p.B = B; p.G = G; p.n_heads = n_heads;
   p.n_cb = cdiv(B, 128); p.n_gb = cdiv(G, 128);
-  const int total_gb = p.n_gb * n_heads;
-  if (do_a) {
-    // gene ranges limited by TMEM (kMaxGb accumulators); split cells to fill the SMs
-    int gpi = cdiv(total_gb, sm_count); if (gpi < 1) gpi = 1; if (gpi > kMaxGb) gpi = kMaxGb;
-    p.gb_per_item = gpi; p.gene_ranges = cdiv(p.n_gb, gpi);
-    int splits = sm_count / (p.gene_ranges * n_heads); if (splits < 1) splits = 1; if (splits > p.n_cb) splits = p.n_cb;
-    p.cb_per_item = cdiv(p.n_cb, splits); p.cell_splits = cdiv(p.n_cb, p.cb_per_item);
-  } else {
-    // (b) only: one cell block per item, genes split so that items ~ SM count
-    p.cb_per_item = 1; p.cell_splits = p.n_cb;
-    int gsplits = sm_count / p.n_cb; if (gsplits < 1) gsplits = 1; if (gsplits > p.n_gb) gsplits = p.n_gb;
-    p.gb_per_item = cdiv(p.n_gb, gsplits); p.gene_ranges = cdiv(p.n_gb, p.gb_per_item);
+  // Work decomposition: items = (head, gene range, cell range), processed by a persistent grid.  Pick the
+  // (gene blocks per item, cell splits) pair with the smallest makespan in tiles; every extra cell split adds
+  // one more atomic pass over the (a) outputs, every extra gene split one more reduce-add over the (b) output.
+  {
+    long best_cost = -1;
+    const int gpi_max = do_a ? kMaxGb : p.n_gb;
+    for (int gpi = 1; gpi <= gpi_max; gpi = (gpi < 4 ? gpi * 2 : gpi + 4)) {
+      const int ranges = cdiv(p.n_gb, gpi);
+      for (int splits = 1; splits <= p.n_cb; splits *= 2) {
+        const int cpi = cdiv(p.n_cb, splits), csplits = cdiv(p.n_cb, cpi);
+        const long items = (long)ranges * n_heads * csplits;
+        const long tiles = (long)gpi * cpi;                                   // tiles per item
+        const long waves = (items + sm_count - 1) / sm_count;
+        long cost = waves * tiles * 16;                                       // makespan (x16 fixed point)
+        if (do_a) cost += (long)(csplits - 1) * ((long)p.n_gb * n_heads * 16 / sm_count + 1) * 2;   // extra atomic passes
+        if (do_b) cost += (long)(ranges - 1) * ((long)p.n_cb * 16 / sm_count + 1) / 4;             // extra reduce-adds
+        if (tiles < 4 && items > sm_count) cost += 64;                        // items too small to fill the pipeline
+        if (best_cost < 0 || cost < best_cost) {
+          best_cost = cost; p.gb_per_item = gpi; p.gene_ranges = ranges; p.cb_per_item = cpi; p.cell_splits = csplits;
+        }
+      }
+    }
   }
   p.total_items = p.gene_ranges * p.cell_splits * n_heads;
   for (int i = 0; i < 3; ++i) { p.dW[i] = dW ? dW[i] : nullptr; p.db[i] = db ? db[i] : nullptr; }
