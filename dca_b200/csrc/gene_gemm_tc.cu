@@ -54,7 +54,7 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
   uint8_t* s_z = smem;                                          // [kZStages][Z | W]
   uint8_t* s_h = s_z + kZStages * kStage;                       // [2][H]
   uint8_t* s_o = s_h + (DO_A ? 2 * kHBytes : 0);                // staging for (b)
-  uint8_t* s_ones = s_o + (DO_B ? kOutBytes : 0);               // [16 x 64] bf16 ones (K-major B operand of the column sums)
+  uint8_t* s_ones = s_o + ((DO_B || (DO_A && !DO_B)) ? kOutBytes : 0);               // [16 x 64] bf16 ones (K-major B operand of the column sums)
   __shared__ uint64_t z_full[kZStages], z_empty[kZStages], h_full[2], h_empty[2], dh_full[2], dh_empty[2], dw_full, dw_empty;
   __shared__ uint32_t tmem_base_s;
 
@@ -208,6 +208,31 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
         mbar_wait(&dw_full, wi & 1);
         tcgen05_fence_after();
         float* dst = p.dW[x.head];
+        if (!DO_B && !p.dW_transposed) {
+          // [128 genes x 64] accumulator == row-major block of dW[G x 64]: swizzled staging + TMA reduce-add
+          for (int gb = x.gb0; gb < x.gb1; ++gb) {
+            if (warp == 4 && lane == 0) bulk_wait_read<0>();
+            named_barrier_sync(3, 128);
+            const int row = quarter * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t v[32];
+              tmem_ld_32x32(tm_dw + ((uint32_t)(quarter * 32) << 16) + (gb - x.gb0) * 64 + c * 32, v);
+              tmem_ld_wait();
+              uint8_t* tile = s_o + c * (kOutBytes / 2);
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<uint4*>(tile + row * 128 + ((q ^ (row & 7)) << 4)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            }
+            fence_proxy_async_smem();
+            named_barrier_sync(3, 128);
+            if (warp == 4 && lane == 0) {
+              tma_reduce_add_2d(&map_o, 0, gb * 128, s_o);
+              tma_reduce_add_2d(&map_o, 32, gb * 128, s_o + kOutBytes / 2);
+              bulk_commit();
+            }
+          }
+        } else
         for (int gb = x.gb0; gb < x.gb1; ++gb) {
           const int g = gb * 128 + quarter * 32 + lane;
           if (COLSUM) {
@@ -236,7 +261,7 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
         if (lane == 0) mbar_arrive(&dw_empty);
       }
     }
-    if (DO_B && warp == 4 && lane == 0) bulk_wait<0>();
+    if (warp == 4 && lane == 0) bulk_wait<0>();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -245,7 +270,7 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
 
 template <bool DO_A, bool DO_B, bool COLSUM>
 constexpr uint32_t smem_bytes() {
-  return kZStages * (kZBytes + (DO_B ? kWBytes : 0)) + (DO_A ? 2 * kHBytes : 0) + (DO_B ? kOutBytes : 0) + (COLSUM ? 2048 : 0) + 1024;
+  return kZStages * (kZBytes + (DO_B ? kWBytes : 0)) + (DO_A ? 2 * kHBytes : 0) + kOutBytes + (COLSUM ? 2048 : 0) + 1024;
 }
 
 }  // namespace gg
@@ -264,32 +289,37 @@ int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, 
   if (do_b) {
     DCA_TRY(make_tensor_map_2d(&mw, W, 2, 1, 64, (uint64_t)n_heads * G, (uint64_t)n_heads * G, 64, 64, 1));
     DCA_TRY(make_tensor_map_2d(&mo, out_b, 4, 0, (uint64_t)B, 64, 64, 128, 32, 1));
-  } else { mw = mz[0]; mo = mz[0]; }
+  } else {
+    mw = mz[0]; mo = mz[0];
+    if (do_a && !dW_transposed) {
+      if (dW_ld != 64) { set_error("gene_gemm_tc: non-transposed dW needs ld == 64"); return DCA_ERR_BAD_ARG; }
+      DCA_TRY(make_tensor_map_2d(&mo, dW[0], 4, 0, (uint64_t)G, 64, 64, 128, 32, 1));
+    }
+  }
   Params p{};
   p.B = B; p.G = G; p.n_heads = n_heads;
   p.n_cb = cdiv(B, 128); p.n_gb = cdiv(G, 128);
-  // Work decomposition: items = (head, gene range, cell range), processed by a persistent grid.  Pick the
-  // (gene blocks per item, cell splits) pair with the smallest makespan in tiles; every extra cell split adds
-  // one more atomic pass over the (a) outputs, every extra gene split one more reduce-add over the (b) output.
-  {
-    long best_cost = -1;
-    const int gpi_max = do_a ? kMaxGb : p.n_gb;
-    for (int gpi = 1; gpi <= gpi_max; gpi = (gpi < 4 ? gpi * 2 : gpi + 4)) {
-      const int ranges = cdiv(p.n_gb, gpi);
-      for (int splits = 1; splits <= p.n_cb; splits *= 2) {
-        const int cpi = cdiv(p.n_cb, splits), csplits = cdiv(p.n_cb, cpi);
-        const long items = (long)ranges * n_heads * csplits;
-        const long tiles = (long)gpi * cpi;                                   // tiles per item
-        const long waves = (items + sm_count - 1) / sm_count;
-        long cost = waves * tiles * 16;                                       // makespan (x16 fixed point)
-        if (do_a) cost += (long)(csplits - 1) * ((long)p.n_gb * n_heads * 16 / sm_count + 1) * 2;   // extra atomic passes
-        if (do_b) cost += (long)(ranges - 1) * ((long)p.n_cb * 16 / sm_count + 1) / 4;             // extra reduce-adds
-        if (tiles < 4 && items > sm_count) cost += 64;                        // items too small to fill the pipeline
-        if (best_cost < 0 || cost < best_cost) {
-          best_cost = cost; p.gb_per_item = gpi; p.gene_ranges = ranges; p.cb_per_item = cpi; p.cell_splits = csplits;
-        }
-      }
-    }
+  // Work decomposition: items = (head, gene range, cell range), processed by a persistent grid.
+  const int total_gb = p.n_gb * n_heads;
+  if (do_a && do_b) {
+    // head backward: gene ranges limited by TMEM (kMaxGb accumulators); split cells to fill the SMs.  The (a)
+    // outputs leave by atomics, so few, fat items (one wave) are preferred.
+    int gpi = cdiv(total_gb, sm_count); if (gpi < 1) gpi = 1; if (gpi > kMaxGb) gpi = kMaxGb;
+    p.gb_per_item = gpi; p.gene_ranges = cdiv(p.n_gb, gpi);
+    int splits = sm_count / (p.gene_ranges * n_heads); if (splits < 1) splits = 1; if (splits > p.n_cb) splits = p.n_cb;
+    p.cb_per_item = cdiv(p.n_cb, splits); p.cell_splits = cdiv(p.n_cb, p.cb_per_item);
+  } else if (do_a) {
+    // encoder backward: outputs leave by TMA reduce-add, extra cell splits are cheap -> ~4 items per SM
+    p.gb_per_item = 1; p.gene_ranges = p.n_gb;
+    int splits = cdiv(4 * sm_count, p.gene_ranges * n_heads); if (splits < 1) splits = 1; if (splits > p.n_cb) splits = p.n_cb;
+    while (splits > 1 && cdiv(p.n_cb, splits) < 4) --splits;          // >= 4 tiles per item
+    p.cb_per_item = cdiv(p.n_cb, splits); p.cell_splits = cdiv(p.n_cb, p.cb_per_item);
+  } else {
+    // encoder forward: one cell block per item, genes split so that there are ~4 items per SM
+    p.cb_per_item = 1; p.cell_splits = p.n_cb;
+    int gsplits = cdiv(4 * sm_count, p.n_cb); if (gsplits < 1) gsplits = 1; if (gsplits > p.n_gb) gsplits = p.n_gb;
+    while (gsplits > 1 && cdiv(p.n_gb, gsplits) < 4) --gsplits;
+    p.gb_per_item = cdiv(p.n_gb, gsplits); p.gene_ranges = cdiv(p.n_gb, p.gb_per_item);
   }
   p.total_items = p.gene_ranges * p.cell_splits * n_heads;
   for (int i = 0; i < 3; ++i) { p.dW[i] = dW ? dW[i] : nullptr; p.db[i] = db ? db[i] : nullptr; }
