@@ -87,7 +87,7 @@ int theta_grad_finish(const float* dtheta, const float* chain, int G, float scal
 int add_reg_grad(const float* w, float* g, int64_t n, float l1, float l2, cudaStream_t s);
 int reg_penalty(const float* w, int64_t n, float l1, float l2, double* acc, cudaStream_t s);
 int rmsprop_update(float* params, const float* grads, float* rms, int64_t n, float lr, float clip,
-                   float rho, float eps, float grad_scale, cudaStream_t s);
+                   float rho, float eps, float grad_scale, __nv_bfloat16* shadow, cudaStream_t s);
 int glorot_fill(float* w, int64_t n, int fan_in, int fan_out, uint64_t seed, uint64_t stream_id, cudaStream_t s);
 int fill_value(float* p, int64_t n, float v, cudaStream_t s);
 int cast_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
@@ -103,11 +103,11 @@ int gather_rows_bf16(const void* X, int x_bf16, int64_t ldx, const int32_t* rows
 
 // ---------------------------------------------------------------- tcgen05 kernels (dense_tc.cu, gene_gemm_tc.cu)
 namespace tc {
-int heads_fwd_tc(const __nv_bfloat16* Hb, int B, const __nv_bfloat16* WhT, const float* bias, int G, int n_heads,
-                 const int kind[3], const float* row_scale, float* const out[3], int64_t ld_out, int sm_count,
+int heads_fwd_tc(const __nv_bfloat16* Hb, int B, const __nv_bfloat16* const W[3], const float* const bias[3], int G,
+                 int n_heads, const int kind[3], const float* row_scale, float* const out[3], int64_t ld_out, int sm_count,
                  cudaStream_t s);
 int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, int G, int n_heads,
-                 const __nv_bfloat16* H, const __nv_bfloat16* W, float* out_b, float* const dW[3], int64_t dW_ld,
+                 const __nv_bfloat16* H, const __nv_bfloat16* const W[3], float* out_b, float* const dW[3], int64_t dW_ld,
                  int dW_transposed, float* const db[3], int sm_count, cudaStream_t s);
 }  // namespace tc
 

@@ -129,7 +129,7 @@ struct Params {
   int B, G, n_heads;
   int kind[3];                 // EPI_MEAN_ACT / EPI_DISP_ACT / EPI_SIGMOID per packed head slot
   int m_tiles, n_tiles_per_head, total_tiles;
-  const float* bias;           // [n_heads * G], packed in head-slot order
+  const float* bias[3];        // per head slot: float[G]
   const float* row_scale;      // [B] or nullptr
 };
 
@@ -145,7 +145,8 @@ __device__ __forceinline__ float act_disp(float z) {
 __device__ __forceinline__ float act_sigmoid(float z) { return rcpf(1.0f + ex2f(-z * 1.442695041f)); }
 
 __global__ void __launch_bounds__(kThreads, 1)
-heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w,
+heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w0,
+                 const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
                  const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
                  const __grid_constant__ CUtensorMap map_o2, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -161,7 +162,7 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < kAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
     fence_barrier_init();
-    tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_w0);
     tma_prefetch_desc(&map_o0); tma_prefetch_desc(&map_o1); tma_prefetch_desc(&map_o2);
   }
   if (warp == 2) tmem_alloc(&tmem_base_s, kAccStages * BN);      // 512 columns
@@ -183,12 +184,15 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
         uint8_t* a = s_ab + (size_t)st * kStageBytes;
         mbar_expect_tx(&full_bar[st], kStageBytes);
         tma_load_2d(a, &map_h, 0, mt * BM, &full_bar[st]);
-        tma_load_2d(a + kABytes, &map_w, 0, hs * p.G + nt * BN, &full_bar[st]);
+        // B = the head kernel in its Keras layout [64 k][G genes] (bf16 shadow): four 64-gene boxes, MN-major
+        const CUtensorMap* mw = hs == 0 ? &map_w0 : (hs == 1 ? &map_w1 : &map_w2);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) tma_load_2d(a + kABytes + j * (kBBytes / 4), mw, nt * BN + j * 64, 0, &full_bar[st]);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 1);     // A = H K-major, B = W MN-major (genes contiguous)
       int it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
         const int st = it % kStages; const uint32_t ph = (it / kStages) & 1;
@@ -199,7 +203,7 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
         const uint32_t a0 = smem_u32(s_ab + (size_t)st * kStageBytes), b0 = a0 + kABytes;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)
-          umma_bf16(tmem + as * BN, make_smem_desc(a0 + k * 32, 0, 1024), make_smem_desc(b0 + k * 32, 0, 1024), idesc, k > 0);
+          umma_bf16(tmem + as * BN, make_smem_desc(a0 + k * 32, 0, 1024), make_smem_desc(b0 + k * 2048, kBBytes / 4, 1024), idesc, k > 0);
         umma_commit(&empty_bar[st]);
         umma_commit(&tfull_bar[as]);
       }
@@ -218,7 +222,7 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
         const int c = ew * 32 + lane;
         if (c < BN) {
           const int g = nt * BN + c;
-          s_bias[as * BN + c] = (g < p.G) ? p.bias[(size_t)hs * p.G + g] : 0.f;
+          s_bias[as * BN + c] = (g < p.G) ? p.bias[hs][g] : 0.f;
         }
       }
       named_barrier_sync(1, kEpiWarps * 32);
@@ -273,31 +277,31 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
 }
 }  // namespace k2
 
-// Host launcher.  Hb: bf16 [B x 64]; WhT: bf16 [n_heads*G x 64] (row = head_slot*G + gene); bias packed likewise.
-int heads_fwd_tc(const __nv_bfloat16* Hb, int B, const __nv_bfloat16* WhT, const float* bias, int G, int n_heads,
-                 const int kind[3], const float* row_scale, float* const out[3], int64_t ld_out, int sm_count,
+// Host launcher.  Hb: bf16 [B x 64]; W[i]: bf16 [64 x G] (Keras layout) and bias[i]: float[G] per head slot.
+int heads_fwd_tc(const __nv_bfloat16* Hb, int B, const __nv_bfloat16* const W[3], const float* const bias[3], int G,
+                 int n_heads, const int kind[3], const float* row_scale, float* const out[3], int64_t ld_out, int sm_count,
                  cudaStream_t s) {
   using namespace k2;
-  if (ld_out % 4 != 0) { set_error("heads_fwd_tc: ld_out must be a multiple of 4 floats (TMA stride)"); return DCA_ERR_BAD_ARG; }
-  CUtensorMap mh, mw, mo[3];
+  if (ld_out % 4 != 0 || G % 8 != 0) { set_error("heads_fwd_tc: G must be a multiple of 8 and ld_out of 4 (TMA strides)"); return DCA_ERR_BAD_ARG; }
+  CUtensorMap mh, mw[3], mo[3];
   DCA_TRY(make_tensor_map_2d(&mh, Hb, 2, 1, (uint64_t)B, 64, 64, BM, BK, 1));
-  DCA_TRY(make_tensor_map_2d(&mw, WhT, 2, 1, (uint64_t)n_heads * G, 64, 64, BN, BK, 1));
   for (int i = 0; i < 3; ++i) {
-    float* o = out[i < n_heads ? i : 0];
-    DCA_TRY(make_tensor_map_2d(&mo[i], o, 4, 0, (uint64_t)B, (uint64_t)G, (uint64_t)ld_out, 32, 32, 1));
+    const int k = i < n_heads ? i : 0;
+    DCA_TRY(make_tensor_map_2d(&mw[i], W[k], 2, 1, 64, (uint64_t)G, (uint64_t)G, 64, 64, 1));
+    DCA_TRY(make_tensor_map_2d(&mo[i], out[k], 4, 0, (uint64_t)B, (uint64_t)G, (uint64_t)ld_out, 32, 32, 1));
   }
   Params p;
   p.B = B; p.G = G; p.n_heads = n_heads;
-  for (int i = 0; i < 3; ++i) p.kind[i] = kind[i];
+  for (int i = 0; i < 3; ++i) { p.kind[i] = kind[i]; p.bias[i] = bias[i < n_heads ? i : 0]; }
   p.m_tiles = cdiv(B, BM); p.n_tiles_per_head = cdiv(G, BN); p.total_tiles = p.m_tiles * p.n_tiles_per_head * n_heads;
-  p.bias = bias; p.row_scale = row_scale;
+  p.row_scale = row_scale;
   static bool attr_set = false;
   if (!attr_set) {
     DCA_CUDA_OK(cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_set = true;
   }
   const int grid = p.total_tiles < sm_count ? p.total_tiles : sm_count;
-  heads_fwd_kernel<<<grid, kThreads, kSmemBytes, s>>>(mh, mw, mo[0], mo[1], mo[2], p);
+  heads_fwd_kernel<<<grid, kThreads, kSmemBytes, s>>>(mh, mw[0], mw[1], mw[2], mo[0], mo[1], mo[2], p);
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }
@@ -357,10 +361,10 @@ extern "C" int dca_tc_probe(const void* A, int32_t a_rows, int32_t a_cols, const
   return DCA_OK;
 }
 
-extern "C" int dca_tc_heads_fwd(const void* Hb, int32_t batch, const void* WhT, const float* bias, int32_t genes,
+extern "C" int dca_tc_heads_fwd(const void* Hb, int32_t batch, const void* Wk, const float* bias, int32_t genes,
                                 int32_t n_heads, const int32_t kind[3], const float* row_scale, float* out0, float* out1,
                                 float* out2, int64_t ld_out, void* stream) {
-  if (!Hb || !WhT || !bias || batch <= 0 || genes <= 0 || n_heads < 1 || n_heads > 3 || !out0) {
+  if (!Hb || !Wk || !bias || batch <= 0 || genes <= 0 || n_heads < 1 || n_heads > 3 || !out0) {
     set_error("dca_tc_heads_fwd: bad argument"); return DCA_ERR_BAD_ARG;
   }
   int dev = 0, sms = 148;
@@ -368,6 +372,11 @@ extern "C" int dca_tc_heads_fwd(const void* Hb, int32_t batch, const void* WhT, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int k[3] = {kind[0], n_heads > 1 ? kind[1] : 0, n_heads > 2 ? kind[2] : 0};
   float* outs[3] = {out0, out1, out2};
-  return tc::heads_fwd_tc((const __nv_bfloat16*)Hb, batch, (const __nv_bfloat16*)WhT, bias, genes, n_heads, k, row_scale,
-                          outs, ld_out, sms, (cudaStream_t)stream);
+  const __nv_bfloat16* W[3]; const float* b[3];
+  for (int i = 0; i < 3; ++i) {
+    const int j = i < n_heads ? i : 0;
+    W[i] = (const __nv_bfloat16*)Wk + (size_t)j * 64 * genes; b[i] = bias + (size_t)j * genes;
+  }
+  return tc::heads_fwd_tc((const __nv_bfloat16*)Hb, batch, W, b, genes, n_heads, k, row_scale, outs, ld_out, sms,
+                          (cudaStream_t)stream);
 }

@@ -159,15 +159,15 @@ int Engine::plan(const dca_config& c) {
   const bool want_tc = c.gemm_path != DCA_GEMM_GENERIC;
   tc_heads = want_tc && L >= 1 && K_head == 64 && (G % 8 == 0);
   tc_enc = want_tc && L >= 1 && c.hidden[0] == 64 && (c.n_in % 8 == 0);
+  // the tcgen05 kernels read the kernels in place from the flat bf16 parameter copy: TMA needs 16-byte aligned bases
+  if (tc_heads) for (int k = 0; k < 3; ++k) if (head_W[k] >= 0 && (head_W[k] % 8) != 0) tc_heads = false;
+  if (tc_enc && (lay[0].W % 8) != 0) tc_enc = false;
+  if (tc_heads || tc_enc) o_pbf = take(2 * (size_t)P);       // bf16 copy of the parameters, same flat layout
   if (tc_heads) {
-    o_whT = take(2 * (size_t)n_slots * G * 64);
-    o_whkm = take(2 * (size_t)n_slots * G * 64);
-    o_biasp = take(sizeof(float) * (size_t)n_slots * G);
     o_h3b = take(2 * B * 64);
     for (int k = 0; k < n_slots; ++k) o_dzb[k] = take(2 * B * (size_t)G);
   }
   if (tc_enc) {
-    o_w1t = take(2 * (size_t)c.n_in * 64);
     o_da1b = take(2 * B * 64);
     o_xb = take(2 * B * (size_t)c.n_in);
   }
@@ -247,7 +247,8 @@ int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, boo
     DCA_TRY(fill_rows_with_bias(a, l.out, Bn, l.out, pp(l.b), s));
     if (i == 0 && cur_xb) {
       const __nv_bfloat16* Z[3] = {cur_xb, cur_xb, cur_xb};
-      DCA_TRY(tc::gene_gemm_tc(1, Z, cur_ldxb, Bn, cfg.n_in, 1, nullptr, bf(o_w1t), a, nullptr, 0, 0, nullptr, sm_count, s));
+      const __nv_bfloat16* W1[3] = {bf(o_pbf) + lay[0].W, bf(o_pbf) + lay[0].W, bf(o_pbf) + lay[0].W};
+      DCA_TRY(tc::gene_gemm_tc(1, Z, cur_ldxb, Bn, cfg.n_in, 1, nullptr, W1, a, nullptr, 0, 0, nullptr, sm_count, s));
     } else {
     GemmArgs g{};
     g.A = hin; g.lda = ldin; g.a_bf16 = in_bf16; g.transA = 0; g.a_rows = gather;
@@ -309,7 +310,9 @@ int Engine::heads_forward(int Bn, float* m_out, float* d_out, float* p_out, int6
       float* outs[3] = {nullptr, nullptr, nullptr};
       for (int k = 0; k < n_slots; ++k) outs[k] = outs_by_head[slot_head[k]];
       for (int k = n_slots; k < 3; ++k) outs[k] = outs[0];
-      return tc::heads_fwd_tc(bf(o_h3b), Bn, bf(o_whT), f(o_biasp), G, n_slots, slot_kind, row_scale, outs, ld_out, sm_count, s);
+      const __nv_bfloat16* Wk[3]; const float* bk[3];
+      for (int k = 0; k < 3; ++k) { const int kk = k < n_slots ? k : 0; Wk[k] = bf(o_pbf) + head_W[slot_head[kk]]; bk[k] = pp(head_b[slot_head[kk]]); }
+      return tc::heads_fwd_tc(bf(o_h3b), Bn, Wk, bk, G, n_slots, slot_kind, row_scale, outs, ld_out, sm_count, s);
     }
   }
   struct H { int k; float* out; int epi; const float* rs; } hs[3] = {
@@ -455,12 +458,13 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
   if (L > 0) DCA_CUDA_OK(cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)Bn * K_head, s));
   float* dz[3] = {Mb, cond ? Db : nullptr, has_pi ? Pb : nullptr};
   if (tc_heads) {
-    const __nv_bfloat16* Z[3]; float* dWp[3]; float* dbp[3];
+    const __nv_bfloat16* Z[3]; const __nv_bfloat16* Wk[3]; float* dWp[3]; float* dbp[3];
     for (int k = 0; k < 3; ++k) {
       const int kk = k < n_slots ? k : 0;
-      Z[k] = bf(o_dzb[kk]); dWp[k] = gp(head_W[slot_head[kk]]); dbp[k] = gp(head_b[slot_head[kk]]);
+      Z[k] = bf(o_dzb[kk]); Wk[k] = bf(o_pbf) + head_W[slot_head[kk]];
+      dWp[k] = gp(head_W[slot_head[kk]]); dbp[k] = gp(head_b[slot_head[kk]]);
     }
-    DCA_TRY(tc::gene_gemm_tc(3, Z, G, Bn, G, n_slots, bf(o_h3b), bf(o_whkm), dh, dWp, G, 1, dbp, sm_count, s));
+    DCA_TRY(tc::gene_gemm_tc(3, Z, G, Bn, G, n_slots, bf(o_h3b), Wk, dh, dWp, G, 1, dbp, sm_count, s));
   } else
   for (int k = 0; k < 3; ++k) {
     if (head_W[k] < 0 || !dz[k]) continue;
@@ -541,8 +545,8 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
 
 int Engine::apply_update(float lr, float clip, float grad_scale, cudaStream_t s) {
   mark(5, s);
-  DCA_TRY(rmsprop_update(pp(0), gp(0), f(o_rms), P, lr, clip, cfg.rms_rho, cfg.rms_eps, grad_scale, s));
-  DCA_TRY(refresh_shadows(s));
+  DCA_TRY(rmsprop_update(pp(0), gp(0), f(o_rms), P, lr, clip, cfg.rms_rho, cfg.rms_eps, grad_scale,
+                         (tc_heads || tc_enc) ? bf(o_pbf) : nullptr, s));   // also refreshes the bf16 operand copy
   mark(-1, s);
   return DCA_OK;
 }
@@ -608,14 +612,11 @@ int Engine::setup_tc() {
   }
   return DCA_OK;
 }
-// Re-derive the bf16 operand-layout copies of the weights from the fp32 master parameters.
+// Re-derive the bf16 copy of the parameters (the tcgen05 kernels read every kernel in its Keras layout, so the
+// "shadow" is a plain element-wise cast; after an optimizer step the RMSprop kernel writes it directly).
 int Engine::refresh_shadows(cudaStream_t s) {
   if (!tc_heads && !tc_enc) return DCA_OK;
-  const float* W[3] = {nullptr, nullptr, nullptr}; const float* b[3] = {nullptr, nullptr, nullptr};
-  for (int k = 0; k < n_slots; ++k) { W[k] = pp(head_W[slot_head[k]]); b[k] = pp(head_b[slot_head[k]]); }
-  return refresh_all_shadows(W, b, n_slots, cfg.n_out, tc_heads ? bf(o_whT) : nullptr, tc_heads ? bf(o_whkm) : nullptr,
-                             tc_heads ? f(o_biasp) : nullptr, tc_enc ? pp(lay[0].W) : nullptr, cfg.n_in,
-                             tc_enc ? bf(o_w1t) : nullptr, s);
+  return cast_to_bf16(pp(0), bf(o_pbf), P, s);
 }
 
 int Engine::init_params(uint64_t seed, cudaStream_t s) {

@@ -68,7 +68,7 @@ struct Engine {
   int sm_count = 148, n_slots = 1;
   int slot_head[3] = {0, -1, -1};          // packed head slot -> head index (0 mean, 1 dispersion, 2 pi)
   int slot_kind[3] = {0, 0, 0};
-  size_t o_whT = 0, o_whkm = 0, o_biasp = 0, o_w1t = 0, o_h3b = 0, o_da1b = 0, o_xb = 0, o_dzb[3] = {0, 0, 0};
+  size_t o_pbf = 0, o_h3b = 0, o_da1b = 0, o_xb = 0, o_dzb[3] = {0, 0, 0};
   const __nv_bfloat16* cur_xb = nullptr; int64_t cur_ldxb = 0;   // bf16 batch input of the current step
   __nv_bfloat16* bf(size_t byte_off) const { return reinterpret_cast<__nv_bfloat16*>(base + byte_off); }
 

@@ -47,7 +47,8 @@ template <bool DO_A, bool DO_B, bool COLSUM>
 __global__ void __launch_bounds__(kThreads, 1)
 gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_constant__ CUtensorMap map_z1,
                  const __grid_constant__ CUtensorMap map_z2, const __grid_constant__ CUtensorMap map_h,
-                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_o, const Params p) {
+                 const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
+                 const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_o, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr uint32_t kStage = kZBytes + (DO_B ? kWBytes : 0);
@@ -64,7 +65,7 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
     for (int i = 0; i < 2; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); mbar_init(&dh_full[i], 1); mbar_init(&dh_empty[i], 4); }
     mbar_init(&dw_full, 1); mbar_init(&dw_empty, 4);
     fence_barrier_init();
-    tma_prefetch_desc(&map_z0); tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_o);
+    tma_prefetch_desc(&map_z0); tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_w0); tma_prefetch_desc(&map_o);
   }
   if (warp == 2) tmem_alloc(&tmem_base_s, kTmemCols);
   if (COLSUM) {   // bf16 1.0 = 0x3F80; every element equal, so the swizzle pattern does not matter
@@ -111,8 +112,13 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
             tma_load_2d(dst, mz, gb * 128, cb * 128, &z_full[st]);
             tma_load_2d(dst + kZBytes / 2, mz, gb * 128 + 64, cb * 128, &z_full[st]);
             if (DO_B) {
-              tma_load_2d(dst + kZBytes, &map_w, x.head * p.G + gb * 128, 0, &z_full[st]);
-              tma_load_2d(dst + kZBytes + kWBytes / 2, &map_w, x.head * p.G + gb * 128 + 64, 0, &z_full[st]);
+              const CUtensorMap* mw = x.head == 0 ? &map_w0 : (x.head == 1 ? &map_w1 : &map_w2);
+              if (DO_A) {      // head backward: W = Keras [64 x G] (K-major B): two [64 feats x 64 genes] boxes
+                tma_load_2d(dst + kZBytes, mw, gb * 128, 0, &z_full[st]);
+                tma_load_2d(dst + kZBytes + kWBytes / 2, mw, gb * 128 + 64, 0, &z_full[st]);
+              } else {         // encoder forward: W = Keras [G x 64] (MN-major B): one [128 genes x 64 feats] box
+                tma_load_2d(dst + kZBytes, mw, 0, gb * 128, &z_full[st]);
+              }
             }
           }
         }
@@ -121,7 +127,7 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc_b = make_idesc_bf16(128, 64, 0, 0);     // Z K-major  x W K-major
+      constexpr uint32_t idesc_b = make_idesc_bf16(128, 64, 0, DO_A ? 0 : 1);   // Z K-major x W (K-major [64xG] | MN-major [Gx64])
       constexpr uint32_t idesc_a = make_idesc_bf16(128, 64, 1, 1);     // Z MN-major x H MN-major
       constexpr uint32_t idesc_c = make_idesc_bf16(128, 16, 1, 0);     // Z MN-major x ones K-major -> column sums
       uint32_t zi = 0, hi = 0, di = 0, wi = 0;
@@ -144,7 +150,8 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   umma_bf16(tm_dh + ds * 64, make_smem_desc(zb + h * (kZBytes / 2) + k * 32, 0, 1024),
-                            make_smem_desc(wb + h * (kWBytes / 2) + k * 32, 0, 1024), idesc_b,
+                            DO_A ? make_smem_desc(wb + h * (kWBytes / 2) + k * 32, 0, 1024)
+                                 : make_smem_desc(wb + (h * 4 + k) * 2048, 0, 1024), idesc_b,
                             (gb > x.gb0 || h > 0 || k > 0) ? 1u : 0u);
             }
             if (DO_A) {
@@ -275,22 +282,27 @@ constexpr uint32_t smem_bytes() {
 
 }  // namespace gg
 
-// Z: bf16 [B x G] per head (ldz elements); H: bf16 [B x 64]; W: bf16 [64 x n_heads*G] (Keras layout, heads packed along
-// columns); out_b: fp32 [B x 64] (+=).  mode: 1 = DO_B (K1), 2 = DO_A (K5), 3 = DO_A|DO_B|COLSUM (K4).
+// Z: bf16 [B x G] per head (ldz elements); H: bf16 [B x 64]; W[i]: bf16 Keras-layout kernels -- [G x 64] for mode 1 (the
+// encoder kernel), [64 x G] per head for mode 3; out_b: fp32 [B x 64] (+=).
+// mode: 1 = DO_B (K1), 2 = DO_A (K5), 3 = DO_A|DO_B|COLSUM (K4).
 int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, int G, int n_heads,
-                 const __nv_bfloat16* H, const __nv_bfloat16* W, float* out_b, float* const dW[3], int64_t dW_ld,
+                 const __nv_bfloat16* H, const __nv_bfloat16* const W[3], float* out_b, float* const dW[3], int64_t dW_ld,
                  int dW_transposed, float* const db[3], int sm_count, cudaStream_t s) {
   using namespace gg;
   if (ldz % 8 != 0) { set_error("gene_gemm_tc: ldz must be a multiple of 8 (16-byte TMA stride)"); return DCA_ERR_BAD_ARG; }
   const bool do_a = mode & 2, do_b = mode & 1;
-  CUtensorMap mz[3], mh, mw, mo;
+  CUtensorMap mz[3], mh, mw[3], mo;
   for (int i = 0; i < 3; ++i) DCA_TRY(make_tensor_map_2d(&mz[i], Z[i < n_heads ? i : 0], 2, 1, (uint64_t)B, (uint64_t)G, (uint64_t)ldz, 128, 64, 1));
   if (do_a) DCA_TRY(make_tensor_map_2d(&mh, H, 2, 1, (uint64_t)B, 64, 64, 128, 64, 1)); else mh = mz[0];
   if (do_b) {
-    DCA_TRY(make_tensor_map_2d(&mw, W, 2, 1, 64, (uint64_t)n_heads * G, (uint64_t)n_heads * G, 64, 64, 1));
+    for (int i = 0; i < 3; ++i) {
+      const __nv_bfloat16* w = W[i < n_heads ? i : 0];
+      if (do_a) DCA_TRY(make_tensor_map_2d(&mw[i], w, 2, 1, 64, (uint64_t)G, (uint64_t)G, 64, 64, 1));
+      else DCA_TRY(make_tensor_map_2d(&mw[i], w, 2, 1, (uint64_t)G, 64, 64, 128, 64, 1));
+    }
     DCA_TRY(make_tensor_map_2d(&mo, out_b, 4, 0, (uint64_t)B, 64, 64, 128, 32, 1));
   } else {
-    mw = mz[0]; mo = mz[0];
+    mw[0] = mw[1] = mw[2] = mz[0]; mo = mz[0];
     if (do_a && !dW_transposed) {
       if (dW_ld != 64) { set_error("gene_gemm_tc: non-transposed dW needs ld == 64"); return DCA_ERR_BAD_ARG; }
       DCA_TRY(make_tensor_map_2d(&mo, dW[0], 4, 0, (uint64_t)G, 64, 64, 128, 32, 1));
@@ -330,7 +342,7 @@ int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, 
     static bool attr = false;                                                                                          \
     constexpr uint32_t sm = smem_bytes<A, Bb, Cc>();                                                                   \
     if (!attr) { DCA_CUDA_OK(cudaFuncSetAttribute(gene_gemm_kernel<A, Bb, Cc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr = true; } \
-    gene_gemm_kernel<A, Bb, Cc><<<grid, kThreads, sm, s>>>(mz[0], mz[1], mz[2], mh, mw, mo, p);                         \
+    gene_gemm_kernel<A, Bb, Cc><<<grid, kThreads, sm, s>>>(mz[0], mz[1], mz[2], mh, mw[0], mw[1], mw[2], mo, p);                         \
   } while (0)
   if (mode == 1) DCA_GG_LAUNCH(false, true, false);
   else if (mode == 2) DCA_GG_LAUNCH(true, false, false);
@@ -357,6 +369,8 @@ extern "C" int dca_tc_gene_gemm(int32_t mode, const void* Z0, const void* Z1, co
   const __nv_bfloat16* Z[3] = {(const __nv_bfloat16*)Z0, (const __nv_bfloat16*)Z1, (const __nv_bfloat16*)Z2};
   float* dW[3] = {dW0, dW1, dW2};
   float* db[3] = {db0, db1, db2};
-  return tc::gene_gemm_tc(mode, Z, ldz, batch, genes, n_heads, (const __nv_bfloat16*)H, (const __nv_bfloat16*)W, out_b, dW,
+  const __nv_bfloat16* Wp[3];
+  for (int i = 0; i < 3; ++i) Wp[i] = (const __nv_bfloat16*)W + (mode == 3 ? (size_t)(i < n_heads ? i : 0) * 64 * genes : 0);
+  return tc::gene_gemm_tc(mode, Z, ldz, batch, genes, n_heads, (const __nv_bfloat16*)H, Wp, out_b, dW,
                           dW_ld, dW_transposed, db, sms, (cudaStream_t)stream);
 }

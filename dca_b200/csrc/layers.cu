@@ -230,14 +230,16 @@ __global__ void reg_penalty_kernel(const float* __restrict__ w, int64_t n, float
 }
 
 __global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ r, int64_t n,
-                               float lr, float clip, float rho, float eps, float gs) {
+                               float lr, float clip, float rho, float eps, float gs, __nv_bfloat16* __restrict__ shadow) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float gi = g[i] * gs;
   if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);       // clipvalue
   const float ri = rho * r[i] + (1.0f - rho) * gi * gi;
   r[i] = ri;
-  p[i] -= lr * gi / (sqrtf(ri) + eps);                      // epsilon outside the sqrt (Keras RMSprop)
+  const float pn = p[i] - lr * gi / (sqrtf(ri) + eps);      // epsilon outside the sqrt (Keras RMSprop)
+  p[i] = pn;
+  if (shadow) shadow[i] = __float2bfloat16_rn(pn);          // bf16 operand copy for the tcgen05 kernels (same layout)
 }
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -407,8 +409,8 @@ int reg_penalty(const float* w, int64_t n, float l1, float l2, double* acc, cuda
 }
 
 int rmsprop_update(float* params, const float* grads, float* rms, int64_t n, float lr, float clip, float rho,
-                   float eps, float grad_scale, cudaStream_t s) {
-  rmsprop_kernel<<<blocks_for(n), 256, 0, s>>>(params, grads, rms, n, lr, clip, rho, eps, grad_scale);
+                   float eps, float grad_scale, __nv_bfloat16* shadow, cudaStream_t s) {
+  rmsprop_kernel<<<blocks_for(n), 256, 0, s>>>(params, grads, rms, n, lr, clip, rho, eps, grad_scale, shadow);
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }

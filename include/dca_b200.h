@@ -222,18 +222,18 @@ int dca_dense_heads_fwd(const float* H, int64_t ldh, int32_t batch, int32_t K, i
                         const float* row_scale,
                         float* m_out, float* d_out, float* pi_out, int64_t ld_out, void* stream);
 
-/* tcgen05 head layer, operands already in MMA layout: Hb = bf16 [batch x 64] (decoder output),
- * WhT = bf16 [n_heads*genes x 64] (row = head_slot*genes + gene: the Keras kernels transposed and
- * stacked), bias = float [n_heads*genes]; kind[i] in {2 MeanAct, 3 DispAct, 4 sigmoid} per head slot.
- * Same arithmetic as dca_dense_heads_fwd with bf16-rounded operands and fp32 accumulation. */
-int dca_tc_heads_fwd(const void* Hb, int32_t batch, const void* WhT, const float* bias, int32_t genes,
+/* tcgen05 head layer: Hb = bf16 [batch x 64] (decoder output), Wk = bf16 [n_heads][64][genes] (the Keras
+ * kernels, read in place as MN-major operands), bias = float [n_heads*genes]; kind[i] in {2 MeanAct,
+ * 3 DispAct, 4 sigmoid} per head slot.  Same arithmetic as dca_dense_heads_fwd with bf16-rounded operands
+ * and fp32 accumulation. */
+int dca_tc_heads_fwd(const void* Hb, int32_t batch, const void* Wk, const float* bias, int32_t genes,
                      int32_t n_heads, const int32_t kind[3], const float* row_scale,
                      float* out0, float* out1, float* out2, int64_t ld_out, void* stream);
 
 /* The gene-wide tcgen05 product kernel (one smem tile of Z = X or dZ feeds both products):
- * mode 1: out_b[B x 64] += Z . W^T (W = bf16 [64 x n_heads*genes])                 -- encoder forward
+ * mode 1: out_b[B x 64] += Z . W (W = bf16 [genes x 64], Keras layout)             -- encoder forward
  * mode 2: dW += Z^T . H (H = bf16 [B x 64])                                       -- encoder backward
- * mode 3: both, plus db = column sums of Z                                        -- head backward
+ * mode 3: both (W = bf16 [n_heads][64][genes]), plus db = column sums of Z         -- head backward
  * Z0..Z2: bf16 [B x genes] per head (leading dim ldz); dW per head: float, dW[f*dW_ld + g] when
  * dW_transposed (Keras [64 x genes]) else dW[g*dW_ld + f].  All outputs are accumulated (+=). */
 int dca_tc_gene_gemm(int32_t mode, const void* Z0, const void* Z1, const void* Z2, int64_t ldz, int32_t batch,

@@ -64,18 +64,18 @@ def test_tc_heads_fwd(B, G, nh):
     sf = np.exp(rng.normal(0, 0.3, B)).astype(np.float32)
     kinds = [2, 3, 4][:nh] if nh == 3 else ([2, 4] if nh == 2 else [2])
     Hb = _bf(H)
-    WhT = torch.cat([_bf(w).t().contiguous() for w in W], 0).contiguous()       # [nh*G x 64]
+    Wk = torch.stack([_bf(w) for w in W], 0).contiguous()                      # [nh][64][G], Keras layout
     bias = torch.as_tensor(np.concatenate(b)).to(DEV)
     sfd = torch.as_tensor(sf).to(DEV)
     outs = [torch.full((B, G), float("nan"), device=DEV) for _ in range(3)]
     karr = (C.c_int32 * 3)(*(kinds + [0] * (3 - nh)))
-    st = lib.dca_tc_heads_fwd(Hb.data_ptr(), B, WhT.data_ptr(), bias.data_ptr(), G, nh, C.byref(karr), sfd.data_ptr(),
+    st = lib.dca_tc_heads_fwd(Hb.data_ptr(), B, Wk.data_ptr(), bias.data_ptr(), G, nh, C.byref(karr), sfd.data_ptr(),
                               outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), G, None)
     L.check(st, "dca_tc_heads_fwd")
     torch.cuda.synchronize()
     Hd = Hb.double().cpu().numpy()
     for i, kind in enumerate(kinds):
-        Wd = WhT[i * G:(i + 1) * G].double().cpu().numpy().T
+        Wd = Wk[i].double().cpu().numpy()
         z = Hd @ Wd + b[i]
         ref = {2: lambda z: O.mean_act(z) * sf[:, None], 3: O.disp_act, 4: O.sigmoid}[kind](z)
         got = outs[i].cpu().numpy()
@@ -101,11 +101,11 @@ def test_tc_encoder_forward_mode1(B, G):
     rng = np.random.default_rng(B * 3 + G)
     X = _bf(rng.normal(0, 1, (B, G)))
     W1 = rng.normal(0, 0.05, (G, 64)).astype(np.float32)
-    W1T = _bf(W1.T)                                       # [64 x G], K(gene)-major
+    W1b = _bf(W1)                                         # [G x 64], Keras layout (MN-major B operand)
     bias = rng.normal(0, 0.3, 64).astype(np.float32)
     out = torch.as_tensor(np.tile(bias, (B, 1))).to(DEV).contiguous()
-    _gg(1, [X], None, W1T, B, G, 1, out_b=out)
-    ref = X.double().cpu().numpy() @ W1T.double().cpu().numpy().T + bias
+    _gg(1, [X], None, W1b, B, G, 1, out_b=out)
+    ref = X.double().cpu().numpy() @ W1b.double().cpu().numpy() + bias
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-5, atol=2e-5)
 
 
@@ -128,12 +128,12 @@ def test_tc_head_backward_mode3(B, G, nh):
     dZ = [_bf(rng.normal(0, 1e-3, (B, G))) for _ in range(nh)]
     H = _bf(np.maximum(rng.normal(0, 1, (B, 64)), 0))
     Wk = [rng.normal(0, 0.2, (64, G)).astype(np.float32) for _ in range(nh)]
-    Wp = _bf(np.concatenate(Wk, 1))                       # [64 x nh*G]
+    Wp = torch.stack([_bf(w) for w in Wk], 0).contiguous()   # [nh][64][G]
     dH = torch.zeros((B, 64), device=DEV)
     dW = [torch.zeros((64, G), device=DEV) for _ in range(nh)]
     db = [torch.zeros(G, device=DEV) for _ in range(nh)]
     _gg(3, dZ, H, Wp, B, G, nh, out_b=dH, dW=dW, dW_ld=G, transposed=1, db=db)
-    Hd = H.double().cpu().numpy(); Wd = Wp.double().cpu().numpy()
+    Hd = H.double().cpu().numpy(); Wd = np.concatenate([Wp[i].double().cpu().numpy() for i in range(nh)], 1)
     ref_dH = np.zeros((B, 64))
     for i in range(nh):
         z = dZ[i].double().cpu().numpy()
