@@ -121,6 +121,7 @@ struct LossArgs {
   double* loss_sum;         // device scalar, overwritten (fwd_bwd) or accumulated (fwd)
   void* ws; size_t ws_bytes;
   // optional fused finalize (engine): loss_slot[0] = loss_sum*inv_n (+penalty), [1] = non-finite flag, epoch acc update
+  int counter_ready = 0;      // the self-resetting block counter inside `ws` is known to be zero (engine-owned workspace)
   float* fin_loss_slot = nullptr; double* fin_epoch_acc = nullptr; const double* fin_penalty = nullptr; int fin_batch = 0;
 };
 size_t loss_workspace_bytes(int B, int G);

@@ -446,6 +446,7 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
   }
   la.dtheta = cond ? nullptr : f(o_dtheta);
   la.loss_sum = d(o_acc) + 4; la.ws = base + o_lossws; la.ws_bytes = loss_ws_bytes;
+  la.counter_ready = 1;
   la.fin_loss_slot = gp(P); la.fin_epoch_acc = d(o_acc); la.fin_penalty = any_pen ? d(o_acc) + 5 : nullptr; la.fin_batch = Bn;
   DCA_TRY(zinb_loss_fwd_bwd(la, s));
   if (!cond) {

@@ -13,6 +13,7 @@
 //             previous layer; ends with da_0 (fp32 + bf16) for the first layer's weight gradient.
 #include "dca_internal.cuh"
 #include "mid_stack.h"
+#include <cstdlib>
 
 namespace dca {
 namespace mid {
@@ -292,10 +293,11 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
       }
     __syncthreads();
     // dh_{l-1}[r][k] = sum_c da[r][c] * W[k][c]: thread = k (= tc), 4 rows at a time, c in groups of 4
-    float dhv[4][4];                                                   // [row group][row in group]
+    constexpr int kRowGroups = kMaxRows / 16;
+    float dhv[kRowGroups][4];                                          // [row group][row in group]
     if (tc < win) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < kRowGroups; ++q) {
         const int r0 = tr * 4 + q * 16;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         if (r0 < rows)
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
     __syncthreads();                                                   // all reads of xh (as h_{l-1}) and g are done
     if (tc < win) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < kRowGroups; ++q)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const int r = tr * 4 + q * 16 + j; if (r < rows) xh[r][tc] = dhv[q][j]; }
     }
@@ -336,13 +338,16 @@ bool mid_supported(const int* widths, int L) {
 }
 
 static int mid_fill(mid::Params& p, int B) {
-  int ctas = cdiv(B, mid::kMaxRows);
-  if (ctas > mid::kMaxCtas) { set_error("mid_stack: batch %d exceeds %d rows", B, mid::kMaxRows * mid::kMaxCtas); return DCA_ERR_UNSUPPORTED; }
+  static const int rows_target = [] { const char* e = getenv("DCA_MID_ROWS"); int v = e ? atoi(e) : 64; return (v >= 16 && v <= mid::kMaxRows) ? v : 64; }();
+  int ctas = cdiv(B, rows_target);
+  if (ctas > mid::kMaxCtas) ctas = mid::kMaxCtas;
+  if ((long long)ctas * mid::kMaxRows < B) { set_error("mid_stack: batch %d exceeds %d rows", B, mid::kMaxRows * mid::kMaxCtas); return DCA_ERR_UNSUPPORTED; }
   // spread rows evenly, at least 16 rows per CTA so tiny batches do not pay for 64 barriers participants
   int rpc = cdiv(B, ctas);
   if (rpc < 16) rpc = 16;
   rpc = (rpc + 3) & ~3;
   if (rpc > mid::kMaxRows) rpc = mid::kMaxRows;
+  while ((long long)rpc * mid::kMaxCtas < B) rpc += 4;
   p.rows_per_cta = rpc; p.n_ctas = cdiv(B, rpc);
   return DCA_OK;
 }

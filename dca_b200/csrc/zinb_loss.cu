@@ -272,6 +272,10 @@ zinb_loss_bwd_compact_kernel(const float* __restrict__ Y, int64_t ldy, const int
 // mbarrier) into a 3-deep ring, eight consumer warps read their 128-bit vectors from the ring.  The gather of
 // the count rows (rows[]) is free -- the producer simply points the copy at row rows[r] -- and the consumers
 // carry no address arithmetic or load latency, only the math, the warp compaction and the coalesced stores.
+struct FoldArgs {
+  unsigned* counter; double* loss_sum; const double* penalty; float* loss_slot; double* epoch_acc; int batch;
+};
+
 constexpr int kStageRows = 3;
 constexpr int kMaxRowsPerBlock = 64;
 constexpr int kStagedThreads = kThreads + 32;      // 8 consumer warps + 1 producer warp
@@ -282,7 +286,7 @@ zinb_loss_bwd_staged_kernel(const float* __restrict__ Y, int64_t ldy, const int3
                             const float* __restrict__ sf, const float* m, const float* d, const float* pi,
                             int64_t ld, int B, int G, float ridge, float inv_n, int rows_per_block,
                             GT* dzm, GT* dzd, GT* dzp, float* __restrict__ dth_acc,
-                            double* __restrict__ loss_partial, const float* __restrict__ lf_global) {
+                            double* __restrict__ loss_partial, const float* __restrict__ lf_global, const FoldArgs fa) {
   extern __shared__ __align__(128) unsigned char smem_loss[];
   constexpr int kArrays = COND_DISP ? 4 : 3;                           // y, m, [d], pi
   constexpr uint32_t kArrBytes = kColsPerBlock * 4;                    // one row segment of one tensor
@@ -427,11 +431,43 @@ zinb_loss_bwd_staged_kernel(const float* __restrict__ Y, int64_t ldy, const int3
   for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(kFull, dsum, o);
   if (lane == 0) red[warp] = dsum;
   tc::named_barrier_sync(1, kThreads);
+  __shared__ int s_last;
   if (threadIdx.x == 0) {
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) t += red[w];
     loss_partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+    __threadfence();
+    const unsigned nblk = gridDim.x * gridDim.y;
+    const unsigned done = atomicAdd(fa.counter, 1u);
+    s_last = (done == nblk - 1);
+    if (s_last) *fa.counter = 0;                                       // self-resetting
+  }
+  tc::named_barrier_sync(1, kThreads);
+  if (!s_last) return;
+  // ---- the last block to finish folds the per-block partials in a FIXED order (deterministic) and finalises
+  __threadfence();
+  const int n = gridDim.x * gridDim.y;
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += kThreads) a += __ldcg(loss_partial + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFull, a, o);
+  if (lane == 0) red[warp] = a;
+  tc::named_barrier_sync(1, kThreads);
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) t += red[w];
+    *fa.loss_sum = t;
+    if (fa.loss_slot) {
+      double l = t * (double)inv_n;
+      if (l != l) l = INFINITY;                                        // _nan2inf, dca/loss.py:148
+      if (fa.penalty) l += *fa.penalty;
+      const float lf32 = (float)l;
+      fa.loss_slot[0] = lf32;
+      fa.loss_slot[1] = (isfinite(lf32)) ? 0.f : 1.f;
+      if (fa.epoch_acc) { fa.epoch_acc[0] += l * (double)fa.batch; fa.epoch_acc[1] += (double)fa.batch; }
+    }
   }
 }
 
@@ -524,17 +560,22 @@ int launch(const LossArgs& a, cudaStream_t s) {
                          ps.row_chunks <= 65535;
   if (staged_ok) {
     grid = dim3(ps.col_blocks, ps.row_chunks);
+    FoldArgs fa{reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.ws) + sizeof(double) * (size_t)kMaxBlocks), a.loss_sum,
+                a.fin_penalty, a.fin_loss_slot, a.fin_epoch_acc, a.fin_batch};
+    if (!a.counter_ready) DCA_CUDA_OK(cudaMemsetAsync(fa.counter, 0, sizeof(unsigned), s));
 #define DCA_STAGED(CD, GT)                                                                                         \
   do {                                                                                                             \
     constexpr size_t sm = (size_t)kStageRows * (CD ? 4 : 3) * kColsPerBlock * 4 + (size_t)(kThreads / 32) * 32 * kVec * 16; \
     static bool attr = false;                                                                                      \
     if (!attr) { DCA_CUDA_OK(cudaFuncSetAttribute(zinb_loss_bwd_staged_kernel<CD, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr = true; } \
     zinb_loss_bwd_staged_kernel<CD, GT><<<grid, kStagedThreads, sm, s>>>(a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, \
-        a.G, a.ridge, a.inv_n, ps.rows_per_block, (GT*)a.dzm, (GT*)a.dzd, (GT*)a.dzp, tpart, lpart, lf_dev);        \
+        a.G, a.ridge, a.inv_n, ps.rows_per_block, (GT*)a.dzm, (GT*)a.dzd, (GT*)a.dzp, tpart, lpart, lf_dev, fa);    \
   } while (0)
     if (a.grad_bf16) { if (cond) DCA_STAGED(true, __nv_bfloat16); else DCA_STAGED(false, __nv_bfloat16); }
     else             { if (cond) DCA_STAGED(true, float); else DCA_STAGED(false, float); }
 #undef DCA_STAGED
+    DCA_LAUNCH_CHECK();
+    return DCA_OK;                                                      // the fold is done by the last block
   } else if (BWD && vec && has_pi) {
 #define DCA_COMPACT(CD, GT)                                                                                   \
   zinb_loss_bwd_compact_kernel<CD, GT><<<grid, block, 0, s>>>(a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, a.G, \
