@@ -7,7 +7,7 @@ namespace mid {
 
 constexpr int kMaxW = 64;          // widest hidden layer handled by the fused kernels
 constexpr int kMaxCtas = 64;
-constexpr int kMaxRows = 128;      // rows per CTA strip  (=> batch <= 8192)
+constexpr int kMaxRows = 64;       // rows per CTA strip  (=> batch <= 4096; larger batches use the per-layer kernels)
 
 struct Params {
   int L, B, training, batchnorm, center, rows_per_cta, n_ctas;
