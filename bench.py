@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--gemm-path", default="auto", choices=["auto", "generic", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-format", default="auto", choices=["auto", "u16", "4", "8", "16"],
+                    help="host format of the streamed count matrix: packed bits per entry (io.pack_counts) or plain uint16")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the CPU baseline sample")
     return ap.parse_args()
 
@@ -340,33 +342,46 @@ def main():
     phases = {k: (v[0] / max(v[1], 1)) for k, v in prof.items()}
     roofline["loss_kernel_fp32_io"] = loss_kernel_standalone(eng, X, Y, sf, stream_idx[:batch], genes, batch, peak)
 
-    # ---- end to end through the public streaming API: the raw counts live in pinned HOST memory (uint16, what a
-    # count matrix is), every step copies its batch host->device (double-buffered, overlapping the previous step's
-    # compute), the device expands / normalises it (dca/io.py:99-109 restated), runs the full training step, and
-    # the step's loss is read back device->host.
+    # ---- end to end through the public streaming API: the raw counts live in pinned HOST memory (bit-packed by
+    # io.pack_counts: 4/8/16 bits per entry + overflow list, or plain uint16), every step copies its batch
+    # host->device (double-buffered, overlapping the previous step's compute), the device expands / normalises it
+    # (dca/io.py:99-109 restated), runs the full training step, and the step's loss is read back device->host.
     e2e = None
     if not a.no_e2e:
         nb = max(2, min(8, cells // batch))
-        assert float(Y[: nb * batch].max().item()) < 65536
-        cnt_h = torch.from_numpy(Y[: nb * batch].cpu().numpy().astype(np.uint16)).pin_memory()
-        sf_h = sf[: nb * batch].cpu().pin_memory()
-        loss_h = torch.zeros(64, dtype=torch.float32).pin_memory()
+        from dca_b200 import io as dio
+        from dca_b200.hostmem import pin_near_gpu, near_gpu
+        counts_np = Y[: nb * batch].cpu().numpy()
+        t_pack = time.perf_counter()
+        if a.e2e_format == "u16":
+            assert float(counts_np.max()) < 65536
+            cnt_h = pin_near_gpu(counts_np.astype(np.uint16), dev.index)
+            fmt = "uint16 raw counts"; tile_bytes = batch * genes * 2
+        else:
+            cnt_h = dio.pack_counts(counts_np, "auto" if a.e2e_format == "auto" else int(a.e2e_format), batch=batch)
+            fmt = "%d-bit packed raw counts + overflow list (%d entries of %d, io.pack_counts)" % (
+                cnt_h.bits, len(cnt_h.entries), counts_np.size)
+            tile_bytes = max(cnt_h.bytes_for_rows(i * batch, (i + 1) * batch) for i in range(nb))
+        t_pack = time.perf_counter() - t_pack
+        sf_h = pin_near_gpu(sf[: nb * batch].cpu(), dev.index)
+        loss_h = pin_near_gpu(torch.zeros(64, dtype=torch.float32), dev.index)
         eng.set_input_transform(gmean, gstd, True, True)
         k_e2e = max(3, min(a.steps, 40))
         P = eng.n_params
 
         def e2e_run(k):
-            eng.stream_begin(cnt_h, sf_h, batch)
+            eng.set_loss_ring(loss_h)           # the step's result, D2H: the update kernel stores the (all-reduced)
+            eng.stream_begin(cnt_h, sf_h, batch)  # batch loss into this pinned host ring every step
             for i in range(k):
                 eng.stream_step(i % nb, (i + 1) % nb if i + 1 < k else -1)
                 if world > 1:
                     dist.all_reduce(eng.grads)
                 eng.apply_update(lr, clip, gscale)
-                loss_h[i % 64: i % 64 + 1].copy_(eng.grads[P:P + 1], non_blocking=True)     # the step's result, D2H
             eng.stream_end()
+            eng.set_loss_ring(None)
 
         # context: raw pinned host->device copy bandwidth of this box (64 MiB, best of 5)
-        probe_h = torch.empty(64 << 20, dtype=torch.uint8).pin_memory(); probe_d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        probe_h = pin_near_gpu(torch.empty(64 << 20, dtype=torch.uint8), dev.index); probe_d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
         h2d_best = 0.0
         for _ in range(5):
             p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -382,9 +397,11 @@ def main():
         if world > 1:
             t = torch.tensor([ems], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ems = float(t.item())
         e2e = {"value": k_e2e * batch * world / (ems * 1e-3), "unit": "cells/sec", "steps": k_e2e,
-               "h2d_bytes_per_step": batch * (genes * 2 + 4), "d2h_bytes_per_step": 4,
-               "host_format": "uint16 raw counts + float32 size factors in pinned memory; X is derived on the device",
-               "api": "DeviceEngine.stream_begin / stream_step / apply_update (C ABI dca_stream_*), loss read back per step",
+               "h2d_bytes_per_step": tile_bytes + 4 * batch, "d2h_bytes_per_step": 4,
+               "host_format": fmt + " + float32 size factors in pinned memory; Y and X are derived on the device",
+               "host_pack_seconds_once": round(t_pack, 3), "host_rows": nb * batch,
+               "api": "DeviceEngine.stream_begin / stream_step / apply_update (C ABI dca_stream_*, dca_set_loss_ring); "
+                      "every step's loss lands in pinned host memory (written by the update kernel)",
                "last_loss": float(loss_h[(k_e2e - 1) % 64]), "h2d_gbs_measured": h2d_best,
                "ms_per_step": ems / k_e2e}
 

@@ -68,7 +68,9 @@ PROTOTYPES = {
     "dca_read_epoch_acc": (C.c_int, [_vp, C.POINTER(C.c_double * 4), _i32, _vp]),
     "dca_train_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _f, _f, C.POINTER(_f), _vp]),
     "dca_set_input_transform": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "dca_set_loss_ring": (C.c_int, [_vp, _vp, _i32]),
     "dca_stream_begin": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "dca_stream_begin_packed": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _i64, _i32, _vp]),
     "dca_stream_step": (C.c_int, [_vp, _i64, _i64, _vp]),
     "dca_stream_end": (C.c_int, [_vp, _vp]),
     "dca_zinb_loss_fwd_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f, _f,
@@ -88,6 +90,7 @@ PROTOTYPES = {
     "dca_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double * 6), C.POINTER(C.c_int64 * 6), _i32]),
     "dca_engine_info": (C.c_int, [_vp, C.POINTER(_i32 * 8)]),
     "dca_launch_count": (C.c_int64, []),
+    "dca_set_tunable": (C.c_int, [C.c_char_p, C.c_int64]),
 }
 
 _lib = None

@@ -87,12 +87,13 @@ int theta_grad_finish(const float* dtheta, const float* chain, int G, float scal
 int add_reg_grad(const float* w, float* g, int64_t n, float l1, float l2, cudaStream_t s);
 int reg_penalty(const float* w, int64_t n, float l1, float l2, double* acc, cudaStream_t s);
 int rmsprop_update(float* params, const float* grads, float* rms, int64_t n, float lr, float clip,
-                   float rho, float eps, float grad_scale, __nv_bfloat16* shadow, cudaStream_t s);
+                   float rho, float eps, float grad_scale, __nv_bfloat16* shadow, float* loss_out, cudaStream_t s);
 int glorot_fill(float* w, int64_t n, int fan_in, int fan_out, uint64_t seed, uint64_t stream_id, cudaStream_t s);
 int fill_value(float* p, int64_t n, float v, cudaStream_t s);
 int cast_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
-int expand_counts(const uint16_t* cnt, const float* sf_in, int M, int n, const float* mean, const float* inv_std, int use_sf,
-                  int use_log1p, float* Yout, void* Xout, int x_bf16, float* sf_out, cudaStream_t s);
+int expand_counts(const void* cnt, int bits, const float* sf_in, int M, int n, const float* mean, const float* inv_std, int use_sf,
+                  int use_log1p, float* Yout, void* Xout, int x_bf16, float* sf_out, const int64_t* ovf_indptr,
+                  const void* ovf_entries, cudaStream_t s);
 int pack_head_shadows(const float* W, const float* b, int G, int slot, int nslots, __nv_bfloat16* whT,
                       __nv_bfloat16* whkm, float* biasp, cudaStream_t s);
 int refresh_all_shadows(const float* const W[3], const float* const b[3], int n_slots, int G, __nv_bfloat16* whT,

@@ -312,7 +312,7 @@ Engine::~Engine() {
   for (auto e : prof.ev) cudaEventDestroy(e);
   for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (hs.copy) cudaStreamDestroy(hs.copy);
-  for (int k = 0; k < 2; ++k) { if (hs.h2d_done[k]) cudaEventDestroy(hs.h2d_done[k]); if (hs.buf_free[k]) cudaEventDestroy(hs.buf_free[k]); }
+  for (int k = 0; k < 2; ++k) { if (hs.ready[k]) cudaEventDestroy(hs.ready[k]); if (hs.step_done[k]) cudaEventDestroy(hs.step_done[k]); }
 }
 
 }  // namespace dca

@@ -173,12 +173,17 @@ int Engine::plan(const dca_config& c) {
   }
   // double-buffered staging of raw uint16 counts streamed from the host + the input transform
   for (int k = 0; k < 2; ++k) { o_cnt[k] = take(sizeof(uint16_t) * B * (size_t)c.n_in); o_sfst[k] = take(sizeof(float) * B); }
+  ovf_cap = (int64_t)(B * (size_t)c.n_in / 32); if (ovf_cap < 4096) ovf_cap = 4096;
+  for (int k = 0; k < 2; ++k) { o_ovp[k] = take(sizeof(int64_t) * (B + 1)); o_ove[k] = take(8 * (size_t)ovf_cap); }
   o_gmean = take(sizeof(float) * (size_t)c.n_in); o_ginv = take(sizeof(float) * (size_t)c.n_in);
   // staging for the host-buffer entry point
   const size_t xb = (c.x_dtype == DCA_BF16) ? 2 : 4;
-  o_stage_x = take(xb * B * (size_t)c.n_in);
-  o_stage_y = take(sizeof(float) * B * (size_t)G);
-  o_stage_sf = take(sizeof(float) * B);
+  for (int k = 0; k < 2; ++k) {
+    o_sx[k] = take(xb * B * (size_t)c.n_in);
+    o_sy[k] = take(sizeof(float) * B * (size_t)G);
+    o_ssf[k] = take(sizeof(float) * B);
+  }
+  o_stage_x = o_sx[0]; o_stage_y = o_sy[0]; o_stage_sf = o_ssf[0];
   arena_bytes = o;
   return DCA_OK;
 }
@@ -546,8 +551,9 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
 
 int Engine::apply_update(float lr, float clip, float grad_scale, cudaStream_t s) {
   mark(5, s);
+  float* ring_slot = loss_ring ? loss_ring + (ring_pos++ % ring_n) : nullptr;
   DCA_TRY(rmsprop_update(pp(0), gp(0), f(o_rms), P, lr, clip, cfg.rms_rho, cfg.rms_eps, grad_scale,
-                         (tc_heads || tc_enc) ? bf(o_pbf) : nullptr, s));   // also refreshes the bf16 operand copy
+                         (tc_heads || tc_enc) ? bf(o_pbf) : nullptr, ring_slot, s));   // also refreshes the bf16 operand copy
   mark(-1, s);
   return DCA_OK;
 }
@@ -870,21 +876,53 @@ extern "C" int dca_engine_info(const dca_handle* h, int32_t info[8]) {
 }
 
 // ------------------------------------------------------------------------------------ streaming from host counts
-// copy batch `i` of the host dataset into staging buffer `b` on the copy stream
+// copy batch `i` of the host dataset into staging buffer `b` and expand it (counts -> Y fp32, X normalised), all on
+// the copy stream: both overlap the training step of the previous batch, which works on the other buffer
 int Engine::stream_prefetch(int64_t i, int b) {
   const int64_t r0 = i * hs.batch;
   const int64_t nb = (hs.n_rows - r0 < hs.batch) ? (hs.n_rows - r0) : hs.batch;
-  DCA_CUDA_OK(cudaStreamWaitEvent(hs.copy, hs.buf_free[b], 0));          // staging buffer b has been consumed
-  if (hs.ld == cfg.n_in)        // contiguous rows: one linear copy (faster than the pitched path)
-    DCA_CUDA_OK(cudaMemcpyAsync(base + o_cnt[b], hs.counts + r0 * hs.ld, sizeof(uint16_t) * (size_t)cfg.n_in * (size_t)nb,
-                                cudaMemcpyHostToDevice, hs.copy));
+  const size_t tight = (size_t)cfg.n_in * (size_t)hs.bits / 8;             // bytes of one packed row
+  DCA_CUDA_OK(cudaStreamWaitEvent(hs.copy, hs.step_done[b], 0));         // the step that read buffer b has finished
+  if (hs.tl_base && hs.tl.size() < 400) hs.tl_mark(hs.copy);
+  if ((size_t)hs.row_bytes == tight)  // contiguous rows: one linear copy (faster than the pitched path)
+    DCA_CUDA_OK(cudaMemcpyAsync(base + o_cnt[b], hs.counts + r0 * hs.row_bytes, tight * (size_t)nb, cudaMemcpyHostToDevice, hs.copy));
   else
-    DCA_CUDA_OK(cudaMemcpy2DAsync(base + o_cnt[b], sizeof(uint16_t) * (size_t)cfg.n_in, hs.counts + r0 * hs.ld,
-                                  sizeof(uint16_t) * (size_t)hs.ld, sizeof(uint16_t) * (size_t)cfg.n_in, (size_t)nb,
+    DCA_CUDA_OK(cudaMemcpy2DAsync(base + o_cnt[b], tight, hs.counts + r0 * hs.row_bytes, (size_t)hs.row_bytes, tight, (size_t)nb,
                                   cudaMemcpyHostToDevice, hs.copy));
   if (hs.sf) DCA_CUDA_OK(cudaMemcpyAsync(base + o_sfst[b], hs.sf + r0, sizeof(float) * (size_t)nb, cudaMemcpyHostToDevice, hs.copy));
-  DCA_CUDA_OK(cudaEventRecord(hs.h2d_done[b], hs.copy));
+  bool has_ovf = false;
+  if (hs.ovf_indptr) {
+    const int64_t e0 = hs.ovf_indptr[r0], e1 = hs.ovf_indptr[r0 + nb];
+    has_ovf = e1 > e0;
+    if (has_ovf) {
+      DCA_CUDA_OK(cudaMemcpyAsync(base + o_ovp[b], hs.ovf_indptr + r0, sizeof(int64_t) * (size_t)(nb + 1), cudaMemcpyHostToDevice, hs.copy));
+      DCA_CUDA_OK(cudaMemcpyAsync(base + o_ove[b], hs.ovf_entries + 8 * e0, 8 * (size_t)(e1 - e0), cudaMemcpyHostToDevice, hs.copy));
+    }
+  }
+  if (hs.tl_base && hs.tl.size() < 400) hs.tl_mark(hs.copy);
+  const int x_bf16 = tc_enc ? 1 : (cfg.x_dtype == DCA_BF16);
+  DCA_TRY(expand_counts(base + o_cnt[b], hs.bits, hs.sf ? f(o_sfst[b]) : nullptr, (int)nb, cfg.n_in,
+                        tf_set == 2 ? f(o_gmean) : nullptr, tf_set == 2 ? f(o_ginv) : nullptr, tf_use_sf && hs.sf,
+                        tf_use_log1p, f(o_sy[b]), base + o_sx[b], x_bf16, f(o_ssf[b]),
+                        has_ovf ? reinterpret_cast<const int64_t*>(base + o_ovp[b]) : nullptr,
+                        has_ovf ? (const void*)(base + o_ove[b]) : nullptr, hs.copy));
+  DCA_CUDA_OK(cudaEventRecord(hs.ready[b], hs.copy));
+  if (hs.tl_base && hs.tl.size() < 400) hs.tl_mark(hs.copy);
   hs.pref_idx = i;
+  return DCA_OK;
+}
+
+extern "C" int dca_set_loss_ring(dca_handle* h, float* host_ring, int32_t n_slots) {
+  DCA_NEED_HANDLE(h);
+  Engine& e = h->e;
+  if (!host_ring || n_slots <= 0) { e.loss_ring = nullptr; e.ring_n = 0; e.ring_pos = 0; return DCA_OK; }
+  void* dptr = nullptr;
+  if (cudaHostGetDevicePointer(&dptr, host_ring, 0) != cudaSuccess || !dptr) {
+    cudaGetLastError();
+    set_error("dca_set_loss_ring: the buffer is not pinned (mapped) host memory");
+    return DCA_ERR_BAD_ARG;
+  }
+  e.loss_ring = reinterpret_cast<float*>(dptr); e.ring_n = n_slots; e.ring_pos = 0;
   return DCA_OK;
 }
 
@@ -903,27 +941,52 @@ extern "C" int dca_set_input_transform(dca_handle* h, const float* gene_mean_hos
   return DCA_OK;
 }
 
-extern "C" int dca_stream_begin(dca_handle* h, const uint16_t* counts_host, int64_t ld_counts, const float* sf_host,
-                                int64_t n_rows, int32_t batch, void* stream) {
+extern "C" int dca_stream_begin_packed(dca_handle* h, const void* packed_host, int32_t bits, int64_t row_bytes,
+                                       const int64_t* ovf_indptr_host, const void* ovf_entries_host, const float* sf_host,
+                                       int64_t n_rows, int32_t batch, void* stream) {
   DCA_NEED_HANDLE(h);
   Engine& e = h->e;
-  if (!counts_host || n_rows <= 0 || batch <= 0 || batch > e.cfg.max_batch || ld_counts < e.cfg.n_in) { set_error("dca_stream_begin: bad argument"); return DCA_ERR_BAD_ARG; }
+  if (!packed_host || n_rows <= 0 || batch <= 0 || batch > e.cfg.max_batch) { set_error("dca_stream_begin: bad argument"); return DCA_ERR_BAD_ARG; }
+  if (bits != 4 && bits != 8 && bits != 16) { set_error("dca_stream_begin: bits must be 4, 8 or 16 (got %d)", bits); return DCA_ERR_BAD_ARG; }
+  if (row_bytes < (int64_t)e.cfg.n_in * bits / 8) { set_error("dca_stream_begin: row stride smaller than a packed row"); return DCA_ERR_BAD_ARG; }
+  if ((ovf_indptr_host == nullptr) != (ovf_entries_host == nullptr)) { set_error("dca_stream_begin: give both overflow arrays or neither"); return DCA_ERR_BAD_ARG; }
   if (e.cfg.n_in != e.cfg.n_out) { set_error("dca_stream_begin: needs n_in == n_out"); return DCA_ERR_UNSUPPORTED; }
   if (e.cfg.n_in % 8 != 0) { set_error("dca_stream_begin: n_in must be a multiple of 8"); return DCA_ERR_UNSUPPORTED; }
   if (!e.tf_set) { set_error("dca_stream_begin: call dca_set_input_transform first"); return DCA_ERR_BAD_ARG; }
+  if (ovf_indptr_host) {
+    for (int64_t r0 = 0; r0 < n_rows; r0 += batch) {
+      const int64_t r1 = (r0 + batch < n_rows) ? r0 + batch : n_rows;
+      const int64_t cnt = ovf_indptr_host[r1] - ovf_indptr_host[r0];
+      if (cnt < 0 || cnt > e.ovf_cap) {
+        set_error("dca_stream_begin: batch starting at row %lld has %lld overflow entries (capacity %lld): pack with more bits",
+                  (long long)r0, (long long)cnt, (long long)e.ovf_cap);
+        return DCA_ERR_BAD_ARG;
+      }
+    }
+  }
   auto& hs = e.hs;
   if (!hs.copy) {
     DCA_CUDA_OK(cudaStreamCreateWithFlags(&hs.copy, cudaStreamNonBlocking));
     for (int k = 0; k < 2; ++k) {
-      DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.h2d_done[k], cudaEventDisableTiming));
-      DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.buf_free[k], cudaEventDisableTiming));
+      DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.ready[k], cudaEventDisableTiming));
+      DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.step_done[k], cudaEventDisableTiming));
     }
   }
   cudaStream_t s = (cudaStream_t)stream;
-  for (int k = 0; k < 2; ++k) DCA_CUDA_OK(cudaEventRecord(hs.buf_free[k], s));   // both staging buffers start free
-  hs.counts = counts_host; hs.ld = ld_counts; hs.sf = sf_host; hs.n_rows = n_rows; hs.batch = batch;
+  for (int k = 0; k < 2; ++k) DCA_CUDA_OK(cudaEventRecord(hs.step_done[k], s));   // both staging buffers start free
+  hs.counts = reinterpret_cast<const unsigned char*>(packed_host); hs.row_bytes = row_bytes; hs.bits = bits;
+  hs.ovf_indptr = ovf_indptr_host; hs.ovf_entries = reinterpret_cast<const unsigned char*>(ovf_entries_host);
+  hs.sf = sf_host; hs.n_rows = n_rows; hs.batch = batch;
   hs.pref_idx = -1; hs.step_no = 0; hs.active = true;
+  { const char* v = getenv("DCA_STREAM_DIAG");
+    if (v && atoi(v) == 2) { hs.tl.clear(); if (!hs.tl_base) cudaEventCreate(&hs.tl_base); cudaEventRecord(hs.tl_base, s); } }
   return DCA_OK;
+}
+
+extern "C" int dca_stream_begin(dca_handle* h, const uint16_t* counts_host, int64_t ld_counts, const float* sf_host,
+                                int64_t n_rows, int32_t batch, void* stream) {
+  return dca_stream_begin_packed(h, counts_host, 16, ld_counts * (int64_t)sizeof(uint16_t), nullptr, nullptr, sf_host, n_rows,
+                                 batch, stream);
 }
 
 extern "C" int dca_stream_step(dca_handle* h, int64_t i, int64_t next, void* stream) {
@@ -938,22 +1001,21 @@ extern "C" int dca_stream_step(dca_handle* h, int64_t i, int64_t next, void* str
   if (hs.pref_idx != i) DCA_TRY(e.stream_prefetch(i, b));           // not prefetched by the previous step: fetch now
   const int64_t r0 = i * hs.batch;
   const int nb = (int)((hs.n_rows - r0 < hs.batch) ? (hs.n_rows - r0) : hs.batch);
-  DCA_CUDA_OK(cudaStreamWaitEvent(s, hs.h2d_done[b], 0));
-  const bool to_xb = e.tc_enc;                      // bf16 batch straight into the tcgen05 encoder's input buffer
-  void* xdst = to_xb ? (void*)e.bf(e.o_xb) : (void*)(e.base + e.o_stage_x);
-  const int x_bf16 = to_xb ? 1 : (e.cfg.x_dtype == DCA_BF16);
-  DCA_TRY(expand_counts(reinterpret_cast<const uint16_t*>(e.base + e.o_cnt[b]), hs.sf ? e.f(e.o_sfst[b]) : nullptr, nb, e.cfg.n_in,
-                        e.tf_set == 2 ? e.f(e.o_gmean) : nullptr, e.tf_set == 2 ? e.f(e.o_ginv) : nullptr, e.tf_use_sf && hs.sf,
-                        e.tf_use_log1p, e.f(e.o_stage_y), xdst, x_bf16, e.f(e.o_stage_sf), s));
-  DCA_CUDA_OK(cudaEventRecord(hs.buf_free[b], s));
   ++hs.step_no;
   hs.pref_idx = -1;
-  if (next >= 0) DCA_TRY(e.stream_prefetch(next, b ^ 1));           // next batch's copy overlaps this batch's compute
+  if (next >= 0) DCA_TRY(e.stream_prefetch(next, b ^ 1));           // next batch: copy + expansion overlap this step
+  DCA_CUDA_OK(cudaStreamWaitEvent(s, hs.ready[b], 0));
+  const bool tl_on = hs.tl_base && hs.tl.size() < 400;
+  if (tl_on) hs.tl_mark(s);
   static const int diag = [] { const char* v = getenv("DCA_STREAM_DIAG"); return v ? atoi(v) : 0; }();
-  if (diag == 1) return DCA_OK;                     // diagnosis: copies + expansion only
-  e.x_override_bf16 = to_xb ? 1 : 0;
-  const int st = e.train_step(xdst, e.cfg.n_in, e.f(e.o_stage_y), e.cfg.n_out, e.f(e.o_stage_sf), nullptr, nb, s, 0);
-  e.x_override_bf16 = 0;
+  int st = DCA_OK;
+  if (diag != 1) {                                  // (1 = diagnosis: copies + expansion only)
+    e.x_override_bf16 = e.tc_enc ? 1 : 0;           // the tcgen05 encoder reads the expanded bf16 batch in place
+    st = e.train_step(e.base + e.o_sx[b], e.cfg.n_in, e.f(e.o_sy[b]), e.cfg.n_out, e.f(e.o_ssf[b]), nullptr, nb, s, 0);
+    e.x_override_bf16 = 0;
+  }
+  DCA_CUDA_OK(cudaEventRecord(hs.step_done[b], s));
+  if (tl_on) hs.tl_mark(s);
   return st;
 }
 
@@ -962,6 +1024,15 @@ extern "C" int dca_stream_end(dca_handle* h, void* stream) {
   auto& hs = h->e.hs;
   if (hs.copy) DCA_CUDA_OK(cudaStreamSynchronize(hs.copy));
   DCA_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-  hs.active = false; hs.counts = nullptr;
+  if (hs.tl_base && !hs.tl.empty()) {   // order of marks per step: [copy0 c0 c1 (first step only)] x0 x1 | copy-next c0 c1 | step-end
+    fprintf(stderr, "[dca stream timeline, ms since stream_begin; first 3 marks: copy/expand of batch 0; then per step: "
+                    "next_copy_start next_copy_end next_expand_end step_start step_end]\n");
+    std::vector<float> t(hs.tl.size());
+    for (size_t k = 0; k < hs.tl.size(); ++k) { t[k] = -1.f; cudaEventElapsedTime(&t[k], hs.tl_base, hs.tl[k]); cudaEventDestroy(hs.tl[k]); }
+    for (size_t k = 0; k < t.size(); ++k) fprintf(stderr, "%.3f%s", t[k], ((k + 1 - 3) % 5 == 0 && k >= 3) ? "\n" : " ");
+    fprintf(stderr, "\n");
+    hs.tl.clear();
+  }
+  hs.active = false; hs.counts = nullptr; hs.ovf_indptr = nullptr; hs.ovf_entries = nullptr;
   return DCA_OK;
 }

@@ -29,7 +29,8 @@ struct Engine {
   size_t o_params = 0, o_grads = 0, o_rms = 0, o_state = 0, o_acc = 0;
   size_t o_head[3] = {0, 0, 0}, o_dh[2] = {0, 0}, o_dsum = 0, o_dprod = 0, o_scratch = 0;
   size_t o_theta = 0, o_chain = 0, o_dtheta = 0, o_sfb = 0, o_lossws = 0, loss_ws_bytes = 0;
-  size_t o_stage_x = 0, o_stage_y = 0, o_stage_sf = 0;
+  size_t o_stage_x = 0, o_stage_y = 0, o_stage_sf = 0;       // == o_sx[0], o_sy[0], o_ssf[0]
+  size_t o_sx[2] = {0, 0}, o_sy[2] = {0, 0}, o_ssf[2] = {0, 0};  // double-buffered expanded batch (streaming path)
   // head input of the current forward (set by forward())
   const void* head_in = nullptr; int64_t head_ld = 0; int head_bf16 = 0; const int32_t* head_rows = nullptr;
   // CUDA-graph replay of the training step (captured from the same launch sequence on the 2nd call with a key)
@@ -44,11 +45,21 @@ struct Engine {
                       cudaStream_t s, int phase);
   // streaming from host counts
   size_t o_cnt[2] = {0, 0}, o_sfst[2] = {0, 0}, o_gmean = 0, o_ginv = 0;
+  size_t o_ovp[2] = {0, 0}, o_ove[2] = {0, 0};     // overflow list of a staged batch: indptr[B+1] (int64), entries (8 B each)
+  int64_t ovf_cap = 0;                              // entries per staging buffer
   int tf_use_sf = 1, tf_use_log1p = 1, tf_set = 0, x_override_bf16 = 0;
+  float* loss_ring = nullptr; int ring_n = 0; int64_t ring_pos = 0;   // mapped host mirror of the per-step loss
   struct HostStream {
-    const uint16_t* counts = nullptr; int64_t ld = 0; const float* sf = nullptr; int64_t n_rows = 0; int batch = 0;
-    cudaStream_t copy = nullptr; cudaEvent_t h2d_done[2] = {nullptr, nullptr}, buf_free[2] = {nullptr, nullptr};
+    const unsigned char* counts = nullptr; int64_t row_bytes = 0; int bits = 16;       // packed host count matrix
+    const int64_t* ovf_indptr = nullptr; const unsigned char* ovf_entries = nullptr;   // host CSR overflow list (or null)
+    const float* sf = nullptr; int64_t n_rows = 0; int batch = 0;
+    cudaStream_t copy = nullptr;                      // copies AND the expansion kernel of the next batch run here
+    cudaEvent_t ready[2] = {nullptr, nullptr};        // copy stream: batch in buffer b is expanded (Y, X, sf ready)
+    cudaEvent_t step_done[2] = {nullptr, nullptr};    // compute stream: the step that read buffer b has finished
     int64_t pref_idx = -1, step_no = 0; bool active = false;
+    // DCA_STREAM_DIAG=2: device-side timeline (events) of the first steps, printed by dca_stream_end
+    std::vector<cudaEvent_t> tl; cudaEvent_t tl_base = nullptr;
+    void tl_mark(cudaStream_t st) { cudaEvent_t e; if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); tl.push_back(e); } }
   } hs;
   int stream_prefetch(int64_t i, int buf);
   // optional phase timing

@@ -230,9 +230,14 @@ __global__ void reg_penalty_kernel(const float* __restrict__ w, int64_t n, float
 }
 
 __global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ r, int64_t n,
-                               float lr, float clip, float rho, float eps, float gs, __nv_bfloat16* __restrict__ shadow) {
+                               float lr, float clip, float rho, float eps, float gs, __nv_bfloat16* __restrict__ shadow,
+                               float* loss_out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (i == 0 && loss_out) {             // the step's (all-reduced) mean loss, mirrored into mapped HOST memory
+    *loss_out = g[n] * gs;              // grads[P] is the loss slot
+    __threadfence_system();
+  }
   float gi = g[i] * gs;
   if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);       // clipvalue
   const float ri = rho * r[i] + (1.0f - rho) * gi * gi;
@@ -267,27 +272,67 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
   if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
 
-// uint16 counts -> Y (fp32 target) and X = ((log1p)(y/sf) - mean_g) * inv_std_g (network input), 8 genes per thread
-template <typename XT>
-__global__ void expand_counts_kernel(const uint16_t* __restrict__ cnt, const float* __restrict__ sf_in, int M, int n,
+// packed counts (BITS = 4 / 8 / 16 per entry, row-major, gene c of a 4-bit row in byte c/2, low nibble = even c)
+// -> Y (fp32 target) and X = ((log1p)(y/sf) - mean_g) * inv_std_g (network input), 8 genes per thread.
+// With an overflow list the value 2^BITS-1 is an escape: the true count is looked up in the row's (short,
+// gene-sorted) segment of the CSR list.  log1p uses MUFU lg2 (relative error ~1e-6 for y/sf >= 1e-2, far
+// below the bf16 rounding of the encoder input and the 2e-5 parity tolerance of the fp32 path).
+__device__ __forceinline__ float normalise_count(float y, float inv_s, int use_log1p, const float* mean,
+                                                 const float* inv_std, int c) {
+  float v = y * inv_s;                                    // sc.pp.normalize_per_cell   dca/io.py:99-100
+  if (use_log1p) v = 0.6931471805599453f * __log2f(1.0f + v);   // sc.pp.log1p (MUFU lg2)   dca/io.py:105-106
+  return mean ? (v - mean[c]) * inv_std[c] : v;           // sc.pp.scale                dca/io.py:108-109
+}
+
+__device__ __noinline__ float overflow_lookup(const int64_t* __restrict__ indptr, const int2* __restrict__ entries, int r, int c,
+                                              float fallback) {
+  const int64_t base = indptr[0];
+  int64_t lo = indptr[r] - base, hi = indptr[r + 1] - base;
+  while (lo < hi) {                                       // entries of a row are sorted by gene
+    const int64_t mid = (lo + hi) >> 1;
+    const int g = entries[mid].x;
+    if (g == c) return __int_as_float(entries[mid].y);
+    if (g < c) lo = mid + 1; else hi = mid;
+  }
+  return fallback;
+}
+
+template <int BITS, typename XT>
+__global__ void expand_counts_kernel(const unsigned char* __restrict__ cnt, const float* __restrict__ sf_in, int M, int n,
                                      const float* __restrict__ mean, const float* __restrict__ inv_std, int use_sf,
-                                     int use_log1p, float* __restrict__ Yout, XT* __restrict__ Xout, float* __restrict__ sf_out) {
+                                     int use_log1p, float* __restrict__ Yout, XT* __restrict__ Xout, float* __restrict__ sf_out,
+                                     const int64_t* __restrict__ ovf_indptr, const int2* __restrict__ ovf_entries) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int per_row = n / 8;
   if (i >= (int64_t)M * per_row) return;
   const int r = (int)(i / per_row), c = (int)(i % per_row) * 8;
   const float s = sf_in ? sf_in[r] : 1.0f;
   if (c == 0 && sf_out) sf_out[r] = s;
-  const uint4 raw = *reinterpret_cast<const uint4*>(cnt + (int64_t)r * n + c);
-  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  const float inv_s = use_sf ? 1.0f / s : 1.0f;
+  uint32_t q[8];
+  const unsigned char* src = cnt + ((int64_t)r * n + c) * BITS / 8;
+  if (BITS == 16) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(src);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { q[2 * k] = w[k] & 0xffffu; q[2 * k + 1] = w[k] >> 16; }
+  } else if (BITS == 8) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(src);
+    const uint32_t w[2] = {raw.x, raw.y};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+  } else {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = (w >> (4 * k)) & 0xfu;
+  }
+  constexpr uint32_t kEsc = (1u << BITS) - 1u;
   float y[8], x[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { y[2 * k] = (float)(w[k] & 0xffffu); y[2 * k + 1] = (float)(w[k] >> 16); }
-#pragma unroll
   for (int k = 0; k < 8; ++k) {
-    float v = use_sf ? y[k] / s : y[k];                   // sc.pp.normalize_per_cell   dca/io.py:99-100
-    if (use_log1p) v = log1pf(v);                         // sc.pp.log1p                dca/io.py:105-106
-    x[k] = mean ? (v - mean[c + k]) * inv_std[c + k] : v; // sc.pp.scale                dca/io.py:108-109
+    y[k] = (float)q[k];
+    if (ovf_indptr && q[k] == kEsc) y[k] = overflow_lookup(ovf_indptr, ovf_entries, r, c + k, y[k]);
+    x[k] = normalise_count(y[k], inv_s, use_log1p, mean, inv_std, c + k);
   }
   float* yo = Yout + (int64_t)r * n + c;
   *reinterpret_cast<float4*>(yo) = make_float4(y[0], y[1], y[2], y[3]);
@@ -409,8 +454,8 @@ int reg_penalty(const float* w, int64_t n, float l1, float l2, double* acc, cuda
 }
 
 int rmsprop_update(float* params, const float* grads, float* rms, int64_t n, float lr, float clip, float rho,
-                   float eps, float grad_scale, __nv_bfloat16* shadow, cudaStream_t s) {
-  rmsprop_kernel<<<blocks_for(n), 256, 0, s>>>(params, grads, rms, n, lr, clip, rho, eps, grad_scale, shadow);
+                   float eps, float grad_scale, __nv_bfloat16* shadow, float* loss_out, cudaStream_t s) {
+  rmsprop_kernel<<<blocks_for(n), 256, 0, s>>>(params, grads, rms, n, lr, clip, rho, eps, grad_scale, shadow, loss_out);
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }
@@ -503,11 +548,23 @@ int gather_rows_bf16(const void* X, int x_bf16, int64_t ldx, const int32_t* rows
   return DCA_OK;
 }
 
-int expand_counts(const uint16_t* cnt, const float* sf_in, int M, int n, const float* mean, const float* inv_std, int use_sf,
-                  int use_log1p, float* Yout, void* Xout, int x_bf16, float* sf_out, cudaStream_t s) {
+int expand_counts(const void* cnt, int bits, const float* sf_in, int M, int n, const float* mean, const float* inv_std, int use_sf,
+                  int use_log1p, float* Yout, void* Xout, int x_bf16, float* sf_out, const int64_t* ovf_indptr,
+                  const void* ovf_entries, cudaStream_t s) {
   const int64_t tot = (int64_t)M * (n / 8);
-  if (x_bf16) expand_counts_kernel<__nv_bfloat16><<<blocks_for(tot), 256, 0, s>>>(cnt, sf_in, M, n, mean, inv_std, use_sf, use_log1p, Yout, (__nv_bfloat16*)Xout, sf_out);
-  else expand_counts_kernel<float><<<blocks_for(tot), 256, 0, s>>>(cnt, sf_in, M, n, mean, inv_std, use_sf, use_log1p, Yout, (float*)Xout, sf_out);
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(cnt);
+  const int2* oe = ovf_indptr ? reinterpret_cast<const int2*>(ovf_entries) : nullptr;
+  if (!oe) ovf_indptr = nullptr;
+#define DCA_EXPAND(BITS)                                                                                             \
+  do {                                                                                                               \
+    if (x_bf16) expand_counts_kernel<BITS, __nv_bfloat16><<<blocks_for(tot), 256, 0, s>>>(src, sf_in, M, n, mean, inv_std, use_sf, use_log1p, Yout, (__nv_bfloat16*)Xout, sf_out, ovf_indptr, oe); \
+    else expand_counts_kernel<BITS, float><<<blocks_for(tot), 256, 0, s>>>(src, sf_in, M, n, mean, inv_std, use_sf, use_log1p, Yout, (float*)Xout, sf_out, ovf_indptr, oe); \
+  } while (0)
+  if (bits == 16) DCA_EXPAND(16);
+  else if (bits == 8) DCA_EXPAND(8);
+  else if (bits == 4) DCA_EXPAND(4);
+  else { set_error("expand_counts: bits must be 4, 8 or 16 (got %d)", bits); return DCA_ERR_BAD_ARG; }
+#undef DCA_EXPAND
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }

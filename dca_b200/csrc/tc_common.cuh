@@ -51,6 +51,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, with a sleep between polls: a waiting warp stops competing for issue slots with the warps that do
+// the arithmetic (matters in issue-bound kernels).  The first poll is immediate.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t polls = 0;
+  long long t0 = 0;
+  do {
+    if (sleep_ns) __nanosleep(sleep_ns);
+    if ((++polls & 0x3FFF) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  } while (!mbar_try_wait(bar, parity));
+}
+
 // ------------------------------------------------------------------------------------ fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -8,6 +8,7 @@
 // The loss scalar is reduced thread -> warp shuffle -> shared memory -> one double per block,
 // and a second tiny kernel folds the block partials (deterministic, no float atomics).
 #include "dca_internal.cuh"
+#include <string>
 #include "zinb_math.cuh"
 #include "tc_common.cuh"
 #include <cstdlib>
@@ -19,15 +20,28 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kVec = 4;
 constexpr int kColsPerBlock = kThreads * kVec;   // 1024 genes per block
-constexpr int kTargetBlocks = 148 * 16;          // ~4 waves of 4 resident blocks per SM
 constexpr int kMaxBlocks = 65536;                // bound of the per-block loss-partial buffer
+
+// Launch tunables (dca_set_tunable; defaults chosen from the sweep in profiles/r1_loss_sweep.log)
+struct LossTune { int target_blocks; unsigned producer_sleep_ns, consumer_sleep_ns; };
+LossTune g_tune = {0 /* auto */, 0u, 0u};
+
+int sm_count_cached() {
+  static int n = 0;
+  if (!n) { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148; }
+  return n;
+}
 
 struct Plan { int col_blocks, rows_per_block, row_chunks; };
 
 inline Plan make_plan(int B, int G, int cols_per_block, int max_rpb = 1 << 30) {
   Plan p;
   p.col_blocks = cdiv(G, cols_per_block);
-  int chunks = kTargetBlocks / p.col_blocks;
+  // auto: small batches (C2: 4096 x 2000) run as ONE wave of 3 resident blocks per SM (block start-up and the
+  // partial last wave cost 15 % there), large ones as ~5 waves for dynamic balance (profiles/r1_loss_sweep.log)
+  const int target = g_tune.target_blocks > 0 ? g_tune.target_blocks
+                     : ((long long)B * G <= (32ll << 20) ? 3 * sm_count_cached() : 16 * sm_count_cached());
+  int chunks = target / p.col_blocks;
   if (chunks < 1) chunks = 1;
   if (chunks > B) chunks = B;
   int rpb = cdiv(B, chunks);
@@ -277,7 +291,7 @@ struct FoldArgs {
 };
 
 constexpr int kStageRows = 3;
-constexpr int kMaxRowsPerBlock = 64;
+constexpr int kMaxRowsPerBlock = 256;
 constexpr int kStagedThreads = kThreads + 32;      // 8 consumer warps + 1 producer warp
 
 template <bool COND_DISP, typename GT>
@@ -286,7 +300,8 @@ zinb_loss_bwd_staged_kernel(const float* __restrict__ Y, int64_t ldy, const int3
                             const float* __restrict__ sf, const float* m, const float* d, const float* pi,
                             int64_t ld, int B, int G, float ridge, float inv_n, int rows_per_block,
                             GT* dzm, GT* dzd, GT* dzp, float* __restrict__ dth_acc,
-                            double* __restrict__ loss_partial, const float* __restrict__ lf_global, const FoldArgs fa) {
+                            double* __restrict__ loss_partial, const float* __restrict__ lf_global, const FoldArgs fa,
+                            const unsigned producer_sleep_ns, const unsigned consumer_sleep_ns) {
   extern __shared__ __align__(128) unsigned char smem_loss[];
   constexpr int kArrays = COND_DISP ? 4 : 3;                           // y, m, [d], pi
   constexpr uint32_t kArrBytes = kColsPerBlock * 4;                    // one row segment of one tensor
@@ -304,10 +319,10 @@ zinb_loss_bwd_staged_kernel(const float* __restrict__ Y, int64_t ldy, const int3
   const int r0 = blockIdx.y * rows_per_block;
   const int nrows = min(rows_per_block, B - r0);
   if (threadIdx.x < zmath::kLogFactN) lf[threadIdx.x] = lf_global[threadIdx.x];
-  if (threadIdx.x < nrows) {
-    const int yr = rows ? rows[r0 + threadIdx.x] : (r0 + threadIdx.x);
-    s_row[threadIdx.x] = yr;
-    s_sf[threadIdx.x] = sf ? sf[yr] : 1.0f;
+  for (int t = threadIdx.x; t < nrows; t += kStagedThreads) {
+    const int yr = rows ? rows[r0 + t] : (r0 + t);
+    s_row[t] = yr;
+    s_sf[t] = sf ? sf[yr] : 1.0f;
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStageRows; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], kThreads / 32); }
@@ -321,7 +336,7 @@ zinb_loss_bwd_staged_kernel(const float* __restrict__ Y, int64_t ldy, const int3
       const uint32_t bytes = (uint32_t)ncols * 4u;
       for (int i = 0; i < nrows; ++i) {
         const int st = i % kStageRows; const uint32_t ph = (i / kStageRows) & 1;
-        tc::mbar_wait(&empty_bar[st], ph ^ 1);
+        tc::mbar_wait_backoff(&empty_bar[st], ph ^ 1, producer_sleep_ns);
         unsigned char* dst = smem_loss + (size_t)st * kStageBytes;
         tc::mbar_expect_tx(&full_bar[st], bytes * kArrays);
         const int64_t off = (int64_t)(r0 + i) * ld + c0;
@@ -358,7 +373,7 @@ zinb_loss_bwd_staged_kernel(const float* __restrict__ Y, int64_t ldy, const int3
   for (int i = 0; i < nrows; ++i) {
     const int st = i % kStageRows; const uint32_t ph = (i / kStageRows) & 1;
     const unsigned char* src = smem_loss + (size_t)st * kStageBytes + (size_t)threadIdx.x * 16;
-    tc::mbar_wait(&full_bar[st], ph);
+    tc::mbar_wait_backoff(&full_bar[st], ph, consumer_sleep_ns);
     float4 vy = make_float4(0.f, 0.f, 0.f, 0.f), vm = vy, vd = vy, vp = vy;
     if (active) {
       vy = *reinterpret_cast<const float4*>(src);
@@ -569,7 +584,8 @@ int launch(const LossArgs& a, cudaStream_t s) {
     static bool attr = false;                                                                                      \
     if (!attr) { DCA_CUDA_OK(cudaFuncSetAttribute(zinb_loss_bwd_staged_kernel<CD, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr = true; } \
     zinb_loss_bwd_staged_kernel<CD, GT><<<grid, kStagedThreads, sm, s>>>(a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, \
-        a.G, a.ridge, a.inv_n, ps.rows_per_block, (GT*)a.dzm, (GT*)a.dzd, (GT*)a.dzp, tpart, lpart, lf_dev, fa);    \
+        a.G, a.ridge, a.inv_n, ps.rows_per_block, (GT*)a.dzm, (GT*)a.dzd, (GT*)a.dzp, tpart, lpart, lf_dev, fa,     \
+        g_tune.producer_sleep_ns, g_tune.consumer_sleep_ns);                                                       \
   } while (0)
     if (a.grad_bf16) { if (cond) DCA_STAGED(true, __nv_bfloat16); else DCA_STAGED(false, __nv_bfloat16); }
     else             { if (cond) DCA_STAGED(true, float); else DCA_STAGED(false, float); }
@@ -632,6 +648,16 @@ int loss_finalize(const double* loss_sum, const double* penalty, float inv_n, in
 
 // ------------------------------------------------------------------------------------ C ABI
 using namespace dca;
+
+extern "C" int dca_set_tunable(const char* name, int64_t value) {
+  if (!name) { set_error("dca_set_tunable: null name"); return DCA_ERR_BAD_ARG; }
+  const std::string n(name);
+  if (n == "loss_target_blocks" && value >= 0 && value <= kMaxBlocks) g_tune.target_blocks = (int)value;
+  else if (n == "loss_producer_sleep_ns" && value >= 0 && value <= 100000) g_tune.producer_sleep_ns = (unsigned)value;
+  else if (n == "loss_consumer_sleep_ns" && value >= 0 && value <= 100000) g_tune.consumer_sleep_ns = (unsigned)value;
+  else { set_error("dca_set_tunable: unknown name or value out of range (%s = %lld)", name, (long long)value); return DCA_ERR_BAD_ARG; }
+  return DCA_OK;
+}
 
 extern "C" int dca_zinb_loss_workspace_bytes(int32_t batch, int32_t genes, size_t* bytes) {
   if (!bytes || batch <= 0 || genes <= 0) { set_error("dca_zinb_loss_workspace_bytes: bad argument"); return DCA_ERR_BAD_ARG; }

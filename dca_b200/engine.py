@@ -254,16 +254,48 @@ class DeviceEngine:
         check(self.lib.dca_set_input_transform(self.handle, mean.ctypes.data, inv.ctypes.data, int(use_size_factors),
                                                int(use_log1p), self._stream()), "dca_set_input_transform")
 
-    def stream_begin(self, counts_u16: torch.Tensor, sf: Optional[torch.Tensor], batch: int):
-        """counts_u16: HOST uint16 tensor [n_rows x n_in] (pin it), sf: HOST float32 [n_rows] or None."""
-        if counts_u16.dtype != torch.uint16 or counts_u16.dim() != 2 or counts_u16.shape[1] != self.n_in or counts_u16.stride(1) != 1:
-            raise ValueError("counts must be a uint16 (rows, %d) row-major host tensor" % self.n_in)
-        if counts_u16.is_cuda or (sf is not None and sf.is_cuda):
+    def stream_begin(self, counts, sf: Optional[torch.Tensor], batch: int):
+        """Train from HOST memory.  counts: a HOST uint16 tensor [n_rows x n_in] (pin it, hostmem.pin_near_gpu), or an
+        io.PackedCounts (4/8/16 bits per entry + overflow list, see io.pack_counts) whose arrays are pinned
+        here; sf: HOST float32 [n_rows] or None."""
+        if sf is not None and sf.is_cuda:
             raise ValueError("stream_begin takes HOST tensors")
-        self._stream_keep = (counts_u16, sf)
-        check(self.lib.dca_stream_begin(self.handle, counts_u16.data_ptr(), counts_u16.stride(0),
-                                        None if sf is None else sf.data_ptr(), counts_u16.shape[0], batch, self._stream()),
-              "dca_stream_begin")
+        if isinstance(counts, torch.Tensor):
+            if counts.dtype != torch.uint16 or counts.dim() != 2 or counts.shape[1] != self.n_in or counts.stride(1) != 1:
+                raise ValueError("counts must be a uint16 (rows, %d) row-major host tensor" % self.n_in)
+            if counts.is_cuda:
+                raise ValueError("stream_begin takes HOST tensors")
+            self._stream_keep = (counts, sf)
+            check(self.lib.dca_stream_begin(self.handle, counts.data_ptr(), counts.stride(0),
+                                            None if sf is None else sf.data_ptr(), counts.shape[0], batch, self._stream()),
+                  "dca_stream_begin")
+            return
+        pc = counts
+        if pc.n_genes != self.n_in:
+            raise ValueError("packed counts have %d genes, the engine %d" % (pc.n_genes, self.n_in))
+
+        from .hostmem import pin_near_gpu
+
+        def pinned(a, view):                      # pinned pages on the GPU's NUMA node (hostmem.py)
+            return pin_near_gpu(np.ascontiguousarray(a).view(view), self.device.index or 0)
+        packed = pinned(pc.packed, np.uint8)
+        indptr = pinned(pc.indptr, np.int64)
+        entries = pinned(pc.entries if len(pc.entries) else np.zeros(1, dtype=pc.entries.dtype), np.uint8)
+        self._stream_keep = (packed, indptr, entries, sf)
+        check(self.lib.dca_stream_begin_packed(self.handle, packed.data_ptr(), pc.bits, packed.shape[-1] if packed.dim() == 2 else 0,
+                                               indptr.data_ptr(), entries.data_ptr(), None if sf is None else sf.data_ptr(),
+                                               pc.n_rows, batch, self._stream()), "dca_stream_begin_packed")
+
+    def set_loss_ring(self, ring: Optional[torch.Tensor]):
+        """Mirror every step's loss into the pinned host float32 tensor `ring` (slot k % len for the k-th
+        apply_update after this call); None switches it off."""
+        if ring is None:
+            check(self.lib.dca_set_loss_ring(self.handle, None, 0), "dca_set_loss_ring"); self._ring_keep = None
+            return
+        if ring.dtype != torch.float32 or ring.is_cuda or not ring.is_pinned() or not ring.is_contiguous():
+            raise ValueError("the loss ring must be a contiguous pinned float32 host tensor")
+        self._ring_keep = ring
+        check(self.lib.dca_set_loss_ring(self.handle, ring.data_ptr(), ring.numel()), "dca_set_loss_ring")
 
     def stream_step(self, batch_index: int, next_batch_index: int = -1):
         """Forward + loss + backward of host batch `batch_index`; the copy of `next_batch_index` overlaps it."""

@@ -160,6 +160,12 @@ int dca_predict(dca_handle* h, const void* X, int64_t ldx, const float* sf, cons
 int dca_read_loss(dca_handle* h, float* loss_host, int32_t* nonfinite_host, void* stream);
 int dca_read_epoch_acc(dca_handle* h, double acc_host[4], int32_t reset, void* stream);
 
+/* Mirror every step's loss into pinned (mapped) HOST memory without a copy in the stream: the k-th
+ * dca_apply_update after this call stores grads[P] * grad_scale (the batch loss, averaged over ranks once the
+ * gradient buffer was all-reduced) into host_ring[k % n_slots] from inside the update kernel.  The host reads a
+ * slot after synchronising on a later event.  NULL / 0 switches it off. */
+int dca_set_loss_ring(dca_handle* h, float* host_ring, int32_t n_slots);
+
 /* End-to-end variant with HOST buffers (pinned recommended): copies the batch
  * (x_host: batch x n_in of cfg.x_dtype, y_host: batch x n_out float, sf_host: batch float)
  * to the device, runs dca_train_step + dca_apply_update, copies the loss back and waits. */
@@ -180,6 +186,16 @@ int dca_set_input_transform(dca_handle* h, const float* gene_mean_host, const fl
  * exactly as for the resident path.  Requires n_in == n_out. */
 int dca_stream_begin(dca_handle* h, const uint16_t* counts_host, int64_t ld_counts, const float* sf_host,
                      int64_t n_rows, int32_t batch, void* stream);
+/* Same, from a bit-PACKED count matrix (fewer PCIe bytes per step): `bits` = 4, 8 or 16 per entry, row-major,
+ * row stride `row_bytes` (a 4-bit row keeps gene c in byte c/2, low nibble = even c).  Counts >= 2^bits-1 are
+ * stored as the escape value 2^bits-1 and listed in a CSR overflow list over ALL rows: ovf_indptr_host
+ * int64[n_rows+1], ovf_entries_host {int32 gene; float count}[ovf_indptr[n_rows]] sorted by row; each step
+ * copies its batch's segment with the tile and patches the escapes on the device.  Both NULL: no escapes
+ * (2^bits-1 is a literal count).  A batch may carry at most max_batch*n_in/32 (>= 4096) overflow entries.
+ * dca_b200/io.py:pack_counts builds the format; dca_stream_begin(...) == bits 16 without an overflow list. */
+int dca_stream_begin_packed(dca_handle* h, const void* packed_host, int32_t bits, int64_t row_bytes,
+                            const int64_t* ovf_indptr_host, const void* ovf_entries_host, const float* sf_host,
+                            int64_t n_rows, int32_t batch, void* stream);
 int dca_stream_step(dca_handle* h, int64_t batch_index, int64_t next_batch_index /* -1: none */, void* stream);
 int dca_stream_end(dca_handle* h, void* stream);
 
@@ -263,6 +279,10 @@ int dca_engine_info(const dca_handle* h, int32_t info[8]);
 
 /* Number of kernels this library has launched in this process (all handles, all streams). */
 int64_t dca_launch_count(void);
+/* Launch tunables of the loss kernel (process-wide; set them BEFORE the first training step of an engine,
+ * a captured step graph keeps the values it was recorded with): "loss_target_blocks",
+ * "loss_producer_sleep_ns", "loss_consumer_sleep_ns".  Profiling aid -- no reference counterpart. */
+int dca_set_tunable(const char* name, int64_t value);
 
 #ifdef __cplusplus
 }

@@ -410,6 +410,65 @@ def test_stream_from_host_counts_matches_resident_path():
         e2.stream_end()
 
 
+@pytest.mark.parametrize("bits", [4, 8, 16, "auto"])
+def test_stream_packed_counts_equals_uint16_stream(bits):
+    """dca_stream_begin_packed (4/8/16 bits per entry + overflow list) expands to the same Y and X as the plain
+    uint16 stream: loss trajectories are identical; large counts travel through the overflow list."""
+    from dca_b200.engine import DeviceEngine
+    from dca_b200 import io
+    N, G, B = 600, 264, 256
+    Y = synth_counts(N, G, 37)
+    rng = np.random.default_rng(5)
+    for _ in range(400):                                    # counts that need the escape in every width
+        Y[rng.integers(N), rng.integers(G)] = float(rng.choice([15, 16, 40, 254, 255, 256, 3000, 60000]))
+    _, sf = O.normalize_inputs(Y)
+    l = np.log1p(Y / sf[:, None].astype(np.float32)).astype(np.float32)
+    mean = l.mean(0, dtype=np.float64); std = np.sqrt(l.var(0, ddof=1, dtype=np.float64))
+    pc = io.pack_counts(Y, bits, batch=B)
+    assert np.array_equal(io.unpack_counts(pc), Y.astype(np.float32))
+    e1 = DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=3, gemm_path="generic")
+    e2 = DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=3, gemm_path="generic")
+    sfh = torch.from_numpy(sf).pin_memory()
+    for e in (e1, e2):
+        e.set_input_transform(mean, std, True, True)
+    e1.stream_begin(torch.from_numpy(Y.astype(np.uint16)).pin_memory(), sfh, B)
+    e2.stream_begin(pc, sfh, B)
+    nb = (N + B - 1) // B
+    for i in range(nb):
+        nxt = i + 1 if i + 1 < nb else -1
+        e1.stream_step(i, nxt); e1.apply_update(1e-3, 5.0)
+        e2.stream_step(i, nxt); e2.apply_update(1e-3, 5.0)
+        l1, l2 = e1.read_loss(), e2.read_loss()
+        assert abs(l1 - l2) <= 1e-6 * abs(l1), (bits, i, l1, l2)
+    e1.stream_end(); e2.stream_end()
+    # capacity check: a batch with too many escapes is refused with a message
+    dense = np.full((B, G), 20.0, dtype=np.float32)
+    with pytest.raises(ValueError, match="overflow"):
+        e2.stream_begin(io.pack_counts(dense, 4), None, B)
+
+
+def test_loss_ring_mirrors_every_step_loss():
+    """dca_set_loss_ring: slot k % n of the pinned host ring holds the loss of the k-th update."""
+    from dca_b200.engine import DeviceEngine
+    B, G = 128, 264
+    X, Y, sf = _problem(B, G, 43)
+    e = DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=5, gemm_path="generic")
+    Xd, Yd, sfd = _t(X), _t(Y), _t(sf)
+    ring = torch.full((4,), -1.0).pin_memory()
+    with pytest.raises(ValueError):
+        e.set_loss_ring(torch.zeros(4))                     # not pinned
+    e.set_loss_ring(ring)
+    want = []
+    for k in range(6):
+        e.train_step(Xd, Yd, sfd); e.apply_update(1e-3, 5.0)
+        want.append(e.read_loss())
+        torch.cuda.synchronize()
+        assert ring[k % 4].item() == pytest.approx(want[-1], rel=1e-6), (k, ring, want)
+    e.set_loss_ring(None)
+    e.train_step(Xd, Yd, sfd); e.apply_update(1e-3, 5.0); torch.cuda.synchronize()
+    assert ring[2].item() == pytest.approx(want[2], rel=1e-6)      # untouched after switching off
+
+
 @pytest.mark.parametrize("gemm_path", ["generic", "tcgen05"])
 def test_two_phase_step_equals_single_call(gemm_path):
     """dca_train_step_phase(1) + (2) == dca_train_step; after phase 1 the head bucket of the gradient is final."""

@@ -134,3 +134,25 @@ def test_shard_bounds():
     assert [shard_bounds(10, r, 4, equal=True) for r in range(4)] == [(0, 2), (2, 4), (4, 6), (6, 8)]
     b = [shard_bounds(10, r, 4) for r in range(4)]
     assert b[0][0] == 0 and b[-1][1] == 10 and all(b[i][1] == b[i + 1][0] for i in range(3))
+
+
+def test_pack_counts_round_trip_and_auto_width():
+    """Packed host format of the streaming path (dca_stream_begin_packed): lossless, escapes listed row-sorted."""
+    from dca_b200 import io
+    rng = np.random.default_rng(0)
+    C = rng.poisson(0.3, (130, 64)).astype(np.int64)
+    C[3, 5] = 300; C[3, 6] = 15; C[10, 63] = 70000; C[129, 0] = 14; C[0, 1] = 255
+    for bits in (4, 8, 16, "auto"):
+        pc = io.pack_counts(C, bits, batch=32)
+        assert np.array_equal(io.unpack_counts(pc), C.astype(np.float32))
+        assert pc.indptr[0] == 0 and pc.indptr[-1] == len(pc.entries) and np.all(np.diff(pc.indptr) >= 0)
+        esc = (1 << pc.bits) - 1
+        assert len(pc.entries) == int((C >= esc).sum())
+        assert pc.packed.shape == (130, 64 * pc.bits // 8 // pc.packed.itemsize)
+    assert io.pack_counts(C, "auto").bits == 4                        # sparse small counts: 4 bits win
+    assert io.pack_counts(np.full((8, 64), 100), "auto").bits == 8    # everything >= 15: 8 bits win
+    assert io.pack_counts(np.full((8, 64), 1000), "auto").bits == 16
+    with pytest.raises(ValueError):
+        io.pack_counts(np.full((4, 12), 1.0))                         # genes not a multiple of 8
+    with pytest.raises(ValueError):
+        io.pack_counts(np.full((4, 16), 0.5))                         # not integer counts
