@@ -122,6 +122,11 @@ def check(status: int, what: str = ""):
         raise DcaError("%s failed (status %d): %s" % (what or "dca_b200", status, msg))
 
 
+def set_tunable(name: str, value: int):
+    """Process-wide launch tunables / switches (dca_set_tunable in include/dca_b200.h)."""
+    check(load().dca_set_tunable(name.encode(), int(value)), "dca_set_tunable")
+
+
 def default_config() -> Config:
     cfg = Config()
     load().dca_config_default(C.byref(cfg))

@@ -110,6 +110,11 @@ int heads_fwd_tc(const __nv_bfloat16* Hb, int B, const __nv_bfloat16* const W[3]
 int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, int G, int n_heads,
                  const __nv_bfloat16* H, const __nv_bfloat16* const W[3], float* out_b, float* const dW[3], int64_t dW_ld,
                  int dW_transposed, float* const db[3], int sm_count, cudaStream_t s);
+int flash_zinb_tc(const __nv_bfloat16* H3, int B, int G, const __nv_bfloat16* const W[3], const float* const bias[3],
+                  const float* Y, int64_t ldy, const int32_t* rows, const float* sf, float ridge, float inv_n,
+                  float* dH3, float* const dW[3], float* const db[3], void* ws, size_t ws_bytes, double* loss_sum,
+                  const double* penalty, float* loss_slot, double* epoch_acc, int batch, const float* lf_dev, int sm_count,
+                  cudaStream_t s);
 }  // namespace tc
 
 // ---------------------------------------------------------------- ZINB loss (zinb_loss.cu)
@@ -126,6 +131,8 @@ struct LossArgs {
   float* fin_loss_slot = nullptr; double* fin_epoch_acc = nullptr; const double* fin_penalty = nullptr; int fin_batch = 0;
 };
 size_t loss_workspace_bytes(int B, int G);
+extern int g_fused_heads_default;       // dca_set_tunable("fused_heads", 0 | 1)
+const float* loss_log_fact_table();      // device table of log(k!), k < 64 (filled on first use)
 int zinb_loss_fwd_bwd(const LossArgs& a, cudaStream_t s);
 int zinb_loss_fwd(const LossArgs& a, cudaStream_t s);
 // writes grads[P] = loss_sum*inv_n + penalty, grads[P+1] = nonfinite flag, epoch acc update

@@ -161,6 +161,11 @@ int Engine::plan(const dca_config& c) {
   tc_enc = want_tc && L >= 1 && c.hidden[0] == 64 && (c.n_in % 8 == 0);
   // the tcgen05 kernels read the kernels in place from the flat bf16 parameter copy: TMA needs 16-byte aligned bases
   if (tc_heads) for (int k = 0; k < 3; ++k) if (head_W[k] >= 0 && (head_W[k] % 8) != 0) tc_heads = false;
+  {
+    const char* ev = getenv("DCA_FUSED_HEADS");
+    const bool want = ev ? atoi(ev) != 0 : g_fused_heads_default != 0;
+    fused_heads = want && tc_heads && cond && has_pi && L >= 1 && (G % 8 == 0);
+  }
   if (tc_enc && (lay[0].W % 8) != 0) tc_enc = false;
   if (tc_heads || tc_enc) o_pbf = take(2 * (size_t)P);       // bf16 copy of the parameters, same flat layout
   if (tc_heads) {
@@ -434,11 +439,24 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
   DCA_TRY(forward(X, ldx, rows, Bn, true, s));
   mark(1, s);
   float* Mb = f(o_head[0]); float* Db = f(o_head[1]); float* Pb = f(o_head[2]);
+  const float inv_n = 1.0f / ((float)Bn * (float)G);
+  const bool fuse = fused_heads && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+  if (fuse) {
+    // heads forward + loss + head backward in ONE kernel (flash_zinb.cu): no B x G tensor reaches HBM
+    mark(2, s);
+    DCA_CUDA_OK(cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)Bn * K_head, s));
+    const float* lf_dev = loss_log_fact_table();
+    if (!lf_dev) return DCA_ERR_CUDA;
+    const __nv_bfloat16* Wk[3]; const float* bk[3]; float* dWp[3]; float* dbp[3];
+    for (int k = 0; k < 3; ++k) { Wk[k] = bf(o_pbf) + head_W[k]; bk[k] = pp(head_b[k]); dWp[k] = gp(head_W[k]); dbp[k] = gp(head_b[k]); }
+    DCA_TRY(tc::flash_zinb_tc(bf(o_h3b), Bn, G, Wk, bk, Y, ldy, rows, sf, cfg.ridge, inv_n, dh, dWp, dbp, base + o_lossws,
+                              loss_ws_bytes, d(o_acc) + 4, any_pen ? d(o_acc) + 5 : nullptr, gp(P), d(o_acc), Bn, lf_dev,
+                              sm_count, s));
+  } else {
   DCA_TRY(heads_forward(Bn, Mb, cond ? Db : nullptr, has_pi ? Pb : nullptr, G, nullptr, s));
   if (!cond) DCA_TRY(theta_prepare(pp(theta_off), G, f(o_theta), f(o_chain), s));
   mark(2, s);
 
-  const float inv_n = 1.0f / ((float)Bn * (float)G);
   LossArgs la{};
   la.Y = Y; la.ldy = ldy; la.rows = rows; la.sf = sf;
   la.m = Mb; la.d = cond ? Db : f(o_theta); la.pi = has_pi ? Pb : nullptr; la.ld = G;
@@ -489,6 +507,7 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
       DCA_TRY(gemm_auto(b, s));
     }
   }
+  }  // !fuse
   }  // phase != 2
   if (phase == 1) { mark(-1, s); return DCA_OK; }
   // ---- hidden stack backward

@@ -76,6 +76,7 @@ struct Engine {
   void mid_params(mid::Params& p, int Bn, bool training);
   // tcgen05 path: flags + operand-layout shadows / bf16 activations in the arena
   bool tc_heads = false, tc_enc = false;
+  bool fused_heads = false;       // flash_zinb.cu replaces K2 + K3 + K4 of the training step (zinb-conddisp only)
   int sm_count = 148, n_slots = 1;
   int slot_head[3] = {0, -1, -1};          // packed head slot -> head index (0 mean, 1 dispersion, 2 pi)
   int slot_kind[3] = {0, 0, 0};

@@ -1,0 +1,426 @@
+// Fused head forward -> ZINB loss + gradient -> head backward for the conditional-dispersion ZINB model
+// (replaces K2 + K3 + K4 of one training step, dca/network.py:369-381 + dca/loss.py:122-148 +
+// their autodiff).  The B x 3G head activations and their gradients never reach HBM:
+//
+//   per tile (128 cells x 64 genes, all three heads):
+//     MMA1   Z[128 x 192] = H3[128 x 64] . [Wm | Wd | Wp][64 x 3*64]          -> TMEM (fp32)
+//     epilogue (16 warps)  z + bias -> MeanAct / DispAct / sigmoid -> ZINB NLL and d/dz (zinb_math.cuh, same
+//                          arithmetic and warp compaction as the stand-alone loss kernel) -> dZ bf16 written into
+//                          shared memory in the SWIZZLE_128B operand layout
+//     MMA2   dH3[128 x 64]  = sum_h dZ_h[128 x 64] . W_h^T                    (dZ as K-major A)
+//     MMA3   dW_h[64g x 64] += dZ_h^T . H3, db_h += dZ_h^T . 1                (the same bytes as MN-major A; two
+//                          heads stacked per M = 128 accumulator)
+//   HBM traffic: the count tile (4 B / element) in, 1/64 of it out.  dH3 leaves per tile by TMA reduce-add,
+//   dW / db stay in TMEM over all cell blocks of a gene tile and are added to the gradient buffer once.
+//
+// Warp roles (768 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-19 loss epilogue, 20-23 flush.
+#include "engine.h"
+#include "tc_common.cuh"
+#include "head_act.cuh"
+#include "zinb_math.cuh"
+
+namespace dca {
+namespace tc {
+namespace fz {
+
+constexpr int kEpiWarp0 = 4, kEpiWarps = 16, kFlushWarp0 = 20, kFlushWarps = 4;
+constexpr int kThreads = (kFlushWarp0 + kFlushWarps) * 32;     // 768
+constexpr uint32_t kHBytes = 128 * 64 * 2;                     // [128 cells x 64 feats] bf16
+constexpr uint32_t kWBox = 64 * 64 * 2, kWBytes = 3 * kWBox;   // per head [64 feats x 64 genes] bf16
+constexpr uint32_t kZBox = 128 * 64 * 2, kZBytes = 3 * kZBox;  // per head [128 cells x 64 genes] bf16
+constexpr uint32_t kOutBytes = 2 * 128 * 32 * 4;               // dH3 staging: two [128 x 32] fp32 tiles
+constexpr uint32_t kQueueBytes = 128 * 16;                     // per epilogue warp: 128 items of 16 B
+constexpr uint32_t kOffH = 0, kOffW = kOffH + 2 * kHBytes, kOffZ = kOffW + kWBytes, kOffO = kOffZ + 2 * kZBytes,
+                   kOffOnes = kOffO + kOutBytes, kOffQ = kOffOnes + 2048, kSmemUsed = kOffQ + kEpiWarps * kQueueBytes;
+constexpr uint32_t kSmemBytes = kSmemUsed + 1024;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmD1 = 0, kTmDh = 192, kTmDw = 320, kTmCs = 448;   // 192 + 2*64 + 2*64 + 2*16 = 480 columns
+
+struct Params {
+  int B, G, n_cb, n_gt, total_tiles;
+  const float* Y; int64_t ldy; const int32_t* rows; const float* sf;
+  const float* bias[3];
+  float* dW[3]; int64_t dW_ld; float* db[3];
+  float ridge, inv_n;
+  const float* lf_global;
+  double* loss_partial; unsigned* counter; double* loss_sum; const double* penalty; float* loss_slot; double* epoch_acc;
+  int batch;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w0,
+                  const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
+                  const __grid_constant__ CUtensorMap map_o, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_h = smem + kOffH; uint8_t* s_w = smem + kOffW; uint8_t* s_z = smem + kOffZ; uint8_t* s_o = smem + kOffO;
+  uint8_t* s_ones = smem + kOffOnes; uint8_t* s_q = smem + kOffQ;
+  __shared__ uint64_t h_full[2], h_empty[2], w_full, w_empty, d1_full, d1_empty, dz_full[2], dz_empty[2], dh_full[2], dh_empty[2],
+      dw_full, dw_empty;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float lf[zmath::kLogFactN];
+  __shared__ double red[kEpiWarps];
+  __shared__ int s_last;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1);
+      mbar_init(&dz_full[i], kEpiWarps); mbar_init(&dz_empty[i], 1);
+      mbar_init(&dh_full[i], 1); mbar_init(&dh_empty[i], kFlushWarps);
+    }
+    mbar_init(&w_full, 1); mbar_init(&w_empty, 1);
+    mbar_init(&d1_full, 1); mbar_init(&d1_empty, kEpiWarps);
+    mbar_init(&dw_full, 1); mbar_init(&dw_empty, kFlushWarps);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_w0); tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2);
+    tma_prefetch_desc(&map_o);
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, kTmemCols);
+  if (threadIdx.x < zmath::kLogFactN) lf[threadIdx.x] = p.lf_global[threadIdx.x];
+  for (int i = threadIdx.x; i < 2048 / 4; i += kThreads) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3F803F80u;   // bf16 ones
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  // this CTA's contiguous range of tiles; tile t -> gene tile t / n_cb, cell block t % n_cb (cells fastest, so the
+  // weight tile and the dW accumulators stay put over a run of cell blocks = one "segment")
+  const int t0 = (int)((long long)p.total_tiles * blockIdx.x / gridDim.x);
+  const int t1 = (int)((long long)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t hi = 0, seg = 0;
+      for (int t = t0; t < t1; ++t) {
+        const int gt = t / p.n_cb, cb = t % p.n_cb;
+        if (t == t0 || cb == 0) {
+          mbar_wait(&w_empty, (seg & 1) ^ 1); ++seg;
+          mbar_expect_tx(&w_full, kWBytes);
+          tma_load_2d(s_w, &map_w0, gt * 64, 0, &w_full);
+          tma_load_2d(s_w + kWBox, &map_w1, gt * 64, 0, &w_full);
+          tma_load_2d(s_w + 2 * kWBox, &map_w2, gt * 64, 0, &w_full);
+        }
+        const uint32_t hs = hi & 1, hp = (hi >> 1) & 1; ++hi;
+        mbar_wait(&h_empty[hs], hp ^ 1);
+        mbar_expect_tx(&h_full[hs], kHBytes);
+        tma_load_2d(s_h + hs * kHBytes, &map_h, 0, cb * 128, &h_full[hs]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_1 = make_idesc_bf16(128, 192, 0, 1);   // H K-major x [Wm|Wd|Wp] MN-major (genes contiguous)
+      constexpr uint32_t idesc_b = make_idesc_bf16(128, 64, 0, 0);    // dZ K-major x W K-major ([64 feats x genes])
+      constexpr uint32_t idesc_a = make_idesc_bf16(128, 64, 1, 1);    // dZ MN-major (2 heads stacked) x H MN-major
+      constexpr uint32_t idesc_c = make_idesc_bf16(128, 16, 1, 0);    // dZ MN-major x ones -> column sums
+      const uint32_t wb = smem_u32(s_w), ob = smem_u32(s_ones);
+      uint32_t hi = 0, ti = 0, dhi = 0, seg = 0;
+      struct Pend { int valid; uint32_t hs, zb, zph; int first, last; } pend = {0, 0, 0, 0, 0, 0};
+      auto mma23 = [&](const Pend& u) {
+        mbar_wait(&dz_full[u.zb], u.zph);
+        const uint32_t ds = dhi & 1, dp = (dhi >> 1) & 1; ++dhi;
+        mbar_wait(&dh_empty[ds], dp ^ 1);
+        if (u.first) mbar_wait(&dw_empty, ((seg - 1) & 1) ^ 1);       // previous segment's dW has been flushed
+        tcgen05_fence_after();
+        const uint32_t zb = smem_u32(s_z + u.zb * kZBytes), hb = smem_u32(s_h + u.hs * kHBytes);
+#pragma unroll
+        for (int h = 0; h < 3; ++h)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + kTmDh + ds * 64, make_smem_desc(zb + h * kZBox + k * 32, 0, 1024),
+                      make_smem_desc(wb + h * kWBox + k * 32, 0, 1024), idesc_b, (h > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&dh_full[ds]);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {                                  // accumulator 0: heads (0,1); 1: heads (1,2)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t da = make_smem_desc(zb + a * kZBox + k * 2048, kZBox, 1024);
+            const uint32_t acc = (u.first && k == 0) ? 0u : 1u;
+            umma_bf16(tmem + kTmDw + a * 64, da, make_smem_desc(hb + k * 2048, 0, 1024), idesc_a, acc);
+            umma_bf16(tmem + kTmCs + a * 16, da, make_smem_desc(ob + (k & 3) * 32, 0, 1024), idesc_c, acc);
+          }
+        }
+        umma_commit(&dz_empty[u.zb]);
+        umma_commit(&h_empty[u.hs]);
+        if (u.last) { umma_commit(&dw_full); umma_commit(&w_empty); }
+      };
+      for (int t = t0; t < t1; ++t, ++ti) {
+        const int cb = t % p.n_cb;
+        const bool new_seg = (t == t0 || cb == 0);
+        if (new_seg) {
+          if (pend.valid) { mma23(pend); pend.valid = 0; }             // drain before the weight tile changes
+          mbar_wait(&w_full, seg & 1); ++seg;
+        }
+        const uint32_t hs = hi & 1, hp = (hi >> 1) & 1; ++hi;
+        mbar_wait(&h_full[hs], hp);
+        mbar_wait(&d1_empty, (ti & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t hb = smem_u32(s_h + hs * kHBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + kTmD1, make_smem_desc(hb + k * 32, 0, 1024), make_smem_desc(wb + k * 2048, kWBox, 1024), idesc_1, k > 0);
+        umma_commit(&d1_full);
+        if (pend.valid) mma23(pend);
+        pend.valid = 1; pend.hs = hs; pend.zb = ti & 1; pend.zph = (ti >> 1) & 1; pend.first = new_seg;
+        pend.last = (t + 1 == t1) || ((t + 1) % p.n_cb == 0);
+      }
+      if (pend.valid) mma23(pend);
+    }
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
+    // ===================================================== loss epilogue
+    using Ops = zmath::FastOps;
+    constexpr unsigned kFull = 0xffffffffu;
+    const int ew = warp - kEpiWarp0, quarter = warp & 3, cg = ew >> 2;
+    float4* q = reinterpret_cast<float4*>(s_q + ew * kQueueBytes);
+    const unsigned lt = (1u << lane) - 1u;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    float lsum = 0.f;
+    uint32_t ti = 0;
+    for (int t = t0; t < t1; ++t, ++ti) {
+      const int gt = t / p.n_cb, cb = t % p.n_cb;
+      const int grow = cb * 128 + row;
+      const bool valid_row = grow < p.B;
+      int yr = 0; float sfv = 1.0f;
+      if (valid_row) { yr = p.rows ? p.rows[grow] : grow; sfv = p.sf ? p.sf[yr] : 1.0f; }
+      const float* yrow = p.Y + (int64_t)yr * p.ldy;
+      const uint32_t zbuf = ti & 1, zph = (ti >> 1) & 1;
+      uint8_t* zrow = s_z + zbuf * kZBytes + row * 128;
+      mbar_wait(&d1_full, ti & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t zm[8], zd[8], zp[8];
+        const uint32_t tcol = tmem + kTmD1 + lane_off + (uint32_t)(cg * 16 + half * 8);
+        tmem_ld_32x8(tcol, zm); tmem_ld_32x8(tcol + 64, zd); tmem_ld_32x8(tcol + 128, zp);
+        tmem_ld_wait();
+        if (half == 1) {                                      // accumulator fully read: release it to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d1_empty);
+        }
+        uint32_t om[4], od[4], op[4];                           // 8 bf16 per head = one 16-byte chunk of the dZ row
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int g0 = gt * 64 + cg * 16 + half * 8 + sub * 4;
+          const bool active = valid_row && g0 < p.G;            // G % 4 == 0: a group of 4 genes is all in or all out
+          float y[4] = {0.f, 0.f, 0.f, 0.f}, mm[4], dd[4], pp[4];
+          if (g0 < p.G) {
+            const float4 bm = *reinterpret_cast<const float4*>(p.bias[0] + g0);
+            const float4 bd = *reinterpret_cast<const float4*>(p.bias[1] + g0);
+            const float4 bp = *reinterpret_cast<const float4*>(p.bias[2] + g0);
+            const float bmv[4] = {bm.x, bm.y, bm.z, bm.w}, bdv[4] = {bd.x, bd.y, bd.z, bd.w}, bpv[4] = {bp.x, bp.y, bp.z, bp.w};
+            if (valid_row) { const float4 vy = *reinterpret_cast<const float4*>(yrow + g0); y[0] = vy.x; y[1] = vy.y; y[2] = vy.z; y[3] = vy.w; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              mm[j] = act_mean(__uint_as_float(zm[sub * 4 + j]) + bmv[j]);
+              dd[j] = act_disp(__uint_as_float(zd[sub * 4 + j]) + bdv[j]);
+              pp[j] = act_sigmoid(__uint_as_float(zp[sub * 4 + j]) + bpv[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mm[j] = 1.f; dd[j] = 1.f; pp[j] = 0.5f; }
+          }
+          // ---- queue the non-zero counts of this warp's 32 rows x 4 genes (ballot compaction: ordered by j, lane)
+          unsigned bal[4];
+          int nz = 0, pos[4], base = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool is_nz = active && !(y[j] < 1e-8f);              // loss.py:138
+            bal[j] = __ballot_sync(kFull, is_nz);
+            nz |= is_nz ? (1 << j) : 0;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { pos[j] = base + __popc(bal[j] & lt); base += __popc(bal[j]); }
+          const int total = base;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (nz & (1 << j)) q[pos[j]] = make_float4(y[j], mm[j] * sfv, dd[j], pp[j]);
+          __syncwarp();
+          float gm[4], gd[4], gp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            gm[j] = gd[j] = gp[j] = 0.f;
+            if (active && !(nz & (1 << j))) {
+              const zmath::Elem e = zmath::zinb_elem_zero<Ops, true>(mm[j], sfv, dd[j], pp[j], p.ridge);
+              lsum += e.loss; gm[j] = e.gm; gd[j] = e.gd; gp[j] = e.gp;
+            }
+          }
+          for (int k = lane; k < total; k += 32) {
+            const float4 it = q[k];
+            const zmath::Elem e = zmath::zinb_elem_nb_mu<Ops>(it.x, it.y, it.z, it.w, p.ridge, lf);
+            q[k] = make_float4(e.loss, e.gm, e.gd, e.gp);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (nz & (1 << j)) {
+              const float4 e = q[pos[j]];
+              lsum += e.x; gm[j] = (mm[j] > 1e-5f && mm[j] < 1e6f) ? e.y : 0.f; gd[j] = e.z; gp[j] = e.w;
+            }
+          __syncwarp();
+          om[sub * 2] = pack_bf16x2(gm[0] * p.inv_n, gm[1] * p.inv_n); om[sub * 2 + 1] = pack_bf16x2(gm[2] * p.inv_n, gm[3] * p.inv_n);
+          od[sub * 2] = pack_bf16x2(gd[0] * p.inv_n, gd[1] * p.inv_n); od[sub * 2 + 1] = pack_bf16x2(gd[2] * p.inv_n, gd[3] * p.inv_n);
+          op[sub * 2] = pack_bf16x2(gp[0] * p.inv_n, gp[1] * p.inv_n); op[sub * 2 + 1] = pack_bf16x2(gp[2] * p.inv_n, gp[3] * p.inv_n);
+        }
+        if (half == 0) mbar_wait(&dz_empty[zbuf], zph ^ 1);     // the MMAs that read this dZ buffer two tiles ago are done
+        const uint32_t chunk = (uint32_t)(((cg * 2 + half) ^ (row & 7)) << 4);     // SWIZZLE_128B: 16-byte chunk ^ (row % 8)
+        *reinterpret_cast<uint4*>(zrow + chunk) = make_uint4(om[0], om[1], om[2], om[3]);
+        *reinterpret_cast<uint4*>(zrow + kZBox + chunk) = make_uint4(od[0], od[1], od[2], od[3]);
+        *reinterpret_cast<uint4*>(zrow + 2 * kZBox + chunk) = make_uint4(op[0], op[1], op[2], op[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dz_full[zbuf]);
+    }
+    // ---- loss: CTA partial, the last CTA folds all partials in a fixed order and finalises (as in zinb_loss.cu)
+    double dsum = (double)lsum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(kFull, dsum, o);
+    if (lane == 0) red[ew] = dsum;
+    named_barrier_sync(2, kEpiWarps * 32);
+    if (ew == 0 && lane == 0) {
+      double tsum = 0.0;
+#pragma unroll
+      for (int w = 0; w < kEpiWarps; ++w) tsum += red[w];
+      p.loss_partial[blockIdx.x] = tsum;
+      __threadfence();
+      const unsigned done = atomicAdd(p.counter, 1u);
+      s_last = (done == gridDim.x - 1);
+      if (s_last) *p.counter = 0;                                       // self-resetting
+    }
+    named_barrier_sync(2, kEpiWarps * 32);
+    if (s_last && ew == 0) {
+      __threadfence();
+      double a = 0.0;
+      for (int i = lane; i < (int)gridDim.x; i += 32) a += __ldcg(p.loss_partial + i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFull, a, o);
+      if (lane == 0) {
+        *p.loss_sum = a;
+        if (p.loss_slot) {
+          double l = a * (double)p.inv_n;
+          if (l != l) l = INFINITY;                                     // _nan2inf, dca/loss.py:148
+          if (p.penalty) l += *p.penalty;
+          const float lf32 = (float)l;
+          p.loss_slot[0] = lf32;
+          p.loss_slot[1] = (isfinite(lf32)) ? 0.f : 1.f;
+          if (p.epoch_acc) { p.epoch_acc[0] += l * (double)p.batch; p.epoch_acc[1] += (double)p.batch; }
+        }
+      }
+    }
+  } else if (warp >= kFlushWarp0) {
+    // ===================================================== flush: dH3 per tile, dW / db per segment
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    uint32_t dhi = 0, seg = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int gt = t / p.n_cb, cb = t % p.n_cb;
+      const uint32_t ds = dhi & 1, dp = (dhi >> 1) & 1; ++dhi;
+      mbar_wait(&dh_full[ds], dp);
+      tcgen05_fence_after();
+      if (warp == kFlushWarp0 && lane == 0) bulk_wait_read<0>();        // previous reduce has read the staging tiles
+      named_barrier_sync(3, kFlushWarps * 32);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem + kTmDh + lane_off + ds * 64 + c * 32, v);
+        tmem_ld_wait();
+        uint8_t* tile = s_o + c * (kOutBytes / 2);
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq)
+          *reinterpret_cast<uint4*>(tile + row * 128 + ((qq ^ (row & 7)) << 4)) = make_uint4(v[qq * 4], v[qq * 4 + 1], v[qq * 4 + 2], v[qq * 4 + 3]);
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      named_barrier_sync(3, kFlushWarps * 32);
+      if (lane == 0) mbar_arrive(&dh_empty[ds]);
+      if (warp == kFlushWarp0 && lane == 0) {
+        tma_reduce_add_2d(&map_o, 0, cb * 128, s_o);
+        tma_reduce_add_2d(&map_o, 32, cb * 128, s_o + kOutBytes / 2);
+        bulk_commit();
+      }
+      const bool last = (t + 1 == t1) || ((t + 1) % p.n_cb == 0);
+      if (last) {
+        mbar_wait(&dw_full, seg & 1); ++seg;
+        tcgen05_fence_after();
+        const int g = gt * 64 + (row & 63);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          // accumulator 0: lanes 0-63 = head 0, 64-127 = head 1;  accumulator 1: lanes 64-127 = head 2 (0-63 duplicate head 1)
+          const int head = a == 0 ? (row >> 6) : 2;
+          const bool mine = (a == 0 || row >= 64) && g < p.G;
+          uint32_t cs[16];
+          tmem_ld_32x16(tmem + kTmCs + lane_off + a * 16, cs);
+          tmem_ld_wait();
+          if (mine && p.db[head]) atomicAdd(p.db[head] + g, __uint_as_float(cs[0]));
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem + kTmDw + lane_off + a * 64 + c * 32, v);
+            tmem_ld_wait();
+            if (mine) {
+              float* dst = p.dW[head];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) atomicAdd(dst + (int64_t)(c * 32 + j) * p.dW_ld + g, __uint_as_float(v[j]));
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dw_empty);
+      }
+    }
+    if (warp == kFlushWarp0 && lane == 0) bulk_wait<0>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+}
+
+}  // namespace fz
+
+// H3: bf16 [B x 64]; W[h]: bf16 Keras-layout head kernels [64 x G] (mean, dispersion, pi); bias[h]: float[G];
+// Y: float counts (row gather through rows[], ldy); outputs: dH3 (+=, fp32 [B x 64]), dW[h] (+=, [64 x G]),
+// db[h] (+=, [G]), loss partial fold into loss_sum / loss_slot / epoch_acc like zinb_loss_fwd_bwd.
+int flash_zinb_tc(const __nv_bfloat16* H3, int B, int G, const __nv_bfloat16* const W[3], const float* const bias[3],
+                  const float* Y, int64_t ldy, const int32_t* rows, const float* sf, float ridge, float inv_n,
+                  float* dH3, float* const dW[3], float* const db[3], void* ws, size_t ws_bytes, double* loss_sum,
+                  const double* penalty, float* loss_slot, double* epoch_acc, int batch, const float* lf_dev, int sm_count,
+                  cudaStream_t s) {
+  using namespace fz;
+  if (G % 8 != 0 || ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(Y) & 15) != 0) {
+    set_error("flash_zinb_tc: needs G %% 8 == 0 and 16-byte aligned count rows"); return DCA_ERR_BAD_ARG;
+  }
+  if (!ws || ws_bytes < sizeof(double) * 65536 + 256) { set_error("flash_zinb_tc: workspace too small"); return DCA_ERR_BAD_ARG; }
+  CUtensorMap mh, mw[3], mo;
+  DCA_TRY(make_tensor_map_2d(&mh, H3, 2, 1, (uint64_t)B, 64, 64, 128, 64, 1));
+  for (int i = 0; i < 3; ++i) DCA_TRY(make_tensor_map_2d(&mw[i], W[i], 2, 1, 64, (uint64_t)G, (uint64_t)G, 64, 64, 1));
+  DCA_TRY(make_tensor_map_2d(&mo, dH3, 4, 0, (uint64_t)B, 64, 64, 128, 32, 1));
+  Params p{};
+  p.B = B; p.G = G; p.n_cb = cdiv(B, 128); p.n_gt = cdiv(G, 64); p.total_tiles = p.n_cb * p.n_gt;
+  p.Y = Y; p.ldy = ldy; p.rows = rows; p.sf = sf;
+  for (int i = 0; i < 3; ++i) { p.bias[i] = bias[i]; p.dW[i] = dW[i]; p.db[i] = db[i]; }
+  p.dW_ld = G; p.ridge = ridge; p.inv_n = inv_n; p.lf_global = lf_dev;
+  p.loss_partial = reinterpret_cast<double*>(ws);
+  p.counter = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + sizeof(double) * 65536);
+  p.loss_sum = loss_sum; p.penalty = penalty; p.loss_slot = loss_slot; p.epoch_acc = epoch_acc; p.batch = batch;
+  static bool attr = false;
+  if (!attr) { DCA_CUDA_OK(cudaFuncSetAttribute(flash_zinb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)); attr = true; }
+  const int grid = p.total_tiles < sm_count ? p.total_tiles : sm_count;
+  flash_zinb_kernel<<<grid, kThreads, kSmemBytes, s>>>(mh, mw[0], mw[1], mw[2], mo, p);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+}  // namespace tc
+}  // namespace dca

@@ -629,6 +629,9 @@ int launch(const LossArgs& a, cudaStream_t s) {
 
 }  // namespace
 
+const float* loss_log_fact_table() { return log_fact_table_device(); }
+int g_fused_heads_default = 1;            // engines created from now on use the fused head/loss/backward kernel
+
 size_t loss_workspace_bytes(int B, int G) {
   (void)B; (void)G;
   return sizeof(double) * (size_t)kMaxBlocks + 256;
@@ -655,6 +658,7 @@ extern "C" int dca_set_tunable(const char* name, int64_t value) {
   if (n == "loss_target_blocks" && value >= 0 && value <= kMaxBlocks) g_tune.target_blocks = (int)value;
   else if (n == "loss_producer_sleep_ns" && value >= 0 && value <= 100000) g_tune.producer_sleep_ns = (unsigned)value;
   else if (n == "loss_consumer_sleep_ns" && value >= 0 && value <= 100000) g_tune.consumer_sleep_ns = (unsigned)value;
+  else if (n == "fused_heads" && (value == 0 || value == 1)) g_fused_heads_default = (int)value;
   else { set_error("dca_set_tunable: unknown name or value out of range (%s = %lld)", name, (long long)value); return DCA_ERR_BAD_ARG; }
   return DCA_OK;
 }

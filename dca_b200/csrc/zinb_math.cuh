@@ -165,10 +165,12 @@ DCA_HD float one_minus_exp_neg(float d) {
 }
 
 // Chain rule through the output activations + ridge, shared by both branches.
-template <class Ops, bool HAS_PI, bool COND_DISP>
+template <class Ops, bool HAS_PI, bool COND_DISP, bool MASK_M = true>
 DCA_HD void finish_elem(Elem& o, float dth, float dpi, float m, float th, float pi, float ridge) {
-  const bool m_pass = (m > 1e-5f) && (m < 1e6f);           // clip_by_value gradient mask (network.py:38)
-  o.gm = m_pass ? o.gm : 0.f;
+  if (MASK_M) {
+    const bool m_pass = (m > 1e-5f) && (m < 1e6f);         // clip_by_value gradient mask (network.py:38)
+    o.gm = m_pass ? o.gm : 0.f;
+  }
   if (COND_DISP) {
     const bool d_pass = (th > 1e-4f) && (th < 1e4f);       // DispAct clip mask (network.py:39)
     o.gd = d_pass ? dth * one_minus_exp_neg<Ops>(th) : 0.f;
@@ -219,6 +221,24 @@ DCA_HD Elem zinb_elem_nb(float y, float m, float sf, float th, float pi, float r
   }
   o.loss = nb;
   finish_elem<Ops, HAS_PI, COND_DISP>(o, s.f + y * s.rden - dg, dpi, m, th, pi, ridge);
+  return o;
+}
+
+// NB branch of a ZINB conditional-dispersion element given mu = m * sf directly; the MeanAct clip mask on gm is
+// left to the caller (used where another thread than the element's owner evaluates the queued NB elements).
+template <class Ops>
+DCA_HD Elem zinb_elem_nb_mu(float y, float mu, float th, float pi, float ridge, const float* lf_table) {
+  const Shared s = shared_terms<Ops>(mu, 1.0f, th);
+  Elem o;
+  float lg, dg;
+  lgam_digam_diff<Ops>(s.te, y, lg, dg);
+  float nb = lgamma_1p<Ops>(y, lf_table) - lg + s.th * s.L1 - y * (kLn2 * Ops::lg2((s.mu + kEps) * s.rden));
+  if (nb != nb) nb = INFINITY;                             // _nan2inf  loss.py:105
+  o.gm = s.th * (s.mu - y) * s.rden;
+  const float qq = 1.0f - pi + kEps;
+  nb -= kLn2 * Ops::lg2(qq);                               // loss.py:130
+  o.loss = nb;
+  finish_elem<Ops, true, true, false>(o, s.f + y * s.rden - dg, Ops::rcp(qq), 1.0f, th, pi, ridge);
   return o;
 }
 

@@ -447,6 +447,45 @@ def test_stream_packed_counts_equals_uint16_stream(bits):
         e2.stream_begin(io.pack_counts(dense, 4), None, B)
 
 
+@pytest.mark.parametrize("shape", [(256, 264), (300, 2000), (4096, 2000), (128, 64)])
+def test_fused_heads_kernel_equals_three_kernel_path(shape):
+    """flash_zinb.cu (heads forward + ZINB loss/gradient + head backward in one kernel) against the unfused
+    K2 + K3 + K4 sequence: same rounding points, so loss and every gradient agree to accumulation-order noise;
+    ragged cell blocks (B % 128 != 0), a partial gene tile (G % 64 != 0) and row gather are covered."""
+    from dca_b200.engine import DeviceEngine
+    from dca_b200 import _lib
+    B, G = shape
+    N = B + 37
+    Y = synth_counts(N, G, 51); Y[0, :4] = [0, 17, 40, 3000]
+    X, sf = O.normalize_inputs(Y)
+    rows = torch.as_tensor(np.random.default_rng(3).permutation(N)[:B].astype(np.int32)).to(DEV)
+    engines = []
+    for fused in (1, 0):
+        _lib.set_tunable("fused_heads", fused)
+        engines.append(DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=9, gemm_path="tcgen05", ridge=0.01))
+    _lib.set_tunable("fused_heads", 1)
+    e1, e2 = engines
+    Xd, Yd, sfd = _t(X), _t(Y), _t(sf)
+    for step in range(3):                        # direct call, graph capture, graph replay
+        for e in (e1, e2):
+            e.train_step(Xd, Yd, sfd, rows=rows)
+        torch.cuda.synchronize()
+        l1, l2 = e1.read_loss(), e2.read_loss()
+        assert abs(l1 - l2) <= 2e-6 * abs(l2), (step, l1, l2)
+        G1, G2 = e1.grads.cpu().numpy(), e2.grads.cpu().numpy()
+        scale = float(np.max(np.abs(G2[: e2.n_params])))     # (biases in front of a BatchNorm have a pure-noise gradient)
+        for name, off, r, c in e2.param_info:
+            g1, g2 = G1[off: off + r * c], G2[off: off + r * c]
+            # dW1 sits behind the bf16 rounding of dA1: an fp32 ulp of order noise in dH3 can flip that rounding (2^-9)
+            rtol = 4e-3 if name == "enc0/kernel" else 2e-4
+            assert np.max(np.abs(g1 - g2)) <= rtol * np.max(np.abs(g2)) + 1e-6 * scale, (step, name, np.max(np.abs(g1 - g2)), np.max(np.abs(g2)), scale)
+        for e in (e1, e2):
+            e.apply_update(1e-3, 5.0)
+        # keep the replicas identical: RMSprop's first steps amplify accumulation-order noise in near-zero gradients
+        torch.cuda.synchronize()
+        e1.params.copy_(e2.params); e1.rms.copy_(e2.rms); e1.bn_state.copy_(e2.bn_state); e1.params_changed()
+
+
 def test_loss_ring_mirrors_every_step_loss():
     """dca_set_loss_ring: slot k % n of the pinned host ring holds the loss of the k-th update."""
     from dca_b200.engine import DeviceEngine
