@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--gemm-path", default="auto", choices=["auto", "generic", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fused", action="store_true",
+                    help="run head forward + loss + head backward as the ONE fused kernel (flash_zinb.cu) instead of K2 + K3 + K4")
     ap.add_argument("--e2e-format", default="auto", choices=["auto", "u16", "4", "8", "16"],
                     help="host format of the streamed count matrix: packed bits per entry (io.pack_counts) or plain uint16")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the CPU baseline sample")
@@ -258,6 +260,9 @@ def main():
 
     X, Y, sf, zero_frac, gmean, gstd = synth_on_device(cells, genes, dev, 1234 + rank, {"float32": torch.float32, "bfloat16": torch.bfloat16}[a.x_dtype])
     n_train = int(cells * 0.9)                                  # validation_split=0.1 tail, dca/train.py:96
+    if a.fused:
+        from dca_b200 import _lib as _dl
+        _dl.set_tunable("fused_heads", 1)
     eng = DeviceEngine(genes, genes, HIDDEN, ae_type, True, max_batch=batch, x_dtype=a.x_dtype,
                        gemm_path=a.gemm_path, device=dev, seed=0)
     if world > 1:
@@ -340,6 +345,15 @@ def main():
                 "bytes_per_element": 4 + 4 * nh + einfo["grad_bytes"] * nh, "engine": einfo,
                 "share_of_step": (loss_ms / max(loss_n, 1)) / step_ms_prof if step_ms_prof > 0 else None}
     phases = {k: (v[0] / max(v[1], 1)) for k, v in prof.items()}
+    if a.fused:
+        # the fused kernel moves 4 B / element (the counts) and is bound by the fp32 / MUFU loss arithmetic, not by HBM
+        # or the tensor pipe: its HBM fraction is reported for completeness only
+        roofline["kernel"] = "flash_zinb_kernel (heads forward + ZINB loss/gradient + heads backward fused; issue-bound)"
+        roofline["bytes_per_element"] = 4
+        roofline["algorithmic_bytes_per_launch"] = batch * genes * 4
+        roofline["achieved"] = (batch * genes * 4) / (loss_ms / max(loss_n, 1) * 1e-3) / 1e9 if loss_n else None
+        roofline["frac"] = roofline["achieved"] / peak if roofline["achieved"] else None
+        roofline["traffic"] = None
     roofline["loss_kernel_fp32_io"] = loss_kernel_standalone(eng, X, Y, sf, stream_idx[:batch], genes, batch, peak)
 
     # ---- end to end through the public streaming API: the raw counts live in pinned HOST memory (bit-packed by

@@ -34,7 +34,10 @@ constexpr uint32_t kOffH = 0, kOffW = kOffH + 2 * kHBytes, kOffZ = kOffW + kWByt
                    kOffOnes = kOffO + kOutBytes, kOffQ = kOffOnes + 2048, kSmemUsed = kOffQ + kEpiWarps * kQueueBytes;
 constexpr uint32_t kSmemBytes = kSmemUsed + 1024;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmD1 = 0, kTmDh = 192, kTmDw = 320, kTmCs = 448;   // 192 + 2*64 + 2*64 + 2*16 = 480 columns
+// TMEM (512 columns): two pre-activation accumulators of 192 columns (double-buffered over tiles) and the two dW
+// accumulators.  Once the epilogue has consumed accumulator b, the head-backward products of the same tile reuse
+// its columns: dH3 at +0..63, the per-tile column sums (bias gradient) at +64..95.
+constexpr uint32_t kTmD1 = 0, kTmD1Stride = 192, kTmDhOff = 0, kTmCsOff = 64, kTmDw = 384;
 
 struct Params {
   int B, G, n_cb, n_gt, total_tiles;
@@ -47,6 +50,17 @@ struct Params {
   int batch;
 };
 
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
+
+// NB branch of one queued element; deliberately not inlined (one copy of the lgamma / digamma code keeps the
+// epilogue loop inside the instruction cache)
+__device__ __noinline__ float4 nb_item(float4 it, float ridge, const float* lf) {
+  const zmath::Elem e = zmath::zinb_elem_nb_mu<zmath::FastOps>(it.x, it.y, it.z, it.w, ridge, lf);
+  return make_float4(e.loss, e.gm, e.gd, e.gp);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -57,11 +71,13 @@ flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
                   const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
                   const __grid_constant__ CUtensorMap map_o, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET (not by an integer round trip) so that the compiler keeps the shared address space
+  // and emits LDS / STS instead of generic loads and stores
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_h = smem + kOffH; uint8_t* s_w = smem + kOffW; uint8_t* s_z = smem + kOffZ; uint8_t* s_o = smem + kOffO;
   uint8_t* s_ones = smem + kOffOnes; uint8_t* s_q = smem + kOffQ;
-  __shared__ uint64_t h_full[2], h_empty[2], w_full, w_empty, d1_full, d1_empty, dz_full[2], dz_empty[2], dh_full[2], dh_empty[2],
-      dw_full, dw_empty;
+  __shared__ uint64_t h_full[2], h_empty[2], w_full, w_empty, d1_full[2], d1_empty[2], dz_full[2], dz_empty[2], dh_full[2],
+      dh_empty[2], dw_full, dw_empty;
   __shared__ uint32_t tmem_base_s;
   __shared__ float lf[zmath::kLogFactN];
   __shared__ double red[kEpiWarps];
@@ -73,9 +89,9 @@ flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1);
       mbar_init(&dz_full[i], kEpiWarps); mbar_init(&dz_empty[i], 1);
       mbar_init(&dh_full[i], 1); mbar_init(&dh_empty[i], kFlushWarps);
+      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], kEpiWarps);
     }
     mbar_init(&w_full, 1); mbar_init(&w_empty, 1);
-    mbar_init(&d1_full, 1); mbar_init(&d1_empty, kEpiWarps);
     mbar_init(&dw_full, 1); mbar_init(&dw_empty, kFlushWarps);
     fence_barrier_init();
     tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_w0); tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2);
@@ -122,33 +138,31 @@ flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       constexpr uint32_t idesc_a = make_idesc_bf16(128, 64, 1, 1);    // dZ MN-major (2 heads stacked) x H MN-major
       constexpr uint32_t idesc_c = make_idesc_bf16(128, 16, 1, 0);    // dZ MN-major x ones -> column sums
       const uint32_t wb = smem_u32(s_w), ob = smem_u32(s_ones);
-      uint32_t hi = 0, ti = 0, dhi = 0, seg = 0;
-      struct Pend { int valid; uint32_t hs, zb, zph; int first, last; } pend = {0, 0, 0, 0, 0, 0};
+      uint32_t hi = 0, ti = 0, seg = 0;
+      struct Pend { int valid; uint32_t hs, b, ph; int first, last; } pend = {0, 0, 0, 0, 0, 0};
       auto mma23 = [&](const Pend& u) {
-        mbar_wait(&dz_full[u.zb], u.zph);
-        const uint32_t ds = dhi & 1, dp = (dhi >> 1) & 1; ++dhi;
-        mbar_wait(&dh_empty[ds], dp ^ 1);
+        mbar_wait(&dz_full[u.b], u.ph);                                // the epilogue has written dZ of this tile
         if (u.first) mbar_wait(&dw_empty, ((seg - 1) & 1) ^ 1);       // previous segment's dW has been flushed
         tcgen05_fence_after();
-        const uint32_t zb = smem_u32(s_z + u.zb * kZBytes), hb = smem_u32(s_h + u.hs * kHBytes);
+        const uint32_t zb = smem_u32(s_z + u.b * kZBytes), hb = smem_u32(s_h + u.hs * kHBytes);
+        const uint32_t tm = tmem + kTmD1 + u.b * kTmD1Stride;          // consumed pre-activation accumulator: reuse
 #pragma unroll
         for (int h = 0; h < 3; ++h)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + kTmDh + ds * 64, make_smem_desc(zb + h * kZBox + k * 32, 0, 1024),
+            umma_bf16(tm + kTmDhOff, make_smem_desc(zb + h * kZBox + k * 32, 0, 1024),
                       make_smem_desc(wb + h * kWBox + k * 32, 0, 1024), idesc_b, (h > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&dh_full[ds]);
 #pragma unroll
         for (int a = 0; a < 2; ++a) {                                  // accumulator 0: heads (0,1); 1: heads (1,2)
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const uint64_t da = make_smem_desc(zb + a * kZBox + k * 2048, kZBox, 1024);
-            const uint32_t acc = (u.first && k == 0) ? 0u : 1u;
-            umma_bf16(tmem + kTmDw + a * 64, da, make_smem_desc(hb + k * 2048, 0, 1024), idesc_a, acc);
-            umma_bf16(tmem + kTmCs + a * 16, da, make_smem_desc(ob + (k & 3) * 32, 0, 1024), idesc_c, acc);
+            umma_bf16(tm + kTmCsOff + a * 16, da, make_smem_desc(ob + (k & 3) * 32, 0, 1024), idesc_c, k > 0 ? 1u : 0u);
+            umma_bf16(tmem + kTmDw + a * 64, da, make_smem_desc(hb + k * 2048, 0, 1024), idesc_a, (u.first && k == 0) ? 0u : 1u);
           }
         }
-        umma_commit(&dz_empty[u.zb]);
+        umma_commit(&dh_full[u.b]);
+        umma_commit(&dz_empty[u.b]);
         umma_commit(&h_empty[u.hs]);
         if (u.last) { umma_commit(&dw_full); umma_commit(&w_empty); }
       };
@@ -160,19 +174,44 @@ flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           mbar_wait(&w_full, seg & 1); ++seg;
         }
         const uint32_t hs = hi & 1, hp = (hi >> 1) & 1; ++hi;
+        const uint32_t bb = ti & 1, ph = (ti >> 1) & 1;
         mbar_wait(&h_full[hs], hp);
-        mbar_wait(&d1_empty, (ti & 1) ^ 1);
+        mbar_wait(&d1_empty[bb], ph ^ 1);                              // epilogue of tile ti-2 has read the accumulator
+        mbar_wait(&dh_empty[bb], ph ^ 1);                              // flush of tile ti-2 has read dH3 / column sums
         tcgen05_fence_after();
         const uint32_t hb = smem_u32(s_h + hs * kHBytes);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + kTmD1, make_smem_desc(hb + k * 32, 0, 1024), make_smem_desc(wb + k * 2048, kWBox, 1024), idesc_1, k > 0);
-        umma_commit(&d1_full);
+          umma_bf16(tmem + kTmD1 + bb * kTmD1Stride, make_smem_desc(hb + k * 32, 0, 1024), make_smem_desc(wb + k * 2048, kWBox, 1024), idesc_1, k > 0);
+        umma_commit(&d1_full[bb]);
         if (pend.valid) mma23(pend);
-        pend.valid = 1; pend.hs = hs; pend.zb = ti & 1; pend.zph = (ti >> 1) & 1; pend.first = new_seg;
+        pend.valid = 1; pend.hs = hs; pend.b = bb; pend.ph = ph; pend.first = new_seg;
         pend.last = (t + 1 == t1) || ((t + 1) % p.n_cb == 0);
       }
       if (pend.valid) mma23(pend);
+    }
+  } else if (warp == 3) {
+    // ===================================================== L2 prefetch of the count rows, two tiles ahead of the epilogue
+    // (the epilogue threads read their own row segments straight from global memory; this turns their DRAM
+    // latency into L2 latency without spending shared memory on a staging tile)
+    auto prefetch_tile = [&](int tt) {
+      const int gt = tt / p.n_cb, cb = tt % p.n_cb;
+      const int g0 = gt * 64;
+      const uint32_t bytes = (uint32_t)min(64, p.G - g0) * 4u;
+      for (int r = lane; r < 128; r += 32) {
+        const int grow = cb * 128 + r;
+        if (grow < p.B) {
+          const int yr = p.rows ? p.rows[grow] : grow;
+          bulk_prefetch_l2(p.Y + (int64_t)yr * p.ldy + g0, bytes);
+        }
+      }
+    };
+    prefetch_tile(t0);
+    if (t0 + 1 < t1) prefetch_tile(t0 + 1);
+    uint32_t ti = 0;
+    for (int t = t0; t < t1; ++t, ++ti) {
+      if (t + 2 < t1) prefetch_tile(t + 2);
+      mbar_wait_backoff(&dz_full[ti & 1], (ti >> 1) & 1, 500);   // pace: the epilogue has finished tile t
     }
   } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
     // ===================================================== loss epilogue
@@ -194,47 +233,64 @@ flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       const float* yrow = p.Y + (int64_t)yr * p.ldy;
       const uint32_t zbuf = ti & 1, zph = (ti >> 1) & 1;
       uint8_t* zrow = s_z + zbuf * kZBytes + row * 128;
-      mbar_wait(&d1_full, ti & 1);
+      mbar_wait_backoff(&d1_full[zbuf], zph, 64);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
+        // ---- operands of 8 genes x 3 heads: counts and biases from global/L2, pre-activations from TMEM
+        const int gh = gt * 64 + cg * 16 + half * 8;
+        const bool cols_in = gh < p.G;                          // G % 8 == 0: the 8 genes are all in or all out
+        const bool active = valid_row && cols_in;
+        float y[8], bm[8], bd[8], bp[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { y[j] = 0.f; bm[j] = bd[j] = bp[j] = 0.f; }
+        if (active) {
+          const float4 a = *reinterpret_cast<const float4*>(yrow + gh), b = *reinterpret_cast<const float4*>(yrow + gh + 4);
+          y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
+        }
+        if (cols_in) {
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const float4 a = *reinterpret_cast<const float4*>(p.bias[0] + gh + 4 * v);
+            const float4 b = *reinterpret_cast<const float4*>(p.bias[1] + gh + 4 * v);
+            const float4 c = *reinterpret_cast<const float4*>(p.bias[2] + gh + 4 * v);
+            bm[4 * v] = a.x; bm[4 * v + 1] = a.y; bm[4 * v + 2] = a.z; bm[4 * v + 3] = a.w;
+            bd[4 * v] = b.x; bd[4 * v + 1] = b.y; bd[4 * v + 2] = b.z; bd[4 * v + 3] = b.w;
+            bp[4 * v] = c.x; bp[4 * v + 1] = c.y; bp[4 * v + 2] = c.z; bp[4 * v + 3] = c.w;
+          }
+        }
         uint32_t zm[8], zd[8], zp[8];
-        const uint32_t tcol = tmem + kTmD1 + lane_off + (uint32_t)(cg * 16 + half * 8);
+        const uint32_t tcol = tmem + kTmD1 + zbuf * kTmD1Stride + lane_off + (uint32_t)(cg * 16 + half * 8);
         tmem_ld_32x8(tcol, zm); tmem_ld_32x8(tcol + 64, zd); tmem_ld_32x8(tcol + 128, zp);
         tmem_ld_wait();
         if (half == 1) {                                      // accumulator fully read: release it to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&d1_empty);
+          if (lane == 0) mbar_arrive(&d1_empty[zbuf]);
         }
-        uint32_t om[4], od[4], op[4];                           // 8 bf16 per head = one 16-byte chunk of the dZ row
+        float mm[8], dd[8], pp[8];
 #pragma unroll
+        for (int j = 0; j < 8; ++j) {                           // 24 independent activation chains
+          mm[j] = act_mean(__uint_as_float(zm[j]) + bm[j]);
+          dd[j] = act_disp(__uint_as_float(zd[j]) + bd[j]);
+          pp[j] = act_sigmoid(__uint_as_float(zp[j]) + bp[j]);
+        }
+        if (half == 0) mbar_wait_backoff(&dz_empty[zbuf], zph ^ 1, 64);   // the MMAs that read this dZ buffer two tiles ago are done
+        // SWIZZLE_128B: 16-byte chunk (8 genes) ^ (row % 8); each pass over 4 genes fills one 8-byte half of it
+        uint8_t* zdst = zrow + (uint32_t)(((cg * 2 + half) ^ (row & 7)) << 4);
+#pragma unroll 1
         for (int sub = 0; sub < 2; ++sub) {
-          const int g0 = gt * 64 + cg * 16 + half * 8 + sub * 4;
-          const bool active = valid_row && g0 < p.G;            // G % 4 == 0: a group of 4 genes is all in or all out
-          float y[4] = {0.f, 0.f, 0.f, 0.f}, mm[4], dd[4], pp[4];
-          if (g0 < p.G) {
-            const float4 bm = *reinterpret_cast<const float4*>(p.bias[0] + g0);
-            const float4 bd = *reinterpret_cast<const float4*>(p.bias[1] + g0);
-            const float4 bp = *reinterpret_cast<const float4*>(p.bias[2] + g0);
-            const float bmv[4] = {bm.x, bm.y, bm.z, bm.w}, bdv[4] = {bd.x, bd.y, bd.z, bd.w}, bpv[4] = {bp.x, bp.y, bp.z, bp.w};
-            if (valid_row) { const float4 vy = *reinterpret_cast<const float4*>(yrow + g0); y[0] = vy.x; y[1] = vy.y; y[2] = vy.z; y[3] = vy.w; }
+          float ys[4], ms[4], ds[4], ps[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              mm[j] = act_mean(__uint_as_float(zm[sub * 4 + j]) + bmv[j]);
-              dd[j] = act_disp(__uint_as_float(zd[sub * 4 + j]) + bdv[j]);
-              pp[j] = act_sigmoid(__uint_as_float(zp[sub * 4 + j]) + bpv[j]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { mm[j] = 1.f; dd[j] = 1.f; pp[j] = 0.5f; }
+          for (int j = 0; j < 4; ++j) {
+            ys[j] = sub ? y[4 + j] : y[j]; ms[j] = sub ? mm[4 + j] : mm[j]; ds[j] = sub ? dd[4 + j] : dd[j]; ps[j] = sub ? pp[4 + j] : pp[j];
           }
           // ---- queue the non-zero counts of this warp's 32 rows x 4 genes (ballot compaction: ordered by j, lane)
           unsigned bal[4];
           int nz = 0, pos[4], base = 0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const bool is_nz = active && !(y[j] < 1e-8f);              // loss.py:138
+            const bool is_nz = active && !(ys[j] < 1e-8f);              // loss.py:138
             bal[j] = __ballot_sync(kFull, is_nz);
             nz |= is_nz ? (1 << j) : 0;
           }
@@ -243,39 +299,31 @@ flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           const int total = base;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (nz & (1 << j)) q[pos[j]] = make_float4(y[j], mm[j] * sfv, dd[j], pp[j]);
+            if (nz & (1 << j)) q[pos[j]] = make_float4(ys[j], ms[j] * sfv, ds[j], ps[j]);
           __syncwarp();
+          // ---- zero branch for all four elements, branch-free (independent chains interleave); selected below
           float gm[4], gd[4], gp[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            gm[j] = gd[j] = gp[j] = 0.f;
-            if (active && !(nz & (1 << j))) {
-              const zmath::Elem e = zmath::zinb_elem_zero<Ops, true>(mm[j], sfv, dd[j], pp[j], p.ridge);
-              lsum += e.loss; gm[j] = e.gm; gd[j] = e.gd; gp[j] = e.gp;
-            }
+            const zmath::Elem e = zmath::zinb_elem_zero_bf<Ops, true>(ms[j], sfv, ds[j], ps[j], p.ridge);
+            const bool use = active && !(nz & (1 << j));
+            lsum += use ? e.loss : 0.f; gm[j] = use ? e.gm : 0.f; gd[j] = use ? e.gd : 0.f; gp[j] = use ? e.gp : 0.f;
           }
-          for (int k = lane; k < total; k += 32) {
-            const float4 it = q[k];
-            const zmath::Elem e = zmath::zinb_elem_nb_mu<Ops>(it.x, it.y, it.z, it.w, p.ridge, lf);
-            q[k] = make_float4(e.loss, e.gm, e.gd, e.gp);
-          }
+          for (int k = lane; k < total; k += 32) q[k] = nb_item(q[k], p.ridge, lf);
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (nz & (1 << j)) {
               const float4 e = q[pos[j]];
-              lsum += e.x; gm[j] = (mm[j] > 1e-5f && mm[j] < 1e6f) ? e.y : 0.f; gd[j] = e.z; gp[j] = e.w;
+              const float mj = ms[j];
+              lsum += e.x; gm[j] = (mj > 1e-5f && mj < 1e6f) ? e.y : 0.f; gd[j] = e.z; gp[j] = e.w;
             }
           __syncwarp();
-          om[sub * 2] = pack_bf16x2(gm[0] * p.inv_n, gm[1] * p.inv_n); om[sub * 2 + 1] = pack_bf16x2(gm[2] * p.inv_n, gm[3] * p.inv_n);
-          od[sub * 2] = pack_bf16x2(gd[0] * p.inv_n, gd[1] * p.inv_n); od[sub * 2 + 1] = pack_bf16x2(gd[2] * p.inv_n, gd[3] * p.inv_n);
-          op[sub * 2] = pack_bf16x2(gp[0] * p.inv_n, gp[1] * p.inv_n); op[sub * 2 + 1] = pack_bf16x2(gp[2] * p.inv_n, gp[3] * p.inv_n);
+          uint8_t* zd8 = zdst + sub * 8;
+          *reinterpret_cast<uint2*>(zd8) = make_uint2(pack_bf16x2(gm[0] * p.inv_n, gm[1] * p.inv_n), pack_bf16x2(gm[2] * p.inv_n, gm[3] * p.inv_n));
+          *reinterpret_cast<uint2*>(zd8 + kZBox) = make_uint2(pack_bf16x2(gd[0] * p.inv_n, gd[1] * p.inv_n), pack_bf16x2(gd[2] * p.inv_n, gd[3] * p.inv_n));
+          *reinterpret_cast<uint2*>(zd8 + 2 * kZBox) = make_uint2(pack_bf16x2(gp[0] * p.inv_n, gp[1] * p.inv_n), pack_bf16x2(gp[2] * p.inv_n, gp[3] * p.inv_n));
         }
-        if (half == 0) mbar_wait(&dz_empty[zbuf], zph ^ 1);     // the MMAs that read this dZ buffer two tiles ago are done
-        const uint32_t chunk = (uint32_t)(((cg * 2 + half) ^ (row & 7)) << 4);     // SWIZZLE_128B: 16-byte chunk ^ (row % 8)
-        *reinterpret_cast<uint4*>(zrow + chunk) = make_uint4(om[0], om[1], om[2], om[3]);
-        *reinterpret_cast<uint4*>(zrow + kZBox + chunk) = make_uint4(od[0], od[1], od[2], od[3]);
-        *reinterpret_cast<uint4*>(zrow + 2 * kZBox + chunk) = make_uint4(op[0], op[1], op[2], op[3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -322,28 +370,41 @@ flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    uint32_t dhi = 0, seg = 0;
-    for (int t = t0; t < t1; ++t) {
+    uint32_t ti = 0, seg = 0;
+    for (int t = t0; t < t1; ++t, ++ti) {
       const int gt = t / p.n_cb, cb = t % p.n_cb;
-      const uint32_t ds = dhi & 1, dp = (dhi >> 1) & 1; ++dhi;
-      mbar_wait(&dh_full[ds], dp);
+      const uint32_t bb = ti & 1, ph = (ti >> 1) & 1;
+      const uint32_t tm = tmem + kTmD1 + bb * kTmD1Stride + lane_off;
+      const int g = gt * 64 + (row & 63);
+      mbar_wait_backoff(&dh_full[bb], ph, 256);
       tcgen05_fence_after();
       if (warp == kFlushWarp0 && lane == 0) bulk_wait_read<0>();        // previous reduce has read the staging tiles
       named_barrier_sync(3, kFlushWarps * 32);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem + kTmDh + lane_off + ds * 64 + c * 32, v);
+        tmem_ld_32x32(tm + kTmDhOff + c * 32, v);
         tmem_ld_wait();
         uint8_t* tile = s_o + c * (kOutBytes / 2);
 #pragma unroll
         for (int qq = 0; qq < 8; ++qq)
           *reinterpret_cast<uint4*>(tile + row * 128 + ((qq ^ (row & 7)) << 4)) = make_uint4(v[qq * 4], v[qq * 4 + 1], v[qq * 4 + 2], v[qq * 4 + 3]);
       }
+      {
+        // bias gradient of this tile: column sums of dZ.  accumulator 0: lanes 0-63 = head 0, 64-127 = head 1;
+        // accumulator 1: lanes 64-127 = head 2 (lanes 0-63 duplicate head 1)
+        uint32_t cs[32];
+        tmem_ld_32x32(tm + kTmCsOff, cs);
+        tmem_ld_wait();
+        if (g < p.G) {
+          atomicAdd(p.db[row >> 6] + g, __uint_as_float(cs[0]));
+          if (row >= 64) atomicAdd(p.db[2] + g, __uint_as_float(cs[16]));
+        }
+      }
       tcgen05_fence_before();
       fence_proxy_async_smem();
       named_barrier_sync(3, kFlushWarps * 32);
-      if (lane == 0) mbar_arrive(&dh_empty[ds]);
+      if (lane == 0) mbar_arrive(&dh_empty[bb]);
       if (warp == kFlushWarp0 && lane == 0) {
         tma_reduce_add_2d(&map_o, 0, cb * 128, s_o);
         tma_reduce_add_2d(&map_o, 32, cb * 128, s_o + kOutBytes / 2);
@@ -351,18 +412,12 @@ flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       }
       const bool last = (t + 1 == t1) || ((t + 1) % p.n_cb == 0);
       if (last) {
-        mbar_wait(&dw_full, seg & 1); ++seg;
+        mbar_wait_backoff(&dw_full, seg & 1, 64); ++seg;
         tcgen05_fence_after();
-        const int g = gt * 64 + (row & 63);
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-          // accumulator 0: lanes 0-63 = head 0, 64-127 = head 1;  accumulator 1: lanes 64-127 = head 2 (0-63 duplicate head 1)
           const int head = a == 0 ? (row >> 6) : 2;
           const bool mine = (a == 0 || row >= 64) && g < p.G;
-          uint32_t cs[16];
-          tmem_ld_32x16(tmem + kTmCs + lane_off + a * 16, cs);
-          tmem_ld_wait();
-          if (mine && p.db[head]) atomicAdd(p.db[head] + g, __uint_as_float(cs[0]));
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t v[32];

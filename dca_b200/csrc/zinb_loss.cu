@@ -630,7 +630,7 @@ int launch(const LossArgs& a, cudaStream_t s) {
 }  // namespace
 
 const float* loss_log_fact_table() { return log_fact_table_device(); }
-int g_fused_heads_default = 1;            // engines created from now on use the fused head/loss/backward kernel
+int g_fused_heads_default = 0;            // 1: engines created from now on use the fused head/loss/backward kernel
 
 size_t loss_workspace_bytes(int B, int G) {
   (void)B; (void)G;

@@ -204,6 +204,49 @@ DCA_HD Elem zinb_elem_zero(float m, float sf, float th, float pi, float ridge) {
   return o;
 }
 
+// The same zero-branch arithmetic without control flow (both sides of the two series/MUFU choices are evaluated
+// and selected): a thread can then interleave the independent chains of several elements, which matters where few
+// warps are resident (the fused head/loss/backward kernel).  Results equal zinb_elem_zero's.
+template <class Ops, bool COND_DISP>
+DCA_HD Elem zinb_elem_zero_bf(float m, float sf, float th_in, float pi, float ridge) {
+  const float mu = m * sf;
+  const float th = fminf(th_in, 1e6f);
+  const float te = th + kEps;
+  const float rden = Ops::rcp(te + mu);
+  const float q = mu * rden;
+  float p = fmaf(q, 0.125f, 0.142857143f);
+  p = fmaf(q, p, 0.166666667f); p = fmaf(q, p, 0.2f); p = fmaf(q, p, 0.25f);
+  p = fmaf(q, p, 0.333333333f); p = fmaf(q, p, 0.5f);
+  const float f_ser = q * q * p, L1_ser = q + f_ser;
+  const float L1_log = -kLn2 * Ops::lg2(te * rden), f_log = L1_log - q;
+  const bool small_q = q < 0.0625f;
+  const float L1 = small_q ? L1_ser : L1_log, f = small_q ? f_ser : f_log;
+  const float z = Ops::ex2(-th * L1 * kLog2e);
+  const float omp = 1.0f - pi;
+  const float D = pi + omp * z + kEps;
+  const float rD = Ops::rcp(D);
+  Elem o;
+  o.loss = -kLn2 * Ops::lg2(D);
+  const float w = omp * z * rD;
+  o.gm = w * th * q;
+  o.gm = ((m > 1e-5f) && (m < 1e6f)) ? o.gm : 0.f;
+  const float dth = w * f;
+  if (COND_DISP) {
+    float pp = fmaf(th_in, 0.0416666667f, -0.166666667f);
+    pp = fmaf(th_in, pp, 0.5f);
+    const float ome_ser = th_in - th_in * th_in * pp;
+    const float ome_exp = 1.0f - Ops::ex2(-th_in * kLog2e);
+    const float ome = th_in < 0.03125f ? ome_ser : ome_exp;
+    o.gd = ((th_in > 1e-4f) && (th_in < 1e4f)) ? dth * ome : 0.f;
+  } else {
+    o.gd = dth;
+  }
+  o.loss = fmaf(ridge * pi, pi, o.loss);                    // ridge defaults to 0: adds an exact 0
+  const float dpi = fmaf(2.0f * ridge, pi, (z - 1.0f) * rD);
+  o.gp = dpi * (pi * (1.0f - pi));
+  return o;
+}
+
 // NB branch of loss.py:87-88,130 (all elements of NB models; y >= 1e-8 for ZINB models)
 template <class Ops, bool HAS_PI, bool COND_DISP>
 DCA_HD Elem zinb_elem_nb(float y, float m, float sf, float th, float pi, float ridge, const float* lf_table) {
