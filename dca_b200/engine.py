@@ -278,9 +278,10 @@ class DeviceEngine:
 
         def pinned(a, view):                      # pinned pages on the GPU's NUMA node (hostmem.py)
             return pin_near_gpu(np.ascontiguousarray(a).view(view), self.device.index or 0)
-        packed = pinned(pc.packed, np.uint8)
-        indptr = pinned(pc.indptr, np.int64)
-        entries = pinned(pc.entries if len(pc.entries) else np.zeros(1, dtype=pc.entries.dtype), np.uint8)
+        if getattr(pc, "_pinned", None) is None:      # pin once per PackedCounts (cudaHostAlloc costs milliseconds)
+            pc._pinned = (pinned(pc.packed, np.uint8), pinned(pc.indptr, np.int64),
+                          pinned(pc.entries if len(pc.entries) else np.zeros(1, dtype=pc.entries.dtype), np.uint8))
+        packed, indptr, entries = pc._pinned
         self._stream_keep = (packed, indptr, entries, sf)
         check(self.lib.dca_stream_begin_packed(self.handle, packed.data_ptr(), pc.bits, packed.shape[-1] if packed.dim() == 2 else 0,
                                                indptr.data_ptr(), entries.data_ptr(), None if sf is None else sf.data_ptr(),

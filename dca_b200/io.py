@@ -167,6 +167,7 @@ class PackedCounts:
 
     def __init__(self, packed, bits, n_genes, indptr, entries):
         self.packed, self.bits, self.n_genes, self.indptr, self.entries = packed, bits, n_genes, indptr, entries
+        self._pinned = None            # pinned host copies, made by DeviceEngine.stream_begin on first use
 
     @property
     def n_rows(self):

@@ -463,7 +463,7 @@ def test_fused_heads_kernel_equals_three_kernel_path(shape):
     for fused in (1, 0):
         _lib.set_tunable("fused_heads", fused)
         engines.append(DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=9, gemm_path="tcgen05", ridge=0.01))
-    _lib.set_tunable("fused_heads", 1)
+    _lib.set_tunable("fused_heads", 0)                                   # back to the default
     e1, e2 = engines
     Xd, Yd, sfd = _t(X), _t(Y), _t(sf)
     for step in range(3):                        # direct call, graph capture, graph replay
