@@ -144,13 +144,40 @@ def read_genelist(filename):
     return genelist
 
 
-def write_text_matrix(matrix, filename, rownames=None, colnames=None, transpose=False):
-    """dca/io.py:120-129: TSV, '%.6f'."""
-    if transpose:
-        matrix = matrix.T
-        rownames, colnames = colnames, rownames
-    pd.DataFrame(matrix, index=rownames, columns=colnames).to_csv(
-        filename, sep='\t', index=(rownames is not None), header=(colnames is not None), float_format='%.6f')
+def write_text_matrix(matrix, filename, rownames=None, colnames=None, transpose=False, threads=0):
+    """TSV with '%.6f' values, the files of dca/io.py:120-129 byte for byte.  float32 / float64 matrices go through
+    the multi-threaded native writer (dca_write_text_matrix); anything else through pandas like the reference."""
+    import ctypes as C
+    m = np.asarray(matrix)
+    native = m.ndim == 2 and m.dtype in (np.float32, np.float64) and m.size > 0
+    if native:
+        try:
+            from . import _lib
+            lib = _lib.load()
+        except Exception:           # library not built: formatting on the host needs no GPU, fall through
+            native = False
+    if not native:
+        if transpose:
+            m = m.T
+            rownames, colnames = colnames, rownames
+        pd.DataFrame(m, index=rownames, columns=colnames).to_csv(
+            filename, sep='\t', index=(rownames is not None), header=(colnames is not None), float_format='%.6f')
+        return
+    m = np.ascontiguousarray(m)
+
+    def labels(names, n):
+        if names is None:
+            return None, None
+        vals = [str(v).encode() for v in list(names)]
+        if len(vals) != n:
+            raise ValueError("got %d labels for %d rows/columns" % (len(vals), n))
+        arr = (C.c_char_p * n)(*vals)
+        return arr, vals
+    rn, _keep_r = labels(rownames, m.shape[0])
+    cn, _keep_c = labels(colnames, m.shape[1])
+    _lib.check(lib.dca_write_text_matrix(os.fsencode(filename), m.ctypes.data, int(m.dtype == np.float64), m.shape[0],
+                                         m.shape[1], m.shape[1], rn, cn, int(bool(transpose)), int(threads)),
+               "dca_write_text_matrix")
 
 
 def read_pickle(inputfile):

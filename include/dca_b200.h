@@ -278,6 +278,16 @@ int dca_profile_read(dca_handle* h, double ms[DCA_N_PHASES], int64_t counts[DCA_
 int dca_engine_info(const dca_handle* h, int32_t info[8]);
 
 /* Number of kernels this library has launched in this process (all handles, all streams). */
+/* ---- host-side output writer ------------------------------------------------------------------- */
+/* Replaces write_text_matrix (dca/io.py:120-129: pandas to_csv(sep='\t', float_format='%.6f')) byte for byte:
+ * optional header line of column labels (preceded by an empty cell when row labels are given), one line per
+ * row "label\tv\tv...", NaN as an empty field, labels quoted only when they contain a tab, quote or newline.
+ * matrix: HOST float32 (is_float64 = 0) or float64 rows x cols, leading dimension ld; transpose != 0 writes the
+ * transposed matrix (labels swap roles) without materialising it.  threads <= 0: up to 16 hardware threads. */
+int dca_write_text_matrix(const char* path, const void* matrix, int32_t is_float64, int64_t rows, int64_t cols,
+                          int64_t ld, const char* const* row_names, const char* const* col_names,
+                          int32_t transpose, int32_t threads);
+
 int64_t dca_launch_count(void);
 /* Launch tunables of the loss kernel (process-wide; set them BEFORE the first training step of an engine,
  * a captured step graph keeps the values it was recorded with): "loss_target_blocks",

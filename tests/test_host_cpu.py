@@ -156,3 +156,37 @@ def test_pack_counts_round_trip_and_auto_width():
         io.pack_counts(np.full((4, 12), 1.0))                         # genes not a multiple of 8
     with pytest.raises(ValueError):
         io.pack_counts(np.full((4, 16), 0.5))                         # not integer counts
+
+
+def _pandas_tsv(m, path, rownames, colnames, transpose):
+    if transpose:
+        m = m.T; rownames, colnames = colnames, rownames
+    pd.DataFrame(m, index=rownames, columns=colnames).to_csv(path, sep='\t', index=(rownames is not None),
+                                                             header=(colnames is not None), float_format='%.6f')
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_native_text_writer_is_byte_identical_to_pandas(tmp_path, dtype):
+    """dca_write_text_matrix (multi-threaded, fixed-point digits) == pandas to_csv(sep='\\t', float_format='%.6f'),
+    the writer of dca/io.py:120-129: rounding ties, negative zero, NaN / inf, huge and tiny values, labels that
+    need quoting, with and without labels, transposed and not."""
+    from dca_b200 import io
+    rng = np.random.default_rng(0)
+    m = (rng.standard_normal((37, 23)) * np.exp(rng.normal(0, 4, (37, 23)))).astype(dtype)
+    m[0, :8] = [0.0, -0.0, 1 / 128, 3 / 128, -5 / 128, 0.0000005, -0.0000005, 1234567.0000005]
+    m[1, :6] = [np.nan, np.inf, -np.inf, 1e-12, -1e-12, 9.9999995]
+    m[2, :4] = [8.1e9, -3.4e38 if dtype == np.float32 else -1.7e300, 0.1234565, 2.5e-7]
+    m[3, :] = np.arange(23) / 128.0 + 0.5 / 128.0            # every value a rounding tie at the 7th decimal
+    rows = ["cell%d" % i for i in range(37)]; rows[4] = 'we"ird\tname'
+    cols = ["g%d" % j for j in range(23)]
+    cases = [(rows, cols, False), (rows, cols, True), (None, cols, False), (rows, None, True), (None, None, False)]
+    for k, (rn, cn, tr) in enumerate(cases):
+        a, b = tmp_path / ("native%d.tsv" % k), tmp_path / ("pandas%d.tsv" % k)
+        io.write_text_matrix(m, str(a), rownames=rn, colnames=cn, transpose=tr, threads=3)
+        _pandas_tsv(m, str(b), rn, cn, tr)
+        assert a.read_bytes() == b.read_bytes(), (dtype, k)
+    big = rng.random((3000, 50)).astype(dtype)               # several chunks per thread
+    a, b = tmp_path / "big_native.tsv", tmp_path / "big_pandas.tsv"
+    io.write_text_matrix(big, str(a), rownames=None, colnames=None, transpose=True)
+    _pandas_tsv(big, str(b), None, None, True)
+    assert a.read_bytes() == b.read_bytes()
