@@ -303,7 +303,13 @@ Engine::~Engine() {
   for (auto e : prof.ev) cudaEventDestroy(e);
   for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (hs.copy) cudaStreamDestroy(hs.copy);
-  for (int k = 0; k < 2; ++k) { if (hs.ready[k]) cudaEventDestroy(hs.ready[k]); if (hs.step_done[k]) cudaEventDestroy(hs.step_done[k]); }
+  if (hs.expand) cudaStreamDestroy(hs.expand);
+  for (int k = 0; k < 2; ++k) {
+    if (hs.ready[k]) cudaEventDestroy(hs.ready[k]);
+    if (hs.step_done[k]) cudaEventDestroy(hs.step_done[k]);
+    if (hs.h2d_done[k]) cudaEventDestroy(hs.h2d_done[k]);
+    if (hs.cnt_free[k]) cudaEventDestroy(hs.cnt_free[k]);
+  }
 }
 
 }  // namespace dca

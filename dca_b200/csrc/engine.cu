@@ -895,13 +895,14 @@ extern "C" int dca_engine_info(const dca_handle* h, int32_t info[8]) {
 }
 
 // ------------------------------------------------------------------------------------ streaming from host counts
-// copy batch `i` of the host dataset into staging buffer `b` and expand it (counts -> Y fp32, X normalised), all on
-// the copy stream: both overlap the training step of the previous batch, which works on the other buffer
+// copy batch `i` of the host dataset into staging buffer `b` (copy stream) and expand it (counts -> Y fp32, X
+// normalised; low-priority expand stream): both overlap the training step of the previous batch, which works on the
+// other buffer pair, and the copy of batch i+1 does not wait for the expansion of batch i
 int Engine::stream_prefetch(int64_t i, int b) {
   const int64_t r0 = i * hs.batch;
   const int64_t nb = (hs.n_rows - r0 < hs.batch) ? (hs.n_rows - r0) : hs.batch;
   const size_t tight = (size_t)cfg.n_in * (size_t)hs.bits / 8;             // bytes of one packed row
-  DCA_CUDA_OK(cudaStreamWaitEvent(hs.copy, hs.step_done[b], 0));         // the step that read buffer b has finished
+  DCA_CUDA_OK(cudaStreamWaitEvent(hs.copy, hs.cnt_free[b], 0));          // the expansion two batches ago has consumed staging b
   if (hs.tl_base && hs.tl.size() < 400) hs.tl_mark(hs.copy);
   if ((size_t)hs.row_bytes == tight)  // contiguous rows: one linear copy (faster than the pitched path)
     DCA_CUDA_OK(cudaMemcpyAsync(base + o_cnt[b], hs.counts + r0 * hs.row_bytes, tight * (size_t)nb, cudaMemcpyHostToDevice, hs.copy));
@@ -918,15 +919,20 @@ int Engine::stream_prefetch(int64_t i, int b) {
       DCA_CUDA_OK(cudaMemcpyAsync(base + o_ove[b], hs.ovf_entries + 8 * e0, 8 * (size_t)(e1 - e0), cudaMemcpyHostToDevice, hs.copy));
     }
   }
+  DCA_CUDA_OK(cudaEventRecord(hs.h2d_done[b], hs.copy));
   if (hs.tl_base && hs.tl.size() < 400) hs.tl_mark(hs.copy);
+  // expansion on its own low-priority stream: the next copy does not queue behind it, the step's kernels go first
+  DCA_CUDA_OK(cudaStreamWaitEvent(hs.expand, hs.h2d_done[b], 0));
+  DCA_CUDA_OK(cudaStreamWaitEvent(hs.expand, hs.step_done[b], 0));       // the step that read the expanded buffers b has finished
   const int x_bf16 = tc_enc ? 1 : (cfg.x_dtype == DCA_BF16);
   DCA_TRY(expand_counts(base + o_cnt[b], hs.bits, hs.sf ? f(o_sfst[b]) : nullptr, (int)nb, cfg.n_in,
                         tf_set == 2 ? f(o_gmean) : nullptr, tf_set == 2 ? f(o_ginv) : nullptr, tf_use_sf && hs.sf,
                         tf_use_log1p, f(o_sy[b]), base + o_sx[b], x_bf16, f(o_ssf[b]),
                         has_ovf ? reinterpret_cast<const int64_t*>(base + o_ovp[b]) : nullptr,
-                        has_ovf ? (const void*)(base + o_ove[b]) : nullptr, hs.copy));
-  DCA_CUDA_OK(cudaEventRecord(hs.ready[b], hs.copy));
-  if (hs.tl_base && hs.tl.size() < 400) hs.tl_mark(hs.copy);
+                        has_ovf ? (const void*)(base + o_ove[b]) : nullptr, hs.expand));
+  DCA_CUDA_OK(cudaEventRecord(hs.cnt_free[b], hs.expand));
+  DCA_CUDA_OK(cudaEventRecord(hs.ready[b], hs.expand));
+  if (hs.tl_base && hs.tl.size() < 400) hs.tl_mark(hs.expand);
   hs.pref_idx = i;
   return DCA_OK;
 }
@@ -985,14 +991,22 @@ extern "C" int dca_stream_begin_packed(dca_handle* h, const void* packed_host, i
   }
   auto& hs = e.hs;
   if (!hs.copy) {
+    int least = 0, greatest = 0;
+    DCA_CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     DCA_CUDA_OK(cudaStreamCreateWithFlags(&hs.copy, cudaStreamNonBlocking));
+    DCA_CUDA_OK(cudaStreamCreateWithPriority(&hs.expand, cudaStreamNonBlocking, least));
     for (int k = 0; k < 2; ++k) {
+      DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.h2d_done[k], cudaEventDisableTiming));
+      DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.cnt_free[k], cudaEventDisableTiming));
       DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.ready[k], cudaEventDisableTiming));
       DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.step_done[k], cudaEventDisableTiming));
     }
   }
   cudaStream_t s = (cudaStream_t)stream;
-  for (int k = 0; k < 2; ++k) DCA_CUDA_OK(cudaEventRecord(hs.step_done[k], s));   // both staging buffers start free
+  for (int k = 0; k < 2; ++k) {                                                   // both staging buffers start free
+    DCA_CUDA_OK(cudaEventRecord(hs.step_done[k], s));
+    DCA_CUDA_OK(cudaEventRecord(hs.cnt_free[k], s));
+  }
   hs.counts = reinterpret_cast<const unsigned char*>(packed_host); hs.row_bytes = row_bytes; hs.bits = bits;
   hs.ovf_indptr = ovf_indptr_host; hs.ovf_entries = reinterpret_cast<const unsigned char*>(ovf_entries_host);
   hs.sf = sf_host; hs.n_rows = n_rows; hs.batch = batch;
@@ -1042,6 +1056,7 @@ extern "C" int dca_stream_end(dca_handle* h, void* stream) {
   DCA_NEED_HANDLE(h);
   auto& hs = h->e.hs;
   if (hs.copy) DCA_CUDA_OK(cudaStreamSynchronize(hs.copy));
+  if (hs.expand) DCA_CUDA_OK(cudaStreamSynchronize(hs.expand));
   DCA_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
   if (hs.tl_base && !hs.tl.empty()) {   // order of marks per step: [copy0 c0 c1 (first step only)] x0 x1 | copy-next c0 c1 | step-end
     fprintf(stderr, "[dca stream timeline, ms since stream_begin; first 3 marks: copy/expand of batch 0; then per step: "

@@ -53,8 +53,11 @@ struct Engine {
     const unsigned char* counts = nullptr; int64_t row_bytes = 0; int bits = 16;       // packed host count matrix
     const int64_t* ovf_indptr = nullptr; const unsigned char* ovf_entries = nullptr;   // host CSR overflow list (or null)
     const float* sf = nullptr; int64_t n_rows = 0; int batch = 0;
-    cudaStream_t copy = nullptr;                      // copies AND the expansion kernel of the next batch run here
-    cudaEvent_t ready[2] = {nullptr, nullptr};        // copy stream: batch in buffer b is expanded (Y, X, sf ready)
+    cudaStream_t copy = nullptr;                      // host->device copies of the next batch
+    cudaStream_t expand = nullptr;                    // its expansion kernel (lowest priority: yields SMs to the step)
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr};     // copy stream: raw staging buffer b has arrived
+    cudaEvent_t cnt_free[2] = {nullptr, nullptr};     // expand stream: raw staging buffer b has been consumed
+    cudaEvent_t ready[2] = {nullptr, nullptr};        // expand stream: batch in buffer b is expanded (Y, X, sf ready)
     cudaEvent_t step_done[2] = {nullptr, nullptr};    // compute stream: the step that read buffer b has finished
     int64_t pref_idx = -1, step_no = 0; bool active = false;
     // DCA_STREAM_DIAG=2: device-side timeline (events) of the first steps, printed by dca_stream_end

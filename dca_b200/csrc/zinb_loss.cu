@@ -23,8 +23,8 @@ constexpr int kColsPerBlock = kThreads * kVec;   // 1024 genes per block
 constexpr int kMaxBlocks = 65536;                // bound of the per-block loss-partial buffer
 
 // Launch tunables (dca_set_tunable; defaults chosen from the sweep in profiles/r1_loss_sweep.log)
-struct LossTune { int target_blocks; unsigned producer_sleep_ns, consumer_sleep_ns; };
-LossTune g_tune = {0 /* auto */, 0u, 0u};
+struct LossTune { int target_blocks; unsigned producer_sleep_ns, consumer_sleep_ns; int branch_free; };
+LossTune g_tune = {0 /* auto */, 0u, 0u, 1 /* branch-free zero branch: -7 % at 4096 x 20000, profiles/r1_loss_sweep2.log */};
 
 int sm_count_cached() {
   static int n = 0;
@@ -294,7 +294,7 @@ constexpr int kStageRows = 3;
 constexpr int kMaxRowsPerBlock = 256;
 constexpr int kStagedThreads = kThreads + 32;      // 8 consumer warps + 1 producer warp
 
-template <bool COND_DISP, typename GT>
+template <bool COND_DISP, typename GT, bool BF>
 __global__ void __launch_bounds__(kStagedThreads, 3)
 zinb_loss_bwd_staged_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __restrict__ rows,
                             const float* __restrict__ sf, const float* m, const float* d, const float* pi,
@@ -408,7 +408,11 @@ zinb_loss_bwd_staged_kernel(const float* __restrict__ Y, int64_t ldy, const int3
 #pragma unroll
     for (int j = 0; j < kVec; ++j) {
       gm[j] = gd[j] = gp[j] = 0.f;
-      if (active && !(nz & (1 << j))) {
+      if (BF) {   // branch-free: the four independent chains of a thread interleave (zinb_math.cuh)
+        const zmath::Elem e = zmath::zinb_elem_zero_bf<Ops, COND_DISP>(mm[j], row_sf, dd[j], pp[j], ridge);
+        const bool use = active && !(nz & (1 << j));
+        lsum += use ? e.loss : 0.f; gm[j] = use ? e.gm : 0.f; gd[j] = use ? e.gd : 0.f; gp[j] = use ? e.gp : 0.f;
+      } else if (active && !(nz & (1 << j))) {
         const zmath::Elem e = zmath::zinb_elem_zero<Ops, COND_DISP>(mm[j], row_sf, dd[j], pp[j], ridge);
         lsum += e.loss; gm[j] = e.gm; gd[j] = e.gd; gp[j] = e.gp;
       }
@@ -578,17 +582,19 @@ int launch(const LossArgs& a, cudaStream_t s) {
     FoldArgs fa{reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.ws) + sizeof(double) * (size_t)kMaxBlocks), a.loss_sum,
                 a.fin_penalty, a.fin_loss_slot, a.fin_epoch_acc, a.fin_batch};
     if (!a.counter_ready) DCA_CUDA_OK(cudaMemsetAsync(fa.counter, 0, sizeof(unsigned), s));
-#define DCA_STAGED(CD, GT)                                                                                         \
+#define DCA_STAGED2(CD, GT, BFV)                                                                                   \
   do {                                                                                                             \
     constexpr size_t sm = (size_t)kStageRows * (CD ? 4 : 3) * kColsPerBlock * 4 + (size_t)(kThreads / 32) * 32 * kVec * 16; \
     static bool attr = false;                                                                                      \
-    if (!attr) { DCA_CUDA_OK(cudaFuncSetAttribute(zinb_loss_bwd_staged_kernel<CD, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr = true; } \
-    zinb_loss_bwd_staged_kernel<CD, GT><<<grid, kStagedThreads, sm, s>>>(a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, \
+    if (!attr) { DCA_CUDA_OK(cudaFuncSetAttribute(zinb_loss_bwd_staged_kernel<CD, GT, BFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr = true; } \
+    zinb_loss_bwd_staged_kernel<CD, GT, BFV><<<grid, kStagedThreads, sm, s>>>(a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, \
         a.G, a.ridge, a.inv_n, ps.rows_per_block, (GT*)a.dzm, (GT*)a.dzd, (GT*)a.dzp, tpart, lpart, lf_dev, fa,     \
         g_tune.producer_sleep_ns, g_tune.consumer_sleep_ns);                                                       \
   } while (0)
+#define DCA_STAGED(CD, GT) do { if (g_tune.branch_free) DCA_STAGED2(CD, GT, true); else DCA_STAGED2(CD, GT, false); } while (0)
     if (a.grad_bf16) { if (cond) DCA_STAGED(true, __nv_bfloat16); else DCA_STAGED(false, __nv_bfloat16); }
     else             { if (cond) DCA_STAGED(true, float); else DCA_STAGED(false, float); }
+#undef DCA_STAGED2
 #undef DCA_STAGED
     DCA_LAUNCH_CHECK();
     return DCA_OK;                                                      // the fold is done by the last block
@@ -659,6 +665,7 @@ extern "C" int dca_set_tunable(const char* name, int64_t value) {
   else if (n == "loss_producer_sleep_ns" && value >= 0 && value <= 100000) g_tune.producer_sleep_ns = (unsigned)value;
   else if (n == "loss_consumer_sleep_ns" && value >= 0 && value <= 100000) g_tune.consumer_sleep_ns = (unsigned)value;
   else if (n == "fused_heads" && (value == 0 || value == 1)) g_fused_heads_default = (int)value;
+  else if (n == "loss_branch_free" && (value == 0 || value == 1)) g_tune.branch_free = (int)value;
   else { set_error("dca_set_tunable: unknown name or value out of range (%s = %lld)", name, (long long)value); return DCA_ERR_BAD_ARG; }
   return DCA_OK;
 }

@@ -151,12 +151,9 @@ def write_text_matrix(matrix, filename, rownames=None, colnames=None, transpose=
     m = np.asarray(matrix)
     native = m.ndim == 2 and m.dtype in (np.float32, np.float64) and m.size > 0
     if native:
-        try:
-            from . import _lib
-            lib = _lib.load()
-        except Exception:           # library not built: formatting on the host needs no GPU, fall through
-            native = False
-    if not native:
+        from . import _lib
+        lib = _lib.load()           # raises when libdca_b200.so has not been built
+    if not native:                  # non-float / empty / 1-d input: the reference's own pandas call
         if transpose:
             m = m.T
             rownames, colnames = colnames, rownames

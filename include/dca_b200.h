@@ -291,7 +291,7 @@ int dca_write_text_matrix(const char* path, const void* matrix, int32_t is_float
 int64_t dca_launch_count(void);
 /* Launch tunables of the loss kernel (process-wide; set them BEFORE the first training step of an engine,
  * a captured step graph keeps the values it was recorded with): "loss_target_blocks",
- * "loss_producer_sleep_ns", "loss_consumer_sleep_ns"; "fused_heads" (0 | 1, default 0): engines created afterwards
+ * "loss_producer_sleep_ns", "loss_consumer_sleep_ns", "loss_branch_free" (0 | 1, default 1); "fused_heads" (0 | 1, default 0): engines created afterwards
  * run head forward + loss + head backward of a zinb-conddisp training step as one fused kernel (flash_zinb.cu)
  * instead of three (environment override DCA_FUSED_HEADS).  Profiling aid -- no reference counterpart. */
 int dca_set_tunable(const char* name, int64_t value);
