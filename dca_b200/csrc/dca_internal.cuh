@@ -94,11 +94,6 @@ int cast_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s)
 int expand_counts(const void* cnt, int bits, const float* sf_in, int M, int n, const float* mean, const float* inv_std, int use_sf,
                   int use_log1p, float* Yout, void* Xout, int x_bf16, float* sf_out, const int64_t* ovf_indptr,
                   const void* ovf_entries, cudaStream_t s);
-int pack_head_shadows(const float* W, const float* b, int G, int slot, int nslots, __nv_bfloat16* whT,
-                      __nv_bfloat16* whkm, float* biasp, cudaStream_t s);
-int refresh_all_shadows(const float* const W[3], const float* const b[3], int n_slots, int G, __nv_bfloat16* whT,
-                        __nv_bfloat16* whkm, float* biasp, const float* W1, int n_in, __nv_bfloat16* w1t, cudaStream_t s);
-int transpose_w1_shadow(const float* W, int n_in, __nv_bfloat16* wt, cudaStream_t s);
 int gather_rows_bf16(const void* X, int x_bf16, int64_t ldx, const int32_t* rows, int M, int n, __nv_bfloat16* out,
                      cudaStream_t s);
 
@@ -136,7 +131,5 @@ const float* loss_log_fact_table();      // device table of log(k!), k < 64 (fil
 int zinb_loss_fwd_bwd(const LossArgs& a, cudaStream_t s);
 int zinb_loss_fwd(const LossArgs& a, cudaStream_t s);
 // writes grads[P] = loss_sum*inv_n + penalty, grads[P+1] = nonfinite flag, epoch acc update
-int loss_finalize(const double* loss_sum, const double* penalty, float inv_n, int batch,
-                  float* loss_slot, double* epoch_acc, cudaStream_t s);
 
 }  // namespace dca

@@ -104,43 +104,7 @@ __global__ void relu_fwd_kernel(const float* __restrict__ a, int64_t ld, int M, 
   if (hb) hb[i] = __float2bfloat16_rn(v);
 }
 
-// Operand-layout shadows of the head weights for the tcgen05 kernels (one 64-gene x 64-k tile per block):
-//   whT [(slot*G + g) * 64 + k]        bf16  K-major B operand of the head forward kernel
-//   whkm[k * (nslots*G) + slot*G + g]  bf16  Keras layout, heads packed along columns (head backward)
-//   biasp[slot*G + g]
-__global__ void pack_heads_kernel(const float* __restrict__ W, const float* __restrict__ b, int G, int slot, int nslots,
-                                  __nv_bfloat16* __restrict__ whT, __nv_bfloat16* __restrict__ whkm,
-                                  float* __restrict__ biasp) {
-  __shared__ float t[64][65];
-  const int g0 = blockIdx.x * 64, tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 256 threads
-  for (int k = ty; k < 64; k += 4) {
-    const int g = g0 + tx;
-    const float v = (g < G) ? W[(int64_t)k * G + g] : 0.f;
-    t[k][tx] = v;
-    if (g < G) whkm[(int64_t)k * nslots * G + (int64_t)slot * G + g] = __float2bfloat16_rn(v);
-  }
-  __syncthreads();
-  for (int gi = ty; gi < 64; gi += 4) {
-    const int g = g0 + gi;
-    if (g < G) whT[((int64_t)slot * G + g) * 64 + tx] = __float2bfloat16_rn(t[tx][gi]);
-  }
-  if (threadIdx.x < 64 && g0 + threadIdx.x < G) biasp[(int64_t)slot * G + g0 + threadIdx.x] = b[g0 + threadIdx.x];
-}
 
-// W1 [n_in x 64] (Keras) -> W1T [64 x n_in] bf16 (gene-contiguous K-major operand of the encoder forward)
-__global__ void transpose_w1_kernel(const float* __restrict__ W, int n_in, __nv_bfloat16* __restrict__ wt) {
-  __shared__ float t[64][65];
-  const int g0 = blockIdx.x * 64, tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  for (int gi = ty; gi < 64; gi += 4) {
-    const int g = g0 + gi;
-    t[gi][tx] = (g < n_in) ? W[(int64_t)g * 64 + tx] : 0.f;
-  }
-  __syncthreads();
-  for (int f = ty; f < 64; f += 4) {
-    const int g = g0 + tx;
-    if (g < n_in) wt[(int64_t)f * n_in + g] = __float2bfloat16_rn(t[tx][f]);
-  }
-}
 
 // out[r][0..n) = bf16(X[rows[r]][0..n)), 8 elements per thread (n % 8 == 0, 16-byte aligned rows)
 template <typename T>
@@ -470,71 +434,6 @@ int glorot_fill(float* w, int64_t n, int fan_in, int fan_out, uint64_t seed, uin
 int fill_value(float* p, int64_t n, float v, cudaStream_t s) {
   if (n <= 0) return DCA_OK;
   fill_kernel<<<blocks_for(n), 256, 0, s>>>(p, n, v);
-  DCA_LAUNCH_CHECK();
-  return DCA_OK;
-}
-
-// all operand shadows in ONE launch: blocks [0, n_slots*gt) pack head tiles, the rest transpose W1
-struct ShadowJob {
-  const float* W[3]; const float* b[3]; int n_slots, G, gt;
-  __nv_bfloat16* whT; __nv_bfloat16* whkm; float* biasp;
-  const float* W1; int n_in; __nv_bfloat16* w1t;
-};
-__global__ void refresh_shadows_kernel(const ShadowJob j) {
-  __shared__ float t[64][65];
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  const int head_blocks = j.whT ? j.n_slots * j.gt : 0;
-  if ((int)blockIdx.x < head_blocks) {
-    const int slot = blockIdx.x / j.gt, g0 = (blockIdx.x % j.gt) * 64, G = j.G;
-    const float* W = j.W[slot];
-    for (int k = ty; k < 64; k += 4) {
-      const int g = g0 + tx;
-      const float v = (g < G) ? W[(int64_t)k * G + g] : 0.f;
-      t[k][tx] = v;
-      if (g < G) j.whkm[(int64_t)k * j.n_slots * G + (int64_t)slot * G + g] = __float2bfloat16_rn(v);
-    }
-    __syncthreads();
-    for (int gi = ty; gi < 64; gi += 4) {
-      const int g = g0 + gi;
-      if (g < G) j.whT[((int64_t)slot * G + g) * 64 + tx] = __float2bfloat16_rn(t[tx][gi]);
-    }
-    if (threadIdx.x < 64 && g0 + threadIdx.x < G) j.biasp[(int64_t)slot * G + g0 + threadIdx.x] = j.b[slot][g0 + threadIdx.x];
-  } else {
-    const int g0 = (blockIdx.x - head_blocks) * 64;
-    for (int gi = ty; gi < 64; gi += 4) {
-      const int g = g0 + gi;
-      t[gi][tx] = (g < j.n_in) ? j.W1[(int64_t)g * 64 + tx] : 0.f;
-    }
-    __syncthreads();
-    for (int f = ty; f < 64; f += 4) {
-      const int g = g0 + tx;
-      if (g < j.n_in) j.w1t[(int64_t)f * j.n_in + g] = __float2bfloat16_rn(t[tx][f]);
-    }
-  }
-}
-
-int refresh_all_shadows(const float* const W[3], const float* const b[3], int n_slots, int G, __nv_bfloat16* whT,
-                        __nv_bfloat16* whkm, float* biasp, const float* W1, int n_in, __nv_bfloat16* w1t, cudaStream_t s) {
-  ShadowJob j{};
-  for (int i = 0; i < 3; ++i) { j.W[i] = W ? W[i] : nullptr; j.b[i] = b ? b[i] : nullptr; }
-  j.n_slots = n_slots; j.G = G; j.gt = cdiv(G, 64); j.whT = whT; j.whkm = whkm; j.biasp = biasp;
-  j.W1 = W1; j.n_in = n_in; j.w1t = w1t;
-  const int blocks = (whT ? n_slots * j.gt : 0) + (w1t ? cdiv(n_in, 64) : 0);
-  if (blocks == 0) return DCA_OK;
-  refresh_shadows_kernel<<<blocks, 256, 0, s>>>(j);
-  DCA_LAUNCH_CHECK();
-  return DCA_OK;
-}
-
-int pack_head_shadows(const float* W, const float* b, int G, int slot, int nslots, __nv_bfloat16* whT,
-                      __nv_bfloat16* whkm, float* biasp, cudaStream_t s) {
-  pack_heads_kernel<<<cdiv(G, 64), 256, 0, s>>>(W, b, G, slot, nslots, whT, whkm, biasp);
-  DCA_LAUNCH_CHECK();
-  return DCA_OK;
-}
-
-int transpose_w1_shadow(const float* W, int n_in, __nv_bfloat16* wt, cudaStream_t s) {
-  transpose_w1_kernel<<<cdiv(n_in, 64), 256, 0, s>>>(W, n_in, wt);
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }

@@ -505,7 +505,7 @@ __global__ void fold_partials_kernel(const double* __restrict__ part, int n, dou
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (threadIdx.x == 0) {
       *out = accumulate ? (*out + a) : a;
-      if (loss_slot) {                                            // fused finalize (see loss_finalize_kernel)
+      if (loss_slot) {                                            // fused finalize
         double l = a * (double)inv_n;
         if (l != l) l = INFINITY;                                 // _nan2inf, dca/loss.py:148
         if (penalty) l += *penalty;
@@ -516,17 +516,6 @@ __global__ void fold_partials_kernel(const double* __restrict__ part, int n, dou
       }
     }
   }
-}
-
-__global__ void loss_finalize_kernel(const double* loss_sum, const double* penalty, float inv_n, int batch,
-                                     float* loss_slot, double* epoch_acc) {
-  double l = (*loss_sum) * (double)inv_n;
-  if (l != l) l = INFINITY;                                   // _nan2inf, dca/loss.py:148
-  if (penalty) l += *penalty;
-  const float lf = (float)l;
-  loss_slot[0] = lf;
-  loss_slot[1] = (isfinite(lf)) ? 0.f : 1.f;
-  if (epoch_acc) { epoch_acc[0] += l * (double)batch; epoch_acc[1] += (double)batch; }
 }
 
 __device__ float g_log_fact[zmath::kLogFactN];
@@ -645,13 +634,6 @@ size_t loss_workspace_bytes(int B, int G) {
 
 int zinb_loss_fwd_bwd(const LossArgs& a, cudaStream_t s) { return launch<true>(a, s); }
 int zinb_loss_fwd(const LossArgs& a, cudaStream_t s) { return launch<false>(a, s); }
-
-int loss_finalize(const double* loss_sum, const double* penalty, float inv_n, int batch, float* loss_slot,
-                  double* epoch_acc, cudaStream_t s) {
-  loss_finalize_kernel<<<1, 1, 0, s>>>(loss_sum, penalty, inv_n, batch, loss_slot, epoch_acc);
-  DCA_LAUNCH_CHECK();
-  return DCA_OK;
-}
 
 }  // namespace dca
 

@@ -40,6 +40,22 @@ def run(k, sync_every=0):
     return e0.elapsed_time(e1) / k
 
 
+def resident(k):
+    rows = torch.arange(batch, device=dev, dtype=torch.int32)
+    with torch.cuda.stream(st):
+        for _ in range(k):
+            eng.train_step(X, Y, sf, rows=rows); eng.apply_update(1e-3, 5.0, 1.0)
+    torch.cuda.synchronize()
+
+
 run(8)
+print("fresh engine:        30 steps %.3f ms/step, 60 steps %.3f" % (run(30), run(60)), flush=True)
+resident(40)
+print("after 40 resident:   30 steps %.3f ms/step, 60 steps %.3f" % (run(30), run(60)), flush=True)
+eng.profile(True); resident(20); eng.profile_read(); eng.profile(False)
+print("after profiled pass: 30 steps %.3f ms/step, 60 steps %.3f" % (run(30), run(60)), flush=True)
+time.sleep(0.3)
+print("after 0.3 s idle:    30 steps %.3f ms/step, 60 steps %.3f" % (run(30), run(60)), flush=True)
+sys.exit(0)
 for k in (6, 12, 30, 60, 120):
     print("steps %4d: free-running %.3f ms/step | host <= 2 steps ahead %.3f | <= 4 ahead %.3f" % (k, run(k), run(k, 2), run(k, 4)), flush=True)
