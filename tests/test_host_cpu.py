@@ -190,3 +190,28 @@ def test_native_text_writer_is_byte_identical_to_pandas(tmp_path, dtype):
     io.write_text_matrix(big, str(a), rownames=None, colnames=None, transpose=True)
     _pandas_tsv(big, str(b), None, None, True)
     assert a.read_bytes() == b.read_bytes()
+
+
+def test_hostmem_helpers_are_noops_without_a_gpu():
+    """hostmem.py: without CUDA the NUMA helpers change nothing and return plain host tensors."""
+    import os
+    import torch
+    from dca_b200 import hostmem
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    before = os.sched_getaffinity(0)
+    assert hostmem.gpu_local_cpus(0) is None
+    with hostmem.near_gpu(0):
+        assert os.sched_getaffinity(0) == before
+    t = hostmem.pin_near_gpu(np.arange(6, dtype=np.float32).reshape(2, 3))
+    assert isinstance(t, torch.Tensor) and t.shape == (2, 3) and not t.is_cuda
+    assert os.sched_getaffinity(0) == before
+
+
+def test_packed_counts_batch_bytes():
+    from dca_b200 import io
+    C = np.zeros((10, 16), dtype=np.int64); C[2, 3] = 99; C[7, 0] = 20
+    pc = io.pack_counts(C, 4, batch=4)
+    assert pc.bytes_for_rows(0, 4) == 4 * 8 + 8 * 5 + 8 * 1          # tile + indptr segment + one overflow entry
+    assert pc.bytes_for_rows(4, 8) == 4 * 8 + 8 * 5 + 8 * 1
+    assert pc.bytes_for_rows(8, 10) == 2 * 8 + 8 * 3
