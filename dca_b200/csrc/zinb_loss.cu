@@ -688,6 +688,23 @@ extern "C" int dca_zinb_elem_host(int32_t ae_type, float y, float m, float sf, f
   static bool lf_ready = false;
   if (!lf_ready) { zmath::fill_log_fact(lf); lf_ready = true; }
   using P = zmath::PreciseOps;
+  if (ae_type & 0x100) {
+    // the formulations the staged / fused kernels run: branch-free zero branch, NB branch evaluated from mu by a
+    // different lane than the element's owner (which then applies the MeanAct clip mask)
+    const int base = ae_type & 0xff;
+    if (base != DCA_AE_ZINB_CONDDISP && base != DCA_AE_ZINB) { set_error("dca_zinb_elem_host: kernel variant needs a ZINB type"); return DCA_ERR_BAD_ARG; }
+    if (y < 1e-8f) {
+      e = base == DCA_AE_ZINB_CONDDISP ? zmath::zinb_elem_zero_bf<P, true>(m, sf, d, pi, ridge)
+                                       : zmath::zinb_elem_zero_bf<P, false>(m, sf, d, pi, ridge);
+    } else if (base == DCA_AE_ZINB_CONDDISP) {
+      e = zmath::zinb_elem_nb_mu<P>(y, m * sf, d, pi, ridge, lf);
+      if (!(m > 1e-5f && m < 1e6f)) e.gm = 0.f;
+    } else {
+      e = zmath::zinb_elem<P, true, false>(y, m, sf, d, pi, ridge, lf);
+    }
+    out[0] = e.loss; out[1] = e.gm; out[2] = e.gd; out[3] = e.gp;
+    return DCA_OK;
+  }
   switch (ae_type) {
     case DCA_AE_ZINB_CONDDISP: e = zmath::zinb_elem<P, true, true>(y, m, sf, d, pi, ridge, lf); break;
     case DCA_AE_ZINB: e = zmath::zinb_elem<P, true, false>(y, m, sf, d, pi, ridge, lf); break;

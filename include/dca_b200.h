@@ -223,7 +223,9 @@ int dca_zinb_loss_fwd(const float* Y, int64_t ldy, const int32_t* rows, const fl
 
 /* HOST mirror of the per-element device arithmetic of the loss kernel (same source compiled for
  * the CPU); a testing aid so the formulas can be checked against the oracle without a GPU.
- * out = {element loss, dL/dzm, dL/dzd (or raw dL/dtheta for const-disp types), dL/dzp}, not / N. */
+ * out = {element loss, dL/dzm, dL/dzd (or raw dL/dtheta for const-disp types), dL/dzp}, not / N.
+ * ae_type | 0x100 (ZINB types) evaluates the formulations the staged / fused kernels execute instead: the
+ * branch-free zero branch and the NB branch computed from mu = m * sf with the MeanAct mask applied afterwards. */
 int dca_zinb_elem_host(int32_t ae_type, float y, float m, float sf, float d, float pi, float ridge,
                        float out[4]);
 

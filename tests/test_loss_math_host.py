@@ -8,11 +8,11 @@ from oracle import dca_oracle as O
 from dca_b200 import _lib
 
 
-def _host_elem(ae_type, y, m, sf, d, pi, ridge):
+def _host_elem(ae_type, y, m, sf, d, pi, ridge, kernel_variant=False):
     lib = _lib.load()
     out = (C.c_float * 4)()
     res = np.zeros((len(y), 4), np.float32)
-    t = _lib.AE_TYPE_IDS[ae_type]
+    t = _lib.AE_TYPE_IDS[ae_type] | (0x100 if kernel_variant else 0)
     for i in range(len(y)):
         assert lib.dca_zinb_elem_host(t, float(y[i]), float(m[i]), float(sf[i]), float(d[i]), float(pi[i]),
                                       float(ridge), C.byref(out)) == 0
@@ -79,3 +79,25 @@ def test_host_math_clip_bounds():
     assert np.all(np.isfinite(got))
     ref = O.zinb_loss_elem(y, m * sf, d, pi)
     np.testing.assert_allclose(got[:, 0], ref, rtol=2e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("ae_type", ["zinb-conddisp", "zinb"])
+@pytest.mark.parametrize("ridge", [0.0, 0.05])
+def test_kernel_formulations_equal_the_reference_formulation(ae_type, ridge):
+    """The branch-free zero branch (staged + fused kernels) and the NB branch evaluated from mu = m*sf with the
+    clip mask applied by the owner (fused kernel) return what the plain per-element function returns -- including
+    the series / MUFU switch points (q = 1/16, d = 1/32), the clip bounds and rows with extreme size factors."""
+    y, m, sf, d, pi = _cases(4000, 11)
+    m[:6] = [1e-5, 1e6, 2e-5, 5e5, 1.0, 1.0]; d[:6] = [1e-4, 1e4, 0.03125, 0.031, 0.0313, 9e3]
+    sf[6:10] = [1e-3, 1e3, 1.0, 1.0]
+    # q = mu / (theta + mu) around 1/16
+    m[10:14] = [1.0 / 15.0, 0.0666, 0.0667, 0.07]; sf[10:14] = 1.0; d[10:14] = 1.0; y[10:14] = 0
+    y, m, sf, d, pi = [a.astype(np.float32).astype(np.float64) for a in (y, m, sf, d, pi)]
+    a = _host_elem(ae_type, y, m, sf, d, pi, ridge).astype(np.float64)
+    b = _host_elem(ae_type, y, m, sf, d, pi, ridge, kernel_variant=True).astype(np.float64)
+    assert np.all(np.isfinite(a) == np.isfinite(b))
+    fin = np.isfinite(a)
+    scale = np.maximum(np.abs(a), 1e-30)
+    err = np.where(fin, np.abs(a - b) / scale, 0.0)
+    k = np.unravel_index(int(np.argmax(err)), err.shape)
+    assert err[k] <= 2e-6, (ae_type, ridge, k, a[k], b[k], y[k[0]], m[k[0]], sf[k[0]], d[k[0]], pi[k[0]])
