@@ -113,3 +113,113 @@ extern "C" int dca_write_text_matrix(const char* path, const void* matrix, int32
   if (st != 0 || cl != 0) { set_error("dca_write_text_matrix: write to %s failed", path); return DCA_ERR_CUDA; }
   return DCA_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Host-side packer of a raw count matrix into the streaming format of dca_stream_begin_packed (bits per entry +
+// row-sorted CSR overflow list): the multi-threaded counterpart of dca_b200/io.py:pack_counts.  No device code.
+namespace dca {
+namespace {
+
+template <typename T>
+inline bool count_value(T v, double& out) { out = (double)v; return out >= 0.0 && out == std::floor(out); }
+
+template <typename F>
+void parallel_rows(int64_t rows, int threads, F&& fn) {
+  if (threads < 1) threads = 1;
+  if (threads > rows) threads = (int)std::max<int64_t>(rows, 1);
+  std::vector<std::thread> th;
+  const int64_t per = (rows + threads - 1) / threads;
+  for (int t = 1; t < threads; ++t) th.emplace_back([&, t] { fn(std::min(rows, t * per), std::min(rows, (t + 1) * per)); });
+  fn(0, std::min(rows, per));
+  for (auto& x : th) x.join();
+}
+
+// pass 1: per row, the number of entries >= 15, >= 255, >= 65535 (the escape values of the three widths); returns
+// false when an entry is negative or not an integer
+template <typename T>
+bool escape_counts(const T* m, int64_t rows, int64_t cols, int64_t ld, int64_t* per_row /* [3][rows] */, int threads) {
+  std::vector<int> bad((size_t)std::max(threads, 1) + 1, 0);
+  parallel_rows(rows, threads, [&](int64_t a, int64_t b) {
+    for (int64_t r = a; r < b; ++r) {
+      const T* row = m + r * ld; int64_t c4 = 0, c8 = 0, c16 = 0; bool ok = true;
+      for (int64_t j = 0; j < cols; ++j) {
+        double v; ok &= count_value(row[j], v);
+        c4 += v >= 15.0; c8 += v >= 255.0; c16 += v >= 65535.0;
+      }
+      per_row[r] = c4; per_row[rows + r] = c8; per_row[2 * rows + r] = c16;
+      if (!ok) bad[0] = 1;
+    }
+  });
+  return bad[0] == 0;
+}
+
+template <typename T>
+void pack_rows(const T* m, int64_t rows, int64_t cols, int64_t ld, int bits, unsigned char* packed, const int64_t* indptr,
+               unsigned char* entries, int threads) {
+  const double esc = (double)((1u << bits) - 1u);
+  const int64_t row_bytes = cols * bits / 8;
+  parallel_rows(rows, threads, [&](int64_t a, int64_t b) {
+    for (int64_t r = a; r < b; ++r) {
+      const T* row = m + r * ld; unsigned char* out = packed + r * row_bytes;
+      int64_t k = indptr[r];
+      auto emit = [&](int64_t j, double v) {
+        int32_t g = (int32_t)j; float c = (float)v;
+        memcpy(entries + 8 * k, &g, 4); memcpy(entries + 8 * k + 4, &c, 4); ++k;
+      };
+      if (bits == 4) {
+        for (int64_t j = 0; j < cols; j += 2) {
+          double v0 = (double)row[j], v1 = (double)row[j + 1];
+          if (v0 >= esc) { emit(j, v0); v0 = esc; }
+          if (v1 >= esc) { emit(j + 1, v1); v1 = esc; }
+          out[j >> 1] = (unsigned char)((unsigned)v0 | ((unsigned)v1 << 4));
+        }
+      } else if (bits == 8) {
+        for (int64_t j = 0; j < cols; ++j) { double v = (double)row[j]; if (v >= esc) { emit(j, v); v = esc; } out[j] = (unsigned char)v; }
+      } else {
+        uint16_t* o16 = reinterpret_cast<uint16_t*>(out);
+        for (int64_t j = 0; j < cols; ++j) { double v = (double)row[j]; if (v >= esc) { emit(j, v); v = esc; } o16[j] = (uint16_t)v; }
+      }
+    }
+  });
+}
+
+}  // namespace
+}  // namespace dca
+
+// dtype: 0 float32, 1 float64, 2 uint16, 3 int32, 4 int64.  per_row: int64 [3][rows] (escapes at 4 / 8 / 16 bits).
+extern "C" int dca_count_escapes(const void* counts, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, int64_t* per_row,
+                                 int32_t threads) {
+  if (!counts || !per_row || rows < 0 || cols < 0 || ld < cols) { set_error("dca_count_escapes: bad argument"); return DCA_ERR_BAD_ARG; }
+  if (threads <= 0) { threads = (int)std::thread::hardware_concurrency(); if (threads > 32) threads = 32; if (threads < 1) threads = 1; }
+  bool ok = false;
+  switch (dtype) {
+    case 0: ok = escape_counts((const float*)counts, rows, cols, ld, per_row, threads); break;
+    case 1: ok = escape_counts((const double*)counts, rows, cols, ld, per_row, threads); break;
+    case 2: ok = escape_counts((const uint16_t*)counts, rows, cols, ld, per_row, threads); break;
+    case 3: ok = escape_counts((const int32_t*)counts, rows, cols, ld, per_row, threads); break;
+    case 4: ok = escape_counts((const int64_t*)counts, rows, cols, ld, per_row, threads); break;
+    default: set_error("dca_count_escapes: unknown dtype %d", dtype); return DCA_ERR_BAD_ARG;
+  }
+  if (!ok) { set_error("dca_count_escapes: counts must be non-negative integers"); return DCA_ERR_BAD_ARG; }
+  return DCA_OK;
+}
+
+// packed: rows x (cols*bits/8) bytes; indptr: int64[rows+1] (exclusive prefix sum of the per-row escape counts of this
+// width, as returned by dca_count_escapes); entries: 8 bytes each, indptr[rows] of them.
+extern "C" int dca_pack_counts(const void* counts, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, int32_t bits,
+                               void* packed, const int64_t* indptr, void* entries, int32_t threads) {
+  if (!counts || !packed || !indptr || rows < 0 || cols < 0 || ld < cols || (indptr[rows] > 0 && !entries)) { set_error("dca_pack_counts: bad argument"); return DCA_ERR_BAD_ARG; }
+  if (bits != 4 && bits != 8 && bits != 16) { set_error("dca_pack_counts: bits must be 4, 8 or 16"); return DCA_ERR_BAD_ARG; }
+  if (cols % 8 != 0) { set_error("dca_pack_counts: the number of genes must be a multiple of 8"); return DCA_ERR_BAD_ARG; }
+  if (threads <= 0) { threads = (int)std::thread::hardware_concurrency(); if (threads > 32) threads = 32; if (threads < 1) threads = 1; }
+  unsigned char* p = (unsigned char*)packed; unsigned char* e = (unsigned char*)entries;
+  switch (dtype) {
+    case 0: pack_rows((const float*)counts, rows, cols, ld, bits, p, indptr, e, threads); break;
+    case 1: pack_rows((const double*)counts, rows, cols, ld, bits, p, indptr, e, threads); break;
+    case 2: pack_rows((const uint16_t*)counts, rows, cols, ld, bits, p, indptr, e, threads); break;
+    case 3: pack_rows((const int32_t*)counts, rows, cols, ld, bits, p, indptr, e, threads); break;
+    case 4: pack_rows((const int64_t*)counts, rows, cols, ld, bits, p, indptr, e, threads); break;
+    default: set_error("dca_pack_counts: unknown dtype %d", dtype); return DCA_ERR_BAD_ARG;
+  }
+  return DCA_OK;
+}

@@ -210,39 +210,52 @@ class PackedCounts:
 OVERFLOW_ENTRY = np.dtype([("gene", "<i4"), ("count", "<f4")])
 
 
-def pack_counts(counts, bits="auto", batch=None):
+_NATIVE_DTYPES = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.uint16): 2, np.dtype(np.int32): 3,
+                  np.dtype(np.int64): 4}
+
+
+def _choose_bits(per_row, n, g, batch):
+    """Smallest total bytes among 4 / 8 / 16 bits whose per-batch overflow fits the device staging capacity.
+    per_row: int64 [3][n] escapes per row at each width."""
+    best = None
+    for w, b in enumerate((4, 8, 16)):
+        pr = per_row[w]
+        if batch:
+            cap = max(4096, batch * g // 32)
+            worst = max(int(pr[i:i + batch].sum()) for i in range(0, max(n, 1), batch)) if n else 0
+            if worst > cap:
+                continue
+        total = n * g * b / 8.0 + 8.0 * float(pr.sum())
+        if best is None or total < best[0]:
+            best = (total, b)
+    if best is None:
+        raise ValueError("no packing width fits the overflow capacity")
+    return best[1]
+
+
+def pack_counts(counts, bits="auto", batch=None, native=True, threads=0):
     """Pack an integer-valued count matrix (cells x genes, any numeric dtype) into `bits` bits per entry.
 
     Counts >= 2**bits - 1 are stored as the escape value 2**bits - 1 and listed (row-sorted) in the overflow
     CSR: indptr int64[n_rows+1], entries {int32 gene, float32 count}.  bits='auto' picks the width in
     (4, 8, 16) with the fewest total bytes whose per-batch overflow (when `batch` is given) stays under
-    batch*genes/32 entries (the device staging capacity)."""
+    batch*genes/32 entries (the device staging capacity).  native=True runs the multi-threaded packer of the
+    library (dca_count_escapes / dca_pack_counts); native=False is the NumPy statement of the same format."""
     C = np.asarray(counts)
     if C.ndim != 2:
         raise ValueError("counts must be a 2-d matrix")
     n, g = C.shape
     if g % 8 != 0:
         raise ValueError("the number of genes must be a multiple of 8 for the packed format (got %d)" % g)
+    if bits != "auto" and bits not in (4, 8, 16):
+        raise ValueError("bits must be 4, 8, 16 or 'auto'")
+    if native and n > 0:
+        return _pack_counts_native(C, bits, batch, threads)
     if C.size and (C.min() < 0 or np.any(C != np.floor(C))):
         raise ValueError("counts must be non-negative integers")
     if bits == "auto":
-        best = None
-        for b in (4, 8, 16):
-            over = C >= (1 << b) - 1
-            per_row = over.sum(1)
-            if batch:
-                cap = max(4096, batch * g // 32)
-                worst = max(int(per_row[i:i + batch].sum()) for i in range(0, max(n, 1), batch)) if n else 0
-                if worst > cap:
-                    continue
-            total = n * g * b / 8.0 + 8.0 * float(per_row.sum())
-            if best is None or total < best[0]:
-                best = (total, b)
-        if best is None:
-            raise ValueError("no packing width fits the overflow capacity")
-        bits = best[1]
-    if bits not in (4, 8, 16):
-        raise ValueError("bits must be 4, 8, 16 or 'auto'")
+        per_row = np.stack([(C >= (1 << b) - 1).sum(1) for b in (4, 8, 16)]).astype(np.int64)
+        bits = _choose_bits(per_row, n, g, batch)
     esc = (1 << bits) - 1
     over = C >= esc
     base = np.where(over, esc, C).astype(np.uint16 if bits == 16 else np.uint8)
@@ -257,6 +270,31 @@ def pack_counts(counts, bits="auto", batch=None):
     entries["gene"] = cols
     entries["count"] = C[rows, cols]
     return PackedCounts(np.ascontiguousarray(packed), bits, g, indptr, entries)
+
+
+def _pack_counts_native(C, bits, batch, threads):
+    from . import _lib
+    lib = _lib.load()
+    if C.dtype not in _NATIVE_DTYPES:
+        C = C.astype(np.float64 if C.dtype.kind == "f" else np.int64)
+    C = np.ascontiguousarray(C)
+    n, g = C.shape
+    dt = _NATIVE_DTYPES[C.dtype]
+    per_row = np.zeros((3, n), dtype=np.int64)
+    st = lib.dca_count_escapes(C.ctypes.data, dt, n, g, g, per_row.ctypes.data, int(threads))
+    if st != 0:
+        msg = lib.dca_last_error().decode("utf-8", "replace")
+        raise ValueError("counts must be non-negative integers" if "non-negative" in msg else msg)
+    if bits == "auto":
+        bits = _choose_bits(per_row, n, g, batch)
+    w = (4, 8, 16).index(bits)
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(per_row[w], out=indptr[1:])
+    packed = np.empty((n, g // 2) if bits == 4 else (n, g), dtype=np.uint16 if bits == 16 else np.uint8)
+    entries = np.empty(int(indptr[-1]), dtype=OVERFLOW_ENTRY)
+    _lib.check(lib.dca_pack_counts(C.ctypes.data, dt, n, g, g, bits, packed.ctypes.data, indptr.ctypes.data,
+                                   entries.ctypes.data if len(entries) else None, int(threads)), "dca_pack_counts")
+    return PackedCounts(packed, bits, g, indptr, entries)
 
 
 def unpack_counts(pc: PackedCounts):

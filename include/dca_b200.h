@@ -290,6 +290,17 @@ int dca_write_text_matrix(const char* path, const void* matrix, int32_t is_float
                           int64_t ld, const char* const* row_names, const char* const* col_names,
                           int32_t transpose, int32_t threads);
 
+/* Host-side packer for dca_stream_begin_packed (multi-threaded counterpart of dca_b200/io.py:pack_counts; no
+ * reference counterpart).  counts: HOST matrix rows x cols (ld elements per row) of dtype 0 float32, 1 float64,
+ * 2 uint16, 3 int32, 4 int64 holding non-negative integers.  dca_count_escapes fills per_row[w*rows + r] with the
+ * number of entries of row r that need the overflow list at width w (0: 4 bits, 1: 8 bits, 2: 16 bits);
+ * dca_pack_counts writes the packed matrix and the overflow entries given indptr = exclusive prefix sum of the
+ * chosen width's per-row counts (int64[rows+1]). */
+int dca_count_escapes(const void* counts, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, int64_t* per_row,
+                      int32_t threads);
+int dca_pack_counts(const void* counts, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, int32_t bits,
+                    void* packed, const int64_t* indptr, void* entries, int32_t threads);
+
 int64_t dca_launch_count(void);
 /* Launch tunables of the loss kernel (process-wide; set them BEFORE the first training step of an engine,
  * a captured step graph keeps the values it was recorded with): "loss_target_blocks",

@@ -215,3 +215,21 @@ def test_packed_counts_batch_bytes():
     assert pc.bytes_for_rows(0, 4) == 4 * 8 + 8 * 5 + 8 * 1          # tile + indptr segment + one overflow entry
     assert pc.bytes_for_rows(4, 8) == 4 * 8 + 8 * 5 + 8 * 1
     assert pc.bytes_for_rows(8, 10) == 2 * 8 + 8 * 3
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.uint16, np.int32, np.int64, np.int16])
+def test_native_count_packer_equals_numpy_statement(dtype):
+    """dca_count_escapes + dca_pack_counts (multi-threaded) == the NumPy statement of the packed format."""
+    from dca_b200 import io
+    rng = np.random.default_rng(3)
+    C = rng.poisson(0.4, (300, 72)).astype(np.int64)
+    C[3, 5] = 300; C[3, 6] = 15; C[10, 63] = 30000; C[299, 0] = 14; C[0, 1] = 255; C[0, 2] = 254; C[7, :] = 20
+    C = C.astype(dtype)
+    for bits in (4, 8, 16, "auto"):
+        a = io.pack_counts(C, bits, batch=64, native=True, threads=3)
+        b = io.pack_counts(C, bits, batch=64, native=False)
+        assert a.bits == b.bits and a.packed.dtype == b.packed.dtype
+        assert np.array_equal(a.packed, b.packed) and np.array_equal(a.indptr, b.indptr) and np.array_equal(a.entries, b.entries)
+        assert np.array_equal(io.unpack_counts(a), C.astype(np.float32))
+    with pytest.raises(ValueError, match="non-negative integers"):
+        io.pack_counts(np.where(C > 0, -1, 0).astype(np.int32) if np.issubdtype(dtype, np.integer) else C + 0.5)
