@@ -233,3 +233,23 @@ def test_native_count_packer_equals_numpy_statement(dtype):
         assert np.array_equal(io.unpack_counts(a), C.astype(np.float32))
     with pytest.raises(ValueError, match="non-negative integers"):
         io.pack_counts(np.where(C > 0, -1, 0).astype(np.int32) if np.issubdtype(dtype, np.integer) else C + 0.5)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the keys of
+    the bench contract; it needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "cells/sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"] and "model" not in line["config"]
