@@ -13,33 +13,15 @@ from .train import train
 from .network import AE_types
 
 
-def dca(adata,
-        mode='denoise',
-        ae_type='nb-conddisp',
-        normalize_per_cell=True,
-        scale=True,
-        log1p=True,
-        hidden_size=(64, 32, 64),  # network args
-        hidden_dropout=0.,
-        batchnorm=True,
-        activation='relu',
-        init='glorot_uniform',
+def dca(adata, mode='denoise', ae_type='nb-conddisp', normalize_per_cell=True, scale=True, log1p=True,
+        # network
+        hidden_size=(64, 32, 64), hidden_dropout=0., batchnorm=True, activation='relu', init='glorot_uniform',
         network_kwds={},
-        epochs=300,               # training args
-        reduce_lr=10,
-        early_stop=15,
-        batch_size=32,
-        optimizer='RMSprop',
-        learning_rate=None,
-        random_state=0,
-        threads=None,
-        verbose=False,
-        training_kwds={},
-        return_model=False,
-        return_info=False,
-        copy=False,
-        check_counts=True,
-        ):
+        # training
+        epochs=300, reduce_lr=10, early_stop=15, batch_size=32, optimizer='RMSprop', learning_rate=None,
+        random_state=0, threads=None, verbose=False, training_kwds={},
+        # outputs
+        return_model=False, return_info=False, copy=False, check_counts=True):
     """Deep count autoencoder (DCA) API -- drop-in for ``dca.api.dca`` (dca/api.py:19-211).
 
     Parameters and return values are those of the reference (see its docstring,
@@ -59,48 +41,26 @@ def dca(adata,
     torch.manual_seed(random_state)
     os.environ['PYTHONHASHSEED'] = '0'
 
-    # this creates adata.raw with raw counts and copies adata if copy==True
-    adata = read_dataset(adata,
-                         transpose=False,
-                         test_split=False,
-                         copy=copy,
-                         check_counts=check_counts)
+    # raw counts go to adata.raw; the input object is copied only when copy=True  (dca/api.py:156-160)
+    adata = read_dataset(adata, transpose=False, test_split=False, copy=copy, check_counts=check_counts)
 
-    # check for zero genes                                                 (dca/api.py:163-164)
+    # all-zero genes are an error, as in the reference                    (dca/api.py:163-164)
     nonzero_genes, _ = filter_genes_mask(adata.X, min_counts=1)
     assert nonzero_genes.all(), 'Please remove all-zero genes before using DCA.'
 
-    adata = normalize(adata,
-                      filter_min_counts=False,  # no filtering, keep cell and gene idxs same
-                      size_factors=normalize_per_cell,
-                      normalize_input=scale,
+    # no filtering here: cell and gene indices stay those of the caller    (dca/api.py:166-170)
+    adata = normalize(adata, filter_min_counts=False, size_factors=normalize_per_cell, normalize_input=scale,
                       logtrans_input=log1p)
 
-    network_kwds = {**network_kwds,
-                    'hidden_size': hidden_size,
-                    'hidden_dropout': hidden_dropout,
-                    'batchnorm': batchnorm,
-                    'activation': activation,
-                    'init': init}
-
-    input_size = output_size = adata.n_vars
-    net = AE_types[ae_type](input_size=input_size,
-                            output_size=output_size,
-                            **network_kwds)
+    net_args = dict(network_kwds, hidden_size=hidden_size, hidden_dropout=hidden_dropout, batchnorm=batchnorm,
+                    activation=activation, init=init)
+    net = AE_types[ae_type](input_size=adata.n_vars, output_size=adata.n_vars, **net_args)
     net.save()
     net.build(max_batch=batch_size, seed=random_state)
 
-    training_kwds = {**training_kwds,
-                     'epochs': epochs,
-                     'reduce_lr': reduce_lr,
-                     'early_stop': early_stop,
-                     'batch_size': batch_size,
-                     'optimizer': optimizer,
-                     'verbose': verbose,
-                     'threads': threads,
-                     'learning_rate': learning_rate}
-
-    hist = train(adata[adata.obs.dca_split == 'train'], net, **training_kwds)
+    fit_args = dict(training_kwds, epochs=epochs, reduce_lr=reduce_lr, early_stop=early_stop, batch_size=batch_size,
+                    optimizer=optimizer, verbose=verbose, threads=threads, learning_rate=learning_rate)
+    hist = train(adata[adata.obs.dca_split == 'train'], net, **fit_args)
     res = net.predict(adata, mode, return_info, copy)
     adata = res if copy else adata
 
