@@ -8,8 +8,11 @@
 A "step" is one training batch of the hot path: forward (Dense stack, BatchNorm, three-head
 output activations), ZINB loss + gradient, backward, gradient all-reduce (N > 1), clip + RMSprop.
 Metric: cells/sec = steps * batch * n_gpus / device time (CUDA events, max over ranks).
-Workload at N = 1: BASELINE.json configs[1] -- synthetic 10k cells x 2k genes, zinb-conddisp,
-hidden 64,32,64; every rank holds its own 10k-cell shard for N > 1 (weak scaling).
+Workload (``--workload auto``): at N = 1 the largest single-GPU configuration of BASELINE.json,
+configs[2] -- synthetic 68k cells x 20k genes (PBMC shape), zinb-conddisp, hidden 64,32,64;
+under torchrun (N > 1) every rank holds one shard of configs[4] (1M x 20k over 8 GPUs = 125k x 20k
+per GPU).  Every step trains 4096 cells per GPU in both cases (weak scaling), so the per-GPU work of
+a step is identical at every N.  Both arms (ours / --impl reference) print the SAME metric string.
 """
 from __future__ import annotations
 
@@ -33,6 +36,11 @@ WORKLOADS = {
     "c5shard": (125000, 20000, "zinb-conddisp", "synthetic 125k cells x 20k genes per GPU (BASELINE configs[4] shard, 1M/8)"),
 }
 HIDDEN = (64, 32, 64)
+# ONE metric string for both arms (the driver divides the two values only when metric / unit / direction agree)
+METRIC = "cells/sec (ZINB AE epoch, device-timed)"
+METRIC_NOTE = ("cells per second through the training step of the ZINB autoencoder epoch loop: forward + ZINB loss + backward "
+               "+ gradient all-reduce (N > 1) + clip/RMSprop, batch 4096 cells per GPU; ours: CUDA events, max over ranks; "
+               "reference arm: host wall clock of the torch-CPU restatement (TensorFlow is not installable in this image)")
 
 
 def parse():
@@ -41,9 +49,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("DCA_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("DCA_BENCH_WORKLOAD", "auto"), choices=["auto"] + sorted(WORKLOADS),
+                    help="auto: c3 (68k x 20k, the largest single-GPU config) at N = 1, c5shard (125k x 20k per GPU) for N > 1")
     ap.add_argument("--batch", type=int, default=4096, help="cells per GPU per step")
-    ap.add_argument("--x-dtype", default="float32", choices=["float32", "bfloat16"])
+    ap.add_argument("--x-dtype", default="auto", choices=["auto", "float32", "bfloat16"],
+                    help="storage type of the normalised input X in HBM; auto = bfloat16 on the tcgen05 path (the GEMM rounds X "
+                         "to bf16 there anyway, so the results are bit-identical to float32 storage) and float32 otherwise")
     ap.add_argument("--gemm-path", default="auto", choices=["auto", "generic", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -145,9 +156,38 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
+_THREADS_CACHE = {}
+
+
+def pick_cpu_threads(net_factory, Xt, Yt, sft, probe_batch=1024):
+    """Thread count of the CPU arm: the fastest of a few candidates, each timed over 3 warmed steps of a reduced
+    batch (per-step cost is linear in the batch), chosen ONCE per process and then kept fixed."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({ncpu, max(1, ncpu // 2), max(1, min(ncpu, 32)), max(1, min(ncpu, 16))}, reverse=True)
+    key = (Xt.shape[1], probe_batch)
+    if key in _THREADS_CACHE:
+        return _THREADS_CACHE[key], cands
+    net = net_factory()
+    b = min(probe_batch, Xt.shape[0])
+    best, threads = None, cands[0]
+    for c in cands:
+        torch.set_num_threads(c)
+        net.train_step(Xt[:b], Yt[:b], sft[:b])                      # warm-up at this thread count
+        t = time.perf_counter()
+        for _ in range(3):
+            net.train_step(Xt[:b], Yt[:b], sft[:b])
+        el = time.perf_counter() - t
+        if best is None or el < best:
+            best, threads = el, c
+    _THREADS_CACHE[key] = threads
+    return threads, cands
+
+
 def cpu_reference_arm(n_genes, ae_type, batch, seconds, steps=None, warmup=1, seed=0):
-    """torch-CPU restatement of the reference training step, all host threads, on a bounded sample:
-    batches of `batch` cells drawn from a min(16384, 4*batch)-row slice of the same synthetic shape."""
+    """torch-CPU restatement of the reference training step on the box's host cores, on a bounded sample:
+    batches of `batch` cells drawn from a min(16384, 4*batch)-row slice of the same synthetic shape.
+    steps=None: run for about `seconds` of CPU work (the cpu_baseline leg of our arm); otherwise exactly
+    `warmup` untimed + `steps` timed steps (the --impl reference arm)."""
     from oracle import dca_oracle as O
     from oracle.torch_ref import TorchRefNet
     from tests.util import synth_counts
@@ -156,38 +196,29 @@ def cpu_reference_arm(n_genes, ae_type, batch, seconds, steps=None, warmup=1, se
     Y = synth_counts(n, n_genes, seed)
     X, sf = O.normalize_inputs(Y)
     p0 = O.init_params(n_genes, n_genes, HIDDEN, ae_type, True, seed=0, dtype=np.float32)
-    net = TorchRefNet(p0, HIDDEN, ae_type, True, dtype=torch.float32)
     Xt, Yt, sft = torch.from_numpy(X), torch.from_numpy(Y), torch.from_numpy(sf)
+    threads, cands = pick_cpu_threads(lambda: TorchRefNet(p0, HIDDEN, ae_type, True, dtype=torch.float32), Xt, Yt, sft)
+    torch.set_num_threads(threads)
+    net = TorchRefNet(p0, HIDDEN, ae_type, True, dtype=torch.float32)
     rng = np.random.default_rng(0)
 
     def one():
         idx = torch.from_numpy(rng.permutation(n)[:batch])
         return net.train_step(Xt[idx], Yt[idx], sft[idx])
 
-    # the reference arm may use every host thread; oversubscribing small ops hurts torch, so probe a few
-    # thread counts (one step each) and keep the fastest -- the strongest CPU baseline we can give it
-    cands = sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 32), min(ncpu, 16)}, reverse=True)
-    best, threads = None, ncpu
-    torch.set_num_threads(ncpu); one()
-    for c in cands:
-        torch.set_num_threads(c)
-        t = time.perf_counter(); one(); el = time.perf_counter() - t
-        if best is None or el < best:
-            best, threads = el, c
-    torch.set_num_threads(threads)
     for _ in range(warmup):
         one()
     t0 = time.perf_counter(); done = 0
     while True:
         one(); done += 1
         el = time.perf_counter() - t0
-        if (steps is not None and done >= steps) or (steps is None and el >= seconds) or el > 20 * seconds:
+        if (steps is not None and done >= steps) or (steps is None and el >= seconds):
             break
     return {"value": done * batch / el, "unit": "cells/sec", "cores": threads, "kind": "port",
-            "sample": "%d steps of batch %d on a %d-cell x %d-gene slice; torch-CPU fp32 restatement of the reference "
-                      "path (TensorFlow unavailable in image); %d of %d host threads (fastest of %s)"
-                      % (done, batch, n, n_genes, threads, ncpu, cands),
-            "ms_per_step": 1e3 * el / done, "steps": done}
+            "sample": "%d timed steps (after %d warm-up) of batch %d on a %d-cell x %d-gene slice; torch-CPU fp32 restatement of "
+                      "the reference path (TensorFlow unavailable in image); %d of %d host threads (fastest of %s over 3 warmed "
+                      "probe steps each, then fixed)" % (done, warmup, batch, n, n_genes, threads, ncpu, cands),
+            "ms_per_step": 1e3 * el / done, "steps": done, "warmup": warmup}
 
 
 def loss_kernel_standalone(eng, X, Y, sf, rows, genes, batch, peak):
@@ -227,8 +258,15 @@ def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.workload == "auto":
+        a.workload = "c3" if world == 1 else "c5shard"
     cells, genes, ae_type, desc = WORKLOADS[a.workload]
     batch = a.batch
+    tc_shape = (a.gemm_path != "generic") and genes % 8 == 0 and HIDDEN[0] == 64 and HIDDEN[-1] == 64
+    if a.x_dtype == "auto":
+        a.x_dtype = "bfloat16" if tc_shape else "float32"
+    # what the arithmetic really is: bf16 operands / fp32 accumulation in the gene-wide GEMMs (tcgen05), fp32 everywhere else
+    dtype_label = "bf16-gemm/f32-acc/f32-loss" if tc_shape else "f32"
     config = {"workload": desc, "ae_type": ae_type, "hidden": list(HIDDEN), "cells_per_gpu": cells, "genes": genes,
               "batch_per_gpu": batch, "global_batch": batch * max(world, 1), "x_dtype": a.x_dtype,
               "optimizer": "RMSprop(lr=1e-3, clipvalue=5)", "batchnorm": "per-rank batch statistics",
@@ -239,9 +277,9 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_arm(genes, ae_type, batch, a.cpu_seconds, steps=a.steps, warmup=min(a.warmup, 2))
-        line = {"impl": "reference", "metric": "cells/sec (ZINB AE train step, host-timed, torch-CPU restatement of the reference)",
-                "value": r["value"], "unit": "cells/sec", "n_gpus": a.gpus, "steps": r["steps"], "warmup": min(a.warmup, 2),
+        r = cpu_reference_arm(genes, ae_type, batch, a.cpu_seconds, steps=a.steps, warmup=a.warmup)
+        line = {"impl": "reference", "metric": METRIC, "metric_note": METRIC_NOTE,
+                "value": r["value"], "unit": "cells/sec", "n_gpus": a.gpus, "steps": r["steps"], "warmup": r["warmup"],
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -336,7 +374,9 @@ def main():
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             tj = json.load(f).get(a.workload)
         if tj and batch == 4096:
-            traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]; traffic_src = tj["source"]
+            traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+            traffic_src = "static: one ncu --set full capture of this kernel at this batch shape, " + tj["source"] + \
+                          " (not re-measured inside this run: ncu cannot run inside the timed process)"
     except Exception:
         pass
     roofline = {"kernel": "zinb_loss_bwd_staged_kernel (phase loss_fwd_bwd: K3 + partial fold)", "bound": "hbm", "achieved": ach,
@@ -432,10 +472,10 @@ def main():
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        line = {"metric": "cells/sec (ZINB AE train step: fwd + ZINB loss + bwd + allreduce + clip/RMSprop, device-timed)",
+        line = {"metric": METRIC, "metric_note": METRIC_NOTE,
                 "value": value, "unit": "cells/sec", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if a.x_dtype == "float32" else "bf16-in/f32", "data": "synthetic (zero fraction %.3f)" % zero_frac,
+                "dtype": dtype_label, "data": "synthetic (zero fraction %.3f)" % zero_frac,
                 "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "phase_ms": phases, "final_loss": final_loss,
                 "impl": "ours"}

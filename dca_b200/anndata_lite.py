@@ -77,6 +77,21 @@ class AnnData:
 
     T = property(transpose)
 
+    # in-place boolean subsetting with anndata's (private but long-stable) method names: what scanpy's filter_* and
+    # normalize_per_cell call on the caller's object
+    def _inplace_subset_obs(self, mask):
+        mask = np.asarray(mask)
+        self.X = self.X[mask]
+        self.obs = self.obs[mask] if mask.dtype == bool else self.obs.iloc[mask]
+        self.obsm = {k: np.asarray(v)[mask] for k, v in self.obsm.items()}
+        if self._raw is not None:
+            self._raw = self._raw[mask]
+
+    def _inplace_subset_var(self, mask):
+        mask = np.asarray(mask)
+        self.X = self.X[:, mask]
+        self.var = self.var[mask] if mask.dtype == bool else self.var.iloc[mask]
+
     def __getitem__(self, idx):
         if isinstance(idx, tuple):
             raise NotImplementedError("anndata_lite supports row subsetting only")

@@ -631,6 +631,7 @@ int Engine::setup_tc() {
   int dev = 0;
   DCA_CUDA_OK(cudaGetDevice(&dev));
   DCA_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (mid_ok && !mid_device_ok()) mid_ok = false;   // grid-barrier kernels need a cooperative launch of <= 64 CTAs: else per-layer path
   if (tc_heads || tc_enc) {
     int major = 0;
     DCA_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));

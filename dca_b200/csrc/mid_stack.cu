@@ -36,11 +36,19 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n, unsigned
       __threadfence();
       atomicAdd(&bar[kGenWord], 1u);
     } else {
-      unsigned cur;
+      // bounded: the kernels are launched cooperatively (co-residency is guaranteed by the driver), so a barrier that
+      // does not open within seconds means a lost participant -- trap (kernel error) instead of hanging the GPU
+      unsigned cur, polls = 0;
+      long long t0 = 0;
       for (;;) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&bar[kGenWord]) : "memory");
         if (cur != gen) break;
         __nanosleep(40);
+        if ((++polls & 0xFFF) == 0) {
+          const long long now = clock64();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 8000000000ll) __trap();
+        }
       }
     }
     __threadfence();
@@ -364,20 +372,48 @@ static int mid_attr() {
   return DCA_OK;
 }
 
+// The grid barrier needs every CTA resident at once: the kernels are launched COOPERATIVELY (the driver then either
+// guarantees co-residency or fails the launch; capturable into CUDA graphs), and mid_device_ok() checks once per
+// device that max-active-blocks x SM count covers the largest grid, so that the engine can fall back to the per-layer
+// kernels (MIG slice, tiny part) instead of failing at launch time.
+bool mid_device_ok() {
+  static thread_local int ok_dev = -1, ok = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  if (ok_dev == dev) return ok != 0;
+  ok_dev = dev; ok = 0;
+  if (mid_attr() != DCA_OK) return false;
+  int coop = 0, sms = 0, nf = 0, nb = 0;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) return false;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nf, mid::mid_forward_kernel, mid::kThreads, mid::kSmemBytes) != cudaSuccess) return false;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mid::mid_backward_kernel, mid::kThreads, mid::kSmemBytes) != cudaSuccess) return false;
+  ok = ((long long)nf * sms >= mid::kMaxCtas && (long long)nb * sms >= mid::kMaxCtas) ? 1 : 0;
+  return ok != 0;
+}
+
+template <class K>
+static int mid_launch(K kernel, mid::Params& p, cudaStream_t s) {
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3((unsigned)p.n_ctas); lc.blockDim = dim3(mid::kThreads); lc.dynamicSmemBytes = mid::kSmemBytes; lc.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  DCA_CUDA_OK(cudaLaunchKernelEx(&lc, kernel, p));
+  count_launch(1);
+  return DCA_OK;
+}
+
 int mid_forward(mid::Params& p, cudaStream_t s) {
   DCA_TRY(mid_fill(p, p.B));
   DCA_TRY(mid_attr());
-  mid::mid_forward_kernel<<<p.n_ctas, mid::kThreads, mid::kSmemBytes, s>>>(p);
-  DCA_LAUNCH_CHECK();
-  return DCA_OK;
+  return mid_launch(mid::mid_forward_kernel, p, s);
 }
 
 int mid_backward(mid::Params& p, cudaStream_t s) {
   DCA_TRY(mid_fill(p, p.B));
   DCA_TRY(mid_attr());
-  mid::mid_backward_kernel<<<p.n_ctas, mid::kThreads, mid::kSmemBytes, s>>>(p);
-  DCA_LAUNCH_CHECK();
-  return DCA_OK;
+  return mid_launch(mid::mid_backward_kernel, p, s);
 }
 
 }  // namespace dca

@@ -33,6 +33,7 @@ struct Params {
 }  // namespace mid
 
 bool mid_supported(const int* widths, int L);
+bool mid_device_ok();   // cooperative launch available and the largest grid fits the device
 size_t mid_partial_doubles();
 int mid_forward(mid::Params& p, cudaStream_t s);
 int mid_backward(mid::Params& p, cudaStream_t s);

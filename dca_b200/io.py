@@ -73,68 +73,64 @@ def filter_genes_mask(X, min_counts=1):
     return counts >= min_counts, counts
 
 
-def _subset(adata, rows=None, cols=None):
-    X = _dense(adata.X)
-    obs, var = adata.obs, adata.var
+def _inplace_subset(adata, rows=None, cols=None):
+    """Boolean-mask subsetting IN PLACE (what scanpy's filter_genes / filter_cells / normalize_per_cell do to the
+    caller's object): anndata.AnnData and the lite stand-in both provide _inplace_subset_var / _inplace_subset_obs."""
     if cols is not None:
-        X = X[:, cols]; var = var[cols]
+        adata._inplace_subset_var(np.asarray(cols))
     if rows is not None:
-        X = X[rows]; obs = obs[rows]
-    return AnnData(X, obs=obs, var=var, uns=dict(getattr(adata, "uns", {})))
+        adata._inplace_subset_obs(np.asarray(rows))
 
 
 def normalize(adata, filter_min_counts=True, size_factors=True, normalize_input=True, logtrans_input=True):
     """dca/io.py:88-111 with scanpy's arithmetic restated:
     filter_genes/filter_cells(min_counts=1); raw copy; normalize_per_cell (each cell scaled to the
     median total count; zero-count cells dropped as scanpy does); size_factors = n_counts/median;
-    log1p (natural); scale (zero mean, unit variance with ddof=1, no clipping)."""
-    if not isinstance(adata, AnnData):
-        # real anndata object: work on a lite copy carrying the same fields, results are written back below
-        lite = AnnData(_dense(adata.X), obs=adata.obs, var=adata.var, uns=dict(adata.uns))
-    else:
-        lite = adata
+    log1p (natural); scale (zero mean, unit variance with ddof=1, no clipping).
 
+    Like the reference, this MUTATES the object it is given -- X, obs['n_counts'], obs['size_factors'], raw and (when
+    filtering) the set of cells / genes -- and returns the same object, for the lite stand-in and for a real
+    anndata.AnnData alike (only attribute assignment and the two in-place subsetting methods are used)."""
     if filter_min_counts:
-        gmask, _ = filter_genes_mask(lite.X, 1)
+        gmask, _ = filter_genes_mask(adata.X, 1)                       # dca/io.py:90-92
         if not gmask.all():
-            lite = _subset(lite, cols=gmask)
-        cmask = np.asarray(lite.X.sum(axis=1)).reshape(-1) >= 1
+            _inplace_subset(adata, cols=gmask)
+        cmask = np.asarray(_dense(adata.X).sum(axis=1)).reshape(-1) >= 1
         if not cmask.all():
-            lite = _subset(lite, rows=cmask)
+            _inplace_subset(adata, rows=cmask)
 
-    if size_factors or normalize_input or logtrans_input:
-        lite.raw = lite.copy()
+    if size_factors or normalize_input or logtrans_input:              # dca/io.py:94-97
+        adata.raw = adata.copy()
     else:
-        lite.raw = lite
+        adata.raw = adata
 
-    if size_factors:
-        n_counts = lite.X.sum(axis=1, dtype=np.float64)
+    X = _dense(adata.X)
+    if size_factors:                                                   # dca/io.py:99-101
+        n_counts = np.asarray(X.sum(axis=1, dtype=np.float64)).reshape(-1)
         keep = n_counts >= 1                         # normalize_per_cell filters cells with < 1 count
         if not keep.all():
-            raw = lite.raw
-            lite = _subset(lite, rows=keep)
-            from .anndata_lite import _Raw
-            lite.raw = _Raw(raw.X[keep], raw.var)
+            _inplace_subset(adata, rows=keep)        # anndata subsets .raw along obs as well
+            X = _dense(adata.X)
             n_counts = n_counts[keep]
         med = np.median(n_counts)
-        lite.obs['n_counts'] = n_counts
-        lite.X = (lite.X / (n_counts / med)[:, None]).astype(np.float32)
-        lite.obs['size_factors'] = (n_counts / med).astype(np.float32)
+        adata.obs['n_counts'] = n_counts
+        X = (X / (n_counts / med)[:, None]).astype(np.float32)
+        adata.obs['size_factors'] = (n_counts / med).astype(np.float32)
     else:
-        lite.obs['size_factors'] = np.float32(1.0)
+        adata.obs['size_factors'] = np.float32(1.0)                    # dca/io.py:102-103
 
-    if logtrans_input:
-        lite.X = np.log1p(lite.X)
+    if logtrans_input:                                                 # dca/io.py:105-106
+        X = np.log1p(X)
 
-    if normalize_input:
-        mean = lite.X.mean(axis=0, dtype=np.float64)
-        var = lite.X.var(axis=0, ddof=1, dtype=np.float64) if lite.n_obs > 1 else np.ones(lite.n_vars)
+    if normalize_input:                                                # dca/io.py:108-109
+        mean = X.mean(axis=0, dtype=np.float64)
+        var = X.var(axis=0, ddof=1, dtype=np.float64) if X.shape[0] > 1 else np.ones(X.shape[1])
         std = np.sqrt(var)
         std[std == 0] = 1.0
-        lite.X = ((lite.X - mean) / std).astype(np.float32)
+        X = ((X - mean) / std).astype(np.float32)
 
-    lite.X = np.ascontiguousarray(lite.X, dtype=np.float32)
-    return lite
+    adata.X = np.ascontiguousarray(X, dtype=np.float32)
+    return adata
 
 
 def read_genelist(filename):

@@ -69,6 +69,26 @@ def test_api_inplace_and_errors():
         dca(_adata(), ae_type='zinb-elempi', epochs=1)
 
 
+def test_api_mutates_a_real_anndata_in_place(monkeypatch):
+    """dca(adata, copy=False) on a (duck-typed) real anndata.AnnData: the results land on the caller's object
+    (dca/io.py:88-111, dca/api.py:166-211), and copy=True returns an object of the caller's class."""
+    from tests.util import install_fake_anndata
+    from dca_b200.api import dca
+    Fake = install_fake_anndata(monkeypatch)
+    Y = synth_counts(200, 64, 5)
+    ad = Fake(Y.copy())
+    out = dca(ad, ae_type='zinb-conddisp', epochs=1, return_info=True, mode='denoise')
+    assert out is None
+    assert not np.allclose(ad.X[:10], Y[:10]) and np.all(np.isfinite(ad.X))
+    np.testing.assert_array_equal(ad.raw.X, Y)
+    assert 'size_factors' in ad.obs.columns and 'dca_split' in ad.obs.columns
+    assert set(ad.obsm) >= {'X_dca_dispersion', 'X_dca_dropout'} and 'dca_loss_history' in ad.uns
+    ad2 = Fake(Y.copy())
+    ret = dca(ad2, ae_type='nb-conddisp', epochs=1, copy=True)
+    assert type(ret) is Fake and ret is not ad2 and 'dca_split' not in ad2.obs.columns
+    np.testing.assert_array_equal(ad2.X, Y)
+
+
 def test_training_reduces_loss_and_early_stop_history():
     from dca_b200.api import dca
     adata = _adata(400, 80, 3)

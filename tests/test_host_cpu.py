@@ -242,7 +242,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--workload", "c2"],
                          capture_output=True, text=True, timeout=300, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
@@ -250,6 +251,40 @@ def test_bench_reference_arm_prints_the_contract_line():
                 "scaling", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "cells/sec" and line["value"] > 0
+    # both arms print ONE shared metric string (the driver only divides values whose metric / unit / direction agree)
+    import re
+    src = open(os.path.join(root, "bench.py")).read()
+    assert len(re.findall(r'"metric": METRIC\b', src)) == 2 and line["metric"] == re.search(r'^METRIC = "(.*)"$', src, re.M).group(1)
+    assert line["warmup"] == 1 and line["steps"] == 1
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_normalize_mutates_a_real_anndata_in_place(monkeypatch):
+    """dca/io.py:88-111 works on the caller's object (scanpy's pp functions are in-place): X, obs, raw and the
+    filtered cell / gene sets must land on the SAME object, for a real anndata.AnnData as for the lite stand-in."""
+    from tests.util import install_fake_anndata
+    from dca_b200 import io
+    from dca_b200.anndata_lite import AnnData, is_anndata
+    Fake = install_fake_anndata(monkeypatch)
+    Y = synth_counts(50, 20, 3)
+    Y[7] = 0                                        # a zero-count cell: normalize_per_cell drops it
+    Y[:, 5] = 0                                     # an all-zero gene: filter_genes drops it (filter_min_counts=True)
+    for cls in (Fake, AnnData):
+        ad = cls(Y.copy())
+        assert is_anndata(ad)
+        same = io.read_dataset(ad, check_counts=True)
+        assert same is ad
+        out = io.normalize(ad, filter_min_counts=True)
+        assert out is ad                                             # mutated in place, like the reference
+        assert ad.X.shape == (49, 19) and ad.raw.X.shape == (49, 19)
+        keep_r = np.arange(50) != 7; keep_c = np.arange(20) != 5
+        np.testing.assert_array_equal(ad.raw.X, Y[keep_r][:, keep_c])
+        X, sf = O.normalize_inputs(Y[keep_r][:, keep_c])
+        np.testing.assert_allclose(ad.X, X, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(np.asarray(ad.obs["size_factors"]), sf, rtol=1e-6)
+        assert "n_counts" in ad.obs.columns and len(ad.obs) == 49 and len(ad.var) == 19
+        # without filtering the zero-count cell is still dropped by normalize_per_cell, on the same object
+        ad2 = cls(Y[:, keep_c].copy())
+        assert io.normalize(ad2, filter_min_counts=False) is ad2 and ad2.X.shape == (49, 19) and ad2.raw.X.shape == (49, 19)
