@@ -61,6 +61,11 @@ PROTOTYPES = {
     "dca_train_step": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
     "dca_train_step_phase": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp]),
     "dca_grad_buckets": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "dca_comm_unique_id": (C.c_int, [_vp]),
+    "dca_comm_init": (C.c_int, [_vp, _vp, _i32, _i32]),
+    "dca_comm_destroy": (C.c_int, [_vp]),
+    "dca_allreduce": (C.c_int, [_vp, _vp]),
+    "dca_train_step_dp": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
     "dca_apply_update": (C.c_int, [_vp, _f, _f, _f, _vp]),
     "dca_eval_step": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
     "dca_predict": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),

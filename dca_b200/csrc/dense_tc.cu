@@ -300,6 +300,7 @@ int heads_fwd_tc(const __nv_bfloat16* Hb, int B, const __nv_bfloat16* const W[3]
 }  // namespace tc
 
 Engine::~Engine() {
+  comm_destroy();
   for (auto e : prof.ev) cudaEventDestroy(e);
   for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (hs.copy) cudaStreamDestroy(hs.copy);

@@ -375,12 +375,12 @@ int Engine::penalty(cudaStream_t s, bool& any) {
 // ------------------------------------------------------------------------------------ train step
 int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows,
                        int Bn, cudaStream_t s, int phase) {
-  if (phase < 0 || phase > 2) { set_error("dca_train_step: phase must be 0, 1 or 2"); return DCA_ERR_BAD_ARG; }
+  if (phase < 0 || phase > 3) { set_error("dca_train_step: phase must be 0, 1, 2 or 3"); return DCA_ERR_BAD_ARG; }
   if (!X || !Y) { set_error("dca_train_step: X and Y must not be NULL"); return DCA_ERR_BAD_ARG; }
   if (Bn <= 0 || Bn > cfg.max_batch) { set_error("dca_train_step: batch %d outside (0, max_batch=%d]", Bn, cfg.max_batch); return DCA_ERR_BAD_ARG; }
   // the legacy default stream (handle 0) cannot be captured: stay on the direct path there
   if (!graphs_enabled || prof.on || s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread)
-    return train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, phase);
+    return phase == 3 ? train_step_dp_body(X, ldx, Y, ldy, sf, rows, Bn, s) : train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, phase);
   // ---- CUDA-graph replay: the launch sequence only depends on (pointers, leading dims, batch); the batch's row
   // indices are copied into a fixed buffer so that the captured kernels read them from a stable address.
   StepGraph* g = nullptr;
@@ -396,7 +396,8 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
     // capture on the second call with this key (the first, direct call has done every one-time initialisation)
     const long long l0 = g_launches.load();
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      const int st = train_step_body(X, ldx, Y, ldy, sf, rows ? rbuf : nullptr, Bn, s, phase);
+      const int st = phase == 3 ? train_step_dp_body(X, ldx, Y, ldy, sf, rows ? rbuf : nullptr, Bn, s)
+                                : train_step_body(X, ldx, Y, ldy, sf, rows ? rbuf : nullptr, Bn, s, phase);
       cudaGraph_t graph = nullptr;
       const cudaError_t ce = cudaStreamEndCapture(s, &graph);
       if (st == DCA_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
@@ -422,7 +423,7 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
     return DCA_OK;
   }
   if (g->seen < 1000) ++g->seen;
-  return train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, phase);
+  return phase == 3 ? train_step_dp_body(X, ldx, Y, ldy, sf, rows, Bn, s) : train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, phase);
 }
 
 // phase 0: whole step; 1: forward + loss + head backward (the head gradients -- 98 % of the parameters -- are then
@@ -669,7 +670,6 @@ int Engine::init_params(uint64_t seed, cudaStream_t s) {
 // ==================================================================================== C ABI
 using namespace dca;
 
-struct dca_handle { Engine e; void* owned = nullptr; int device = 0; };
 
 extern "C" int dca_version(void) { return DCA_B200_VERSION; }
 extern "C" const char* dca_last_error(void) { return g_err; }

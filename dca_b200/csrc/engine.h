@@ -87,6 +87,15 @@ struct Engine {
   const __nv_bfloat16* cur_xb = nullptr; int64_t cur_ldxb = 0;   // bf16 batch input of the current step
   __nv_bfloat16* bf(size_t byte_off) const { return reinterpret_cast<__nv_bfloat16*>(base + byte_off); }
 
+  // data-parallel gradient exchange (comm.cu): NCCL communicator owned by the engine, resolved with dlopen
+  void* comm = nullptr; int comm_world = 1, comm_rank = 0;
+  cudaStream_t comm_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int comm_init(const void* id128, int rank, int world);
+  int comm_destroy();
+  int allreduce_range(int64_t lo, int64_t hi, cudaStream_t s);
+  int train_step_dp_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
+                         cudaStream_t s);
+
   ~Engine();
   int plan(const dca_config& c);
   void bind(void* base_);
@@ -118,3 +127,6 @@ struct Engine {
 };
 
 }  // namespace dca
+
+// the opaque handle of the C ABI (include/dca_b200.h)
+struct dca_handle { dca::Engine e; void* owned = nullptr; int device = 0; };

@@ -23,8 +23,9 @@ constexpr int kColsPerBlock = kThreads * kVec;   // 1024 genes per block
 constexpr int kMaxBlocks = 65536;                // bound of the per-block loss-partial buffer
 
 // Launch tunables (dca_set_tunable; defaults chosen from the sweep in profiles/r1_loss_sweep.log)
-struct LossTune { int target_blocks; unsigned producer_sleep_ns, consumer_sleep_ns; int branch_free; };
-LossTune g_tune = {0 /* auto */, 0u, 0u, 1 /* branch-free zero branch: -7 % at 4096 x 20000, profiles/r1_loss_sweep2.log */};
+struct LossTune { int target_blocks; unsigned producer_sleep_ns, consumer_sleep_ns; int branch_free; int ring; };
+LossTune g_tune = {0 /* auto */, 0u, 0u, 1 /* branch-free zero branch: -7 % at 4096 x 20000, profiles/r1_loss_sweep2.log */,
+                   1 /* per-warp rings + f32x2 arithmetic (zinb_loss_bwd_ring_kernel); 0 = block-wide ring (staged kernel) */};
 
 int sm_count_cached() {
   static int n = 0;
@@ -490,6 +491,231 @@ zinb_loss_bwd_staged_kernel(const float* __restrict__ Y, int64_t ldy, const int3
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// "Ring" kernel (default for ZINB backward on aligned shapes): operands are staged through shared memory by the
+// threads themselves -- every thread streams the 16 bytes it owns of each tensor row (4 consecutive genes of y, m,
+// [d], pi) with cp.async (LDGSTS, L2-only) into a kRing-deep ring of its own, kRing rows ahead of the arithmetic,
+// and reads them back with one 128-bit LDS per tensor.  A thread only ever reads what it copied itself, so the
+// pipeline needs no barrier of any kind (cp.async.wait_group orders a thread's own copies), no producer warp and
+// no single-lane issue path: in the block-wide bulk-copy ring of zinb_loss_bwd_staged_kernel a warp could run at
+// most three rows ahead of the slowest warp of its block (the one that met a large count and took the Stirling
+// path), and a fifth of all issued instructions were mbarrier polls of warps waiting for a slot their neighbour
+// had not released (profiles/r1_ncu_k3_v5_c3: 3-instruction loops executed 9-13x per row).  The gather of the count
+// rows costs one address computation (rows[] cached in shared memory).  The arithmetic runs on f32x2 pairs
+// (zinb_math.cuh: zinb_zero_pair / finish_factors_pair), the queued non-zero counts return raw derivatives only
+// (zinb_nb_raw) and the activation chain / clip masks / 1/N are applied once per element by its owner.
+constexpr int kRing = 3;                                  // rows in flight per thread
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool COND_DISP, typename GT>
+__global__ void __launch_bounds__(kThreads, 3)
+zinb_loss_bwd_ring_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __restrict__ rows,
+                          const float* __restrict__ sf, const float* m, const float* d, const float* pi,
+                          int64_t ld, int B, int G, float ridge, float inv_n, int rows_per_block,
+                          GT* dzm, GT* dzd, GT* dzp, float* __restrict__ dth_acc,
+                          double* __restrict__ loss_partial, const float* __restrict__ lf_global, const FoldArgs fa) {
+  extern __shared__ __align__(128) unsigned char smem_ring[];
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kArrays = COND_DISP ? 4 : 3;                           // y, m, [d], pi
+  constexpr uint32_t kSegBytes = kThreads * 16;                        // one block-row segment of one tensor (4 KB)
+  constexpr uint32_t kSlotBytes = kArrays * kSegBytes;
+  float4* items = reinterpret_cast<float4*>(smem_ring + kRing * kSlotBytes);           // [8 warps][128]
+  __shared__ double red[kWarps];
+  __shared__ float lf[zmath::kLogFactN];
+  __shared__ float s_sf[kMaxRowsPerBlock];
+  __shared__ int s_row[kMaxRowsPerBlock];
+  __shared__ int s_last;
+
+  using Ops = zmath::FastOps;
+  using namespace zmath;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * kColsPerBlock;
+  const bool active = c0 + (int)threadIdx.x * kVec < G;                // G % 4 == 0 on this path
+  // threads past the last gene (only in the last column block) work on a DUPLICATE of the last valid vector: they copy,
+  // load and compute like everyone else (no divergence, nothing uninitialised) and only their results are dropped
+  const int col = active ? (int)threadIdx.x * kVec : (G - c0 - kVec);
+  const int r0 = blockIdx.y * rows_per_block;
+  const int nrows = min(rows_per_block, B - r0);
+  if (threadIdx.x < kLogFactN) lf[threadIdx.x] = lf_global[threadIdx.x];
+  for (int t = threadIdx.x; t < nrows; t += kThreads) {
+    const int yr = rows ? rows[r0 + t] : (r0 + t);
+    s_row[t] = yr;
+    s_sf[t] = sf ? sf[yr] : 1.0f;
+  }
+  __syncthreads();
+
+  const uint32_t my = tc::smem_u32(smem_ring) + threadIdx.x * 16;      // my 16 bytes inside every segment
+  const uint32_t ring_end = my + kRing * kSlotBytes;
+  const float* ysrc = Y + c0 + col;
+  const float* msrc = m + (int64_t)r0 * ld + c0 + col;
+  const float* dsrc = COND_DISP ? d + (int64_t)r0 * ld + c0 + col : nullptr;
+  const float* psrc = pi + (int64_t)r0 * ld + c0 + col;
+  const uint32_t ldy32 = (uint32_t)ldy;                                // leading dimensions are < 2^32 elements
+  // copy cursor: the row that is streamed next, its slot and the advancing source pointers (no per-row 64-bit multiplies)
+  int nxt = 0;
+  uint32_t wslot = my;
+  auto cp16 = [](uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  };
+  auto issue_next = [&]() {                                            // stream row `nxt` of my 4 genes into the next slot
+    cp16(wslot, ysrc + (uint64_t)((uint32_t)s_row[nxt]) * ldy32);
+    cp16(wslot + kSegBytes, msrc);
+    if (COND_DISP) cp16(wslot + 2 * kSegBytes, dsrc);
+    cp16(wslot + (kArrays - 1) * kSegBytes, psrc);
+    msrc += ld; psrc += ld;
+    if (COND_DISP) dsrc += ld;
+    ++nxt; wslot += kSlotBytes;
+    if (wslot == ring_end) wslot = my;
+  };
+
+  float lsum_lg = 0.f, lsum_nb = 0.f, lsum_r = 0.f;      // sum of lg2(D) over my zero counts | NLL of the items I evaluated | ridge
+  float tacc[kVec] = {0.f, 0.f, 0.f, 0.f};
+  {
+#pragma unroll
+    for (int i = 0; i < kRing; ++i) {                                  // one group per row, empty groups keep the count fixed
+      if (i < nrows) issue_next();
+      cp_async_commit();
+    }
+    float4* q = items + warp * (32 * kVec);
+    float thg[kVec] = {1.f, 1.f, 1.f, 1.f};
+    if (!COND_DISP) {
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) thg[j] = d[c0 + col + j];
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    GT* om = dzm + (int64_t)r0 * ld + c0 + col;
+    GT* od = COND_DISP ? dzd + (int64_t)r0 * ld + c0 + col : nullptr;
+    GT* op = dzp + (int64_t)r0 * ld + c0 + col;
+    uint32_t rslot = my;
+    auto lds128 = [](uint32_t addr) {
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+      return v;
+    };
+    for (int i = 0; i < nrows; ++i) {
+      cp_async_wait<kRing - 1>();                                      // my copies of row i have landed
+      const float4 vy = lds128(rslot), vm = lds128(rslot + kSegBytes);
+      const float4 vd = COND_DISP ? lds128(rslot + 2 * kSegBytes) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 vp = lds128(rslot + (kArrays - 1) * kSegBytes);
+      rslot += kSlotBytes;
+      if (rslot == ring_end) rslot = my;
+      const float row_sf = s_sf[i];
+      const float y[kVec] = {vy.x, vy.y, vy.z, vy.w};
+      const float2 mA = make_float2(vm.x, vm.y), mB = make_float2(vm.z, vm.w);
+      const float2 dA = COND_DISP ? make_float2(vd.x, vd.y) : make_float2(thg[0], thg[1]);
+      const float2 dB = COND_DISP ? make_float2(vd.z, vd.w) : make_float2(thg[2], thg[3]);
+      const float2 pA = make_float2(vp.x, vp.y), pB = make_float2(vp.z, vp.w);
+      const float2 muA = mul2(mA, splat(row_sf)), muB = mul2(mB, splat(row_sf));        // dca/layers.py:85
+      const float mu[kVec] = {muA.x, muA.y, muB.x, muB.y};
+      const float dd[kVec] = {dA.x, dA.y, dB.x, dB.y};
+      const float pp[kVec] = {pA.x, pA.y, pB.x, pB.y};
+      // ---- queue the non-zero counts of this warp's strip (ballot compaction: items ordered by j, then lane)
+      bool isnz[kVec];
+      int pos[kVec], base = 0;
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) {
+        isnz[j] = active && !(y[j] < 1e-8f);                           // loss.py:138
+        const unsigned bal = __ballot_sync(kFull, isnz[j]);
+        pos[j] = base + __popc(bal & lt); base += __popc(bal);
+      }
+      const int total = base;
+#pragma unroll
+      for (int j = 0; j < kVec; ++j)
+        if (isnz[j]) q[pos[j]] = make_float4(y[j], mu[j], dd[j], pp[j]);
+      __syncwarp();
+      // the operands of row i have been consumed (they fed the ballots / the queue): refill my slot with row i + kRing
+      if (nxt < nrows) issue_next();
+      cp_async_commit();
+      // ---- zero branch of my four elements, two f32x2 chains
+      Raw2 zA = zinb_zero_pair<Ops>(muA, dA, pA), zB = zinb_zero_pair<Ops>(muB, dB, pB);
+      const Fin2 fA = finish_factors_pair<Ops, COND_DISP>(mA, dA, pA, inv_n), fB = finish_factors_pair<Ops, COND_DISP>(mB, dB, pB, inv_n);
+      lsum_lg += ((active && !isnz[0]) ? zA.lgD.x : 0.f) + ((active && !isnz[1]) ? zA.lgD.y : 0.f)
+               + ((active && !isnz[2]) ? zB.lgD.x : 0.f) + ((active && !isnz[3]) ? zB.lgD.y : 0.f);
+      // ---- dense NB pass over the queue (item k by lane k mod 32): raw derivatives back into the queue
+      for (int k = lane; k < total; k += 32) {
+        const float4 it = q[k];
+        const Raw1 e = zinb_nb_raw<Ops>(it.x, it.y, it.z, it.w, lf);
+        lsum_nb += e.loss;
+        q[k] = make_float4(e.gmu, e.dth, e.dpi, 0.f);
+      }
+      __syncwarp();
+      if (isnz[0]) { const float4 e = q[pos[0]]; zA.gmu.x = e.x; zA.dth.x = e.y; zA.dpi.x = e.z; }
+      if (isnz[1]) { const float4 e = q[pos[1]]; zA.gmu.y = e.x; zA.dth.y = e.y; zA.dpi.y = e.z; }
+      if (isnz[2]) { const float4 e = q[pos[2]]; zB.gmu.x = e.x; zB.dth.x = e.y; zB.dpi.x = e.z; }
+      if (isnz[3]) { const float4 e = q[pos[3]]; zB.gmu.y = e.x; zB.dth.y = e.y; zB.dpi.y = e.z; }
+      __syncwarp();
+      if (ridge != 0.f) {                                              // loss.py:139-140 (uniform; ridge defaults to 0)
+        if (active) lsum_r += ridge * (pA.x * pA.x + pA.y * pA.y + pB.x * pB.x + pB.y * pB.y);
+        zA.dpi = fma2(splat(2.0f * ridge), pA, zA.dpi); zB.dpi = fma2(splat(2.0f * ridge), pB, zB.dpi);
+      }
+      if (active) {
+        if (!COND_DISP) { tacc[0] += zA.dth.x; tacc[1] += zA.dth.y; tacc[2] += zB.dth.x; tacc[3] += zB.dth.y; }
+        const float2 gmA = mul2(zA.gmu, fA.fm), gmB = mul2(zB.gmu, fB.fm);
+        const float2 gpA = mul2(zA.dpi, fA.fp), gpB = mul2(zB.dpi, fB.fp);
+        st4(om, gmA.x, gmA.y, gmB.x, gmB.y);
+        if (COND_DISP) {
+          const float2 gdA = mul2(zA.dth, fA.fd), gdB = mul2(zB.dth, fB.fd);
+          st4(od, gdA.x, gdA.y, gdB.x, gdB.y);
+        }
+        st4(op, gpA.x, gpA.y, gpB.x, gpB.y);
+      }
+      om += ld; op += ld;
+      if (COND_DISP) od += ld;
+    }
+    if (!COND_DISP && active) {
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) atomicAdd(dth_acc + c0 + col + j, tacc[j]);
+    }
+  }
+  // ---- block reduction, then the last block to finish folds the per-block partials in a FIXED order
+  double dsum = (double)lsum_nb + (double)lsum_r - (double)kLn2 * (double)lsum_lg;       // -log D = -ln2 * lg2 D
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(kFull, dsum, o);
+  if (lane == 0) red[warp] = dsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += red[w];
+    loss_partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+    __threadfence();
+    const unsigned nblk = gridDim.x * gridDim.y;
+    const unsigned done = atomicAdd(fa.counter, 1u);
+    s_last = (done == nblk - 1);
+    if (s_last) *fa.counter = 0;                                       // self-resetting
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int n = gridDim.x * gridDim.y;
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += kThreads) a += __ldcg(loss_partial + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFull, a, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += red[w];
+    *fa.loss_sum = t;
+    if (fa.loss_slot) {
+      double l = t * (double)inv_n;
+      if (l != l) l = INFINITY;                                        // _nan2inf, dca/loss.py:148
+      if (fa.penalty) l += *fa.penalty;
+      const float lf32 = (float)l;
+      fa.loss_slot[0] = lf32;
+      fa.loss_slot[1] = (isfinite(lf32)) ? 0.f : 1.f;
+      if (fa.epoch_acc) { fa.epoch_acc[0] += l * (double)fa.batch; fa.epoch_acc[1] += (double)fa.batch; }
+    }
+  }
+}
+
 __global__ void fold_partials_kernel(const double* __restrict__ part, int n, double* out, int accumulate,
                                      const double* penalty, float inv_n, int batch, float* loss_slot, double* epoch_acc) {
   __shared__ double sm[32];
@@ -571,6 +797,21 @@ int launch(const LossArgs& a, cudaStream_t s) {
     FoldArgs fa{reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.ws) + sizeof(double) * (size_t)kMaxBlocks), a.loss_sum,
                 a.fin_penalty, a.fin_loss_slot, a.fin_epoch_acc, a.fin_batch};
     if (!a.counter_ready) DCA_CUDA_OK(cudaMemsetAsync(fa.counter, 0, sizeof(unsigned), s));
+#define DCA_RING(CD, GT)                                                                                          \
+  do {                                                                                                             \
+    constexpr size_t sm = (size_t)kRing * (CD ? 4 : 3) * kColsPerBlock * 4 + (size_t)(kThreads / 32) * 32 * kVec * 16; \
+    static bool attr = false;                                                                                      \
+    if (!attr) { DCA_CUDA_OK(cudaFuncSetAttribute(zinb_loss_bwd_ring_kernel<CD, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr = true; } \
+    zinb_loss_bwd_ring_kernel<CD, GT><<<grid, kThreads, sm, s>>>(a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, a.G, a.ridge, \
+        a.inv_n, ps.rows_per_block, (GT*)a.dzm, (GT*)a.dzd, (GT*)a.dzp, tpart, lpart, lf_dev, fa);                  \
+  } while (0)
+    if (g_tune.ring) {
+      if (a.grad_bf16) { if (cond) DCA_RING(true, __nv_bfloat16); else DCA_RING(false, __nv_bfloat16); }
+      else             { if (cond) DCA_RING(true, float); else DCA_RING(false, float); }
+      DCA_LAUNCH_CHECK();
+      return DCA_OK;                                                    // the fold is done by the last block
+    }
+#undef DCA_RING
 #define DCA_STAGED2(CD, GT, BFV)                                                                                   \
   do {                                                                                                             \
     constexpr size_t sm = (size_t)kStageRows * (CD ? 4 : 3) * kColsPerBlock * 4 + (size_t)(kThreads / 32) * 32 * kVec * 16; \
@@ -648,6 +889,7 @@ extern "C" int dca_set_tunable(const char* name, int64_t value) {
   else if (n == "loss_consumer_sleep_ns" && value >= 0 && value <= 100000) g_tune.consumer_sleep_ns = (unsigned)value;
   else if (n == "fused_heads" && (value == 0 || value == 1)) g_fused_heads_default = (int)value;
   else if (n == "loss_branch_free" && (value == 0 || value == 1)) g_tune.branch_free = (int)value;
+  else if (n == "loss_ring" && (value == 0 || value == 1)) g_tune.ring = (int)value;
   else { set_error("dca_set_tunable: unknown name or value out of range (%s = %lld)", name, (long long)value); return DCA_ERR_BAD_ARG; }
   return DCA_OK;
 }
@@ -688,6 +930,25 @@ extern "C" int dca_zinb_elem_host(int32_t ae_type, float y, float m, float sf, f
   static bool lf_ready = false;
   if (!lf_ready) { zmath::fill_log_fact(lf); lf_ready = true; }
   using P = zmath::PreciseOps;
+  if (ae_type & 0x200) {
+    // the formulation of zinb_loss_bwd_ring_kernel: f32x2 zero branch / raw NB derivatives + shared finishing factors
+    const int base = ae_type & 0xff;
+    if (base != DCA_AE_ZINB_CONDDISP && base != DCA_AE_ZINB) { set_error("dca_zinb_elem_host: kernel variant needs a ZINB type"); return DCA_ERR_BAD_ARG; }
+    const bool cd = base == DCA_AE_ZINB_CONDDISP;
+    const float2 m2 = zmath::splat(m), d2 = zmath::splat(d), p2 = zmath::splat(pi), mu2 = zmath::mul2(m2, zmath::splat(sf));
+    const zmath::Fin2 f = cd ? zmath::finish_factors_pair<P, true>(m2, d2, p2, 1.0f) : zmath::finish_factors_pair<P, false>(m2, d2, p2, 1.0f);
+    float loss, gmu, dth, dpi;
+    if (y < 1e-8f) {
+      const zmath::Raw2 z = zmath::zinb_zero_pair<P>(mu2, d2, p2);
+      loss = -zmath::kLn2 * z.lgD.y; gmu = z.gmu.y; dth = z.dth.y; dpi = z.dpi.y;
+    } else {
+      const zmath::Raw1 r = zmath::zinb_nb_raw<P>(y, mu2.x, d, pi, lf);
+      loss = r.loss; gmu = r.gmu; dth = r.dth; dpi = r.dpi;
+    }
+    if (ridge != 0.f) { loss += ridge * pi * pi; dpi = fmaf(2.0f * ridge, pi, dpi); }
+    out[0] = loss; out[1] = gmu * f.fm.y; out[2] = dth * f.fd.y; out[3] = dpi * f.fp.y;
+    return DCA_OK;
+  }
   if (ae_type & 0x100) {
     // the formulations the staged / fused kernels run: branch-free zero branch, NB branch evaluated from mu by a
     // different lane than the element's owner (which then applies the MeanAct clip mask)

@@ -285,6 +285,139 @@ DCA_HD Elem zinb_elem_nb_mu(float y, float mu, float th, float pi, float ridge, 
   return o;
 }
 
+// ------------------------------------------------------------------------------------ packed (f32x2) formulation
+// sm_100 executes fma / mul / add on PAIRS of fp32 values in one instruction (fma.rn.f32x2 -> FFMA2): the element-wise
+// chains below are written over float2 so that two genes of a thread share every FMA-pipe instruction; MUFU, min/max
+// and selects stay scalar.  The host build evaluates the same expressions component-wise (fmaf), so the formulas
+// are unit-tested without a GPU (dca_zinb_elem_host, variant 0x200).
+#if defined(__CUDA_ARCH__)
+DCA_HD float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+DCA_HD float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+DCA_HD float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+#else
+DCA_HD float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+DCA_HD float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+DCA_HD float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+#endif
+DCA_HD float2 splat(float v) { return make_float2(v, v); }
+DCA_HD float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+
+// Raw (un-chained, un-scaled) derivatives of one element: what the two branches of loss.py:138 hand to the shared
+// finishing step  dzm = gmu * [m-clip mask] / N,  dzd = dth * sigmoid(zd) * [d-clip mask] / N,  dzp = dpi * pi (1-pi) / N.
+struct Raw2 { float2 lgD, gmu, dth, dpi; };
+
+// zero branch (y < 1e-8) of two ZINB elements: loss = -ln2 * lgD,  gmu = dL/dmu * mu,  dth = dL/dtheta,  dpi = dL/dpi
+// (branch-free; same arithmetic as zinb_elem_zero_bf).  mu = m * sf is computed by the caller (the NB items need it too).
+template <class Ops>
+DCA_HD Raw2 zinb_zero_pair(float2 mu, float2 th_in, float2 pi) {
+  const float2 th = make_float2(fminf(th_in.x, 1e6f), fminf(th_in.y, 1e6f));          // loss.py:85,134
+  const float2 te = add2(th, splat(kEps));
+  const float2 den = add2(te, mu);
+  const float2 rden = make_float2(Ops::rcp(den.x), Ops::rcp(den.y));
+  const float2 q = mul2(mu, rden);
+  float2 p = fma2(q, splat(0.125f), splat(0.142857143f));
+  p = fma2(q, p, splat(0.166666667f)); p = fma2(q, p, splat(0.2f)); p = fma2(q, p, splat(0.25f));
+  p = fma2(q, p, splat(0.333333333f)); p = fma2(q, p, splat(0.5f));
+  const float2 f_ser = mul2(mul2(q, q), p), L1_ser = add2(q, f_ser);
+  const float2 r = mul2(te, rden);
+  const float2 lg = make_float2(Ops::lg2(r.x), Ops::lg2(r.y));
+  const float2 L1_log = mul2(lg, splat(-kLn2)), f_log = fma2(lg, splat(-kLn2), neg2(q));
+  const bool s0 = q.x < 0.0625f, s1 = q.y < 0.0625f;
+  const float2 L1 = make_float2(s0 ? L1_ser.x : L1_log.x, s1 ? L1_ser.y : L1_log.y);
+  const float2 f = make_float2(s0 ? f_ser.x : f_log.x, s1 ? f_ser.y : f_log.y);
+  const float2 e = mul2(mul2(th, splat(-kLog2e)), L1);
+  const float2 z = make_float2(Ops::ex2(e.x), Ops::ex2(e.y));                           // loss.py:136
+  const float2 omp = fma2(pi, splat(-1.0f), splat(1.0f));
+  const float2 D = add2(fma2(omp, z, pi), splat(kEps));                                // loss.py:137
+  const float2 rD = make_float2(Ops::rcp(D.x), Ops::rcp(D.y));
+  Raw2 o;
+  o.lgD = make_float2(Ops::lg2(D.x), Ops::lg2(D.y));
+  const float2 w = mul2(mul2(omp, z), rD);
+  o.gmu = mul2(mul2(w, th), q);
+  o.dth = mul2(w, f);
+  o.dpi = mul2(add2(z, splat(-1.0f)), rD);
+  return o;
+}
+
+// Finishing factors of two elements (chain rule through MeanAct / DispAct / sigmoid, clip masks, 1/N):
+//   dzm = gmu * fm,  dzd = dth * fd,  dzp = dpi * fp
+struct Fin2 { float2 fm, fd, fp; };
+template <class Ops, bool COND_DISP>
+DCA_HD Fin2 finish_factors_pair(float2 m, float2 th_in, float2 pi, float inv_n) {
+  Fin2 o;
+  o.fm = make_float2(((m.x > 1e-5f) && (m.x < 1e6f)) ? inv_n : 0.f,                     // network.py:38 clip mask
+                     ((m.y > 1e-5f) && (m.y < 1e6f)) ? inv_n : 0.f);
+  if (COND_DISP) {                                                                     // 1 - exp(-d) = sigmoid(zd)
+    float2 pp = fma2(th_in, splat(0.0416666667f), splat(-0.166666667f));
+    pp = fma2(th_in, pp, splat(0.5f));
+    const float2 ser = fma2(neg2(mul2(th_in, th_in)), pp, th_in);
+    const float2 a = mul2(th_in, splat(-kLog2e));
+    const float2 ex = fma2(make_float2(Ops::ex2(a.x), Ops::ex2(a.y)), splat(-1.0f), splat(1.0f));
+    const float2 ome = make_float2(th_in.x < 0.03125f ? ser.x : ex.x, th_in.y < 0.03125f ? ser.y : ex.y);
+    const float2 sc = mul2(ome, splat(inv_n));
+    o.fd = make_float2(((th_in.x > 1e-4f) && (th_in.x < 1e4f)) ? sc.x : 0.f,           // network.py:39 clip mask
+                       ((th_in.y > 1e-4f) && (th_in.y < 1e4f)) ? sc.y : 0.f);
+  } else {
+    o.fd = splat(1.0f);                                   // raw dL/dtheta: summed per gene, chained by theta_grad_finish
+  }
+  const float2 omp = fma2(pi, splat(-1.0f), splat(1.0f));
+  o.fp = mul2(mul2(pi, omp), splat(inv_n));
+  return o;
+}
+
+// One group of up to four factors of the rising product prod_{k<n}(x+k), starting at x0 = x + k0 with nrem = n - k0 >= 1
+// factors left: accumulates lg2 of the group product and the sum of reciprocals, WITHOUT control flow (absent factors
+// are replaced by 1; d/dx of the product by the product rule):  sum 1/t = P'/P.
+template <class Ops>
+DCA_HD void rising_group_masked(float x0, float nrem, float& lg2acc, float& rs) {
+  const bool h1 = nrem > 1.5f, h2 = nrem > 2.5f, h3 = nrem > 3.5f;
+  const float f1 = h1 ? x0 + 1.0f : 1.0f, f2 = h2 ? x0 + 2.0f : 1.0f, f3 = h3 ? x0 + 3.0f : 1.0f;
+  const float a = x0 * f1, ap = f1 + (h1 ? x0 : 0.f);
+  const float b = f2 * f3, bp = (h2 ? f3 : 0.f) + (h3 ? f2 : 0.f);
+  const float P = a * b;
+  lg2acc += Ops::lg2(P);
+  rs = fmaf(fmaf(ap, b, a * bp), Ops::rcp(P), rs);
+}
+
+// NB branch (y >= 1e-8) of one ZINB element from mu = m * sf: element NLL and the raw derivatives of struct Raw2
+// (no clip masks, no activation chain, no ridge: the element's owner applies finish_factors_pair).  Straight-line for
+// integer counts <= 4 (the bulk of a scRNA-seq matrix); counts 5..16 loop over further masked groups, anything else
+// (large or non-integer) takes the shifted-Stirling path of lgam_digam_diff.
+struct Raw1 { float loss, gmu, dth, dpi; };
+template <class Ops>
+DCA_HD Raw1 zinb_nb_raw(float y, float mu, float th_in, float pi, const float* lf_table) {
+  const float th = fminf(th_in, 1e6f);                                                 // loss.py:85
+  const float te = th + kEps;
+  const float rden = Ops::rcp(te + mu);
+  const float q = mu * rden;
+  float p = fmaf(q, 0.125f, 0.142857143f);
+  p = fmaf(q, p, 0.166666667f); p = fmaf(q, p, 0.2f); p = fmaf(q, p, 0.25f);
+  p = fmaf(q, p, 0.333333333f); p = fmaf(q, p, 0.5f);
+  const float f_ser = q * q * p;
+  const float lgr = Ops::lg2(te * rden);
+  const bool small_q = q < 0.0625f;
+  const float L1 = small_q ? q + f_ser : -kLn2 * lgr;                                  // log(1 + mu/(theta+eps))  loss.py:88
+  const float f = small_q ? f_ser : fmaf(-kLn2, lgr, -q);                              // L1 - q
+  float lg, dg;
+  if (y <= 16.f && y == rintf(y)) {
+    float l2 = 0.f, rs = 0.f, x = te, n = y;
+    rising_group_masked<Ops>(x, n, l2, rs);
+    while (n > 4.5f) { x += 4.0f; n -= 4.0f; rising_group_masked<Ops>(x, n, l2, rs); }
+    lg = l2 * kLn2; dg = rs;
+  } else {
+    lgam_digam_diff<Ops>(te, y, lg, dg);
+  }
+  float nb = lgamma_1p<Ops>(y, lf_table) - lg + th * L1 - y * (kLn2 * Ops::lg2((mu + kEps) * rden));
+  if (nb != nb) nb = INFINITY;                             // _nan2inf  loss.py:105
+  const float qq = 1.0f - pi + kEps;
+  Raw1 o;
+  o.loss = nb - kLn2 * Ops::lg2(qq);                       // loss.py:130
+  o.gmu = th * (mu - y) * rden;
+  o.dth = f + y * rden - dg;
+  o.dpi = Ops::rcp(qq);
+  return o;
+}
+
 // y: raw count; m: MeanAct output (before *sf); sf: size factor; th: DispAct output or per-gene
 // theta; pi: sigmoid output; lf_table: log(k!) for k < kLogFactN.
 template <class Ops, bool HAS_PI, bool COND_DISP>

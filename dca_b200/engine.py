@@ -104,6 +104,8 @@ class DeviceEngine:
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
+            if getattr(self, "_comm", False):
+                self.lib.dca_comm_destroy(self.handle); self._comm = False
             self.lib.dca_destroy(self.handle)
             self.handle = C.c_void_p()
 
@@ -189,8 +191,38 @@ class DeviceEngine:
             check(self.lib.dca_train_step_phase(self.handle, _ptr(X), X.stride(0), _ptr(Y), Y.stride(0), _ptr(sf),
                                                 _ptr(rows), b, phase, self._stream()), "dca_train_step_phase")
 
+    def comm_init(self):
+        """Create the engine's own NCCL communicator (dca_comm_init) over the ranks of the default torch.distributed
+        group: rank 0 draws the unique id, torch.distributed carries its 128 bytes to the others.  Afterwards
+        train_step_allreduce runs the gradient exchange inside the library (one CUDA graph per step)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return False
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if dist.get_rank() == 0:
+            buf = (C.c_char * 128)()
+            check(self.lib.dca_comm_unique_id(buf), "dca_comm_unique_id")
+            ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        ident = ident.to(self.device)
+        dist.broadcast(ident, 0)
+        raw = bytes(ident.cpu().numpy().tobytes())
+        with torch.cuda.device(self.device):
+            check(self.lib.dca_comm_init(self.handle, raw, dist.get_rank(), dist.get_world_size()), "dca_comm_init")
+        self._comm = True
+        return True
+
+    def allreduce_grads(self):
+        """Sum all-reduce of the flat gradient buffer (+ loss slot, flag) over the engine's communicator."""
+        check(self.lib.dca_allreduce(self.handle, self._stream()), "dca_allreduce")
+
     def train_step_allreduce(self, X, Y, sf, rows=None):
-        """Data-parallel step: the all-reduce of the head-gradient bucket overlaps the hidden-stack backward."""
+        """Data-parallel step: the all-reduce of the head-gradient bucket overlaps the hidden-stack backward.  With an
+        engine communicator (comm_init) the whole sequence is one library call / one CUDA graph."""
+        if getattr(self, "_comm", False):
+            b = self._check_inputs(X, Y, sf, rows, None)
+            check(self.lib.dca_train_step_dp(self.handle, _ptr(X), X.stride(0), _ptr(Y), Y.stride(0), _ptr(sf), _ptr(rows),
+                                             b, self._stream()), "dca_train_step_dp")
+            return
         import torch.distributed as dist
         self.train_step(X, Y, sf, rows=rows, phase=1)
         w1 = dist.all_reduce(self.grads[self.head_bucket:], async_op=True)

@@ -137,6 +137,21 @@ int dca_train_step_phase(dca_handle* h, const void* X, int64_t ldx, const float*
                          const float* sf, const int32_t* rows, int32_t batch, int32_t phase, void* stream);
 int dca_grad_buckets(const dca_handle* h, int64_t* head_bucket_offset);
 
+/* Data-parallel exchange inside the library (the reference is single-process: dca/train.py:91-98 has no
+ * counterpart).  One NCCL communicator per engine: rank 0 calls dca_comm_unique_id, the 128 bytes travel to the other
+ * ranks by any means (torch.distributed broadcast in dca_b200/engine.py), every rank calls dca_comm_init.  libnccl.so.2
+ * is resolved with dlopen at the first call (DCA_ERR_UNSUPPORTED when absent).
+ *   dca_allreduce      sum all-reduce of DCA_REGION_GRADS (P + 2 floats: gradients, loss slot, non-finite flag) in place.
+ *   dca_train_step_dp  dca_train_step with the exchange fused into the launch sequence: phase 1 -> all-reduce(head bucket)
+ *                      on an internal high-priority stream || phase 2 -> all-reduce(rest) -> join; captured and replayed
+ *                      as ONE CUDA graph like dca_train_step.  Follow with dca_apply_update(grad_scale = 1 / world). */
+int dca_comm_unique_id(void* id128);
+int dca_comm_init(dca_handle* h, const void* id128, int32_t rank, int32_t world);
+int dca_comm_destroy(dca_handle* h);
+int dca_allreduce(dca_handle* h, void* stream);
+int dca_train_step_dp(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy,
+                      const float* sf, const int32_t* rows, int32_t batch, void* stream);
+
 /* clip(g*grad_scale, +-clip) -> RMSprop (rho, eps from config) -> parameters.
  * Replaces keras RMSprop(clipvalue=clip_grad[, lr]) applied by model.fit: dca/train.py:54-57.
  * grad_scale = 1/world_size after a sum all-reduce of DCA_REGION_GRADS, else 1. */

@@ -1,0 +1,340 @@
+"""Parity at the benchmark's sizes and at the edges of the domain (VERDICT r1 "close the parity gaps").
+
+ * the loss kernel at 4096 x 20000 (BASELINE configs[2..4] batch shape) against the float64 oracle on sampled rows,
+   plus a checksum of checksums over the whole batch;
+ * one tcgen05 training step at G = 20000, B = 512 against the same-rounding oracle AND, with a stated bound, against
+   the exact (fp32-semantics) oracle -- loss, every gradient tensor norm-wise -- and predict() after K steps;
+ * device-side edge cases: activations AT their clip bounds, pi -> 0 / 1, large counts, NaN input -> loss inf + flag,
+   a gradient beyond the clip value;
+ * train() epoch semantics against oracle.fit(batch_order=...);
+ * the fused head/loss/backward kernel against the oracle (not against the three-kernel path).
+Needs a B200: -m gpu.  Reference behaviour: dca/loss.py:85-148, dca/network.py:38-39, dca/train.py:54-98.
+"""
+import ctypes as C
+import numpy as np
+import pytest
+import torch
+
+from oracle import dca_oracle as O
+from tests.util import synth_counts, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _L():
+    from dca_b200 import _lib
+    return _lib
+
+
+def _t(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(DEV, dtype)
+
+
+def _loss_call(lib, L, Y, ldy, rows, sf, m, d, pi, B, G, ae, ridge, inv_n, gdt, cond=True):
+    tdt = torch.bfloat16 if gdt == L.BF16 else torch.float32
+    gm = torch.zeros((B, G), dtype=tdt, device=DEV); gd = torch.zeros_like(gm); gp = torch.zeros_like(gm)
+    dth = torch.zeros(G, device=DEV)
+    loss = torch.zeros(1, dtype=torch.float64, device=DEV)
+    nb = C.c_size_t(); assert lib.dca_zinb_loss_workspace_bytes(B, G, C.byref(nb)) == 0
+    ws = torch.zeros(nb.value, dtype=torch.uint8, device=DEV)
+    L.check(lib.dca_zinb_loss_fwd_bwd(Y.data_ptr(), ldy, None if rows is None else rows.data_ptr(), sf.data_ptr(), m.data_ptr(),
+                                      d.data_ptr(), pi.data_ptr(), G, B, G, ae, ridge, inv_n, gm.data_ptr(),
+                                      gd.data_ptr() if cond else None, gp.data_ptr(), gdt, None if cond else dth.data_ptr(),
+                                      loss.data_ptr(), ws.data_ptr(), nb.value, None), "dca_zinb_loss_fwd_bwd")
+    torch.cuda.synchronize()
+    return float(loss.item()), gm, gd, gp, dth
+
+
+def _oracle_rows(y, m, sf, d, pi, ridge=0.0):
+    """float64 oracle of zinb-conddisp elements: element NLL and d/d pre-activation (un-scaled)."""
+    y, m, sf, d, pi = [np.asarray(a, np.float64) for a in (y, m, sf, d, pi)]
+    mu = m * sf[:, None]
+    el = O.zinb_loss_elem(y, mu, d, pi, ridge)
+    dmu, dth, dpi = O.loss_partials(y, mu, d, pi, ridge)
+    gm = dmu * mu * ((m > 1e-5) & (m < 1e6))
+    gd = dth * (1.0 - np.exp(-d)) * ((d > 1e-4) & (d < 1e4))
+    gp = dpi * pi * (1 - pi)
+    return el, gm, gd, gp
+
+
+@pytest.mark.parametrize("ring", [1, 0])
+def test_loss_kernel_at_benchmark_size_vs_oracle(ring):
+    """4096 x 20000, zinb-conddisp, row gather, bf16 and fp32 gradients: sampled rows element-wise against the float64
+    oracle (3e-4 of the tensor scale for fp32 gradients, 2^-8 relative for bf16 storage), the loss of those rows to
+    2e-5, and the whole-batch loss as a checksum of checksums (sum over 8 row slabs computed by separate launches)."""
+    L = _L(); lib = L.load()
+    L.check(lib.dca_set_tunable(b"loss_ring", ring))
+    try:
+        B, G, N = 4096, 20000, 5000
+        g = torch.Generator(device=DEV); g.manual_seed(5)
+        logm = torch.randn(G, device=DEV, generator=g) * 1.5 - 2.0
+        depth = torch.exp(torch.randn(N, 1, device=DEV, generator=g) * 0.35)
+        Y = torch.poisson(torch._standard_gamma(torch.full((N, G), 2.0, device=DEV), generator=g) * depth * torch.exp(logm)[None, :] / 2.0,
+                          generator=g)
+        Y[torch.rand(N, G, device=DEV, generator=g) < 0.2] = 0
+        Y[0, :6] = torch.tensor([0., 17., 40., 1000., 30000., 5.], device=DEV)
+        rows = torch.randperm(N, device=DEV, generator=g)[:B].int().contiguous()
+        rows[0] = 0
+        sf = depth.flatten().contiguous()
+        m = torch.exp(logm[None, :] + torch.randn(B, G, device=DEV, generator=g) * 0.7).clamp(1e-5, 1e6)
+        d = torch.nn.functional.softplus(torch.randn(B, G, device=DEV, generator=g) * 2.0).clamp(1e-4, 1e4)
+        p = torch.sigmoid(torch.randn(B, G, device=DEV, generator=g) * 2.0)
+        inv_n = 1.0 / (B * G)
+        samp = torch.cat([torch.tensor([0], device=DEV), torch.randperm(B, device=DEV, generator=g)[:23]]).sort().values
+        ys = Y[rows[samp].long()].cpu().numpy(); ms, ds, ps = m[samp].cpu().numpy(), d[samp].cpu().numpy(), p[samp].cpu().numpy()
+        sfs = sf[rows[samp].long()].cpu().numpy()
+        el, rgm, rgd, rgp = _oracle_rows(ys, ms, sfs, ds, ps)
+        for gdt, tol in ((L.F32, 3e-4), (L.BF16, 6e-3)):
+            total, gm, gd, gp, _ = _loss_call(lib, L, Y, G, rows, sf, m, d, p, B, G, 0, 0.0, inv_n, gdt)
+            for got, ref, nm in ((gm, rgm, "dzm"), (gd, rgd, "dzd"), (gp, rgp, "dzp")):
+                e = rel_err(got[samp].float().cpu().numpy(), ref * inv_n)
+                assert e < tol, (ring, nm, gdt, e)
+            # loss of the sampled rows alone (a 24-row launch on contiguous copies of their operands)
+            sub_rows = rows[samp].contiguous()
+            l_s, *_ = _loss_call(lib, L, Y, G, sub_rows, sf, m[samp].contiguous(), d[samp].contiguous(), p[samp].contiguous(),
+                                 len(samp), G, 0, 0.0, 1.0, gdt)
+            assert abs(l_s - el.sum()) <= 2e-5 * abs(el.sum()), (ring, l_s, el.sum())
+            # checksum of checksums: the batch loss equals the sum over 8 slabs of 512 rows
+            parts = 0.0
+            for k in range(8):
+                sl = slice(512 * k, 512 * (k + 1))
+                l_k, *_ = _loss_call(lib, L, Y, G, rows[sl].contiguous(), sf, m[sl], d[sl], p[sl], 512, G, 0, 0.0, 1.0, gdt)
+                parts += l_k
+            assert abs(total - parts) <= 1e-6 * abs(parts), (ring, total, parts)
+    finally:
+        L.check(lib.dca_set_tunable(b"loss_ring", 1))
+
+
+@pytest.mark.parametrize("ring", [1, 0])
+@pytest.mark.parametrize("gdt_name", ["f32", "bf16"])
+def test_loss_kernel_edge_cases_on_device(ring, gdt_name):
+    """Activations AT their clip bounds (network.py:38-39: gradient through the clipped activation is zero), pi -> 0 / 1,
+    counts 0 / 1 / 16 / 17 / 1e3 / 3e4, extreme size factors -- on the DEVICE, through the vectorised kernels (shape
+    aligned so that the staged / ring kernels run): everything finite, equal to the float64 oracle."""
+    L = _L(); lib = L.load()
+    L.check(lib.dca_set_tunable(b"loss_ring", ring))
+    try:
+        gdt = L.F32 if gdt_name == "f32" else L.BF16
+        B, G = 64, 1024
+        rng = np.random.default_rng(3)
+        ms = np.array([1e-5, 1e6, 2e-5, 5e5, 1.0, 30.0, 1e-3, 1e3], np.float32)
+        dsv = np.array([1e-4, 1e4, 2e-4, 9e3, 0.03125, 0.031, 1.0, 50.0], np.float32)
+        pis = np.array([0.0, 1.0, 1e-7, 1 - 1e-7, 0.5, 0.01, 0.99, 0.3], np.float32)
+        ysv = np.array([0, 1, 2, 4, 5, 16, 17, 1000, 30000, 0, 0, 3], np.float32)
+        m = rng.choice(ms, (B, G)).astype(np.float32); d = rng.choice(dsv, (B, G)).astype(np.float32)
+        pi = rng.choice(pis, (B, G)).astype(np.float32); Y = rng.choice(ysv, (B, G)).astype(np.float32)
+        sf = np.exp(rng.normal(0, 1.0, B)).astype(np.float32); sf[:3] = [1e-2, 1e2, 1.0]
+        el, rgm, rgd, rgp = _oracle_rows(Y, m, sf, d, pi)
+        assert np.all(np.isfinite(el)) and np.all(np.isfinite(rgm)) and np.all(np.isfinite(rgd)) and np.all(np.isfinite(rgp))
+        total, gm, gd, gp, _ = _loss_call(lib, L, _t(Y), G, None, _t(sf), _t(m), _t(d), _t(pi), B, G, 0, 0.0, 1.0, gdt)
+        assert np.isfinite(total) and abs(total - el.sum()) <= 5e-5 * abs(el.sum()), (total, el.sum())
+        gmn, gdn, gpn = [x.float().cpu().numpy() for x in (gm, gd, gp)]
+        assert np.all(np.isfinite(gmn)) and np.all(np.isfinite(gdn)) and np.all(np.isfinite(gpn))
+        # exactly zero through a clipped activation
+        assert np.all(gmn[(m <= 1e-5) | (m >= 1e6)] == 0) and np.all(gdn[(d <= 1e-4) | (d >= 1e4)] == 0)
+        tol = 3e-4 if gdt == L.F32 else 6e-3
+        # element-wise, relative to max(|ref|, 1e-3 * tensor scale)
+        assert rel_err(gmn, rgm) < tol and rel_err(gdn, rgd) < tol and rel_err(gpn, rgp) < tol
+    finally:
+        L.check(lib.dca_set_tunable(b"loss_ring", 1))
+
+
+@pytest.mark.parametrize("gemm_path", ["generic", "tcgen05"])
+def test_nan_input_gives_inf_loss_and_flag(gemm_path):
+    """_nan2inf (dca/loss.py:105,148): a NaN count makes the batch loss +inf; the engine reports it as inf (flag set)
+    and keeps running -- the next clean batch is finite again."""
+    from dca_b200.engine import DeviceEngine
+    B, G = 128, 256
+    Y = synth_counts(B, G, 2); X, sf = O.normalize_inputs(Y)
+    eng = DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=0, gemm_path=gemm_path)
+    Yd = _t(Y); Xd = _t(X); sfd = _t(sf)
+    eng.train_step(Xd, Yd, sfd)
+    assert np.isfinite(eng.read_loss())
+    Ybad = Yd.clone(); Ybad[5, 7] = float("nan")
+    eng.train_step(Xd, Ybad, sfd)
+    assert eng.read_loss() == float("inf")
+    assert float(eng.grads[eng.n_params + 1].item()) == 1.0              # non-finite flag (include/dca_b200.h)
+    eng.train_step(Xd, Yd, sfd)
+    assert np.isfinite(eng.read_loss()) and float(eng.grads[eng.n_params + 1].item()) == 0.0
+
+
+def test_gradient_clip_fires_like_keras_clipvalue():
+    """RMSprop(clipvalue=5) (dca/train.py:54-57): gradients beyond +-5 are clipped element-wise BEFORE the moving
+    average of squares -- driven with a synthetic gradient buffer so that the clip really binds."""
+    from dca_b200.engine import DeviceEngine
+    G = 64
+    eng = DeviceEngine(G, G, (16, 8, 16), "zinb-conddisp", max_batch=8, seed=0, gemm_path="generic")
+    p0 = eng.params.clone()
+    P = eng.n_params
+    gvals = torch.linspace(-12.0, 12.0, P, device=DEV)
+    ref_p = p0.double().cpu().numpy(); rms = np.zeros(P)
+    for step in range(3):
+        eng.grads[:P] = gvals * (1.0 + step)
+        eng.apply_update(1e-3, 5.0, 1.0)
+        gk = np.clip(gvals.double().cpu().numpy() * (1.0 + step), -5.0, 5.0)
+        rms = 0.9 * rms + 0.1 * gk * gk
+        ref_p = ref_p - 1e-3 * gk / (np.sqrt(rms) + 1e-7)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(eng.params.cpu().numpy(), ref_p, rtol=2e-6, atol=2e-7)
+    big = (gvals.abs() > 5).cpu().numpy()
+    assert big.sum() > P // 3                                             # the clip was active for many elements
+    # all clipped elements moved by exactly the same amount as an element with |g| = 5
+    moved = (eng.params - p0).abs().cpu().numpy()
+    np.testing.assert_allclose(moved[big], moved[big][0], rtol=1e-5)
+
+
+def test_train_history_matches_oracle_fit():
+    """train() (dca/train.py:35-100: shuffle with the NumPy global RNG, validation = tail 10 %, size-weighted epoch
+    loss, val_loss in inference mode, lr in history) against oracle.fit replayed with the same batch order: 1e-4."""
+    from dca_b200.anndata_lite import AnnData
+    from dca_b200 import io
+    from dca_b200.network import AE_types
+    from dca_b200.train import train
+    N, G, bs, epochs = 230, 64, 32, 4
+    Y = synth_counts(N, G, 17)
+    ad = io.normalize(io.read_dataset(AnnData(Y.copy())), filter_min_counts=False)
+    X = np.asarray(ad.X, np.float64); sf = np.asarray(ad.obs["size_factors"], np.float64); Yr = np.asarray(ad.raw.X, np.float64)
+    for ae_type in ("zinb-conddisp", "nb"):
+        net = AE_types[ae_type](input_size=G, output_size=G, hidden_size=(16, 8, 16), gemm_path="generic")
+        net.build(max_batch=bs, seed=3)
+        w0 = net.engine.get_weights()
+        onet = O.OracleNet(G, G, (16, 8, 16), ae_type, True, dtype=np.float64, params={k: v.astype(np.float64) for k, v in w0.items()})
+        split_at = int(N * 0.9)
+        np.random.seed(11)
+        orders = []
+        for _ in range(epochs):
+            o = np.arange(split_at); np.random.shuffle(o); orders.append(o)
+        ref = O.fit(onet, X, Yr, sf, epochs=epochs, batch_size=bs, validation_split=0.1, reduce_lr=10, early_stop=15,
+                    batch_order=orders)
+        np.random.seed(11)
+        hist = train(ad, net, epochs=epochs, batch_size=bs, verbose=False).history
+        assert set(hist) == {"loss", "val_loss", "lr"} and len(hist["loss"]) == epochs
+        np.testing.assert_allclose(hist["loss"], ref["loss"], rtol=1e-4, err_msg=ae_type)
+        np.testing.assert_allclose(hist["val_loss"], ref["val_loss"], rtol=1e-4, err_msg=ae_type)
+        np.testing.assert_allclose(hist["lr"], ref["lr"], rtol=1e-6)
+        # and the trained weights themselves
+        w = net.engine.get_weights()
+        for k in ("mean/kernel", "enc0/kernel", "center/bn_moving_var"):
+            np.testing.assert_allclose(w[k], onet.params[k], rtol=5e-3, atol=5e-4, err_msg=ae_type + " " + k)
+
+
+def _normwise(got, ref):
+    got = np.asarray(got, np.float64).ravel(); ref = np.asarray(ref, np.float64).ravel()
+    return float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-300))
+
+
+# Stated tolerance of the DEFAULT (tcgen05: bf16 GEMM operands, fp32 accumulation, fp32 loss) path against the exact
+# fp32-semantics oracle, i.e. against what the reference's TF-CPU path computes (SURVEY.md 8d "bf16 GEMM / fp32 loss"):
+TC_VS_EXACT = {"loss": 2e-3,          # relative, batch loss of one step
+               "grad_head": 2e-2,     # ||g - g_exact|| / ||g_exact|| per head kernel / bias tensor
+               "grad_hidden": 6e-2,   # same, hidden-stack tensors (behind the bf16 rounding of X, W1, dA1 and ReLU-mask flips)
+               "predict": 2e-2}       # ||out - out_exact|| / ||out_exact|| of mean / dispersion / pi / latent after 5 steps
+
+
+def test_tc_train_step_at_20k_genes_vs_both_oracles():
+    """One default-path training step at G = 20000 (B = 512): against the same-rounding oracle (the kernels do what
+    they claim) and against the EXACT oracle with the stated bounds TC_VS_EXACT (what a user of the fp32 reference
+    sees).  The fused head/loss/backward kernel is checked against the same two oracles."""
+    from dca_b200.engine import DeviceEngine
+    L = _L()
+    B, G, hidden = 512, 20000, (64, 32, 64)
+    Y = synth_counts(B, G, 41); X, sf = O.normalize_inputs(Y)
+    p0 = O.init_params(G, G, hidden, "zinb-conddisp", True, seed=2, dtype=np.float32)
+    rng = np.random.default_rng(3)
+    for k in p0:
+        if k.endswith(("/bias", "/bn_beta")):
+            p0[k] = rng.normal(0, 0.2, p0[k].shape).astype(np.float32)
+    X64, Y64, sf64 = X.astype(np.float64), Y.astype(np.float64), sf.astype(np.float64)
+    same = O.OracleNet(G, G, hidden, "zinb-conddisp", True, dtype=np.float64, params=p0, emulate_bf16=True)
+    exact = O.OracleNet(G, G, hidden, "zinb-conddisp", True, dtype=np.float64, params=p0)
+    l_same, g_same = same.loss_and_grads(X64, Y64, sf64, update_bn=False)
+    l_exact, g_exact = exact.loss_and_grads(X64, Y64, sf64, update_bn=False)
+    report = {}
+    for fused in (0, 1):
+        L.set_tunable("fused_heads", fused)
+        try:
+            eng = DeviceEngine(G, G, hidden, "zinb-conddisp", True, max_batch=B, seed=None, gemm_path="tcgen05")
+        finally:
+            L.set_tunable("fused_heads", 0)
+        eng.set_weights(p0)
+        assert eng.info()["tc_heads"] and eng.info()["tc_encoder"]
+        eng.train_step(_t(X), _t(Y), _t(sf))
+        loss = eng.read_loss()
+        g = eng.grads.cpu().numpy()
+        assert abs(loss - l_same) < 1e-4 * abs(l_same), (fused, loss, l_same)
+        assert abs(loss - l_exact) < TC_VS_EXACT["loss"] * abs(l_exact), (fused, loss, l_exact)
+        for name, off, r, c in eng.param_info:
+            got = g[off: off + r * c]
+            if name.endswith("/bias") and not name.startswith(("mean", "dispersion", "pi")):
+                continue                                  # exactly zero in exact arithmetic (BatchNorm removes it)
+            e_same = np.max(np.abs(got - g_same[name].reshape(-1))) / (np.max(np.abs(g_same[name])) + 1e-30)
+            e_exact = _normwise(got, g_exact[name])
+            report[(fused, name)] = (e_same, e_exact)
+            head = name.startswith(("mean", "dispersion", "pi"))
+            assert e_same < (3e-3 if head else 3e-2), (fused, name, e_same)
+            assert e_exact < (TC_VS_EXACT["grad_head"] if head else TC_VS_EXACT["grad_hidden"]), (fused, name, e_exact)
+        eng.close()
+    print("\n[tc vs oracles @ 512 x 20000] " + "; ".join("%s%s same %.1e exact %.1e" % ("fused:" if f else "", n, a, b)
+                                                          for (f, n), (a, b) in sorted(report.items())))
+
+
+def test_tc_predict_after_training_vs_exact_oracle():
+    """predict() outputs (mean, dispersion, pi, latent -- what parity with the reference is judged on,
+    dca/network.py:188-211,395-405) of the default path after 5 training steps against the EXACT oracle trained on the
+    same batches: norm-wise bound TC_VS_EXACT['predict'] per output, and element-wise 99th percentile for the mean."""
+    from dca_b200.engine import DeviceEngine
+    B, G, hidden = 512, 2000, (64, 32, 64)
+    Y = synth_counts(B, G, 43); X, sf = O.normalize_inputs(Y)
+    p0 = O.init_params(G, G, hidden, "zinb-conddisp", True, seed=5, dtype=np.float32)
+    exact = O.OracleNet(G, G, hidden, "zinb-conddisp", True, dtype=np.float64, params=p0)
+    eng = DeviceEngine(G, G, hidden, "zinb-conddisp", True, max_batch=B, seed=None, gemm_path="tcgen05")
+    eng.set_weights(p0)
+    Xd, Yd, sfd = _t(X), _t(Y), _t(sf)
+    X64, Y64, sf64 = X.astype(np.float64), Y.astype(np.float64), sf.astype(np.float64)
+    for _ in range(5):
+        eng.train_step(Xd, Yd, sfd); eng.apply_update(1e-3, 5.0)
+        l_o = exact.train_step(X64, Y64, sf64)
+        assert abs(eng.read_loss() - l_o) < 5e-3 * abs(l_o)
+    ref = exact.predict(X64, sf64)
+    mean = torch.empty((B, G), device=DEV); disp = torch.empty((B, G), device=DEV); pi = torch.empty((B, G), device=DEV)
+    lat = torch.empty((B, 32), device=DEV)
+    eng.predict(Xd, sfd, mean=mean, disp=disp, pi=pi, latent=lat)
+    torch.cuda.synchronize()
+    errs = {}
+    for got, key in ((mean, "mean"), (disp, "dispersion"), (pi, "pi"), (lat, "latent")):
+        errs[key] = _normwise(got.cpu().numpy(), ref[key])
+        assert errs[key] < TC_VS_EXACT["predict"], (key, errs[key])
+    r = ref["mean"]; gnp = mean.cpu().numpy()
+    q99 = float(np.quantile(np.abs(gnp - r) / (np.abs(r) + 1e-12), 0.99))
+    assert q99 < 5e-2, q99
+    print("\n[tc predict vs exact oracle after 5 steps] " + ", ".join("%s %.1e" % kv for kv in errs.items()) + ", mean q99 %.1e" % q99)
+
+
+def test_fused_heads_kernel_vs_oracle_small():
+    """flash_zinb.cu straight against the same-rounding oracle (loss 1e-4, every gradient tensor 3e-3 / 3e-2 of its
+    scale) on a ragged shape with row gather -- not against the repo's own three-kernel path."""
+    from dca_b200.engine import DeviceEngine
+    L = _L()
+    B, G, hidden = 300, 264, (64, 32, 64)
+    Y = synth_counts(B + 40, G, 21); X, sf = O.normalize_inputs(Y)
+    rows = np.random.default_rng(1).permutation(B + 40)[:B].astype(np.int32)
+    p0 = O.init_params(G, G, hidden, "zinb-conddisp", True, seed=0, dtype=np.float32)
+    same = O.OracleNet(G, G, hidden, "zinb-conddisp", True, dtype=np.float64, params=p0, emulate_bf16=True)
+    L.set_tunable("fused_heads", 1)
+    try:
+        eng = DeviceEngine(G, G, hidden, "zinb-conddisp", True, max_batch=B, seed=None, gemm_path="tcgen05")
+    finally:
+        L.set_tunable("fused_heads", 0)
+    eng.set_weights(p0)
+    eng.train_step(_t(X), _t(Y), _t(sf), rows=torch.as_tensor(rows).to(DEV))
+    loss = eng.read_loss()
+    oloss, og = same.loss_and_grads(X[rows].astype(np.float64), Y[rows].astype(np.float64), sf[rows].astype(np.float64))
+    assert abs(loss - oloss) < 1e-4 * abs(oloss), (loss, oloss)
+    g = eng.grads.cpu().numpy()
+    for name, off, r, c in eng.param_info:
+        if name.endswith("/bias") and not name.startswith(("mean", "dispersion", "pi")):
+            continue
+        ref = og[name].reshape(-1); got = g[off: off + r * c]
+        err = np.max(np.abs(got - ref)) / (np.max(np.abs(ref)) + 1e-30)
+        assert err < (3e-3 if name.startswith(("mean", "dispersion", "pi")) else 3e-2), (name, err)

@@ -12,7 +12,7 @@ def _host_elem(ae_type, y, m, sf, d, pi, ridge, kernel_variant=False):
     lib = _lib.load()
     out = (C.c_float * 4)()
     res = np.zeros((len(y), 4), np.float32)
-    t = _lib.AE_TYPE_IDS[ae_type] | (0x100 if kernel_variant else 0)
+    t = _lib.AE_TYPE_IDS[ae_type] | ({False: 0, True: 0x100, "ring": 0x200}[kernel_variant])
     for i in range(len(y)):
         assert lib.dca_zinb_elem_host(t, float(y[i]), float(m[i]), float(sf[i]), float(d[i]), float(pi[i]),
                                       float(ridge), C.byref(out)) == 0
@@ -94,10 +94,30 @@ def test_kernel_formulations_equal_the_reference_formulation(ae_type, ridge):
     m[10:14] = [1.0 / 15.0, 0.0666, 0.0667, 0.07]; sf[10:14] = 1.0; d[10:14] = 1.0; y[10:14] = 0
     y, m, sf, d, pi = [a.astype(np.float32).astype(np.float64) for a in (y, m, sf, d, pi)]
     a = _host_elem(ae_type, y, m, sf, d, pi, ridge).astype(np.float64)
-    b = _host_elem(ae_type, y, m, sf, d, pi, ridge, kernel_variant=True).astype(np.float64)
-    assert np.all(np.isfinite(a) == np.isfinite(b))
-    fin = np.isfinite(a)
-    scale = np.maximum(np.abs(a), 1e-30)
-    err = np.where(fin, np.abs(a - b) / scale, 0.0)
-    k = np.unravel_index(int(np.argmax(err)), err.shape)
-    assert err[k] <= 2e-6, (ae_type, ridge, k, a[k], b[k], y[k[0]], m[k[0]], sf[k[0]], d[k[0]], pi[k[0]])
+    # True: branch-free zero branch / NB from mu (staged + fused kernels); "ring": the f32x2 pair functions, the masked
+    # rising-product groups and the shared finishing factors of zinb_loss_bwd_ring_kernel (the default loss kernel)
+    for variant, tol in ((True, 2e-6), ("ring", 2e-5)):
+        b = _host_elem(ae_type, y, m, sf, d, pi, ridge, kernel_variant=variant).astype(np.float64)
+        assert np.all(np.isfinite(a) == np.isfinite(b))
+        fin = np.isfinite(a)
+        scale = np.maximum(np.abs(a), 1e-3 * np.max(np.abs(np.where(fin, a, 0.0)), axis=0, keepdims=True) + 1e-30)
+        err = np.where(fin, np.abs(a - b) / scale, 0.0)
+        k = np.unravel_index(int(np.argmax(err)), err.shape)
+        assert err[k] <= tol, (ae_type, ridge, variant, k, a[k], b[k], y[k[0]], m[k[0]], sf[k[0]], d[k[0]], pi[k[0]])
+
+
+@pytest.mark.parametrize("ae_type", ["zinb-conddisp", "zinb"])
+def test_ring_kernel_formulation_matches_oracle(ae_type):
+    """The default loss kernel's formulation (variant 0x200) straight against the float64 oracle, with the counts that
+    walk every path of the masked rising product (1..4 one group, 5..16 further groups, > 16 / non-integer Stirling)."""
+    y, m, sf, d, pi = _cases(3000, 13)
+    y[8:30] = [3, 4, 5, 6, 7, 8, 9, 12, 13, 15, 16, 17, 18, 2.5, 0.5, 100, 63, 64, 65, 5000, 1, 2]
+    y, m, sf, d, pi = [a.astype(np.float32).astype(np.float64) for a in (y, m, sf, d, pi)]
+    got = _host_elem(ae_type, y, m, sf, d, pi, 0.05, kernel_variant="ring").astype(np.float64)
+    ref = _oracle_elem(ae_type, y, m, sf, d, pi, 0.05)
+    for j, nm in enumerate(["loss", "dzm", "dzd", "dzp"]):
+        scale = np.maximum(np.abs(ref[:, j]), 1e-3 * np.max(np.abs(ref[:, j])) + 1e-30)
+        err = np.abs(got[:, j] - ref[:, j]) / scale
+        k = int(np.argmax(err))
+        assert err[k] < 2e-4, "%s %s: rel err %.3g at y=%g m=%g sf=%g d=%g pi=%g got=%g ref=%g" % (
+            ae_type, nm, err[k], y[k], m[k], sf[k], d[k], pi[k], got[k, j], ref[k, j])
