@@ -311,6 +311,8 @@ def main():
                        gemm_path=a.gemm_path, device=dev, seed=0)
     if world > 1:
         dist.broadcast(eng.params, 0); eng.params_changed()
+        if os.environ.get("DCA_BENCH_TORCH_ALLREDUCE", "0") != "1":
+            eng.comm_init()      # NCCL all-reduce enqueued by the library inside the step's CUDA graph (dca_train_step_dp)
     lr, clip, gscale = 1e-3, 5.0, 1.0 / world
     total = a.steps + a.warmup
     gperm = torch.Generator(device=dev); gperm.manual_seed(99 + rank)
@@ -437,7 +439,7 @@ def main():
             for i in range(k):
                 eng.stream_step(i % nb, (i + 1) % nb if i + 1 < k else -1)
                 if world > 1:
-                    dist.all_reduce(eng.grads)
+                    eng.allreduce_grads() if getattr(eng, "_comm", False) else dist.all_reduce(eng.grads)
                 eng.apply_update(lr, clip, gscale)
             eng.stream_end()
             eng.set_loss_ring(None)

@@ -14,7 +14,9 @@ LIB_PATH = os.path.join(_HERE, "libdca_b200.so")
 DCA_MAX_HIDDEN = 8
 DCA_NAME_LEN = 48
 
-AE_TYPE_IDS = {"zinb-conddisp": 0, "zinb": 1, "nb-conddisp": 2, "nb": 3}
+AE_TYPE_IDS = {"zinb-conddisp": 0, "zinb": 1, "nb-conddisp": 2, "nb": 3,
+               # the remaining registry keys of dca/network.py:763-768: shape-general fp32 path (csrc/extra_types.cu)
+               "poisson": 4, "normal": 5, "nb-shared": 6, "zinb-shared": 7, "zinb-elempi": 8, "nb-fork": 9, "zinb-fork": 10}
 F32, BF16 = 0, 1
 GEMM_AUTO, GEMM_GENERIC, GEMM_TCGEN05 = 0, 1, 2
 REGION_PARAMS, REGION_GRADS, REGION_RMS, REGION_BN_STATE, REGION_EPOCH_ACC = 0, 1, 2, 3, 4
@@ -34,6 +36,7 @@ class Config(C.Structure):
         ("l1_enc", C.c_float), ("l2_enc", C.c_float),
         ("bn_momentum", C.c_float), ("bn_eps", C.c_float),
         ("rms_rho", C.c_float), ("rms_eps", C.c_float),
+        ("elempi_shared", C.c_int32),
     ]
 
 

@@ -100,7 +100,7 @@ int Engine::allreduce_range(int64_t lo, int64_t hi, cudaStream_t s) {
 // phase 1 -> [comm stream: all-reduce(head bucket, loss slot, flag)] || phase 2 -> all-reduce(rest) -> join
 int Engine::train_step_dp_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows,
                                int Bn, cudaStream_t s) {
-  const int64_t hb = head_W[0];
+  const int64_t hb = x_kind ? 0 : head_W[0];
   DCA_TRY(train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, 1));
   DCA_CUDA_OK(cudaEventRecord(ev_fork, s));
   DCA_CUDA_OK(cudaStreamWaitEvent(comm_stream, ev_fork, 0));

@@ -47,7 +47,8 @@ enum Epilogue : int {
   EPI_ACCUM = 1,        // C += acc             (atomic when split-K)
   EPI_MEAN_ACT = 2,     // C = clip(exp(acc+bias),1e-5,1e6) [* row_scale]
   EPI_DISP_ACT = 3,     // C = clip(softplus(acc+bias),1e-4,1e4)
-  EPI_SIGMOID = 4       // C = sigmoid(acc+bias)
+  EPI_SIGMOID = 4,      // C = sigmoid(acc+bias)
+  EPI_LINEAR_SCALE = 5  // C = (acc+bias) [* row_scale]     ('normal' type: linear mean head, dca/network.py:147-150)
 };
 
 struct GemmArgs {

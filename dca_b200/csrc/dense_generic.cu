@@ -102,6 +102,7 @@ gemm_kernel(const AT* __restrict__ A, int64_t lda, const int32_t* __restrict__ a
           *c = v; break; }
         case EPI_DISP_ACT: *c = fminf(fmaxf(softplus_f(v), 1e-4f), 1e4f); break;   // DispAct dca/network.py:39
         case EPI_SIGMOID: *c = sigmoid_f(v); break;                // dca/network.py:369
+        case EPI_LINEAR_SCALE: *c = row_scale ? v * row_scale[gm] : v; break;
         default: *c = v; break;
       }
     }

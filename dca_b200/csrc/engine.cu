@@ -52,7 +52,7 @@ int validate(const dca_config* c) {
   if (c->n_hidden < 0 || c->n_hidden > DCA_MAX_HIDDEN) { set_error("n_hidden must be in [0,%d]", DCA_MAX_HIDDEN); return DCA_ERR_BAD_ARG; }
   for (int i = 0; i < c->n_hidden; ++i)
     if (c->hidden[i] <= 0) { set_error("hidden[%d] must be positive", i); return DCA_ERR_BAD_ARG; }
-  if (c->ae_type < 0 || c->ae_type > 3) { set_error("loss type not supported (ae_type=%d)", c->ae_type); return DCA_ERR_UNSUPPORTED; }
+  if (c->ae_type < 0 || c->ae_type > DCA_AE_ZINB_FORK) { set_error("autoencoder type not supported (ae_type=%d)", c->ae_type); return DCA_ERR_UNSUPPORTED; }
   if (c->max_batch <= 0) { set_error("max_batch must be positive"); return DCA_ERR_BAD_ARG; }
   if (c->x_dtype != DCA_F32 && c->x_dtype != DCA_BF16) { set_error("x_dtype must be DCA_F32 or DCA_BF16"); return DCA_ERR_BAD_ARG; }
   if (c->gemm_path < 0 || c->gemm_path > 2) { set_error("unknown gemm_path %d", c->gemm_path); return DCA_ERR_BAD_ARG; }
@@ -83,8 +83,12 @@ int Engine::plan(const dca_config& c) {
   L = c.n_hidden;
   has_pi = (c.ae_type == DCA_AE_ZINB_CONDDISP || c.ae_type == DCA_AE_ZINB);
   cond = (c.ae_type == DCA_AE_ZINB_CONDDISP || c.ae_type == DCA_AE_NB_CONDDISP);
-  params.clear(); states.clear();
+  params.clear(); states.clear(); reg_items.clear();
   int64_t off = 0, soff = 0;
+  x_kind = 0; n_branch = 0; trunk_L = L;
+  if (c.ae_type >= DCA_AE_POISSON) {
+    DCA_TRY(x_plan_params(c, off, soff));
+  } else {
   int prev = c.n_in;
   maxh = 1;
   for (int i = 0; i < L; ++i) {
@@ -102,22 +106,23 @@ int Engine::plan(const dca_config& c) {
     if (h > maxh) maxh = h;
   }
   K_head = prev;
-  const int G = c.n_out;
-  head_W[0] = off; add_tensor(params, off, "mean/kernel", prev, G);
-  head_b[0] = off; add_tensor(params, off, "mean/bias", 1, G);
+  head_W[0] = off; add_tensor(params, off, "mean/kernel", prev, c.n_out);
+  head_b[0] = off; add_tensor(params, off, "mean/bias", 1, c.n_out);
   head_W[1] = head_b[1] = head_W[2] = head_b[2] = theta_off = -1;
   if (cond) {
-    head_W[1] = off; add_tensor(params, off, "dispersion/kernel", prev, G);
-    head_b[1] = off; add_tensor(params, off, "dispersion/bias", 1, G);
+    head_W[1] = off; add_tensor(params, off, "dispersion/kernel", prev, c.n_out);
+    head_b[1] = off; add_tensor(params, off, "dispersion/bias", 1, c.n_out);
   }
   if (has_pi) {
-    head_W[2] = off; add_tensor(params, off, "pi/kernel", prev, G);
-    head_b[2] = off; add_tensor(params, off, "pi/bias", 1, G);
+    head_W[2] = off; add_tensor(params, off, "pi/kernel", prev, c.n_out);
+    head_b[2] = off; add_tensor(params, off, "pi/bias", 1, c.n_out);
   }
-  if (!cond) { theta_off = off; add_tensor(params, off, "dispersion/theta", 1, G); }
+  if (!cond) { theta_off = off; add_tensor(params, off, "dispersion/theta", 1, c.n_out); }
+  }
   P = off; S = soff;
 
   // ---- arena carve-up
+  const int G = c.n_out;
   const size_t B = (size_t)c.max_batch;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes); return at; };
@@ -148,7 +153,7 @@ int Engine::plan(const dca_config& c) {
   loss_ws_bytes = loss_workspace_bytes((int)B, G);
   o_lossws = take(loss_ws_bytes);
   o_rowsbuf = take(sizeof(int32_t) * B);
-  mid_ok = mid_supported(c.hidden, L);
+  mid_ok = !x_kind && mid_supported(c.hidden, L);
   o_bar = take(256);
   o_midpart = take(sizeof(double) * mid_partial_doubles());
   // tcgen05 path (flagship shape): gene-wide layers with a 64-wide partner dimension
@@ -156,7 +161,7 @@ int Engine::plan(const dca_config& c) {
   slot_head[0] = 0; slot_kind[0] = EPI_MEAN_ACT; n_slots = 1;
   if (cond) { slot_head[n_slots] = 1; slot_kind[n_slots] = EPI_DISP_ACT; ++n_slots; }
   if (has_pi) { slot_head[n_slots] = 2; slot_kind[n_slots] = EPI_SIGMOID; ++n_slots; }
-  const bool want_tc = c.gemm_path != DCA_GEMM_GENERIC;
+  const bool want_tc = c.gemm_path != DCA_GEMM_GENERIC && !x_kind;     // the extra AE types run the shape-general fp32 path
   tc_heads = want_tc && L >= 1 && K_head == 64 && (G % 8 == 0);
   tc_enc = want_tc && L >= 1 && c.hidden[0] == 64 && (c.n_in % 8 == 0);
   // the tcgen05 kernels read the kernels in place from the flat bf16 parameter copy: TMA needs 16-byte aligned bases
@@ -189,6 +194,7 @@ int Engine::plan(const dca_config& c) {
     o_ssf[k] = take(sizeof(float) * B);
   }
   o_stage_x = o_sx[0]; o_stage_y = o_sy[0]; o_stage_sf = o_ssf[0];
+  if (x_kind) x_plan_arena(B, take);
   arena_bytes = o;
   return DCA_OK;
 }
@@ -289,6 +295,12 @@ int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, boo
     hin = f(lay[L - 1].o_h); ldin = lay[L - 1].out; in_bf16 = 0; gather = nullptr;
   }
   head_in = hin; head_ld = ldin; head_bf16 = in_bf16; head_rows = gather;
+  return DCA_OK;
+}
+
+int Engine::x_gather_sf(const float* sf, const int32_t* rows, int Bn, cudaStream_t s) {
+  gather_sf_kernel<<<cdiv(Bn, 256), 256, 0, s>>>(sf, rows, Bn, f(o_sfb));
+  DCA_LAUNCH_CHECK();
   return DCA_OK;
 }
 
@@ -430,6 +442,7 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
 // final, so their all-reduce can overlap phase 2); 2: hidden-stack / encoder backward.
 int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows,
                             int Bn, cudaStream_t s, int phase) {
+  if (x_kind) return phase == 2 ? DCA_OK : x_train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s);   // whole step in phase 1
   const int G = cfg.n_out;
   float* dh = f(o_dh[0]); float* dh2 = f(o_dh[1]);
   if (phase != 2) {
@@ -582,6 +595,7 @@ int Engine::eval_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, c
                       int Bn, cudaStream_t s) {
   if (!X || !Y) { set_error("dca_eval_step: X and Y must not be NULL"); return DCA_ERR_BAD_ARG; }
   if (Bn <= 0 || Bn > cfg.max_batch) { set_error("dca_eval_step: batch %d outside (0, max_batch=%d]", Bn, cfg.max_batch); return DCA_ERR_BAD_ARG; }
+  if (x_kind) return x_eval_step(X, ldx, Y, ldy, sf, rows, Bn, s);
   const int G = cfg.n_out;
   DCA_TRY(forward(X, ldx, rows, Bn, false, s));
   float* Mb = f(o_head[0]); float* Db = f(o_head[1]); float* Pb = f(o_head[2]);
@@ -602,6 +616,7 @@ int Engine::predict(const void* X, int64_t ldx, const float* sf, const int32_t* 
                     float* disp_out, float* pi_out, int64_t ld_out, float* latent_out, cudaStream_t s) {
   if (!X) { set_error("dca_predict: X must not be NULL"); return DCA_ERR_BAD_ARG; }
   if (Bn <= 0 || Bn > cfg.max_batch) { set_error("dca_predict: batch %d outside (0, max_batch=%d]", Bn, cfg.max_batch); return DCA_ERR_BAD_ARG; }
+  if (x_kind) return x_predict(X, ldx, sf, rows, Bn, mean_out, disp_out, pi_out, ld_out, latent_out, s);
   const int G = cfg.n_out;
   DCA_TRY(forward(X, ldx, rows, Bn, false, s));
   if (latent_out) {
@@ -653,6 +668,21 @@ int Engine::init_params(uint64_t seed, cudaStream_t s) {
   DCA_CUDA_OK(cudaMemsetAsync(gp(0), 0, sizeof(float) * (size_t)(P + 2), s));
   DCA_CUDA_OK(cudaMemsetAsync(d(o_acc), 0, sizeof(double) * 8, s));
   uint64_t sid = 0;
+  if (x_kind) {
+    // Glorot-uniform for every kernel of the tensor table (1-D element-wise kernels: fan_in = fan_out = length, like Keras)
+    for (auto& t : params) {
+      const std::string nm(t.name);
+      if (nm.size() < 7 || nm.compare(nm.size() - 7, 7, "/kernel") != 0) continue;
+      const int fi = t.rows == 1 ? t.cols : t.rows, fo = t.cols;
+      DCA_TRY(glorot_fill(pp(t.offset), (int64_t)t.rows * t.cols, fi, fo, seed, sid++, s));
+    }
+    if (cfg.batchnorm)
+      for (auto& t : states) {
+        const std::string nm(t.name);
+        DCA_TRY(fill_value(st(t.offset), t.cols, nm.find("moving_var") != std::string::npos ? 1.f : 0.f, s));
+      }
+    return DCA_OK;
+  }
   for (int i = 0; i < L; ++i)
     DCA_TRY(glorot_fill(pp(lay[i].W), (int64_t)lay[i].in * lay[i].out, lay[i].in, lay[i].out, seed, sid++, s));
   for (int k = 0; k < 3; ++k)
@@ -809,7 +839,7 @@ extern "C" int dca_train_step_phase(dca_handle* h, const void* X, int64_t ldx, c
 extern "C" int dca_grad_buckets(const dca_handle* h, int64_t* head_bucket_offset) {
   DCA_NEED_HANDLE(h);
   if (!head_bucket_offset) { set_error("dca_grad_buckets: NULL"); return DCA_ERR_BAD_ARG; }
-  *head_bucket_offset = h->e.head_W[0];      // grads[offset : P+2] are final after phase 1
+  *head_bucket_offset = h->e.x_kind ? 0 : h->e.head_W[0];      // grads[offset : P+2] are final after phase 1
   return DCA_OK;
 }
 extern "C" int dca_apply_update(dca_handle* h, float lr, float clip, float grad_scale, void* stream) {

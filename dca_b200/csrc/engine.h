@@ -1,5 +1,6 @@
 // Engine: arena layout + kernel sequencing (see engine.cu).
 #pragma once
+#include <functional>
 #include <string>
 #include <vector>
 #include "dca_internal.cuh"
@@ -86,6 +87,32 @@ struct Engine {
   size_t o_pbf = 0, o_h3b = 0, o_da1b = 0, o_xb = 0, o_dzb[3] = {0, 0, 0};
   const __nv_bfloat16* cur_xb = nullptr; int64_t cur_ldxb = 0;   // bf16 batch input of the current step
   __nv_bfloat16* bf(size_t byte_off) const { return reinterpret_cast<__nv_bfloat16*>(base + byte_off); }
+
+  // ---- remaining AE types (extra_types.cu): shape-general fp32 path, cfg.ae_type >= DCA_AE_POISSON
+  int x_kind = 0;                 // 0: one of the four flagship types; else the dca_ae_type
+  int n_branch = 0, trunk_L = 0;  // forks: parallel copies of the last decoder layer (mean, disp[, pi]); layers in the trunk
+  Layer brlay[3];
+  int head_N[3] = {0, 0, 0}, head_K[3] = {0, 0, 0};   // output width (G or 1) / input width per head (0 mean, 1 dispersion, 2 pi)
+  int64_t epi_k = -1, epi_c = -1; int epi_n = 0;      // zinb-elempi: element-wise pi kernel / bias offsets, length (G or 1)
+  size_t o_zraw = 0, o_small[4] = {0, 0, 0, 0}, o_xacc = 0;
+  struct RegItem { int64_t off, n; bool enc; };
+  std::vector<RegItem> reg_items;                     // kernels with a regulariser (dca/network.py:113-125)
+  int x_plan_params(const dca_config& c, int64_t& off, int64_t& soff);
+  void x_plan_arena(size_t B, const std::function<size_t(size_t)>& take);
+  int x_layer_fwd(Layer& l, const void* hin, int64_t ldin, int in_bf16, const int32_t* gather, int Bn, bool training, cudaStream_t s);
+  int x_layer_bwd(Layer& l, float* dh, const void* hin, int64_t ldin, int in_bf16, const int32_t* gather, int Bn, float* din,
+                  bool din_accumulate, cudaStream_t s);
+  const float* x_head_in(int k) const;
+  int x_forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, bool training, cudaStream_t s);
+  int x_head_gemm(int k, int Bn, float* out, int64_t ld_out, int epi, const float* row_scale, cudaStream_t s);
+  int x_heads_forward(int Bn, float* Mb, float* Db, float* Pb, const float* row_scale, cudaStream_t s);
+  int x_penalty(cudaStream_t s, bool& any);
+  int x_train_step_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
+                        cudaStream_t s);
+  int x_eval_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn, cudaStream_t s);
+  int x_predict(const void* X, int64_t ldx, const float* sf, const int32_t* rows, int Bn, float* mean_out, float* disp_out,
+                float* pi_out, int64_t ld_out, float* latent_out, cudaStream_t s);
+  int x_gather_sf(const float* sf, const int32_t* rows, int Bn, cudaStream_t s);
 
   // data-parallel gradient exchange (comm.cu): NCCL communicator owned by the engine, resolved with dlopen
   void* comm = nullptr; int comm_world = 1, comm_rank = 0;

@@ -29,7 +29,7 @@ class DeviceEngine:
                  ae_type: str = "zinb-conddisp", batchnorm: bool = True, max_batch: int = 32,
                  x_dtype: str = "float32", ridge: float = 0.0, l1: float = 0.0, l2: float = 0.0,
                  l1_enc: float = 0.0, l2_enc: float = 0.0, gemm_path: str = "auto",
-                 device: Optional[torch.device] = None, seed: Optional[int] = 0):
+                 device: Optional[torch.device] = None, seed: Optional[int] = 0, sharedpi: bool = False):
         if ae_type not in _lib.AE_TYPE_IDS:
             raise NotImplementedError("ae_type %r is not on the accelerated path (supported: %s)"
                                       % (ae_type, sorted(_lib.AE_TYPE_IDS)))
@@ -53,6 +53,7 @@ class DeviceEngine:
         cfg.x_dtype = _lib.BF16 if self.x_dtype == torch.bfloat16 else _lib.F32
         cfg.gemm_path = {"auto": _lib.GEMM_AUTO, "generic": _lib.GEMM_GENERIC, "tcgen05": _lib.GEMM_TCGEN05}[gemm_path]
         cfg.ridge, cfg.l1, cfg.l2, cfg.l1_enc, cfg.l2_enc = ridge, l1, l2, l1_enc, l2_enc
+        cfg.elempi_shared = int(bool(sharedpi))          # zinb-elempi only (dca/network.py:425-427)
         cfg.bn_momentum, cfg.bn_eps = KERAS_DEFAULTS["bn_momentum"], KERAS_DEFAULTS["bn_eps"]
         cfg.rms_rho, cfg.rms_eps = KERAS_DEFAULTS["rms_rho"], KERAS_DEFAULTS["rms_eps"]
         self.cfg = cfg
@@ -241,10 +242,12 @@ class DeviceEngine:
                                      b, self._stream()), "dca_eval_step")
 
     def predict(self, X, sf, rows=None, batch=None, mean=None, disp=None, pi=None, latent=None):
+        """mean (* size factor), dispersion, pi: [batch x n_out] -- for the per-cell heads of 'nb-shared' / 'zinb-shared'
+        dispersion and pi are [batch] (or [batch x 1]); latent: [batch x hidden[center]]."""
         b = self._check_inputs(X, None, sf, rows, batch)
         ld = None
         for t in (mean, disp, pi):
-            if t is not None and t.dim() == 2:
+            if t is not None and t.dim() == 2 and t.shape[1] > 1:
                 ld = t.stride(0) if ld is None else ld
                 if t.stride(0) != ld:
                     raise ValueError("outputs must share a leading dimension")

@@ -2,9 +2,11 @@
 the reference's method surface (.build .save .load_weights .predict .write), backed by the CUDA
 engine instead of Keras graphs.
 
-Accelerated types: 'zinb-conddisp' (dca/network.py:366-421), 'zinb'
-(:496-550), 'nb-conddisp' (:293-339), 'nb' (:249-291).  The other registry keys are accepted
-and raise NotImplementedError at build time (they are re-parameterisations outside the path).
+Flagship types (tcgen05 path): 'zinb-conddisp' (dca/network.py:366-421), 'zinb'
+(:496-550), 'nb-conddisp' (:293-339), 'nb' (:249-291).  The other registry keys -- 'normal' (:143-156),
+'poisson' (:233-246), 'nb-shared' (:341-363), 'zinb-shared' (:465-493), 'zinb-elempi' (:424-462),
+'nb-fork' (:664-760), 'zinb-fork' (:553-661) -- are re-parameterisations of the heads around the same loss
+kernel and run on the shape-general fp32 path of the engine (csrc/extra_types.cu).
 """
 from __future__ import annotations
 
@@ -41,7 +43,8 @@ class Autoencoder:
                  file_path=None,
                  debug=False,
                  x_dtype='float32',
-                 gemm_path='auto'):
+                 gemm_path='auto',
+                 sharedpi=False):
         self.input_size = input_size
         self.output_size = output_size if output_size is not None else input_size
         self.hidden_size = list(hidden_size)
@@ -57,6 +60,7 @@ class Autoencoder:
         self.debug = debug
         self.x_dtype = x_dtype
         self.gemm_path = gemm_path
+        self.sharedpi = sharedpi           # ZINBAutoencoderElemPi only (dca/network.py:425-427)
         self.loss = None
         self.extra_models = {}
         self.model = None          # the reference exposes a Keras model here; ours is .engine
@@ -87,7 +91,7 @@ class Autoencoder:
                                    self.batchnorm, max_batch=max(max_batch, 1), x_dtype=self.x_dtype,
                                    ridge=self.ridge, l1=self.l1_coef, l2=self.l2_coef,
                                    l1_enc=self.l1_enc_coef, l2_enc=self.l2_enc_coef,
-                                   gemm_path=self.gemm_path, seed=self._seed)
+                                   gemm_path=self.gemm_path, seed=self._seed, sharedpi=self.sharedpi)
         self.model = self.engine
         self.encoder = self.engine
         self.loss = self.ae_type
@@ -158,15 +162,16 @@ class Autoencoder:
         sf = np.asarray(adata.obs['size_factors'], dtype=np.float32).reshape(-1)
         N, G = X.shape[0], self.output_size
         bs = min(PREDICT_BATCH, eng.max_batch)
-        cond = self.ae_type in ("zinb-conddisp", "nb-conddisp")
+        cond = self.ae_type not in ("zinb", "nb", "poisson", "normal")     # a dispersion head (vs per-gene theta / none)
+        Gs = 1 if self.ae_type in ("nb-shared", "zinb-shared") else G       # per-cell heads: Dense(1)
         out = {}
         if want_mean: out["mean"] = np.empty((N, G), np.float32)
-        if want_disp: out["dispersion"] = np.empty((N, G), np.float32) if cond else None
-        if want_pi: out["pi"] = np.empty((N, G), np.float32)
+        if want_disp: out["dispersion"] = np.empty((N, Gs), np.float32) if cond else None
+        if want_pi: out["pi"] = np.empty((N, Gs), np.float32)
         if want_latent: out["latent"] = np.empty((N, eng.latent_dim), np.float32)
         mean_d = torch.empty((bs, G), dtype=torch.float32, device=dev) if want_mean else None
-        disp_d = torch.empty((bs, G), dtype=torch.float32, device=dev) if (want_disp and cond) else None
-        pi_d = torch.empty((bs, G), dtype=torch.float32, device=dev) if want_pi else None
+        disp_d = torch.empty((bs, Gs), dtype=torch.float32, device=dev) if (want_disp and cond) else None
+        pi_d = torch.empty((bs, Gs), dtype=torch.float32, device=dev) if want_pi else None
         lat_d = torch.empty((bs, eng.latent_dim), dtype=torch.float32, device=dev) if want_latent else None
         for s in range(0, N, bs):
             e = min(s + bs, N)
@@ -275,18 +280,38 @@ class ZINBConstantDispAutoencoder(_InfoMixin, Autoencoder):   # 'zinb'
     ae_type = "zinb"; has_pi = True; const_disp = True
 
 
-def _not_accelerated(key):
-    class _Unsupported(Autoencoder):
-        ae_type = None
-        registry_key = key
-    _Unsupported.__name__ = "Unsupported_%s" % key.replace("-", "_")
-    return _Unsupported
+class PoissonAutoencoder(Autoencoder):                        # 'poisson'  dca/network.py:233-246
+    ae_type = "poisson"
+
+
+class NormalAutoencoder(Autoencoder):                         # 'normal'   dca/network.py:143-156 (the base class there)
+    ae_type = "normal"
+
+
+class NBSharedAutoencoder(_InfoMixin, Autoencoder):           # 'nb-shared'   dca/network.py:341-363
+    ae_type = "nb-shared"
+
+
+class ZINBSharedAutoencoder(_InfoMixin, Autoencoder):         # 'zinb-shared' dca/network.py:465-493
+    ae_type = "zinb-shared"; has_pi = True
+
+
+class ZINBAutoencoderElemPi(_InfoMixin, Autoencoder):         # 'zinb-elempi' dca/network.py:424-462 (network_kwds sharedpi)
+    ae_type = "zinb-elempi"; has_pi = True
+
+
+class NBForkAutoencoder(_InfoMixin, Autoencoder):             # 'nb-fork'     dca/network.py:664-760
+    ae_type = "nb-fork"
+
+
+class ZINBForkAutoencoder(_InfoMixin, Autoencoder):           # 'zinb-fork'   dca/network.py:553-661
+    ae_type = "zinb-fork"; has_pi = True
 
 
 # same keys as dca/network.py:763-768
-AE_types = {'normal': _not_accelerated('normal'), 'poisson': _not_accelerated('poisson'),
+AE_types = {'normal': NormalAutoencoder, 'poisson': PoissonAutoencoder,
             'nb': NBConstantDispAutoencoder, 'nb-conddisp': NBAutoencoder,
-            'nb-shared': _not_accelerated('nb-shared'), 'nb-fork': _not_accelerated('nb-fork'),
+            'nb-shared': NBSharedAutoencoder, 'nb-fork': NBForkAutoencoder,
             'zinb': ZINBConstantDispAutoencoder, 'zinb-conddisp': ZINBAutoencoder,
-            'zinb-shared': _not_accelerated('zinb-shared'), 'zinb-fork': _not_accelerated('zinb-fork'),
-            'zinb-elempi': _not_accelerated('zinb-elempi')}
+            'zinb-shared': ZINBSharedAutoencoder, 'zinb-fork': ZINBForkAutoencoder,
+            'zinb-elempi': ZINBAutoencoderElemPi}

@@ -112,6 +112,8 @@ def train(adata, network, output_dir=None, optimizer='RMSprop', learning_rate=No
     if world > 1:
         D.broadcast_(eng.params, src=0); D.broadcast_(eng.bn_state, src=0)
         eng.params_changed()
+        if torch.distributed.get_backend() == "nccl":
+            eng.comm_init()          # gradient exchange inside the library: one CUDA graph per step (dca_train_step_dp)
     eng.reset_optimizer()
 
     lr = KERAS_DEFAULTS["rms_lr"] if learning_rate is None else float(learning_rate)

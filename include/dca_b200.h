@@ -45,7 +45,15 @@ typedef enum dca_ae_type {
   DCA_AE_ZINB_CONDDISP = 0,   /* 'zinb-conddisp' ZINBAutoencoder              dca/network.py:366-393 */
   DCA_AE_ZINB = 1,            /* 'zinb'          ZINBConstantDispAutoencoder  dca/network.py:496-522 */
   DCA_AE_NB_CONDDISP = 2,     /* 'nb-conddisp'   NBAutoencoder                dca/network.py:293-316 */
-  DCA_AE_NB = 3               /* 'nb'            NBConstantDispAutoencoder    dca/network.py:249-269 */
+  DCA_AE_NB = 3,              /* 'nb'            NBConstantDispAutoencoder    dca/network.py:249-269 */
+  /* the remaining registry keys: shape-general fp32 path, same loss kernel (extra_types.cu) */
+  DCA_AE_POISSON = 4,         /* 'poisson'       PoissonAutoencoder           dca/network.py:233-246, dca/loss.py:33-48 */
+  DCA_AE_NORMAL = 5,          /* 'normal'        Autoencoder (MSE, linear mean) dca/network.py:143-156 */
+  DCA_AE_NB_SHARED = 6,       /* 'nb-shared'     NBSharedAutoencoder          dca/network.py:341-363 (dispersion per cell) */
+  DCA_AE_ZINB_SHARED = 7,     /* 'zinb-shared'   ZINBSharedAutoencoder        dca/network.py:465-493 (pi, dispersion per cell) */
+  DCA_AE_ZINB_ELEMPI = 8,     /* 'zinb-elempi'   ZINBAutoencoderElemPi        dca/network.py:424-462, dca/layers.py:50-81 */
+  DCA_AE_NB_FORK = 9,         /* 'nb-fork'       NBForkAutoencoder            dca/network.py:664-760 */
+  DCA_AE_ZINB_FORK = 10       /* 'zinb-fork'     ZINBForkAutoencoder          dca/network.py:553-661 */
 } dca_ae_type;
 
 typedef enum dca_dtype { DCA_F32 = 0, DCA_BF16 = 1 } dca_dtype;
@@ -81,12 +89,13 @@ typedef struct dca_config {
   float l1, l2, l1_enc, l2_enc;   /* kernel regularisers, dca/network.py:113-125 */
   float bn_momentum, bn_eps;  /* 0.99, 1e-3 */
   float rms_rho, rms_eps;     /* 0.9, 1e-7 */
+  int32_t elempi_shared;      /* zinb-elempi: network_kwds sharedpi (scalar pi kernel / bias), dca/network.py:425-427,441 */
 } dca_config;
 
 typedef struct dca_handle dca_handle;
 
 typedef struct dca_tensor_info {
-  char name[DCA_NAME_LEN];    /* e.g. "enc0/kernel", "center/bn_beta", "mean/bias", "dispersion/theta" */
+  char name[DCA_NAME_LEN];    /* e.g. "enc0/kernel", "center/bn_beta", "mean/bias", "dispersion/theta", "dec1_last_mean/kernel", "mean_no_act/kernel" */
   int64_t offset;             /* element offset into the region */
   int32_t rows, cols;         /* kernel: (in, out) as in Keras; vectors: rows = 1 */
 } dca_tensor_info;

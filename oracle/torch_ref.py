@@ -42,6 +42,171 @@ def zinb_elem(y, mu, theta, pi, ridge=0.0):
     return res + ridge * pi * pi                                          # :139-140
 
 
+def poisson_elem_sum_and_count(y, mu):
+    """dca/loss.py:33-48: sum of  mu - y log(mu + 1e-10) + lgamma(y + 1)  over the non-NaN targets, and their count."""
+    ok = ~torch.isnan(y)
+    nelem = ok.to(mu.dtype).sum()
+    nelem = torch.where(nelem == 0, torch.ones_like(nelem), nelem)
+    y0 = torch.where(ok, y, torch.zeros_like(y))
+    ret = mu - y0 * torch.log(mu + EPS) + torch.lgamma(y0 + 1.0)
+    return ret.sum(), nelem
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The remaining registry keys of dca/network.py:763-768 (SURVEY.md 8f-4), each a re-parameterisation of the heads:
+#   poisson      :233-246   mean head (MeanAct), poisson_loss (dca/loss.py:33-48)
+#   normal       :143-156   LINEAR mean head, keras mean_squared_error
+#   nb-shared    :341-363   dispersion = Dense(1, DispAct): one theta per CELL
+#   zinb-shared  :465-493   pi = Dense(1, sigmoid) and dispersion = Dense(1, DispAct) per cell
+#   zinb-elempi  :424-462   t = -Dense(G)(h); mean = MeanAct(t); pi = sigmoid(t * k + c) (ElementwiseDense, dca/layers.py:50-81;
+#                           sharedpi: scalar k, c)
+#   nb-fork / zinb-fork :553-760   the decoder layer(s) after 'center' exist once PER HEAD (own Dense + BatchNorm + act)
+EXTRA_TYPES = ("poisson", "normal", "nb-shared", "zinb-shared", "zinb-elempi", "nb-fork", "zinb-fork")
+FORK_BRANCHES = {"nb-fork": ("mean", "disp"), "zinb-fork": ("mean", "disp", "pi")}
+BRANCH_HEAD = {"mean": "mean", "disp": "dispersion", "pi": "pi"}
+
+
+def extra_init_params(n_in, n_out, hidden, ae_type, batchnorm=True, seed=0, dtype="float32", sharedpi=False):
+    """Parameter dict (reference layer names) of the extra types, Glorot-uniform kernels / zero biases like Keras."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    hidden = tuple(hidden)
+    names = layer_names(len(hidden))
+    center = len(hidden) // 2
+    p = {}
+
+    def dense(name, fi, fo, shape=None):
+        lim = math.sqrt(6.0 / (fi + fo))
+        p[name + "/kernel"] = rng.uniform(-lim, lim, size=shape if shape is not None else (fi, fo)).astype(dtype)
+        p[name + "/bias"] = np.zeros(fo if shape is None else shape, dtype)
+
+    def bn(name, h):
+        if batchnorm:
+            p[name + "/bn_beta"] = np.zeros(h, dtype); p[name + "/bn_moving_mean"] = np.zeros(h, dtype)
+            p[name + "/bn_moving_var"] = np.ones(h, dtype)
+    prev = n_in
+    fork = FORK_BRANCHES.get(ae_type)
+    last = {}
+    for i, (nm, h) in enumerate(zip(names, hidden)):
+        if fork and i > center:
+            for br in fork:                               # every fork layer starts from the trunk (dca/network.py:586-596)
+                dense("%s_last_%s" % (nm, br), prev, h); bn("%s_last_%s" % (nm, br), h); last[br] = h
+            continue
+        dense(nm, prev, h); bn(nm, h); prev = h
+    kin = lambda br: last.get(br, prev)
+    if ae_type in ("poisson", "normal"):
+        dense("mean", prev, n_out)
+    elif ae_type == "nb-shared":
+        dense("dispersion", prev, 1); dense("mean", prev, n_out)
+    elif ae_type == "zinb-shared":
+        dense("pi", prev, 1); dense("dispersion", prev, 1); dense("mean", prev, n_out)
+    elif ae_type == "zinb-elempi":
+        dense("dispersion", prev, n_out); dense("mean_no_act", prev, n_out)
+        npi = 1 if sharedpi else n_out
+        dense("pi", npi, npi, shape=(npi,))               # 1-D kernel: Keras computes fan_in = fan_out = shape[0]
+    elif ae_type == "nb-fork":
+        dense("dispersion", kin("disp"), n_out); dense("mean", kin("mean"), n_out)
+    elif ae_type == "zinb-fork":
+        dense("pi", kin("pi"), n_out); dense("dispersion", kin("disp"), n_out); dense("mean", kin("mean"), n_out)
+    else:
+        raise KeyError(ae_type)
+    return p
+
+
+class TorchExtraNet:
+    """float64 autograd statement of one training step of the extra types (the role TF autodiff plays in the reference);
+    same parameter names as the engine.  TEST INFRASTRUCTURE ONLY."""
+
+    def __init__(self, params, hidden, ae_type, batchnorm=True, ridge=0.0, dtype=torch.float64):
+        assert ae_type in EXTRA_TYPES
+        self.hidden = tuple(hidden); self.ae_type = ae_type; self.batchnorm = batchnorm; self.ridge = ridge; self.dtype = dtype
+        self.names = layer_names(len(self.hidden)); self.center = len(self.hidden) // 2
+        self.p = {k: torch.as_tensor(v).to(dtype).clone() for k, v in params.items()}
+        self.train_keys = [k for k in self.p if k.endswith(("/kernel", "/bias", "/bn_beta"))]
+        for k in self.train_keys:
+            self.p[k].requires_grad_(True)
+        self.rms = {k: torch.zeros_like(self.p[k]) for k in self.train_keys}
+        self.mom = KERAS_DEFAULTS["bn_momentum"]; self.bn_eps = KERAS_DEFAULTS["bn_eps"]
+
+    def _layer(self, h, nm, training, stats):
+        a = h @ self.p[nm + "/kernel"] + self.p[nm + "/bias"]
+        pre = a
+        if self.batchnorm:
+            if training:
+                mean = a.mean(0); var = a.var(0, unbiased=False)
+                stats.append((nm, mean.detach(), var.detach()))
+            else:
+                mean = self.p[nm + "/bn_moving_mean"]; var = self.p[nm + "/bn_moving_var"]
+            pre = (a - mean) / torch.sqrt(var + self.bn_eps) + self.p[nm + "/bn_beta"]
+        return a, torch.relu(pre)
+
+    def forward(self, X, sf, training=True):
+        stats = []
+        h = X; latent = None
+        fork = FORK_BRANCHES.get(self.ae_type)
+        branch = {}
+        for i, nm in enumerate(self.names):
+            if fork and i > self.center:
+                for br in fork:
+                    _, branch[br] = self._layer(h, "%s_last_%s" % (nm, br), training, stats)
+                continue
+            a, h = self._layer(h, nm, training, stats)
+            if nm == "center":
+                latent = a
+        hin = lambda br: branch.get(br, h)
+        dense = lambda nm, x: x @ self.p[nm + "/kernel"] + self.p[nm + "/bias"]
+        sfc = sf.reshape(-1, 1)
+        out = {"latent": latent, "stats": stats}
+        t = self.ae_type
+        if t == "normal":
+            out["mean"] = dense("mean", h) * sfc
+        elif t == "zinb-elempi":
+            tt = -dense("mean_no_act", h)
+            out["pi"] = torch.sigmoid(tt * self.p["pi/kernel"] + self.p["pi/bias"]) * torch.ones_like(tt)
+            out["mean"] = torch.clamp(torch.exp(tt), 1e-5, 1e6) * sfc
+            out["dispersion"] = torch.clamp(torch.nn.functional.softplus(dense("dispersion", h)), 1e-4, 1e4)
+        else:
+            out["mean"] = torch.clamp(torch.exp(dense("mean", hin("mean"))), 1e-5, 1e6) * sfc
+            if t != "poisson":
+                out["dispersion"] = torch.clamp(torch.nn.functional.softplus(dense("dispersion", hin("disp"))), 1e-4, 1e4)
+            if t in ("zinb-shared", "zinb-fork"):
+                out["pi"] = torch.sigmoid(dense("pi", hin("pi")))
+        return out
+
+    def loss(self, X, Y, sf, training=True):
+        o = self.forward(X, sf, training)
+        mu = o["mean"]
+        if self.ae_type == "normal":
+            l = ((mu - Y) ** 2).mean()                                   # keras mean_squared_error + batch mean
+        elif self.ae_type == "poisson":
+            s, n = poisson_elem_sum_and_count(Y, mu); l = s / n
+        elif "pi" in o:
+            l = zinb_elem(Y, mu, o["dispersion"].expand_as(mu), o["pi"].expand_as(mu), self.ridge).mean()
+        else:
+            l = nb_elem(Y, mu, o["dispersion"].expand_as(mu)).mean()
+        return l, o["stats"]
+
+    def loss_and_grads(self, X, Y, sf):
+        for k in self.train_keys:
+            self.p[k].grad = None
+        loss, stats = self.loss(X, Y, sf, True)
+        loss.backward()
+        return float(loss.detach()), {k: (self.p[k].grad.detach().clone() if self.p[k].grad is not None else torch.zeros_like(self.p[k]))
+                                      for k in self.train_keys}, stats
+
+    _apply = None
+
+    def train_step(self, X, Y, sf, lr=KERAS_DEFAULTS["rms_lr"], clip=KERAS_DEFAULTS["clipvalue"]):
+        loss, grads, stats = self.loss_and_grads(X, Y, sf)
+        TorchRefNet._apply(self, grads, stats, lr, clip)
+        return loss
+
+    @torch.no_grad()
+    def predict(self, X, sf):
+        o = self.forward(X, sf, False)
+        return {k: v.detach().numpy() for k, v in o.items() if k != "stats" and v is not None}
+
+
 class TorchRefNet:
     """Same parameter names / layouts as oracle.dca_oracle.OracleNet."""
 

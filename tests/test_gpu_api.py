@@ -65,8 +65,35 @@ def test_api_inplace_and_errors():
     bad = _adata(); bad.X[:, 3] = 0
     with pytest.raises(AssertionError, match='all-zero genes'):
         dca(bad, epochs=1)
-    with pytest.raises(NotImplementedError):
-        dca(_adata(), ae_type='zinb-elempi', epochs=1)
+    with pytest.raises(KeyError):
+        dca(_adata(), ae_type='gaussian', epochs=1)
+
+
+def test_api_remaining_ae_types():
+    """The rest of dca/test.py:31-41 ('zinb-elempi' with and without sharedpi) and every other registry key of
+    dca/network.py:763-768 through the public API: outputs changed, info keys present with the reference's shapes."""
+    from dca_b200.api import dca
+    adata = _adata(seed=6)
+    ret = dca(adata, mode='denoise', ae_type='zinb-elempi', copy=True, epochs=1, return_model=False, return_info=True)
+    assert not np.allclose(ret.X[:10], adata.X[:10])
+    assert 'X_dca_dropout' in ret.obsm_keys() and 'dca_loss_history' in ret.uns_keys()
+    ret = dca(adata, mode='denoise', ae_type='zinb-elempi', copy=True, epochs=1, return_model=False, return_info=True,
+              network_kwds={'sharedpi': True})
+    assert not np.allclose(ret.X[:10], adata.X[:10])
+    assert 'X_dca_dropout' in ret.obsm_keys() and ret.obsm['X_dca_dropout'].shape == adata.X.shape
+    for t, disp_shape, has_pi in (('poisson', None, False), ('normal', None, False), ('nb-shared', (300, 1), False),
+                                  ('zinb-shared', (300, 1), True), ('nb-fork', (300, 120), False), ('zinb-fork', (300, 120), True)):
+        ret = dca(adata, mode='denoise', ae_type=t, copy=True, epochs=2, return_info=True, batch_size=64)
+        assert np.all(np.isfinite(ret.X)) and not np.allclose(ret.X[:10], adata.X[:10]), t
+        h = ret.uns['dca_loss_history']
+        assert len(h['loss']) == 2 and np.all(np.isfinite(h['loss'])) and np.all(np.isfinite(h['val_loss'])), t
+        if disp_shape is None:
+            assert 'X_dca_dispersion' not in ret.obsm_keys()
+        else:
+            assert ret.obsm['X_dca_dispersion'].shape == disp_shape, t
+        assert ('X_dca_dropout' in ret.obsm_keys()) == has_pi, t
+        lat = dca(adata, mode='latent', ae_type=t, copy=True, epochs=1, hidden_size=(16, 4, 16))
+        assert lat.obsm['X_dca'].shape == (300, 4), t
 
 
 def test_api_mutates_a_real_anndata_in_place(monkeypatch):

@@ -278,7 +278,9 @@ def test_predict_and_eval_vs_oracle(ae_type):
 def test_engine_errors_are_loud():
     from dca_b200.engine import DeviceEngine
     with pytest.raises(NotImplementedError):
-        DeviceEngine(10, 10, (4,), "poisson")
+        DeviceEngine(10, 10, (4,), "gaussian")
+    with pytest.raises(Exception, match="one decoder layer"):
+        DeviceEngine(10, 10, (8, 4, 8, 8, 8), "zinb-fork")             # forks: exactly one layer after 'center'
     eng = DeviceEngine(10, 10, (4, 2, 4), "zinb", max_batch=8)
     X = torch.zeros((9, 10), device=DEV); Y = torch.zeros((9, 10), device=DEV); sf = torch.ones(9, device=DEV)
     with pytest.raises(ValueError):

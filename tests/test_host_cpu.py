@@ -37,7 +37,11 @@ def test_config_struct_matches_header_and_errors_are_reported():
     assert b"n_in" in lib.dca_last_error()
     cfg.n_in = cfg.n_out = 2000; cfg.max_batch = 4096
     assert lib.dca_arena_bytes(C.byref(cfg), C.byref(n)) == 0 and n.value > 3 * 4096 * 2000 * 4
-    cfg.ae_type = 9
+    cfg.ae_type = 9                                    # nb-fork: (64, 32, 64) has the one decoder layer it needs
+    assert lib.dca_arena_bytes(C.byref(cfg), C.byref(n)) == 0
+    cfg.n_hidden = 5; cfg.hidden[3] = 16; cfg.hidden[4] = 8   # ... two decoder layers after 'center': unsupported, and said so
+    assert lib.dca_arena_bytes(C.byref(cfg), C.byref(n)) == -3 and b"decoder layer" in lib.dca_last_error()
+    cfg.n_hidden = 3; cfg.ae_type = 11
     assert lib.dca_arena_bytes(C.byref(cfg), C.byref(n)) == -3
 
 
@@ -108,9 +112,10 @@ def test_ae_types_registry_keys():
     from dca_b200.network import AE_types
     assert set(AE_types) == {'normal', 'poisson', 'nb', 'nb-conddisp', 'nb-shared', 'nb-fork', 'zinb', 'zinb-conddisp',
                              'zinb-shared', 'zinb-fork', 'zinb-elempi'}
-    net = AE_types['poisson'](input_size=5)
-    with pytest.raises(NotImplementedError):
-        net.build()
+    from dca_b200 import _lib
+    for key, cls in AE_types.items():                     # every registry key maps to an engine type of the same name
+        assert cls.ae_type == key and key in _lib.AE_TYPE_IDS, key
+    assert AE_types['zinb-elempi'](input_size=5, sharedpi=True).sharedpi is True      # dca/network.py:425-427
     import dca.api, dca.network            # alias package resolves
     assert dca.network.AE_types is AE_types
 
