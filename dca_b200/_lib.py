@@ -36,7 +36,7 @@ class Config(C.Structure):
         ("l1_enc", C.c_float), ("l2_enc", C.c_float),
         ("bn_momentum", C.c_float), ("bn_eps", C.c_float),
         ("rms_rho", C.c_float), ("rms_eps", C.c_float),
-        ("elempi_shared", C.c_int32),
+        ("elempi_shared", C.c_int32), ("sync_bn", C.c_int32),
     ]
 
 

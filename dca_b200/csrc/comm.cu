@@ -97,6 +97,16 @@ int Engine::allreduce_range(int64_t lo, int64_t hi, cudaStream_t s) {
   return DCA_OK;
 }
 
+int Engine::bn_allreduce(double* a, double* b, int n, cudaStream_t s) {
+  if (!bn_synced()) return DCA_OK;
+  if (api().GroupStart && b) DCA_NCCL_OK(api().GroupStart());
+  DCA_NCCL_OK(api().AllReduce(a, a, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)comm, s));
+  if (b) DCA_NCCL_OK(api().AllReduce(b, b, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)comm, s));
+  if (api().GroupEnd && b) DCA_NCCL_OK(api().GroupEnd());
+  count_launch(1);
+  return DCA_OK;
+}
+
 // phase 1 -> [comm stream: all-reduce(head bucket, loss slot, flag)] || phase 2 -> all-reduce(rest) -> join
 int Engine::train_step_dp_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows,
                                int Bn, cudaStream_t s) {

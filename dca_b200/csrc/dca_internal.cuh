@@ -79,9 +79,10 @@ int bn_infer_prepare(const float* moving_mean, const float* moving_var, int N, f
 int bias_relu_fwd(const float* a, int64_t ld, int M, int N, float* h, __nv_bfloat16* h_bf16, cudaStream_t s);
 // g = dh * (h > 0), in place on dh
 int relu_bwd(float* dh, const float* h, int64_t ld, int M, int N, cudaStream_t s);
-// da = inv*(g - mean(g) - xhat*mean(g*xhat)); dbeta = sum(g);  sums provided in double
+// da = inv*(g - mean(g) - xhat*mean(g*xhat)); dbeta = sum(g);  sums provided in double; stat_rows: rows behind the
+// sums when they cover more than the M local rows (sync_bn: global batch), 0 = M
 int bn_bwd_apply(float* g_inout, const float* xhat, int64_t ld, int M, int N, const float* inv_std,
-                 const double* sum_g, const double* sum_gx, float* dbeta, cudaStream_t s);
+                 const double* sum_g, const double* sum_gx, float* dbeta, cudaStream_t s, int stat_rows = 0);
 int col_sum_to_float(const double* sum, int N, float* out, cudaStream_t s);
 int theta_prepare(const float* theta_raw, int G, float* theta, float* chain, cudaStream_t s);
 int theta_grad_finish(const float* dtheta, const float* chain, int G, float scale, float* grad_out, cudaStream_t s);

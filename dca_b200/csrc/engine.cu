@@ -276,7 +276,8 @@ int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, boo
     if (cfg.batchnorm) {
       if (training) {
         DCA_TRY(col_sums(a, nullptr, l.out, Bn, l.out, d(o_dsum), d(o_dprod), d(o_scratch), s));
-        DCA_TRY(bn_train_finalize(d(o_dsum), d(o_dprod), Bn, l.out, cfg.bn_eps, cfg.bn_momentum, f(l.o_mean),
+        DCA_TRY(bn_allreduce(d(o_dsum), d(o_dprod), l.out, s));                  // sync_bn: statistics of the global batch
+        DCA_TRY(bn_train_finalize(d(o_dsum), d(o_dprod), bn_rows(Bn), l.out, cfg.bn_eps, cfg.bn_momentum, f(l.o_mean),
                                   f(l.o_inv), st(l.mm), st(l.mv), s));
       } else {
         DCA_TRY(bn_infer_prepare(st(l.mm), st(l.mv), l.out, cfg.bn_eps, f(l.o_mean), f(l.o_inv), s));
@@ -549,6 +550,11 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
     DCA_TRY(relu_bwd(dh, f(l.o_h), l.out, Bn, l.out, s));
     if (cfg.batchnorm) {
       DCA_TRY(col_sums(dh, f(l.o_xhat), l.out, Bn, l.out, d(o_dsum), d(o_dprod), d(o_scratch), s));
+      if (bn_synced()) {          // d beta is this rank's share (the gradient all-reduce sums it); the means are global
+        DCA_TRY(col_sum_to_float(d(o_dsum), l.out, gp(l.beta), s));
+        DCA_TRY(bn_allreduce(d(o_dsum), d(o_dprod), l.out, s));
+        DCA_TRY(bn_bwd_apply(dh, f(l.o_xhat), l.out, Bn, l.out, f(l.o_inv), d(o_dsum), d(o_dprod), nullptr, s, bn_rows(Bn)));
+      } else
       DCA_TRY(bn_bwd_apply(dh, f(l.o_xhat), l.out, Bn, l.out, f(l.o_inv), d(o_dsum), d(o_dprod), gp(l.beta), s));
     }
     if (i == 0 && cur_xb) {

@@ -76,7 +76,7 @@ struct Engine {
   int prof_collect();
   // fused hidden stack (mid_stack.cu)
   bool mid_ok = false; size_t o_bar = 0, o_midpart = 0;
-  bool use_mid(int Bn) const { return mid_ok && Bn <= mid::kMaxRows * mid::kMaxCtas; }
+  bool use_mid(int Bn) const { return mid_ok && !bn_synced() && Bn <= mid::kMaxRows * mid::kMaxCtas; }
   void mid_params(mid::Params& p, int Bn, bool training);
   // tcgen05 path: flags + operand-layout shadows / bf16 activations in the arena
   bool tc_heads = false, tc_enc = false;
@@ -120,6 +120,10 @@ struct Engine {
   int comm_init(const void* id128, int rank, int world);
   int comm_destroy();
   int allreduce_range(int64_t lo, int64_t hi, cudaStream_t s);
+  // sync_bn: sum the BatchNorm column sums (one or two double vectors) over the ranks; bn_rows(Bn) = rows behind the sums
+  bool bn_synced() const { return cfg.sync_bn && comm && comm_world > 1; }
+  int bn_rows(int Bn) const { return bn_synced() ? Bn * comm_world : Bn; }
+  int bn_allreduce(double* a, double* b, int n, cudaStream_t s);
   int train_step_dp_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
                          cudaStream_t s);
 

@@ -236,7 +236,8 @@ int Engine::x_layer_fwd(Layer& l, const void* hin, int64_t ldin, int in_bf16, co
   if (cfg.batchnorm) {
     if (training) {
       DCA_TRY(col_sums(a, nullptr, l.out, Bn, l.out, d(o_dsum), d(o_dprod), d(o_scratch), s));
-      DCA_TRY(bn_train_finalize(d(o_dsum), d(o_dprod), Bn, l.out, cfg.bn_eps, cfg.bn_momentum, f(l.o_mean), f(l.o_inv),
+      DCA_TRY(bn_allreduce(d(o_dsum), d(o_dprod), l.out, s));                    // sync_bn: statistics of the global batch
+      DCA_TRY(bn_train_finalize(d(o_dsum), d(o_dprod), bn_rows(Bn), l.out, cfg.bn_eps, cfg.bn_momentum, f(l.o_mean), f(l.o_inv),
                                 st(l.mm), st(l.mv), s));
     } else {
       DCA_TRY(bn_infer_prepare(st(l.mm), st(l.mv), l.out, cfg.bn_eps, f(l.o_mean), f(l.o_inv), s));
@@ -255,6 +256,11 @@ int Engine::x_layer_bwd(Layer& l, float* dh, const void* hin, int64_t ldin, int 
   DCA_TRY(relu_bwd(dh, f(l.o_h), l.out, Bn, l.out, s));
   if (cfg.batchnorm) {
     DCA_TRY(col_sums(dh, f(l.o_xhat), l.out, Bn, l.out, d(o_dsum), d(o_dprod), d(o_scratch), s));
+    if (bn_synced()) {
+      DCA_TRY(col_sum_to_float(d(o_dsum), l.out, gp(l.beta), s));
+      DCA_TRY(bn_allreduce(d(o_dsum), d(o_dprod), l.out, s));
+      DCA_TRY(bn_bwd_apply(dh, f(l.o_xhat), l.out, Bn, l.out, f(l.o_inv), d(o_dsum), d(o_dprod), nullptr, s, bn_rows(Bn)));
+    } else
     DCA_TRY(bn_bwd_apply(dh, f(l.o_xhat), l.out, Bn, l.out, f(l.o_inv), d(o_dsum), d(o_dprod), gp(l.beta), s));
   }
   GemmArgs g{};

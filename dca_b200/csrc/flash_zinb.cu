@@ -56,9 +56,9 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t byte
 
 // NB branch of one queued element; deliberately not inlined (one copy of the lgamma / digamma code keeps the
 // epilogue loop inside the instruction cache)
-__device__ __noinline__ float4 nb_item(float4 it, float ridge, const float* lf) {
-  const zmath::Elem e = zmath::zinb_elem_nb_mu<zmath::FastOps>(it.x, it.y, it.z, it.w, ridge, lf);
-  return make_float4(e.loss, e.gm, e.gd, e.gp);
+__device__ __noinline__ float4 nb_item(float4 it, const float* lf) {
+  const zmath::Raw1 e = zmath::zinb_nb_raw<zmath::FastOps>(it.x, it.y, it.z, it.w, lf);     // raw derivatives, see zinb_math.cuh
+  return make_float4(e.gmu, e.dth, e.dpi, e.loss);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -222,7 +222,7 @@ flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
     const unsigned lt = (1u << lane) - 1u;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float lsum = 0.f;
+    float lsum = 0.f, lsum_lg = 0.f;            // NLL of the NB items I evaluated (+ ridge) | sum of lg2(D) over my zero counts
     uint32_t ti = 0;
     for (int t = t0; t < t1; ++t, ++ti) {
       const int gt = t / p.n_cb, cb = t % p.n_cb;
@@ -286,43 +286,50 @@ flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
             ys[j] = sub ? y[4 + j] : y[j]; ms[j] = sub ? mm[4 + j] : mm[j]; ds[j] = sub ? dd[4 + j] : dd[j]; ps[j] = sub ? pp[4 + j] : pp[j];
           }
           // ---- queue the non-zero counts of this warp's 32 rows x 4 genes (ballot compaction: ordered by j, lane)
-          unsigned bal[4];
-          int nz = 0, pos[4], base = 0;
+          using namespace zmath;
+          const float2 mA = make_float2(ms[0], ms[1]), mB = make_float2(ms[2], ms[3]);
+          const float2 dA = make_float2(ds[0], ds[1]), dB = make_float2(ds[2], ds[3]);
+          const float2 pA = make_float2(ps[0], ps[1]), pB = make_float2(ps[2], ps[3]);
+          const float2 muA = mul2(mA, splat(sfv)), muB = mul2(mB, splat(sfv));               // dca/layers.py:85
+          const float mu[4] = {muA.x, muA.y, muB.x, muB.y};
+          bool isnz[4];
+          int pos[4], base = 0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const bool is_nz = active && !(ys[j] < 1e-8f);              // loss.py:138
-            bal[j] = __ballot_sync(kFull, is_nz);
-            nz |= is_nz ? (1 << j) : 0;
+            isnz[j] = active && !(ys[j] < 1e-8f);                       // loss.py:138
+            const unsigned bal = __ballot_sync(kFull, isnz[j]);
+            pos[j] = base + __popc(bal & lt); base += __popc(bal);
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { pos[j] = base + __popc(bal[j] & lt); base += __popc(bal[j]); }
           const int total = base;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (nz & (1 << j)) q[pos[j]] = make_float4(ys[j], ms[j] * sfv, ds[j], ps[j]);
+            if (isnz[j]) q[pos[j]] = make_float4(ys[j], mu[j], ds[j], ps[j]);
           __syncwarp();
-          // ---- zero branch for all four elements, branch-free (independent chains interleave); selected below
-          float gm[4], gd[4], gp[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const zmath::Elem e = zmath::zinb_elem_zero_bf<Ops, true>(ms[j], sfv, ds[j], ps[j], p.ridge);
-            const bool use = active && !(nz & (1 << j));
-            lsum += use ? e.loss : 0.f; gm[j] = use ? e.gm : 0.f; gd[j] = use ? e.gd : 0.f; gp[j] = use ? e.gp : 0.f;
+          // ---- zero branch of all four elements as two f32x2 chains (zinb_math.cuh), finishing factors shared with the
+          // queued NB items, which come back as raw derivatives
+          Raw2 zA = zinb_zero_pair<Ops>(muA, dA, pA), zB = zinb_zero_pair<Ops>(muB, dB, pB);
+          const Fin2 fA = finish_factors_pair<Ops, true>(mA, dA, pA, p.inv_n), fB = finish_factors_pair<Ops, true>(mB, dB, pB, p.inv_n);
+          lsum_lg += ((active && !isnz[0]) ? zA.lgD.x : 0.f) + ((active && !isnz[1]) ? zA.lgD.y : 0.f)
+                   + ((active && !isnz[2]) ? zB.lgD.x : 0.f) + ((active && !isnz[3]) ? zB.lgD.y : 0.f);
+          for (int k = lane; k < total; k += 32) { const float4 e = nb_item(q[k], lf); lsum += e.w; q[k] = e; }
+          __syncwarp();
+          if (isnz[0]) { const float4 e = q[pos[0]]; zA.gmu.x = e.x; zA.dth.x = e.y; zA.dpi.x = e.z; }
+          if (isnz[1]) { const float4 e = q[pos[1]]; zA.gmu.y = e.x; zA.dth.y = e.y; zA.dpi.y = e.z; }
+          if (isnz[2]) { const float4 e = q[pos[2]]; zB.gmu.x = e.x; zB.dth.x = e.y; zB.dpi.x = e.z; }
+          if (isnz[3]) { const float4 e = q[pos[3]]; zB.gmu.y = e.x; zB.dth.y = e.y; zB.dpi.y = e.z; }
+          __syncwarp();
+          if (p.ridge != 0.f) {                                         // loss.py:139-140 (uniform; ridge defaults to 0)
+            if (active) lsum += p.ridge * (pA.x * pA.x + pA.y * pA.y + pB.x * pB.x + pB.y * pB.y);
+            zA.dpi = fma2(splat(2.0f * p.ridge), pA, zA.dpi); zB.dpi = fma2(splat(2.0f * p.ridge), pB, zB.dpi);
           }
-          for (int k = lane; k < total; k += 32) q[k] = nb_item(q[k], p.ridge, lf);
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (nz & (1 << j)) {
-              const float4 e = q[pos[j]];
-              const float mj = ms[j];
-              lsum += e.x; gm[j] = (mj > 1e-5f && mj < 1e6f) ? e.y : 0.f; gd[j] = e.z; gp[j] = e.w;
-            }
-          __syncwarp();
+          const float2 msk = splat(active ? 1.0f : 0.0f);              // rows / genes outside the matrix contribute exact zeros
+          const float2 gmA = mul2(mul2(zA.gmu, fA.fm), msk), gmB = mul2(mul2(zB.gmu, fB.fm), msk);
+          const float2 gdA = mul2(mul2(zA.dth, fA.fd), msk), gdB = mul2(mul2(zB.dth, fB.fd), msk);
+          const float2 gpA = mul2(mul2(zA.dpi, fA.fp), msk), gpB = mul2(mul2(zB.dpi, fB.fp), msk);
           uint8_t* zd8 = zdst + sub * 8;
-          *reinterpret_cast<uint2*>(zd8) = make_uint2(pack_bf16x2(gm[0] * p.inv_n, gm[1] * p.inv_n), pack_bf16x2(gm[2] * p.inv_n, gm[3] * p.inv_n));
-          *reinterpret_cast<uint2*>(zd8 + kZBox) = make_uint2(pack_bf16x2(gd[0] * p.inv_n, gd[1] * p.inv_n), pack_bf16x2(gd[2] * p.inv_n, gd[3] * p.inv_n));
-          *reinterpret_cast<uint2*>(zd8 + 2 * kZBox) = make_uint2(pack_bf16x2(gp[0] * p.inv_n, gp[1] * p.inv_n), pack_bf16x2(gp[2] * p.inv_n, gp[3] * p.inv_n));
+          *reinterpret_cast<uint2*>(zd8) = make_uint2(pack_bf16x2(gmA.x, gmA.y), pack_bf16x2(gmB.x, gmB.y));
+          *reinterpret_cast<uint2*>(zd8 + kZBox) = make_uint2(pack_bf16x2(gdA.x, gdA.y), pack_bf16x2(gdB.x, gdB.y));
+          *reinterpret_cast<uint2*>(zd8 + 2 * kZBox) = make_uint2(pack_bf16x2(gpA.x, gpA.y), pack_bf16x2(gpB.x, gpB.y));
         }
       }
       fence_proxy_async_smem();
@@ -330,7 +337,7 @@ flash_zinb_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       if (lane == 0) mbar_arrive(&dz_full[zbuf]);
     }
     // ---- loss: CTA partial, the last CTA folds all partials in a fixed order and finalises (as in zinb_loss.cu)
-    double dsum = (double)lsum;
+    double dsum = (double)lsum - (double)zmath::kLn2 * (double)lsum_lg;        // -log D = -ln2 * lg2 D
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(kFull, dsum, o);
     if (lane == 0) red[ew] = dsum;

@@ -137,11 +137,11 @@ __global__ void relu_bwd_kernel(float* __restrict__ dh, const float* __restrict_
 
 __global__ void bn_bwd_apply_kernel(float* __restrict__ g, const float* __restrict__ xhat, int M, int N,
                                     const float* __restrict__ inv_std, const double* __restrict__ sum_g,
-                                    const double* __restrict__ sum_gx, float* __restrict__ dbeta) {
+                                    const double* __restrict__ sum_gx, float* __restrict__ dbeta, int stat_rows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * N) return;
   const int c = (int)(i % N);
-  const float mg = (float)(sum_g[c] / (double)M), mgx = (float)(sum_gx[c] / (double)M);
+  const float mg = (float)(sum_g[c] / (double)stat_rows), mgx = (float)(sum_gx[c] / (double)stat_rows);
   g[i] = inv_std[c] * (g[i] - mg - xhat[i] * mgx);
   if (i < N && dbeta) dbeta[c] = (float)sum_g[c];
 }
@@ -378,9 +378,10 @@ int relu_bwd(float* dh, const float* h, int64_t ld, int M, int N, cudaStream_t s
 }
 
 int bn_bwd_apply(float* g, const float* xhat, int64_t ld, int M, int N, const float* inv_std, const double* sum_g,
-                 const double* sum_gx, float* dbeta, cudaStream_t s) {
+                 const double* sum_gx, float* dbeta, cudaStream_t s, int stat_rows) {
   (void)ld;
-  bn_bwd_apply_kernel<<<blocks_for((int64_t)M * N), 256, 0, s>>>(g, xhat, M, N, inv_std, sum_g, sum_gx, dbeta);
+  bn_bwd_apply_kernel<<<blocks_for((int64_t)M * N), 256, 0, s>>>(g, xhat, M, N, inv_std, sum_g, sum_gx, dbeta,
+                                                                 stat_rows > 0 ? stat_rows : M);
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }

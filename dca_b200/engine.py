@@ -29,7 +29,8 @@ class DeviceEngine:
                  ae_type: str = "zinb-conddisp", batchnorm: bool = True, max_batch: int = 32,
                  x_dtype: str = "float32", ridge: float = 0.0, l1: float = 0.0, l2: float = 0.0,
                  l1_enc: float = 0.0, l2_enc: float = 0.0, gemm_path: str = "auto",
-                 device: Optional[torch.device] = None, seed: Optional[int] = 0, sharedpi: bool = False):
+                 device: Optional[torch.device] = None, seed: Optional[int] = 0, sharedpi: bool = False,
+                 sync_bn: bool = False):
         if ae_type not in _lib.AE_TYPE_IDS:
             raise NotImplementedError("ae_type %r is not on the accelerated path (supported: %s)"
                                       % (ae_type, sorted(_lib.AE_TYPE_IDS)))
@@ -54,6 +55,7 @@ class DeviceEngine:
         cfg.gemm_path = {"auto": _lib.GEMM_AUTO, "generic": _lib.GEMM_GENERIC, "tcgen05": _lib.GEMM_TCGEN05}[gemm_path]
         cfg.ridge, cfg.l1, cfg.l2, cfg.l1_enc, cfg.l2_enc = ridge, l1, l2, l1_enc, l2_enc
         cfg.elempi_shared = int(bool(sharedpi))          # zinb-elempi only (dca/network.py:425-427)
+        cfg.sync_bn = int(bool(sync_bn))                 # BatchNorm over the global batch in data-parallel runs (comm_init)
         cfg.bn_momentum, cfg.bn_eps = KERAS_DEFAULTS["bn_momentum"], KERAS_DEFAULTS["bn_eps"]
         cfg.rms_rho, cfg.rms_eps = KERAS_DEFAULTS["rms_rho"], KERAS_DEFAULTS["rms_eps"]
         self.cfg = cfg

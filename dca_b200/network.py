@@ -44,7 +44,8 @@ class Autoencoder:
                  debug=False,
                  x_dtype='float32',
                  gemm_path='auto',
-                 sharedpi=False):
+                 sharedpi=False,
+                 sync_bn=False):
         self.input_size = input_size
         self.output_size = output_size if output_size is not None else input_size
         self.hidden_size = list(hidden_size)
@@ -61,6 +62,7 @@ class Autoencoder:
         self.x_dtype = x_dtype
         self.gemm_path = gemm_path
         self.sharedpi = sharedpi           # ZINBAutoencoderElemPi only (dca/network.py:425-427)
+        self.sync_bn = sync_bn             # multi-GPU: BatchNorm statistics over the global batch (no reference counterpart)
         self.loss = None
         self.extra_models = {}
         self.model = None          # the reference exposes a Keras model here; ours is .engine
@@ -91,7 +93,8 @@ class Autoencoder:
                                    self.batchnorm, max_batch=max(max_batch, 1), x_dtype=self.x_dtype,
                                    ridge=self.ridge, l1=self.l1_coef, l2=self.l2_coef,
                                    l1_enc=self.l1_enc_coef, l2_enc=self.l2_enc_coef,
-                                   gemm_path=self.gemm_path, seed=self._seed, sharedpi=self.sharedpi)
+                                   gemm_path=self.gemm_path, seed=self._seed, sharedpi=self.sharedpi,
+                                   sync_bn=self.sync_bn)
         self.model = self.engine
         self.encoder = self.engine
         self.loss = self.ae_type

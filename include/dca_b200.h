@@ -90,6 +90,9 @@ typedef struct dca_config {
   float bn_momentum, bn_eps;  /* 0.99, 1e-3 */
   float rms_rho, rms_eps;     /* 0.9, 1e-7 */
   int32_t elempi_shared;      /* zinb-elempi: network_kwds sharedpi (scalar pi kernel / bias), dca/network.py:425-427,441 */
+  int32_t sync_bn;            /* data-parallel runs (dca_comm_init): BatchNorm statistics over the GLOBAL batch (sum all-reduce of
+                               * the column sums, forward and backward) -- exactly the single-GPU model at the global batch size.
+                               * 0 (default): per-rank batch statistics, no extra collective. */
 } dca_config;
 
 typedef struct dca_handle dca_handle;

@@ -5,12 +5,14 @@ of loss + the three gradient tensors against a float64 torch statement of dca/lo
 Not a test: run by hand on a GPU box,  python tests/diag_loss_ab.py > gpurun_out/loss_ab.log
 """
 import ctypes as C
+import os
 import sys
 
 import numpy as np
 import torch
 
-from dca_b200 import _lib
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dca_b200 import _lib  # noqa: E402
 
 
 def ref64(y, m, sf, d, p, cond):
@@ -73,8 +75,9 @@ def main():
                 gm = torch.zeros((B, G), dtype=tdt, device=dev); gd = torch.zeros_like(gm); gp = torch.zeros_like(gm)
                 dth = torch.zeros(G, device=dev)
                 base = None
-                for ring in (0, 1):
+                for ring, tb in ((0, 0), (1, 0), (1, 148 * 3), (1, 148 * 6), (1, 148 * 9), (1, 148 * 24)):
                     _lib.check(lib.dca_set_tunable(b"loss_ring", ring), "loss_ring")
+                    _lib.check(lib.dca_set_tunable(b"loss_target_blocks", tb), "loss_target_blocks")
                     times = []
                     for it in range(7):
                         flush.zero_()
@@ -98,9 +101,10 @@ def main():
                     e_m = err(gm, rgm); e_p = err(gp, rgp)
                     e_d = err(gd, rgd) if cond else float(((dth.double() * 1.0) - 0).abs().max() * 0)   # dtheta is checked by pytest
                     ms = float(np.median(times)); byts = B * G * (4 + 4 * (3 if cond else 2) + (3 if cond else 2) * gbytes)
-                    print("  ae=%d grad=%s ring=%d  ms=%.4f  %.0f GB/s  loss_rel_dev_vs_ring0=%.1e  grad err vs f64 (of tensor max): m %.1e d %.1e pi %.1e"
-                          % (ae, "bf16" if gbytes == 2 else "fp32", ring, ms, byts / ms / 1e6, abs(val - base) / abs(base), e_m, e_d, e_p), flush=True)
+                    print("  ae=%d grad=%s ring=%d blocks=%4d  ms=%.4f  %.0f GB/s  loss_rel_dev_vs_ring0=%.1e  grad err vs f64 (of tensor max): m %.1e d %.1e pi %.1e"
+                          % (ae, "bf16" if gbytes == 2 else "fp32", ring, tb, ms, byts / ms / 1e6, abs(val - base) / abs(base), e_m, e_d, e_p), flush=True)
     _lib.check(lib.dca_set_tunable(b"loss_ring", 1), "loss_ring")
+    _lib.check(lib.dca_set_tunable(b"loss_target_blocks", 0), "loss_target_blocks")
 
 
 if __name__ == "__main__":

@@ -133,9 +133,16 @@ def test_loss_kernel_edge_cases_on_device(ring, gdt_name):
         assert np.all(np.isfinite(gmn)) and np.all(np.isfinite(gdn)) and np.all(np.isfinite(gpn))
         # exactly zero through a clipped activation
         assert np.all(gmn[(m <= 1e-5) | (m >= 1e6)] == 0) and np.all(gdn[(d <= 1e-4) | (d >= 1e4)] == 0)
-        tol = 3e-4 if gdt == L.F32 else 6e-3
-        # element-wise, relative to max(|ref|, 1e-3 * tensor scale)
-        assert rel_err(gmn, rgm) < tol and rel_err(gdn, rgd) < tol and rel_err(gpn, rgp) < tol
+        # element-wise, relative to max(|ref|, 1e-3 * tensor scale).  Stated tolerance for this EXTREME set: 1e-3 with fp32
+        # gradients (MUFU rcp / lg2 / ex2 approximations at the ends of their ranges; the random-operand tests hold 3e-4)
+        tol = 1e-3 if gdt == L.F32 else 6e-3
+        for got, ref, nm in ((gmn, rgm, "dzm"), (gdn, rgd, "dzd"), (gpn, rgp, "dzp")):
+            scale = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)) + 1e-30)
+            err = np.abs(got - ref) / scale
+            k = np.unravel_index(int(np.argmax(err)), err.shape)
+            print("\n[edge ring=%d %s %s] worst %.2e at y=%g m=%g sf=%g d=%g pi=%g: got %g ref %g"
+                  % (ring, gdt_name, nm, err[k], Y[k], m[k], sf[k[0]], d[k], pi[k], got[k], ref[k]))
+            assert err[k] < tol, (nm, err[k])
     finally:
         L.check(lib.dca_set_tunable(b"loss_ring", 1))
 
