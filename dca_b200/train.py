@@ -74,7 +74,19 @@ def train(adata, network, output_dir=None, optimizer='RMSprop', learning_rate=No
           early_stop=15, batch_size=32, clip_grad=5., save_weights=False,
           validation_split=0.1, tensorboard=False, verbose=True, threads=None,
           **kwds):
-    """Same signature as dca/train.py:35-39.  ``threads`` is accepted and ignored (GPU path)."""
+    """Same signature as dca/train.py:35-39.  ``threads`` is accepted and ignored (GPU path).
+
+    Extra keyword (``training_kwds`` of ``dca()``): ``stream`` -- False (default): the shard lives in HBM for the whole
+    run, rows are reshuffled every epoch exactly like Keras; True / 'auto': train from HOST memory through
+    dca_stream_* (raw counts bit-packed in pinned memory, every step copies its batch host->device while the previous
+    one computes and normalises it on the device, dca/io.py:99-109 restated) -- for matrices that do not fit the GPU
+    ('auto' switches when X + Y would exceed 60 % of the free device memory).  In streaming mode the training rows are
+    shuffled ONCE and every epoch visits the batches in a new random order (documented deviation from Keras' per-epoch
+    row shuffle).  Other keywords of the reference's model.fit (e.g. shuffle=False) are honoured or rejected loudly."""
+    stream = kwds.pop('stream', False)
+    shuffle = kwds.pop('shuffle', True)
+    if kwds:
+        raise TypeError("train() got keyword arguments the accelerated fit loop does not implement: %s" % sorted(kwds))
     if optimizer != 'RMSprop':
         raise NotImplementedError("only the RMSprop optimizer is on the accelerated path (got %r)" % optimizer)
     if tensorboard:
@@ -101,8 +113,17 @@ def train(adata, network, output_dir=None, optimizer='RMSprop', learning_rate=No
     va_lo, va_hi = D.shard_bounds(N - split_at, rank, world, equal=False)
     va_lo += split_at; va_hi += split_at
 
+    if world > 1 and rank == 0 and (split_at % world) and verbose:
+        print("dca: %d training cells do not divide over %d ranks; the last %d are left out of every epoch"
+              % (split_at, world, split_at % world))
     eng = network.ensure_engine(max_batch=batch_size)
     dev = eng.device
+    if stream == 'auto':
+        free = torch.cuda.mem_get_info(dev)[0]
+        stream = (tr_hi - tr_lo + va_hi - va_lo) * X.shape[1] * (4 + eng.params.element_size()) > 0.6 * free
+    if stream:
+        return _fit_stream(eng, network, X, Yh, sf, (tr_lo, tr_hi), (va_lo, va_hi), batch_size, epochs, learning_rate, reduce_lr,
+                           early_stop, clip_grad, world, rank, verbose, save_weights, output_dir, shuffle)
     Xd = _to_device(np.concatenate([X[tr_lo:tr_hi], X[va_lo:va_hi]]), eng.x_dtype, dev)
     Yd = _to_device(np.concatenate([Yh[tr_lo:tr_hi], Yh[va_lo:va_hi]]), torch.float32, dev)
     sfd = _to_device(np.concatenate([sf[tr_lo:tr_hi], sf[va_lo:va_hi]]), torch.float32, dev)
@@ -130,7 +151,118 @@ def train(adata, network, output_dir=None, optimizer='RMSprop', learning_rate=No
     torch.cuda.set_stream(torch.cuda.Stream(dev))
     try:
         hist = _fit_loop(eng, network, Xd, Yd, sfd, n_tr, n_va, steps, batch_size, epochs, ctl, clip_grad, gscale, world, rank,
-                         dev, hist, verbose, save_weights, output_dir)
+                         dev, hist, verbose, save_weights, output_dir, shuffle)
+    finally:
+        torch.cuda.synchronize(dev)
+        torch.cuda.set_stream(prev_stream)
+    if not hist.history["val_loss"]:
+        del hist.history["val_loss"]
+    return hist
+
+
+def _epoch_end(eng, network, hist, ctl, epoch, epochs, n_va, world, rank, dev, verbose, save_weights, output_dir, best_val):
+    """Epoch bookkeeping shared by the resident and the streaming loop: reduce the accumulators over ranks, history,
+    ModelCheckpoint, ReduceLROnPlateau / EarlyStopping.  Returns (stop, best_val)."""
+    acc = np.asarray(eng.read_epoch_acc(reset=True), dtype=np.float64)
+    if world > 1:
+        acc = D.all_reduce_sum_host(acc, dev)
+        if eng.bn_state.numel():
+            D.all_reduce_sum_(eng.bn_state); eng.bn_state.mul_(1.0 / world)
+    loss = acc[0] / acc[1] if acc[1] > 0 else float("nan")
+    if not np.isfinite(loss):
+        loss = float("inf")                       # _nan2inf convention, dca/loss.py:148
+    val = None
+    if n_va > 0 or (world > 1 and acc[3] > 0):
+        val = acc[2] / acc[3] + network.penalty_value()
+        if not np.isfinite(val):
+            val = float("inf")
+    hist.epoch.append(epoch)
+    hist.history["loss"].append(float(loss))
+    hist.history["lr"].append(float(ctl.lr))
+    if val is not None:
+        hist.history["val_loss"].append(float(val))
+    if verbose and rank == 0:
+        print("Epoch %d/%d - loss: %.4f%s - lr: %g" % (epoch + 1, epochs, loss,
+                                                    "" if val is None else " - val_loss: %.4f" % val, ctl.lr))
+    if save_weights and output_dir is not None and rank == 0:
+        mon = val if val is not None else loss
+        if mon < best_val:                       # ModelCheckpoint(save_best_only=True), dca/train.py:64-69
+            best_val = mon
+            network.save_weights(os.path.join(output_dir, "weights.npz"))
+    return ctl.on_epoch_end(epoch, val), best_val
+
+
+def _fit_stream(eng, network, X, Yh, sf, tr, va, batch_size, epochs, learning_rate, reduce_lr, early_stop, clip_grad, world, rank,
+                verbose, save_weights, output_dir, shuffle):
+    """Training from host memory (dca_stream_*): see train().  X is only used for the (small, resident) validation rows;
+    the training rows travel as bit-packed raw counts and are normalised on the device."""
+    from . import io as dio
+    from .hostmem import pin_near_gpu
+    dev = eng.device
+    (tr_lo, tr_hi), (va_lo, va_hi) = tr, va
+    if eng.n_in != eng.n_out or Yh.shape[1] != X.shape[1]:
+        raise NotImplementedError("stream=True needs the raw counts of the input genes as the target (no output_subset)")
+    n_tr, n_va = tr_hi - tr_lo, va_hi - va_lo
+    order0 = np.arange(tr_lo, tr_hi)
+    if shuffle:
+        np.random.shuffle(order0)                 # ONE row shuffle; the epochs permute whole batches
+    Ytr = np.ascontiguousarray(Yh[order0]); sftr = np.ascontiguousarray(sf[order0])
+    # the transform X = (log1p(y / sf) - mean_g) / std_g the host normalisation applied (dca/io.py:99-109), recovered from
+    # (X, raw) of a few hundred rows: two unknowns per gene
+    l = np.log1p(Yh / sf[:, None]) if n_tr + n_va <= 4096 else None
+    if l is None:
+        pick = np.linspace(0, Yh.shape[0] - 1, 4096).astype(np.int64)
+        l = np.log1p(Yh[pick] / sf[pick, None]); xs = X[pick]
+    else:
+        xs = X
+    lm, xm = l.mean(0, dtype=np.float64), xs.mean(0, dtype=np.float64)
+    lv = ((l - lm) * (xs - xm)).sum(0, dtype=np.float64); xv = ((xs - xm) ** 2).sum(0, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        std = np.where(xv > 0, lv / xv, 1.0)       # l = mean + std * x  =>  std = cov(l, x) / var(x)
+    std[~np.isfinite(std) | (std <= 0)] = 1.0
+    mean = lm - std * xm
+    if float(np.max(np.abs((l - mean) / std - xs))) > 1e-2:
+        raise NotImplementedError("stream=True supports the default preprocessing only (size factors + log1p [+ scale], "
+                                  "dca/io.py:99-109): adata.X is not (log1p(raw / size_factors) - mean_g) / std_g")
+    eng.set_input_transform(mean, std, True, True)
+    packed = dio.pack_counts(Ytr, "auto", batch=batch_size)
+    sf_h = pin_near_gpu(torch.from_numpy(sftr.astype(np.float32)), dev.index or 0)
+    Xv = _to_device(X[va_lo:va_hi], eng.x_dtype, dev) if n_va else None
+    Yv = _to_device(Yh[va_lo:va_hi], torch.float32, dev) if n_va else None
+    sfv = _to_device(sf[va_lo:va_hi], torch.float32, dev) if n_va else None
+    if world > 1:
+        D.broadcast_(eng.params, src=0); D.broadcast_(eng.bn_state, src=0)
+        eng.params_changed()
+        if torch.distributed.get_backend() == "nccl":
+            eng.comm_init()
+    eng.reset_optimizer()
+    lr = KERAS_DEFAULTS["rms_lr"] if learning_rate is None else float(learning_rate)
+    ctl = PlateauAndStop(lr, reduce_lr, early_stop, verbose)
+    hist = History()
+    nb = (n_tr + batch_size - 1) // batch_size
+    gscale = 1.0 / world
+    torch.cuda.synchronize(dev)
+    prev_stream = torch.cuda.current_stream(dev)
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
+    best_val = np.inf
+    try:
+        for epoch in range(epochs):
+            border = np.random.permutation(nb) if shuffle else np.arange(nb)
+            eng.read_epoch_acc(reset=True)
+            eng.stream_begin(packed, sf_h, batch_size)
+            for k in range(nb):
+                eng.stream_step(int(border[k]), int(border[k + 1]) if k + 1 < nb else -1)
+                if world > 1:
+                    eng.allreduce_grads() if getattr(eng, "_comm", False) else D.all_reduce_sum_(eng.grads)
+                eng.apply_update(ctl.lr, clip_grad, gscale)
+            eng.stream_end()
+            for s0 in range(0, n_va, batch_size):
+                e = min(s0 + batch_size, n_va)
+                eng.eval_step(Xv[s0:e], Yv[s0:e], sfv[s0:e])
+            stop, best_val = _epoch_end(eng, network, hist, ctl, epoch, epochs, n_va, world, rank, dev, verbose, save_weights,
+                                        output_dir, best_val)
+            if stop:
+                break
     finally:
         torch.cuda.synchronize(dev)
         torch.cuda.set_stream(prev_stream)
@@ -140,12 +272,13 @@ def train(adata, network, output_dir=None, optimizer='RMSprop', learning_rate=No
 
 
 def _fit_loop(eng, network, Xd, Yd, sfd, n_tr, n_va, steps, batch_size, epochs, ctl, clip_grad, gscale, world, rank, dev, hist,
-              verbose, save_weights, output_dir):
+              verbose, save_weights, output_dir, shuffle=True):
     best_val = np.inf
     for epoch in range(epochs):
         # Keras: np.random.shuffle(index_array) with the global NumPy RNG (seeded in api.dca / CLI)
         order = np.arange(n_tr)
-        np.random.shuffle(order)
+        if shuffle:
+            np.random.shuffle(order)
         order_d = torch.from_numpy(order.astype(np.int32)).to(dev)
         eng.read_epoch_acc(reset=True)
         for s in range(steps):
@@ -159,33 +292,9 @@ def _fit_loop(eng, network, Xd, Yd, sfd, n_tr, n_va, steps, batch_size, epochs, 
         for s in range(n_tr, n_tr + n_va, batch_size):
             e = min(s + batch_size, n_tr + n_va)
             eng.eval_step(Xd[s:e], Yd[s:e], sfd[s:e])
-        acc = np.asarray(eng.read_epoch_acc(reset=True), dtype=np.float64)
-        if world > 1:
-            acc = D.all_reduce_sum_host(acc, dev)
-            if eng.bn_state.numel():
-                D.all_reduce_sum_(eng.bn_state); eng.bn_state.mul_(1.0 / world)
-        loss = acc[0] / acc[1] if acc[1] > 0 else float("nan")
-        if not np.isfinite(loss):
-            loss = float("inf")                       # _nan2inf convention, dca/loss.py:148
-        val = None
-        if n_va > 0 or (world > 1 and acc[3] > 0):
-            val = acc[2] / acc[3] + network.penalty_value()
-            if not np.isfinite(val):
-                val = float("inf")
-        hist.epoch.append(epoch)
-        hist.history["loss"].append(float(loss))
-        hist.history["lr"].append(float(ctl.lr))
-        if val is not None:
-            hist.history["val_loss"].append(float(val))
-        if verbose and rank == 0:
-            print("Epoch %d/%d - loss: %.4f%s - lr: %g" % (epoch + 1, epochs, loss,
-                                                        "" if val is None else " - val_loss: %.4f" % val, ctl.lr))
-        if save_weights and output_dir is not None and rank == 0:
-            mon = val if val is not None else loss
-            if mon < best_val:                       # ModelCheckpoint(save_best_only=True), dca/train.py:64-69
-                best_val = mon
-                network.save_weights(os.path.join(output_dir, "weights.npz"))
-        if ctl.on_epoch_end(epoch, val):
+        stop, best_val = _epoch_end(eng, network, hist, ctl, epoch, epochs, n_va, world, rank, dev, verbose, save_weights,
+                                    output_dir, best_val)
+        if stop:
             break
     return hist
 

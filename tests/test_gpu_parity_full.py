@@ -345,3 +345,32 @@ def test_fused_heads_kernel_vs_oracle_small():
         ref = og[name].reshape(-1); got = g[off: off + r * c]
         err = np.max(np.abs(got - ref)) / (np.max(np.abs(ref)) + 1e-30)
         assert err < (3e-3 if name.startswith(("mean", "dispersion", "pi")) else 3e-2), (name, err)
+
+
+def test_train_streaming_from_host_equals_resident_training():
+    """train(stream=True) -- the public-API route to dca_stream_* (bit-packed raw counts in pinned host memory, on-device
+    normalisation, copy of batch i+1 under the step of batch i) -- gives the history of the resident path when both
+    visit the same batches (shuffle=False); 'auto' stays resident for a matrix that fits; unknown fit keywords are
+    rejected instead of swallowed."""
+    from dca_b200.anndata_lite import AnnData
+    from dca_b200 import io
+    from dca_b200.network import AE_types
+    from dca_b200.train import train
+    N, G, bs, epochs = 1000, 64, 128, 3
+    Y = synth_counts(N, G, 29); Y[5, 3] = 300.0                       # one count that needs the overflow list
+    ad = io.normalize(io.read_dataset(AnnData(Y.copy())), filter_min_counts=False)
+    hists = {}
+    for mode in (False, True, "auto"):
+        net = AE_types["zinb-conddisp"](input_size=G, output_size=G, hidden_size=(64, 32, 64), gemm_path="generic")
+        net.build(max_batch=bs, seed=3)
+        hists[mode] = train(ad, net, epochs=epochs, batch_size=bs, verbose=False, stream=mode, shuffle=False).history
+    np.testing.assert_allclose(hists[True]["loss"], hists[False]["loss"], rtol=5e-5)
+    np.testing.assert_allclose(hists[True]["val_loss"], hists[False]["val_loss"], rtol=5e-5)
+    np.testing.assert_allclose(hists["auto"]["loss"], hists[False]["loss"], rtol=1e-7)
+    assert hists[True]["loss"][-1] < hists[True]["loss"][0]
+    net = AE_types["nb"](input_size=G, output_size=G, hidden_size=(16, 8, 16)); net.build(max_batch=bs, seed=0)
+    with pytest.raises(TypeError, match="steps_per_epoch"):
+        train(ad, net, epochs=1, batch_size=bs, verbose=False, steps_per_epoch=3)
+    # default shuffling in streaming mode still trains
+    h = train(ad, net, epochs=2, batch_size=bs, verbose=False, stream=True).history
+    assert np.all(np.isfinite(h["loss"])) and len(h["val_loss"]) == 2
