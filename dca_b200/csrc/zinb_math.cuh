@@ -7,7 +7,8 @@
 //   log(1+mu/te) = -log r =: L1            (series in q for q < 1/16, else lg2)
 //   t2 (loss.py:88) = (theta+y) L1 + y (log te - log(mu+eps)) = theta L1 - y log((mu+eps)/den)
 //   zero_nb (loss.py:136) = r^theta = exp(-theta L1)
-//   d/dmu * mu      = theta (mu - y)/den                 (nb)   |  w theta q          (zero)
+//   d/dmu * mu      = theta (mu + eps - y)/den * mu/(mu+eps)   (nb; the second factor is the eps of log(mu+eps): 1 - 5e-4
+//                     at mu = 2e-7, i.e. MeanAct's floor times a small size factor)   |  w theta q          (zero)
 //   d/dtheta        = [L1 - q] + y/den - (psi(y+te)-psi(te))  (nb)   |  w [L1 - q]   (zero)
 //   lgamma(te)-lgamma(y+te) = -sum_{k<y} log(te+k),  psi(te)-psi(y+te) = -sum_{k<y} 1/(te+k)
 //     (integer y <= 16: product recurrence; otherwise shifted Stirling / asymptotic digamma)
@@ -256,7 +257,7 @@ DCA_HD Elem zinb_elem_nb(float y, float m, float sf, float th, float pi, float r
   lgam_digam_diff<Ops>(s.te, y, lg, dg);
   float nb = lgamma_1p<Ops>(y, lf_table) - lg + s.th * s.L1 - y * (kLn2 * Ops::lg2((s.mu + kEps) * s.rden));
   if (nb != nb) nb = INFINITY;                             // _nan2inf  loss.py:105
-  o.gm = s.th * (s.mu - y) * s.rden;
+  o.gm = s.th * (s.mu + kEps - y) * s.rden * (s.mu * Ops::rcp(s.mu + kEps));
   if (HAS_PI) {
     const float qq = 1.0f - pi + kEps;
     nb -= kLn2 * Ops::lg2(qq);                             // loss.py:130
@@ -277,7 +278,7 @@ DCA_HD Elem zinb_elem_nb_mu(float y, float mu, float th, float pi, float ridge, 
   lgam_digam_diff<Ops>(s.te, y, lg, dg);
   float nb = lgamma_1p<Ops>(y, lf_table) - lg + s.th * s.L1 - y * (kLn2 * Ops::lg2((s.mu + kEps) * s.rden));
   if (nb != nb) nb = INFINITY;                             // _nan2inf  loss.py:105
-  o.gm = s.th * (s.mu - y) * s.rden;
+  o.gm = s.th * (s.mu + kEps - y) * s.rden * (s.mu * Ops::rcp(s.mu + kEps));
   const float qq = 1.0f - pi + kEps;
   nb -= kLn2 * Ops::lg2(qq);                               // loss.py:130
   o.loss = nb;
@@ -407,12 +408,13 @@ DCA_HD Raw1 zinb_nb_raw(float y, float mu, float th_in, float pi, const float* l
   } else {
     lgam_digam_diff<Ops>(te, y, lg, dg);
   }
-  float nb = lgamma_1p<Ops>(y, lf_table) - lg + th * L1 - y * (kLn2 * Ops::lg2((mu + kEps) * rden));
+  const float mue = mu + kEps;
+  float nb = lgamma_1p<Ops>(y, lf_table) - lg + th * L1 - y * (kLn2 * Ops::lg2(mue * rden));
   if (nb != nb) nb = INFINITY;                             // _nan2inf  loss.py:105
   const float qq = 1.0f - pi + kEps;
   Raw1 o;
   o.loss = nb - kLn2 * Ops::lg2(qq);                       // loss.py:130
-  o.gmu = th * (mu - y) * rden;
+  o.gmu = th * (mue - y) * rden * (mu * Ops::rcp(mue));    // exact: the eps of log(mu + eps) kept (see the header note)
   o.dth = f + y * rden - dg;
   o.dpi = Ops::rcp(qq);
   return o;

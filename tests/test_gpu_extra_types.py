@@ -82,8 +82,9 @@ def test_extra_type_trajectory_eval_and_predict(ae_type, sharedpi):
     pi = torch.empty((B, 1 if shared else G), device=DEV) if "pi" in ref else None
     eng.predict(Xd, sfd, mean=mean, disp=disp, pi=pi, latent=lat)
     torch.cuda.synchronize()
-    np.testing.assert_allclose(mean.cpu().numpy(), ref["mean"], rtol=2e-3, atol=1e-6)
-    np.testing.assert_allclose(lat.cpu().numpy(), ref["latent"], rtol=2e-3, atol=1e-5)
+    # tolerances relative to the tensor scale (linear outputs cross zero: 'normal' mean, latent)
+    np.testing.assert_allclose(mean.cpu().numpy(), ref["mean"], rtol=2e-3, atol=5e-4 * np.abs(ref["mean"]).max())
+    np.testing.assert_allclose(lat.cpu().numpy(), ref["latent"], rtol=2e-3, atol=5e-4 * np.abs(ref["latent"]).max())
     if disp is not None:
         np.testing.assert_allclose(disp.cpu().numpy().reshape(ref["dispersion"].shape), ref["dispersion"], rtol=2e-3)
     if pi is not None:

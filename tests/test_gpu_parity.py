@@ -479,7 +479,9 @@ def test_fused_heads_kernel_equals_three_kernel_path(shape):
         for name, off, r, c in e2.param_info:
             g1, g2 = G1[off: off + r * c], G2[off: off + r * c]
             # dW1 sits behind the bf16 rounding of dA1: an fp32 ulp of order noise in dH3 can flip that rounding (2^-9)
-            rtol = 3e-2 if name == "enc0/kernel" else 2e-4
+            # the other hidden-stack tensors see that flip diluted through the 64 -> 32 -> 64 layers
+            head = name.startswith(("mean", "dispersion", "pi"))
+            rtol = 3e-2 if name == "enc0/kernel" else (2e-4 if head else 2e-3)
             assert np.max(np.abs(g1 - g2)) <= rtol * np.max(np.abs(g2)) + 1e-6 * scale, (step, name, np.max(np.abs(g1 - g2)), np.max(np.abs(g2)), scale)
         for e in (e1, e2):
             e.apply_update(1e-3, 5.0)
