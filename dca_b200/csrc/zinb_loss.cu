@@ -510,7 +510,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool COND_DISP, typename GT>
+// IDXQ (tunable loss_ring = 2): the queue of non-zero counts holds one-byte ELEMENT INDICES instead of 16-byte operand
+// copies -- the evaluating lane reads y / m / d / pi of the element from the staging slot itself and writes the three raw
+// derivatives back in place, the owner re-reads its vector -- which frees 15 KB of shared memory for a fourth ring slot.
+template <bool COND_DISP, typename GT, bool IDXQ>
 __global__ void __launch_bounds__(kThreads, 3)
 zinb_loss_bwd_ring_kernel(const float* __restrict__ Y, int64_t ldy, const int32_t* __restrict__ rows,
                           const float* __restrict__ sf, const float* m, const float* d, const float* pi,
@@ -522,7 +525,8 @@ zinb_loss_bwd_ring_kernel(const float* __restrict__ Y, int64_t ldy, const int32_
   constexpr int kArrays = COND_DISP ? 4 : 3;                           // y, m, [d], pi
   constexpr uint32_t kSegBytes = kThreads * 16;                        // one block-row segment of one tensor (4 KB)
   constexpr uint32_t kSlotBytes = kArrays * kSegBytes;
-  float4* items = reinterpret_cast<float4*>(smem_ring + kRing * kSlotBytes);           // [8 warps][128]
+  constexpr int RING = IDXQ ? kRing + 1 : kRing;
+  float4* items = reinterpret_cast<float4*>(smem_ring + RING * kSlotBytes);            // [8 warps][128] operand copies | indices
   __shared__ double red[kWarps];
   __shared__ float lf[zmath::kLogFactN];
   __shared__ float s_sf[kMaxRowsPerBlock];
@@ -549,7 +553,7 @@ zinb_loss_bwd_ring_kernel(const float* __restrict__ Y, int64_t ldy, const int32_
   __syncthreads();
 
   const uint32_t my = tc::smem_u32(smem_ring) + threadIdx.x * 16;      // my 16 bytes inside every segment
-  const uint32_t ring_end = my + kRing * kSlotBytes;
+  const uint32_t ring_end = my + RING * kSlotBytes;
   const float* ysrc = Y + c0 + col;
   const float* msrc = m + (int64_t)r0 * ld + c0 + col;
   const float* dsrc = COND_DISP ? d + (int64_t)r0 * ld + c0 + col : nullptr;
@@ -576,11 +580,14 @@ zinb_loss_bwd_ring_kernel(const float* __restrict__ Y, int64_t ldy, const int32_
   float tacc[kVec] = {0.f, 0.f, 0.f, 0.f};
   {
 #pragma unroll
-    for (int i = 0; i < kRing; ++i) {                                  // one group per row, empty groups keep the count fixed
+    for (int i = 0; i < RING; ++i) {                                   // one group per row, empty groups keep the count fixed
       if (i < nrows) issue_next();
       cp_async_commit();
     }
     float4* q = items + warp * (32 * kVec);
+    unsigned char* qb = reinterpret_cast<unsigned char*>(items) + warp * (32 * kVec);
+    auto lds32 = [](uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; };
+    auto sts32 = [](uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); };
     float thg[kVec] = {1.f, 1.f, 1.f, 1.f};
     if (!COND_DISP) {
 #pragma unroll
@@ -597,7 +604,8 @@ zinb_loss_bwd_ring_kernel(const float* __restrict__ Y, int64_t ldy, const int32_
       return v;
     };
     for (int i = 0; i < nrows; ++i) {
-      cp_async_wait<kRing - 1>();                                      // my copies of row i have landed
+      cp_async_wait<RING - 1>();                                       // my copies of row i have landed
+      const uint32_t cslot = rslot, wstrip = rslot - (uint32_t)lane * 16u;       // my vector / my warp's strip in this slot
       const float4 vy = lds128(rslot), vm = lds128(rslot + kSegBytes);
       const float4 vd = COND_DISP ? lds128(rslot + 2 * kSegBytes) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 vp = lds128(rslot + (kArrays - 1) * kSegBytes);
@@ -625,17 +633,39 @@ zinb_loss_bwd_ring_kernel(const float* __restrict__ Y, int64_t ldy, const int32_
       const int total = base;
 #pragma unroll
       for (int j = 0; j < kVec; ++j)
-        if (isnz[j]) q[pos[j]] = make_float4(y[j], mu[j], dd[j], pp[j]);
+        if (isnz[j]) { if (IDXQ) qb[pos[j]] = (unsigned char)(lane * kVec + j); else q[pos[j]] = make_float4(y[j], mu[j], dd[j], pp[j]); }
       __syncwarp();
-      // the operands of row i have been consumed (they fed the ballots / the queue): refill my slot with row i + kRing
-      if (nxt < nrows) issue_next();
-      cp_async_commit();
+      if (!IDXQ) {
+        // the operands of row i have been consumed (they fed the ballots / the queue): refill my slot with row i + kRing
+        if (nxt < nrows) issue_next();
+        cp_async_commit();
+      }
       // ---- zero branch of my four elements, two f32x2 chains
       Raw2 zA = zinb_zero_pair<Ops>(muA, dA, pA), zB = zinb_zero_pair<Ops>(muB, dB, pB);
       const Fin2 fA = finish_factors_pair<Ops, COND_DISP>(mA, dA, pA, inv_n), fB = finish_factors_pair<Ops, COND_DISP>(mB, dB, pB, inv_n);
       lsum_lg += ((active && !isnz[0]) ? zA.lgD.x : 0.f) + ((active && !isnz[1]) ? zA.lgD.y : 0.f)
                + ((active && !isnz[2]) ? zB.lgD.x : 0.f) + ((active && !isnz[3]) ? zB.lgD.y : 0.f);
       // ---- dense NB pass over the queue (item k by lane k mod 32): raw derivatives back into the queue
+      if (IDXQ) {
+        for (int k = lane; k < total; k += 32) {
+          const int idx = qb[k];
+          const uint32_t e4 = wstrip + (uint32_t)idx * 4u;
+          const float th = COND_DISP ? lds32(e4 + 2 * kSegBytes) : __ldg(d + c0 + warp * (32 * kVec) + idx);
+          const Raw1 e = zinb_nb_raw<Ops>(lds32(e4), lds32(e4 + kSegBytes) * row_sf, th, lds32(e4 + (kArrays - 1) * kSegBytes), lf);
+          lsum_nb += e.loss;
+          sts32(e4, e.gmu); sts32(e4 + kSegBytes, e.dth); sts32(e4 + (kArrays - 1) * kSegBytes, e.dpi);   // in place of y, m, pi
+        }
+        __syncwarp();
+        const float4 r0v = lds128(cslot), r1v = lds128(cslot + kSegBytes), r2v = lds128(cslot + (kArrays - 1) * kSegBytes);
+        zA.gmu.x = isnz[0] ? r0v.x : zA.gmu.x; zA.dth.x = isnz[0] ? r1v.x : zA.dth.x; zA.dpi.x = isnz[0] ? r2v.x : zA.dpi.x;
+        zA.gmu.y = isnz[1] ? r0v.y : zA.gmu.y; zA.dth.y = isnz[1] ? r1v.y : zA.dth.y; zA.dpi.y = isnz[1] ? r2v.y : zA.dpi.y;
+        zB.gmu.x = isnz[2] ? r0v.z : zB.gmu.x; zB.dth.x = isnz[2] ? r1v.z : zB.dth.x; zB.dpi.x = isnz[2] ? r2v.z : zB.dpi.x;
+        zB.gmu.y = isnz[3] ? r0v.w : zB.gmu.y; zB.dth.y = isnz[3] ? r1v.w : zB.dth.y; zB.dpi.y = isnz[3] ? r2v.w : zB.dpi.y;
+        __syncwarp();
+        // the slot has been read back by its owners: refill it with row i + RING
+        if (nxt < nrows) issue_next();
+        cp_async_commit();
+      } else {
       for (int k = lane; k < total; k += 32) {
         const float4 it = q[k];
         const Raw1 e = zinb_nb_raw<Ops>(it.x, it.y, it.z, it.w, lf);
@@ -648,6 +678,7 @@ zinb_loss_bwd_ring_kernel(const float* __restrict__ Y, int64_t ldy, const int32_
       if (isnz[2]) { const float4 e = q[pos[2]]; zB.gmu.x = e.x; zB.dth.x = e.y; zB.dpi.x = e.z; }
       if (isnz[3]) { const float4 e = q[pos[3]]; zB.gmu.y = e.x; zB.dth.y = e.y; zB.dpi.y = e.z; }
       __syncwarp();
+      }
       if (ridge != 0.f) {                                              // loss.py:139-140 (uniform; ridge defaults to 0)
         if (active) lsum_r += ridge * (pA.x * pA.x + pA.y * pA.y + pB.x * pB.x + pB.y * pB.y);
         zA.dpi = fma2(splat(2.0f * ridge), pA, zA.dpi); zB.dpi = fma2(splat(2.0f * ridge), pB, zB.dpi);
@@ -797,14 +828,16 @@ int launch(const LossArgs& a, cudaStream_t s) {
     FoldArgs fa{reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.ws) + sizeof(double) * (size_t)kMaxBlocks), a.loss_sum,
                 a.fin_penalty, a.fin_loss_slot, a.fin_epoch_acc, a.fin_batch};
     if (!a.counter_ready) DCA_CUDA_OK(cudaMemsetAsync(fa.counter, 0, sizeof(unsigned), s));
-#define DCA_RING(CD, GT)                                                                                          \
+#define DCA_RING2(CD, GT, IQ)                                                                                     \
   do {                                                                                                             \
-    constexpr size_t sm = (size_t)kRing * (CD ? 4 : 3) * kColsPerBlock * 4 + (size_t)(kThreads / 32) * 32 * kVec * 16; \
+    constexpr size_t sm = IQ ? (size_t)(kRing + 1) * (CD ? 4 : 3) * kColsPerBlock * 4 + (size_t)(kThreads / 32) * 32 * kVec     \
+                             : (size_t)kRing * (CD ? 4 : 3) * kColsPerBlock * 4 + (size_t)(kThreads / 32) * 32 * kVec * 16; \
     static bool attr = false;                                                                                      \
-    if (!attr) { DCA_CUDA_OK(cudaFuncSetAttribute(zinb_loss_bwd_ring_kernel<CD, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr = true; } \
-    zinb_loss_bwd_ring_kernel<CD, GT><<<grid, kThreads, sm, s>>>(a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, a.G, a.ridge, \
+    if (!attr) { DCA_CUDA_OK(cudaFuncSetAttribute(zinb_loss_bwd_ring_kernel<CD, GT, IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr = true; } \
+    zinb_loss_bwd_ring_kernel<CD, GT, IQ><<<grid, kThreads, sm, s>>>(a.Y, a.ldy, a.rows, a.sf, a.m, a.d, a.pi, a.ld, a.B, a.G, a.ridge, \
         a.inv_n, ps.rows_per_block, (GT*)a.dzm, (GT*)a.dzd, (GT*)a.dzp, tpart, lpart, lf_dev, fa);                  \
   } while (0)
+#define DCA_RING(CD, GT) do { if (g_tune.ring == 2) DCA_RING2(CD, GT, true); else DCA_RING2(CD, GT, false); } while (0)
     if (g_tune.ring) {
       if (a.grad_bf16) { if (cond) DCA_RING(true, __nv_bfloat16); else DCA_RING(false, __nv_bfloat16); }
       else             { if (cond) DCA_RING(true, float); else DCA_RING(false, float); }
@@ -812,6 +845,7 @@ int launch(const LossArgs& a, cudaStream_t s) {
       return DCA_OK;                                                    // the fold is done by the last block
     }
 #undef DCA_RING
+#undef DCA_RING2
 #define DCA_STAGED2(CD, GT, BFV)                                                                                   \
   do {                                                                                                             \
     constexpr size_t sm = (size_t)kStageRows * (CD ? 4 : 3) * kColsPerBlock * 4 + (size_t)(kThreads / 32) * 32 * kVec * 16; \
@@ -889,7 +923,7 @@ extern "C" int dca_set_tunable(const char* name, int64_t value) {
   else if (n == "loss_consumer_sleep_ns" && value >= 0 && value <= 100000) g_tune.consumer_sleep_ns = (unsigned)value;
   else if (n == "fused_heads" && (value == 0 || value == 1)) g_fused_heads_default = (int)value;
   else if (n == "loss_branch_free" && (value == 0 || value == 1)) g_tune.branch_free = (int)value;
-  else if (n == "loss_ring" && (value == 0 || value == 1)) g_tune.ring = (int)value;
+  else if (n == "loss_ring" && value >= 0 && value <= 2) g_tune.ring = (int)value;
   else { set_error("dca_set_tunable: unknown name or value out of range (%s = %lld)", name, (long long)value); return DCA_ERR_BAD_ARG; }
   return DCA_OK;
 }

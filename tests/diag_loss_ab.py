@@ -75,7 +75,7 @@ def main():
                 gm = torch.zeros((B, G), dtype=tdt, device=dev); gd = torch.zeros_like(gm); gp = torch.zeros_like(gm)
                 dth = torch.zeros(G, device=dev)
                 base = None
-                for ring, tb in ((0, 0), (1, 0), (1, 148 * 3), (1, 148 * 6), (1, 148 * 9), (1, 148 * 24)):
+                for ring, tb in ((0, 0), (1, 0), (2, 0), (2, 148 * 12), (2, 148 * 24), (1, 148 * 24)):
                     _lib.check(lib.dca_set_tunable(b"loss_ring", ring), "loss_ring")
                     _lib.check(lib.dca_set_tunable(b"loss_target_blocks", tb), "loss_target_blocks")
                     times = []

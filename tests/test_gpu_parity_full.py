@@ -58,7 +58,7 @@ def _oracle_rows(y, m, sf, d, pi, ridge=0.0):
     return el, gm, gd, gp
 
 
-@pytest.mark.parametrize("ring", [1, 0])
+@pytest.mark.parametrize("ring", [1, 2, 0])
 def test_loss_kernel_at_benchmark_size_vs_oracle(ring):
     """4096 x 20000, zinb-conddisp, row gather, bf16 and fp32 gradients: sampled rows element-wise against the float64
     oracle (3e-4 of the tensor scale for fp32 gradients, 2^-8 relative for bf16 storage), the loss of those rows to
@@ -106,7 +106,7 @@ def test_loss_kernel_at_benchmark_size_vs_oracle(ring):
         L.check(lib.dca_set_tunable(b"loss_ring", 1))
 
 
-@pytest.mark.parametrize("ring", [1, 0])
+@pytest.mark.parametrize("ring", [1, 2, 0])
 @pytest.mark.parametrize("gdt_name", ["f32", "bf16"])
 def test_loss_kernel_edge_cases_on_device(ring, gdt_name):
     """Activations AT their clip bounds (network.py:38-39: gradient through the clipped activation is zero), pi -> 0 / 1,
@@ -379,3 +379,36 @@ def test_train_streaming_from_host_equals_resident_training():
     # default shuffling in streaming mode still trains
     h = train(ad, net, epochs=2, batch_size=bs, verbose=False, stream=True).history
     assert np.all(np.isfinite(h["loss"])) and len(h["val_loss"]) == 2
+
+
+@pytest.mark.parametrize("ring", [0, 1, 2])
+@pytest.mark.parametrize("ae_type", ["zinb", "zinb-conddisp"])
+def test_loss_kernel_variants_vs_oracle(ring, ae_type):
+    """All three ZINB backward kernels (dca_set_tunable loss_ring: 0 block-wide bulk-copy ring, 1 per-thread cp.async
+    ring, 2 the same with the index queue) on an aligned shape with row gather, ridge and a partial last column block,
+    against the float64 oracle -- including the per-gene theta gradient of the constant-dispersion model."""
+    from tests.test_gpu_parity import _oracle_loss, _post_act
+    L = _L(); lib = L.load()
+    L.check(lib.dca_set_tunable(b"loss_ring", ring))
+    try:
+        B, G = 200, 1028 + 1024                       # three column blocks, the last one 4 genes wide
+        N = B + 13
+        Y = synth_counts(N, G, 1); Y[0, :4] = [0, 17, 40, 3000]
+        sf = np.exp(np.random.default_rng(2).normal(0, 0.3, N)).astype(np.float32)
+        rows = np.random.default_rng(3).permutation(N)[:B].astype(np.int32)
+        m, d, pi = _post_act(B, G, 4)
+        cond = ae_type.endswith("conddisp")
+        ref = _oracle_loss(ae_type, Y, sf, m, d, pi, 0.01, rows)
+        dd = _t(d) if cond else _t(d[0])
+        for gdt, tol in ((L.F32, 3e-4), (L.BF16, 6e-3)):
+            total, gm, gd, gp, dth = _loss_call(lib, L, _t(Y), G, torch.as_tensor(rows).to(DEV), _t(sf), _t(m), dd, _t(pi), B, G,
+                                                L.AE_TYPE_IDS[ae_type], 0.01, 1.0 / (B * G), gdt, cond=cond)
+            assert abs(total - ref["sum"]) <= 2e-5 * abs(ref["sum"]), (ring, ae_type, total, ref["sum"])
+            assert rel_err(gm.float().cpu().numpy(), ref["dzm"]) < tol
+            assert rel_err(gp.float().cpu().numpy(), ref["dzp"]) < tol
+            if cond:
+                assert rel_err(gd.float().cpu().numpy(), ref["dzd"]) < tol
+            else:
+                assert rel_err(dth.cpu().numpy(), ref["dtheta"]) < 3e-4
+    finally:
+        L.check(lib.dca_set_tunable(b"loss_ring", 1))
