@@ -640,9 +640,20 @@ zinb_loss_bwd_ring_kernel(const float* __restrict__ Y, int64_t ldy, const int32_
         if (nxt < nrows) issue_next();
         cp_async_commit();
       }
-      // ---- zero branch of my four elements, two f32x2 chains
-      Raw2 zA = zinb_zero_pair<Ops>(muA, dA, pA), zB = zinb_zero_pair<Ops>(muB, dB, pB);
-      const Fin2 fA = finish_factors_pair<Ops, COND_DISP>(mA, dA, pA, inv_n), fB = finish_factors_pair<Ops, COND_DISP>(mB, dB, pB, inv_n);
+      // ---- zero branch of my four elements, two f32x2 chains.  One range test per thread and row (min / max over its four
+      // genes, FMNMX3) decides warp-uniformly whether the clip masks / the small-theta series can be skipped.
+      const float m_lo = fminf(fminf(vm.x, vm.y), fminf(vm.z, vm.w)), m_hi = fmaxf(fmaxf(vm.x, vm.y), fmaxf(vm.z, vm.w));
+      const float d_lo = fminf(fminf(dd[0], dd[1]), fminf(dd[2], dd[3])), d_hi = fmaxf(fmaxf(dd[0], dd[1]), fmaxf(dd[2], dd[3]));
+      const bool plain = (m_lo > 1e-5f) && (m_hi < 1e6f) &&
+                         (COND_DISP ? (d_lo > 0.03125f) && (d_hi < 1e4f) : (d_hi <= 1e6f));   // const-disp: theta is not an activation
+      Raw2 zA, zB; Fin2 fA, fB;
+      if (__all_sync(kFull, plain)) {
+        zA = zinb_zero_pair<Ops, true>(muA, dA, pA); zB = zinb_zero_pair<Ops, true>(muB, dB, pB);
+        fA = finish_factors_pair_plain<Ops, COND_DISP>(dA, pA, inv_n); fB = finish_factors_pair_plain<Ops, COND_DISP>(dB, pB, inv_n);
+      } else {
+        zA = zinb_zero_pair<Ops>(muA, dA, pA); zB = zinb_zero_pair<Ops>(muB, dB, pB);
+        fA = finish_factors_pair<Ops, COND_DISP>(mA, dA, pA, inv_n); fB = finish_factors_pair<Ops, COND_DISP>(mB, dB, pB, inv_n);
+      }
       lsum_lg += ((active && !isnz[0]) ? zA.lgD.x : 0.f) + ((active && !isnz[1]) ? zA.lgD.y : 0.f)
                + ((active && !isnz[2]) ? zB.lgD.x : 0.f) + ((active && !isnz[3]) ? zB.lgD.y : 0.f);
       // ---- dense NB pass over the queue (item k by lane k mod 32): raw derivatives back into the queue

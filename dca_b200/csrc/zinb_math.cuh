@@ -309,9 +309,11 @@ struct Raw2 { float2 lgD, gmu, dth, dpi; };
 
 // zero branch (y < 1e-8) of two ZINB elements: loss = -ln2 * lgD,  gmu = dL/dmu * mu,  dth = dL/dtheta,  dpi = dL/dpi
 // (branch-free; same arithmetic as zinb_elem_zero_bf).  mu = m * sf is computed by the caller (the NB items need it too).
-template <class Ops>
+// TH_BOUNDED: the caller knows theta <= 1e6 (the kernels check the row's theta range once per thread), so the
+// min(theta, 1e6) of loss.py:85,134 is the identity and is skipped.
+template <class Ops, bool TH_BOUNDED = false>
 DCA_HD Raw2 zinb_zero_pair(float2 mu, float2 th_in, float2 pi) {
-  const float2 th = make_float2(fminf(th_in.x, 1e6f), fminf(th_in.y, 1e6f));          // loss.py:85,134
+  const float2 th = TH_BOUNDED ? th_in : make_float2(fminf(th_in.x, 1e6f), fminf(th_in.y, 1e6f));   // loss.py:85,134
   const float2 te = add2(th, splat(kEps));
   const float2 den = add2(te, mu);
   const float2 rden = make_float2(Ops::rcp(den.x), Ops::rcp(den.y));
@@ -378,6 +380,23 @@ DCA_HD void rising_group_masked(float x0, float nrem, float& lg2acc, float& rs) 
   const float P = a * b;
   lg2acc += Ops::lg2(P);
   rs = fmaf(fmaf(ap, b, a * bp), Ops::rcp(P), rs);
+}
+
+// The same factors when every activation of the pair is known to lie strictly inside its clip range and theta >= 1/32
+// (checked once per thread and row with min / max over its four genes, warp-uniform branch): no masks, no series.
+template <class Ops, bool COND_DISP>
+DCA_HD Fin2 finish_factors_pair_plain(float2 th_in, float2 pi, float inv_n) {
+  Fin2 o;
+  o.fm = splat(inv_n);
+  if (COND_DISP) {
+    const float2 a = mul2(th_in, splat(-kLog2e));
+    o.fd = fma2(make_float2(Ops::ex2(a.x), Ops::ex2(a.y)), splat(-inv_n), splat(inv_n));   // (1 - exp(-d)) / N
+  } else {
+    o.fd = splat(1.0f);
+  }
+  const float2 omp = fma2(pi, splat(-1.0f), splat(1.0f));
+  o.fp = mul2(mul2(pi, omp), splat(inv_n));
+  return o;
 }
 
 // NB branch (y >= 1e-8) of one ZINB element from mu = m * sf: element NLL and the raw derivatives of struct Raw2

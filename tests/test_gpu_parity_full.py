@@ -238,7 +238,9 @@ TC_VS_EXACT = {"loss": 2e-3,          # relative, batch loss of one step
                # pre-activation flips the ReLU mask of ~0.4 % of the units, and flipping a fraction f of the entries of dA
                # on/off is a norm-wise change of sqrt(f) ~ 6-8 % whatever the arithmetic (measured 7.7 % for enc0/kernel)
                "grad_hidden": 0.15,
-               "predict_same_weights": 2e-2,   # ||out - out_exact|| / ||out_exact|| of mean / dispersion / pi / latent, same weights
+               # ||out - out_exact|| / ||out_exact|| with the same weights (measured: mean 3.4e-4, dispersion 2.5e-4, pi 1.7e-4,
+               # latent 2.3e-3 -- the pre-BatchNorm center output carries the 0.3 % rounding of the first GEMM directly)
+               "predict_same_weights": 2e-3, "latent_same_weights": 1e-2,
                "predict": 5e-2}       # the same after 5 training steps of both (trajectories diverged; latent: 0.3)
 
 
@@ -324,7 +326,7 @@ def test_tc_predict_vs_exact_oracle():
         print("\n[tc predict vs exact oracle, %s] " % tag + ", ".join("%s %.1e" % kv for kv in errs.items()))
         for key, e in errs.items():
             assert e < bounds.get(key, bounds["*"]), (tag, key, e)
-    compare("same weights", {"*": TC_VS_EXACT["predict_same_weights"]})
+    compare("same weights", {"*": TC_VS_EXACT["predict_same_weights"], "latent": TC_VS_EXACT["latent_same_weights"]})
     for _ in range(5):
         eng.train_step(Xd, Yd, sfd); eng.apply_update(1e-3, 5.0)
         l_o = exact.train_step(X64, Y64, sf64)
