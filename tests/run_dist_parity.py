@@ -31,11 +31,16 @@ def main():
     from dca_b200.engine import DeviceEngine
     ok = True
     msgs = []
-    for gemm_path, G, hidden, tol_self, tol_oracle in (("generic", 200, (16, 8, 16), 2e-5, 2e-3), ("tcgen05", 264, (64, 32, 64), 2e-5, 3e-2)):
+    # batchnorm off: plain data parallelism; batchnorm on + sync_bn: BatchNorm statistics all-reduced over the ranks
+    # (forward and backward), i.e. exactly the single-GPU model at the global batch size
+    for gemm_path, G, hidden, bn, tol_self, tol_oracle in (("generic", 200, (16, 8, 16), False, 2e-5, 2e-3),
+                                                           ("tcgen05", 264, (64, 32, 64), False, 2e-5, 3e-2),
+                                                           ("generic", 200, (16, 8, 16), True, 5e-5, 2e-3),
+                                                           ("tcgen05", 264, (64, 32, 64), True, 2e-3, 3e-2)):
         B = 96
         Y = synth_counts(world * B, G, 7); X, sf = O.normalize_inputs(Y)
-        p0 = O.init_params(G, G, hidden, "zinb-conddisp", False, seed=1, dtype=np.float32)
-        eng = DeviceEngine(G, G, hidden, "zinb-conddisp", False, max_batch=B, seed=None, gemm_path=gemm_path, device=dev)
+        p0 = O.init_params(G, G, hidden, "zinb-conddisp", bn, seed=1, dtype=np.float32)
+        eng = DeviceEngine(G, G, hidden, "zinb-conddisp", bn, max_batch=B, seed=None, gemm_path=gemm_path, device=dev, sync_bn=bn)
         eng.set_weights(p0)
         assert eng.comm_init()
         lo, hi = rank * B, (rank + 1) * B
@@ -55,16 +60,18 @@ def main():
         g_dp = (grads[2][:P] / world).cpu().numpy()
         loss_dp = float(grads[2][P].item()) / world
         # (a) one engine, whole global batch, one GPU
-        big = DeviceEngine(G, G, hidden, "zinb-conddisp", False, max_batch=world * B, seed=None, gemm_path=gemm_path, device=dev)
+        big = DeviceEngine(G, G, hidden, "zinb-conddisp", bn, max_batch=world * B, seed=None, gemm_path=gemm_path, device=dev)
         big.set_weights(p0)
         big.train_step(torch.from_numpy(X).to(dev), torch.from_numpy(Y).to(dev), torch.from_numpy(sf).to(dev))
         torch.cuda.synchronize(dev)
         g_one = big.grads[:P].cpu().numpy(); loss_one = big.read_loss()
         # (b) float64 oracle of the global batch (same bf16 rounding points on the tcgen05 path)
-        net = O.OracleNet(G, G, hidden, "zinb-conddisp", False, dtype=np.float64, params=p0, emulate_bf16=(gemm_path == "tcgen05"))
+        net = O.OracleNet(G, G, hidden, "zinb-conddisp", bn, dtype=np.float64, params=p0, emulate_bf16=(gemm_path == "tcgen05"))
         loss_o, g_o = net.loss_and_grads(X.astype(np.float64), Y.astype(np.float64), sf.astype(np.float64))
         worst_self = worst_or = 0.0
         for name, off, r, c in eng.param_info:
+            if bn and name.endswith("/bias") and not name.startswith(("mean", "dispersion", "pi")):
+                continue                                  # exactly zero in exact arithmetic (BatchNorm removes it): pure noise
             a = g_dp[off: off + r * c]; b = g_one[off: off + r * c]; o = g_o[name].reshape(-1)
             worst_self = max(worst_self, float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30)))
             worst_or = max(worst_or, float(np.max(np.abs(a - o)) / (np.max(np.abs(o)) + 1e-30)))
@@ -72,8 +79,8 @@ def main():
             ok = False
         if worst_or > tol_oracle or abs(loss_dp - loss_o) > 2e-4 * abs(loss_o):
             ok = False
-        msgs.append("%s: all-reduced/R vs one-GPU global batch: grads %.2e (tol %.0e), loss %.2e; vs float64 oracle: grads %.2e "
-                    "(tol %.0e), loss %.2e" % (gemm_path, worst_self, tol_self, abs(loss_dp - loss_one) / abs(loss_one), worst_or,
+        msgs.append("%s%s: all-reduced/R vs one-GPU global batch: grads %.2e (tol %.0e), loss %.2e; vs float64 oracle: grads %.2e "
+                    "(tol %.0e), loss %.2e" % (gemm_path, " + sync_bn" if bn else "", worst_self, tol_self, abs(loss_dp - loss_one) / abs(loss_one), worst_or,
                                                 tol_oracle, abs(loss_dp - loss_o) / abs(loss_o)))
         # replicas identical after the update
         eng.apply_update(1e-3, 5.0, 1.0 / world)
