@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fused", action="store_true",
                     help="run head forward + loss + head backward as the ONE fused kernel (flash_zinb.cu) instead of K2 + K3 + K4")
-    ap.add_argument("--e2e-format", default="auto", choices=["auto", "u16", "4", "8", "16"],
+    ap.add_argument("--e2e-format", default="auto", choices=["auto", "sparse", "dense", "u16", "4", "8", "16"],
                     help="host format of the streamed count matrix: packed bits per entry (io.pack_counts) or plain uint16")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the CPU baseline sample")
     return ap.parse_args()
@@ -422,9 +422,11 @@ def main():
             cnt_h = pin_near_gpu(counts_np.astype(np.uint16), dev.index)
             fmt = "uint16 raw counts"; tile_bytes = batch * genes * 2
         else:
-            cnt_h = dio.pack_counts(counts_np, "auto" if a.e2e_format == "auto" else int(a.e2e_format), batch=batch)
-            fmt = "%d-bit packed raw counts + overflow list (%d entries of %d, io.pack_counts)" % (
-                cnt_h.bits, len(cnt_h.entries), counts_np.size)
+            cnt_h = dio.pack_counts(counts_np, a.e2e_format if a.e2e_format in ("auto", "sparse", "dense") else int(a.e2e_format),
+                                    batch=batch)
+            fmt = ("sparse raw counts: 1-bit non-zero map + 4-bit codes of the non-zero entries" if cnt_h.bits == 1
+                   else "%d-bit packed raw counts" % cnt_h.bits) + " + overflow list (%d entries of %d, io.pack_counts)" % (
+                len(cnt_h.entries), counts_np.size)
             tile_bytes = max(cnt_h.bytes_for_rows(i * batch, (i + 1) * batch) for i in range(nb))
         t_pack = time.perf_counter() - t_pack
         sf_h = pin_near_gpu(sf[: nb * batch].cpu(), dev.index)

@@ -79,6 +79,7 @@ PROTOTYPES = {
     "dca_set_loss_ring": (C.c_int, [_vp, _vp, _i32]),
     "dca_stream_begin": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp]),
     "dca_stream_begin_packed": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "dca_stream_begin_sparse": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "dca_stream_step": (C.c_int, [_vp, _i64, _i64, _vp]),
     "dca_stream_end": (C.c_int, [_vp, _vp]),
     "dca_zinb_loss_fwd_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f, _f,

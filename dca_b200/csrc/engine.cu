@@ -185,6 +185,8 @@ int Engine::plan(const dca_config& c) {
   for (int k = 0; k < 2; ++k) { o_cnt[k] = take(sizeof(uint16_t) * B * (size_t)c.n_in); o_sfst[k] = take(sizeof(float) * B); }
   ovf_cap = (int64_t)(B * (size_t)c.n_in / 32); if (ovf_cap < 4096) ovf_cap = 4096;
   for (int k = 0; k < 2; ++k) { o_ovp[k] = take(sizeof(int64_t) * (B + 1)); o_ove[k] = take(8 * (size_t)ovf_cap); }
+  nib_cap = (int64_t)(B * (size_t)c.n_in / 4) + 64;       // sparse format: up to 50 % non-zero entries per batch
+  for (int k = 0; k < 2; ++k) { o_nibp[k] = take(sizeof(int64_t) * (B + 1)); o_nib[k] = take((size_t)nib_cap); }
   o_gmean = take(sizeof(float) * (size_t)c.n_in); o_ginv = take(sizeof(float) * (size_t)c.n_in);
   // staging for the host-buffer entry point
   const size_t xb = (c.x_dtype == DCA_BF16) ? 2 : 4;
@@ -938,7 +940,8 @@ extern "C" int dca_engine_info(const dca_handle* h, int32_t info[8]) {
 int Engine::stream_prefetch(int64_t i, int b) {
   const int64_t r0 = i * hs.batch;
   const int64_t nb = (hs.n_rows - r0 < hs.batch) ? (hs.n_rows - r0) : hs.batch;
-  const size_t tight = (size_t)cfg.n_in * (size_t)hs.bits / 8;             // bytes of one packed row
+  const bool sparse = hs.bits == 1;
+  const size_t tight = (size_t)cfg.n_in * (size_t)hs.bits / 8;             // bytes of one packed row (sparse: its bitmap)
   DCA_CUDA_OK(cudaStreamWaitEvent(hs.copy, hs.cnt_free[b], 0));          // the expansion two batches ago has consumed staging b
   if (hs.tl_base && hs.tl.size() < 400) hs.tl_mark(hs.copy);
   if ((size_t)hs.row_bytes == tight)  // contiguous rows: one linear copy (faster than the pitched path)
@@ -947,6 +950,11 @@ int Engine::stream_prefetch(int64_t i, int b) {
     DCA_CUDA_OK(cudaMemcpy2DAsync(base + o_cnt[b], tight, hs.counts + r0 * hs.row_bytes, (size_t)hs.row_bytes, tight, (size_t)nb,
                                   cudaMemcpyHostToDevice, hs.copy));
   if (hs.sf) DCA_CUDA_OK(cudaMemcpyAsync(base + o_sfst[b], hs.sf + r0, sizeof(float) * (size_t)nb, cudaMemcpyHostToDevice, hs.copy));
+  if (sparse) {
+    const int64_t n0 = hs.nib_indptr[r0], n1 = hs.nib_indptr[r0 + nb];
+    DCA_CUDA_OK(cudaMemcpyAsync(base + o_nibp[b], hs.nib_indptr + r0, sizeof(int64_t) * (size_t)(nb + 1), cudaMemcpyHostToDevice, hs.copy));
+    if (n1 > n0) DCA_CUDA_OK(cudaMemcpyAsync(base + o_nib[b], hs.nibbles + n0, (size_t)(n1 - n0), cudaMemcpyHostToDevice, hs.copy));
+  }
   bool has_ovf = false;
   if (hs.ovf_indptr) {
     const int64_t e0 = hs.ovf_indptr[r0], e1 = hs.ovf_indptr[r0 + nb];
@@ -962,6 +970,13 @@ int Engine::stream_prefetch(int64_t i, int b) {
   DCA_CUDA_OK(cudaStreamWaitEvent(hs.expand, hs.h2d_done[b], 0));
   DCA_CUDA_OK(cudaStreamWaitEvent(hs.expand, hs.step_done[b], 0));       // the step that read the expanded buffers b has finished
   const int x_bf16 = tc_enc ? 1 : (cfg.x_dtype == DCA_BF16);
+  if (sparse)
+    DCA_TRY(expand_sparse(base + o_cnt[b], reinterpret_cast<const int64_t*>(base + o_nibp[b]), base + o_nib[b],
+                          hs.sf ? f(o_sfst[b]) : nullptr, (int)nb, cfg.n_in, tf_set == 2 ? f(o_gmean) : nullptr,
+                          tf_set == 2 ? f(o_ginv) : nullptr, tf_use_sf && hs.sf, tf_use_log1p, f(o_sy[b]), base + o_sx[b], x_bf16,
+                          f(o_ssf[b]), has_ovf ? reinterpret_cast<const int64_t*>(base + o_ovp[b]) : nullptr,
+                          has_ovf ? (const void*)(base + o_ove[b]) : nullptr, hs.expand));
+  else
   DCA_TRY(expand_counts(base + o_cnt[b], hs.bits, hs.sf ? f(o_sfst[b]) : nullptr, (int)nb, cfg.n_in,
                         tf_set == 2 ? f(o_gmean) : nullptr, tf_set == 2 ? f(o_ginv) : nullptr, tf_use_sf && hs.sf,
                         tf_use_log1p, f(o_sy[b]), base + o_sx[b], x_bf16, f(o_ssf[b]),
@@ -1009,8 +1024,9 @@ extern "C" int dca_stream_begin_packed(dca_handle* h, const void* packed_host, i
   DCA_NEED_HANDLE(h);
   Engine& e = h->e;
   if (!packed_host || n_rows <= 0 || batch <= 0 || batch > e.cfg.max_batch) { set_error("dca_stream_begin: bad argument"); return DCA_ERR_BAD_ARG; }
-  if (bits != 4 && bits != 8 && bits != 16) { set_error("dca_stream_begin: bits must be 4, 8 or 16 (got %d)", bits); return DCA_ERR_BAD_ARG; }
+  if (bits != 1 && bits != 4 && bits != 8 && bits != 16) { set_error("dca_stream_begin: bits must be 4, 8 or 16 (got %d)", bits); return DCA_ERR_BAD_ARG; }
   if (row_bytes < (int64_t)e.cfg.n_in * bits / 8) { set_error("dca_stream_begin: row stride smaller than a packed row"); return DCA_ERR_BAD_ARG; }
+  if (bits == 1 && !e.hs.nib_indptr) { set_error("dca_stream_begin: the sparse format starts with dca_stream_begin_sparse"); return DCA_ERR_BAD_ARG; }
   if ((ovf_indptr_host == nullptr) != (ovf_entries_host == nullptr)) { set_error("dca_stream_begin: give both overflow arrays or neither"); return DCA_ERR_BAD_ARG; }
   if (e.cfg.n_in != e.cfg.n_out) { set_error("dca_stream_begin: needs n_in == n_out"); return DCA_ERR_UNSUPPORTED; }
   if (e.cfg.n_in % 8 != 0) { set_error("dca_stream_begin: n_in must be a multiple of 8"); return DCA_ERR_UNSUPPORTED; }
@@ -1047,10 +1063,31 @@ extern "C" int dca_stream_begin_packed(dca_handle* h, const void* packed_host, i
   hs.counts = reinterpret_cast<const unsigned char*>(packed_host); hs.row_bytes = row_bytes; hs.bits = bits;
   hs.ovf_indptr = ovf_indptr_host; hs.ovf_entries = reinterpret_cast<const unsigned char*>(ovf_entries_host);
   hs.sf = sf_host; hs.n_rows = n_rows; hs.batch = batch;
+  if (bits != 1) { hs.nib_indptr = nullptr; hs.nibbles = nullptr; }
   hs.pref_idx = -1; hs.step_no = 0; hs.active = true;
   { const char* v = getenv("DCA_STREAM_DIAG");
     if (v && atoi(v) == 2) { hs.tl.clear(); if (!hs.tl_base) cudaEventCreate(&hs.tl_base); cudaEventRecord(hs.tl_base, s); } }
   return DCA_OK;
+}
+
+extern "C" int dca_stream_begin_sparse(dca_handle* h, const void* bitmap_host, const int64_t* nib_indptr_host,
+                                       const void* nibbles_host, const int64_t* ovf_indptr_host, const void* ovf_entries_host,
+                                       const float* sf_host, int64_t n_rows, int32_t batch, void* stream) {
+  DCA_NEED_HANDLE(h);
+  Engine& e = h->e;
+  if (!bitmap_host || !nib_indptr_host || !nibbles_host || n_rows <= 0 || batch <= 0) { set_error("dca_stream_begin_sparse: bad argument"); return DCA_ERR_BAD_ARG; }
+  for (int64_t r0 = 0; r0 < n_rows; r0 += batch) {
+    const int64_t r1 = (r0 + batch < n_rows) ? r0 + batch : n_rows;
+    const int64_t nbytes = nib_indptr_host[r1] - nib_indptr_host[r0];
+    if (nbytes < 0 || nbytes > e.nib_cap) {
+      set_error("dca_stream_begin_sparse: batch starting at row %lld has %lld bytes of non-zero codes (capacity %lld = 50 %% non-zeros): "
+                "use the dense 4-bit format", (long long)r0, (long long)nbytes, (long long)e.nib_cap);
+      return DCA_ERR_BAD_ARG;
+    }
+  }
+  e.hs.nib_indptr = nib_indptr_host; e.hs.nibbles = reinterpret_cast<const unsigned char*>(nibbles_host);
+  return dca_stream_begin_packed(h, bitmap_host, 1, (int64_t)e.cfg.n_in / 8, ovf_indptr_host, ovf_entries_host, sf_host, n_rows,
+                                 batch, stream);
 }
 
 extern "C" int dca_stream_begin(dca_handle* h, const uint16_t* counts_host, int64_t ld_counts, const float* sf_host,
@@ -1104,6 +1141,6 @@ extern "C" int dca_stream_end(dca_handle* h, void* stream) {
     fprintf(stderr, "\n");
     hs.tl.clear();
   }
-  hs.active = false; hs.counts = nullptr; hs.ovf_indptr = nullptr; hs.ovf_entries = nullptr;
+  hs.active = false; hs.counts = nullptr; hs.ovf_indptr = nullptr; hs.ovf_entries = nullptr; hs.nib_indptr = nullptr; hs.nibbles = nullptr;
   return DCA_OK;
 }

@@ -48,11 +48,13 @@ struct Engine {
   size_t o_cnt[2] = {0, 0}, o_sfst[2] = {0, 0}, o_gmean = 0, o_ginv = 0;
   size_t o_ovp[2] = {0, 0}, o_ove[2] = {0, 0};     // overflow list of a staged batch: indptr[B+1] (int64), entries (8 B each)
   int64_t ovf_cap = 0;                              // entries per staging buffer
+  size_t o_nibp[2] = {0, 0}, o_nib[2] = {0, 0}; int64_t nib_cap = 0;   // sparse format: nibble indptr (int64[B+1]) + nibble bytes per staging buffer
   int tf_use_sf = 1, tf_use_log1p = 1, tf_set = 0, x_override_bf16 = 0;
   float* loss_ring = nullptr; int ring_n = 0; int64_t ring_pos = 0;   // mapped host mirror of the per-step loss
   struct HostStream {
     const unsigned char* counts = nullptr; int64_t row_bytes = 0; int bits = 16;       // packed host count matrix
     const int64_t* ovf_indptr = nullptr; const unsigned char* ovf_entries = nullptr;   // host CSR overflow list (or null)
+    const int64_t* nib_indptr = nullptr; const unsigned char* nibbles = nullptr;       // bits == 1: sparse format (bitmap in `counts`)
     const float* sf = nullptr; int64_t n_rows = 0; int batch = 0;
     cudaStream_t copy = nullptr;                      // host->device copies of the next batch
     cudaStream_t expand = nullptr;                    // its expansion kernel (lowest priority: yields SMs to the step)

@@ -318,8 +318,15 @@ class DeviceEngine:
         if getattr(pc, "_pinned", None) is None:      # pin once per PackedCounts (cudaHostAlloc costs milliseconds)
             pc._pinned = (pinned(pc.packed, np.uint8), pinned(pc.indptr, np.int64),
                           pinned(pc.entries if len(pc.entries) else np.zeros(1, dtype=pc.entries.dtype), np.uint8))
-        packed, indptr, entries = pc._pinned
-        self._stream_keep = (packed, indptr, entries, sf)
+            if pc.bits == 1:
+                pc._pinned += (pinned(pc.nib_indptr, np.int64), pinned(pc.nibbles, np.uint8))
+        packed, indptr, entries = pc._pinned[:3]
+        self._stream_keep = pc._pinned + (sf,)
+        if pc.bits == 1:                              # sparse format: bitmap + nibble stream (dca_stream_begin_sparse)
+            check(self.lib.dca_stream_begin_sparse(self.handle, packed.data_ptr(), pc._pinned[3].data_ptr(), pc._pinned[4].data_ptr(),
+                                                   indptr.data_ptr(), entries.data_ptr(), None if sf is None else sf.data_ptr(),
+                                                   pc.n_rows, batch, self._stream()), "dca_stream_begin_sparse")
+            return
         check(self.lib.dca_stream_begin_packed(self.handle, packed.data_ptr(), pc.bits, packed.shape[-1] if packed.dim() == 2 else 0,
                                                indptr.data_ptr(), entries.data_ptr(), None if sf is None else sf.data_ptr(),
                                                pc.n_rows, batch, self._stream()), "dca_stream_begin_packed")

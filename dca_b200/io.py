@@ -183,10 +183,13 @@ def read_pickle(inputfile):
 # are >80 % zeros and mostly < 15, so 4 bits per entry + a short overflow list carry the same information
 # as the float32 matrix in 1/8 of the bytes that cross PCIe every step.
 class PackedCounts:
-    """bits-per-entry matrix + CSR overflow list; see pack_counts()."""
+    """bits-per-entry matrix + CSR overflow list; see pack_counts().  bits == 1 is the SPARSE format: ``packed`` is the
+    non-zero bitmap (n_genes/8 bytes per row), ``nibbles`` the 4-bit codes of the non-zero counts in gene order (each row
+    starts on a byte boundary at ``nib_indptr[row]``), codes of 15 escape into the overflow list."""
 
-    def __init__(self, packed, bits, n_genes, indptr, entries):
+    def __init__(self, packed, bits, n_genes, indptr, entries, nib_indptr=None, nibbles=None):
         self.packed, self.bits, self.n_genes, self.indptr, self.entries = packed, bits, n_genes, indptr, entries
+        self.nib_indptr, self.nibbles = nib_indptr, nibbles
         self._pinned = None            # pinned host copies, made by DeviceEngine.stream_begin on first use
 
     @property
@@ -195,12 +198,16 @@ class PackedCounts:
 
     @property
     def nbytes(self):
-        return self.packed.nbytes + self.indptr.nbytes + self.entries.nbytes
+        extra = (self.nib_indptr.nbytes + self.nibbles.nbytes) if self.bits == 1 else 0
+        return self.packed.nbytes + self.indptr.nbytes + self.entries.nbytes + extra
 
     def bytes_for_rows(self, r0, r1):
-        """host->device bytes of one batch [r0, r1): tile + indptr segment + overflow entries."""
-        return (r1 - r0) * self.packed.shape[1] * self.packed.itemsize + 8 * (r1 - r0 + 1) + \
+        """host->device bytes of one batch [r0, r1): tile + indptr segment + overflow entries (+ nibble stream)."""
+        b = (r1 - r0) * self.packed.shape[1] * self.packed.itemsize + 8 * (r1 - r0 + 1) + \
             8 * int(self.indptr[r1] - self.indptr[r0])
+        if self.bits == 1:
+            b += 8 * (r1 - r0 + 1) + int(self.nib_indptr[r1] - self.nib_indptr[r0])
+        return b
 
 
 OVERFLOW_ENTRY = np.dtype([("gene", "<i4"), ("count", "<f4")])
@@ -229,6 +236,37 @@ def _choose_bits(per_row, n, g, batch):
     return best[1]
 
 
+def _pack_sparse(C, batch):
+    """NumPy statement of the sparse format (dca_stream_begin_sparse, include/dca_b200.h)."""
+    n, g = C.shape
+    nz = C != 0
+    bitmap = np.packbits(nz, axis=1, bitorder="little")                    # [n, g/8]
+    rows, cols = np.nonzero(nz)                                             # row-major: by row, then gene
+    vals = C[rows, cols]
+    codes = np.minimum(vals, 15).astype(np.uint8)
+    cnt = np.bincount(rows, minlength=n).astype(np.int64)
+    nib_indptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum((cnt + 1) // 2, out=nib_indptr[1:])                          # every row starts on a byte boundary
+    first = np.zeros(n + 1, dtype=np.int64); np.cumsum(cnt, out=first[1:])
+    k = np.arange(rows.shape[0], dtype=np.int64) - first[rows]             # index of the code inside its row
+    byte = nib_indptr[rows] + (k >> 1)
+    nibbles = np.zeros(int(nib_indptr[-1]) + 16, dtype=np.uint8)           # + slack: the device reads whole bytes
+    even = (k & 1) == 0
+    nibbles[byte[even]] = codes[even]
+    nibbles[byte[~even]] |= (codes[~even] << 4).astype(np.uint8)
+    over = vals >= 15
+    orow, ocol = rows[over], cols[over]
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(orow, minlength=n), out=indptr[1:])
+    entries = np.empty(orow.shape[0], dtype=OVERFLOW_ENTRY)
+    entries["gene"] = ocol; entries["count"] = vals[over]
+    if batch:
+        worst = max(int(nib_indptr[min(i + batch, n)] - nib_indptr[i]) for i in range(0, max(n, 1), batch)) if n else 0
+        if worst > batch * g // 4 + 64:
+            raise ValueError("more than 50 % non-zero entries in a batch: use a dense width (bits=4)")
+    return PackedCounts(np.ascontiguousarray(bitmap), 1, g, indptr, entries, nib_indptr, nibbles)
+
+
 def pack_counts(counts, bits="auto", batch=None, native=True, threads=0):
     """Pack an integer-valued count matrix (cells x genes, any numeric dtype) into `bits` bits per entry.
 
@@ -243,8 +281,21 @@ def pack_counts(counts, bits="auto", batch=None, native=True, threads=0):
     n, g = C.shape
     if g % 8 != 0:
         raise ValueError("the number of genes must be a multiple of 8 for the packed format (got %d)" % g)
-    if bits != "auto" and bits not in (4, 8, 16):
-        raise ValueError("bits must be 4, 8, 16 or 'auto'")
+    if bits not in ("auto", "sparse", "dense") and bits not in (4, 8, 16):
+        raise ValueError("bits must be 4, 8, 16, 'sparse', 'dense' (best dense width) or 'auto' (smallest of all)")
+    if bits in ("sparse", "auto") and n > 0:
+        if C.size and (C.min() < 0 or np.any(C != np.floor(C))):
+            raise ValueError("counts must be non-negative integers")
+        nnz = int(np.count_nonzero(C))
+        # sparse: 1 bit per entry + 4 bits per non-zero (+ 8 B per count >= 15); dense 4-bit: 4 bits per entry
+        if bits == "sparse" or (nnz < 0.45 * C.size and C.size / 8.0 + nnz / 2.0 < 0.8 * C.size / 2.0):
+            try:
+                return _pack_sparse(C, batch)
+            except ValueError:
+                if bits == "sparse":
+                    raise
+    if bits in ("sparse", "dense"):
+        bits = "auto"
     if native and n > 0:
         return _pack_counts_native(C, bits, batch, threads)
     if C.size and (C.min() < 0 or np.any(C != np.floor(C))):
@@ -295,6 +346,18 @@ def _pack_counts_native(C, bits, batch, threads):
 
 def unpack_counts(pc: PackedCounts):
     """Inverse of pack_counts (float32 matrix) -- the host statement of what the device expansion produces."""
+    if pc.bits == 1:
+        nz = np.unpackbits(pc.packed, axis=1, bitorder="little")[:, :pc.n_genes].astype(bool)
+        out = np.zeros((pc.n_rows, pc.n_genes), dtype=np.float32)
+        rows, cols = np.nonzero(nz)
+        cnt = np.bincount(rows, minlength=pc.n_rows).astype(np.int64)
+        first = np.zeros(pc.n_rows + 1, dtype=np.int64); np.cumsum(cnt, out=first[1:])
+        k = np.arange(rows.shape[0], dtype=np.int64) - first[rows]
+        b = pc.nibbles[pc.nib_indptr[rows] + (k >> 1)]
+        out[rows, cols] = np.where(k & 1, b >> 4, b & 0xF)
+        orow = np.repeat(np.arange(pc.n_rows), np.diff(pc.indptr))
+        out[orow, pc.entries["gene"]] = pc.entries["count"]
+        return out
     if pc.bits == 4:
         out = np.empty((pc.n_rows, pc.n_genes), dtype=np.float32)
         out[:, 0::2] = pc.packed & 0xF

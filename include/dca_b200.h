@@ -223,6 +223,15 @@ int dca_stream_begin(dca_handle* h, const uint16_t* counts_host, int64_t ld_coun
 int dca_stream_begin_packed(dca_handle* h, const void* packed_host, int32_t bits, int64_t row_bytes,
                             const int64_t* ovf_indptr_host, const void* ovf_entries_host, const float* sf_host,
                             int64_t n_rows, int32_t batch, void* stream);
+/* Sparse host format for matrices with <= 50 % non-zero entries (scRNA-seq: ~10-20 %): bitmap_host = one bit per entry
+ * (row-major, n_in/8 bytes per row, bit g%8 of byte g/8 set when the count is non-zero), nibbles_host = the non-zero counts
+ * of every row as consecutive 4-bit codes in gene order (low nibble first; 1..14 literal, 15 = escape into the overflow
+ * list above), each row starting on a byte boundary at nib_indptr_host[row] (int64[n_rows+1], byte offsets).  ~0.2 bytes
+ * per entry cross PCIe per step instead of 0.5 (4-bit dense) or the reference's 8 (float32 X + Y, dca/train.py:78-98).
+ * dca_b200/io.py:pack_counts(..., bits='sparse' | 'auto') builds it. */
+int dca_stream_begin_sparse(dca_handle* h, const void* bitmap_host, const int64_t* nib_indptr_host, const void* nibbles_host,
+                            const int64_t* ovf_indptr_host, const void* ovf_entries_host, const float* sf_host,
+                            int64_t n_rows, int32_t batch, void* stream);
 int dca_stream_step(dca_handle* h, int64_t batch_index, int64_t next_batch_index /* -1: none */, void* stream);
 int dca_stream_end(dca_handle* h, void* stream);
 

@@ -412,10 +412,11 @@ def test_stream_from_host_counts_matches_resident_path():
         e2.stream_end()
 
 
-@pytest.mark.parametrize("bits", [4, 8, 16, "auto"])
+@pytest.mark.parametrize("bits", [4, 8, 16, "dense", "sparse", "auto"])
 def test_stream_packed_counts_equals_uint16_stream(bits):
-    """dca_stream_begin_packed (4/8/16 bits per entry + overflow list) expands to the same Y and X as the plain
-    uint16 stream: loss trajectories are identical; large counts travel through the overflow list."""
+    """dca_stream_begin_packed (4/8/16 bits per entry + overflow list) and dca_stream_begin_sparse (non-zero bitmap +
+    4-bit codes of the non-zero counts) expand to the same Y and X as the plain uint16 stream: loss trajectories are
+    identical; large counts travel through the overflow list."""
     from dca_b200.engine import DeviceEngine
     from dca_b200 import io
     N, G, B = 600, 264, 256

@@ -147,14 +147,26 @@ def test_pack_counts_round_trip_and_auto_width():
     rng = np.random.default_rng(0)
     C = rng.poisson(0.3, (130, 64)).astype(np.int64)
     C[3, 5] = 300; C[3, 6] = 15; C[10, 63] = 70000; C[129, 0] = 14; C[0, 1] = 255
-    for bits in (4, 8, 16, "auto"):
+    for bits in (4, 8, 16, "dense"):
         pc = io.pack_counts(C, bits, batch=32)
         assert np.array_equal(io.unpack_counts(pc), C.astype(np.float32))
         assert pc.indptr[0] == 0 and pc.indptr[-1] == len(pc.entries) and np.all(np.diff(pc.indptr) >= 0)
         esc = (1 << pc.bits) - 1
         assert len(pc.entries) == int((C >= esc).sum())
         assert pc.packed.shape == (130, 64 * pc.bits // 8 // pc.packed.itemsize)
-    assert io.pack_counts(C, "auto").bits == 4                        # sparse small counts: 4 bits win
+    assert io.pack_counts(C, "dense").bits == 4                       # small counts: 4 bits win among the dense widths
+    # sparse format (dca_stream_begin_sparse): non-zero bitmap + 4-bit codes in gene order, rows byte-aligned
+    for bits in ("sparse", "auto"):
+        pc = io.pack_counts(C, bits, batch=32)
+        assert pc.bits == 1 and np.array_equal(io.unpack_counts(pc), C.astype(np.float32))
+        assert pc.packed.shape == (130, 8) and pc.nib_indptr[0] == 0
+        nnz = (C != 0).sum(1)
+        assert np.array_equal(np.diff(pc.nib_indptr), (nnz + 1) // 2)
+        assert len(pc.entries) == int((C >= 15).sum()) and pc.nbytes < io.pack_counts(C, 4).nbytes
+    dense_rows = rng.poisson(3.0, (64, 64))                           # ~95 % non-zeros: auto falls back to a dense width
+    assert io.pack_counts(dense_rows, "auto", batch=32).bits == 4
+    with pytest.raises(ValueError, match="50 %"):
+        io.pack_counts(dense_rows, "sparse", batch=32)
     assert io.pack_counts(np.full((8, 64), 100), "auto").bits == 8    # everything >= 15: 8 bits win
     assert io.pack_counts(np.full((8, 64), 1000), "auto").bits == 16
     with pytest.raises(ValueError):
