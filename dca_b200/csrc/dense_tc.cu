@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(128, 1)
 tc_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const ProbeParams p, float* __restrict__ D) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET (not by an integer round trip): the pointer keeps the shared address space, so the
+  // staging stores / bias loads compile to STS / LDS instead of generic ST / LD
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar_load, bar_mma;
   __shared__ uint32_t tmem_base_s;
   uint8_t* sa = smem;
@@ -141,7 +143,9 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
                  const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
                  const __grid_constant__ CUtensorMap map_o2, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET (not by an integer round trip): the pointer keeps the shared address space, so the
+  // staging stores / bias loads compile to STS / LDS instead of generic ST / LD
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_ab = smem;                                           // stages of [A | B]
   uint8_t* s_out = smem + kStages * kStageBytes;                  // epilogue staging
   float* s_bias = reinterpret_cast<float*>(s_out + kOutBytes);    // [kAccStages][BN]

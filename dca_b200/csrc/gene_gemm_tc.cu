@@ -50,7 +50,9 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
                  const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_o, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET (not by an integer round trip): the pointer keeps the shared address space, so the
+  // staging stores / bias loads compile to STS / LDS instead of generic ST / LD
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr uint32_t kStage = kZBytes + (DO_B ? kWBytes : 0);
   uint8_t* s_z = smem;                                          // [kZStages][Z | W]
   uint8_t* s_h = s_z + kZStages * kStage;                       // [2][H]
