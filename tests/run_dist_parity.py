@@ -55,7 +55,7 @@ def main():
         P = eng.n_params
         for it in (1, 2):
             d = (grads[it][:P] - grads[0][:P]).abs().max().item() / grads[0][:P].abs().max().item()
-            if d > 1e-6:
+            if d > 2e-5:           # (the tcgen05 kernels add dW by fp32 atomics: accumulation-order noise between launches)
                 ok = False; msgs.append("%s: call %d differs from the direct call by %.2e" % (gemm_path, it, d))
         g_dp = (grads[2][:P] / world).cpu().numpy()
         loss_dp = float(grads[2][P].item()) / world
