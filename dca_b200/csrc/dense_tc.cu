@@ -126,7 +126,7 @@ constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;  // 16 KB, 32 K
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kChunkBytes = 32 * 32 * 4;                     // one warp's 32x32 fp32 staging tile
 constexpr uint32_t kOutBytes = kEpiWarps * kChunkBytes;           // one staging tile per warp
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + kOutBytes + kAccStages * BN * 4 + 1024;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + kOutBytes + kEpiWarps * 64 * 4 + 1024;
 
 struct Params {
   int B, G, n_heads;
@@ -148,7 +148,7 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_ab = smem;                                           // stages of [A | B]
   uint8_t* s_out = smem + kStages * kStageBytes;                  // epilogue staging
-  float* s_bias = reinterpret_cast<float*>(s_out + kOutBytes);    // [kAccStages][BN]
+  float* s_bias = reinterpret_cast<float*>(s_out + kOutBytes);    // [kEpiWarps][64]: every epilogue warp keeps ITS 64 biases (no block barrier)
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar[kAccStages], tempty_bar[kAccStages];
   __shared__ uint32_t tmem_base_s;
 
@@ -212,15 +212,16 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int hs, nt, mt; decode(t, hs, nt, mt);
       const int as = it % kAccStages; const uint32_t aph = (it / kAccStages) & 1;
-      // bias of this tile -> smem (first 256 epilogue threads, one column each)
+      // bias of this warp's 64 columns -> its private smem slot (a block-wide barrier here cost 3 of every 12 stall cycles,
+      // profiles/r2_ncu_k2_c3_raw.csv: the 16 warps drift by up to two tiles)
       {
-        const int c = ew * 32 + lane;
-        if (c < BN) {
-          const int g = nt * BN + c;
-          s_bias[as * BN + c] = (g < p.G) ? p.bias[hs][g] : 0.f;
-        }
+        float* mine = s_bias + ew * 64;
+        const int g0 = nt * BN + cgrp * 64 + lane;
+        __syncwarp();                                          // the previous tile's reads of the slot are done
+        mine[lane] = (g0 < p.G) ? p.bias[hs][g0] : 0.f;
+        mine[lane + 32] = (g0 + 32 < p.G) ? p.bias[hs][g0 + 32] : 0.f;
+        __syncwarp();
       }
-      named_barrier_sync(1, kEpiWarps * 32);
       mbar_wait(&tfull_bar[as], aph);
       tcgen05_fence_after();
       const int row = mt * BM + quarter * 32 + lane;
@@ -242,7 +243,7 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
         const int col0 = cgrp * 64 + c * 32;
         if (lane == 0) bulk_wait_read<0>();                 // previous store has finished reading the staging tile
         __syncwarp();
-        const float* bz = s_bias + as * BN + col0;
+        const float* bz = s_bias + ew * 64 + c * 32;
         auto emit = [&](auto act) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {

@@ -1047,7 +1047,11 @@ extern "C" int dca_stream_begin_packed(dca_handle* h, const void* packed_host, i
     int least = 0, greatest = 0;
     DCA_CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     DCA_CUDA_OK(cudaStreamCreateWithFlags(&hs.copy, cudaStreamNonBlocking));
-    DCA_CUDA_OK(cudaStreamCreateWithPriority(&hs.expand, cudaStreamNonBlocking, least));
+    // expansion stream: HIGHEST priority.  Its blocks only find room between the (persistent, one CTA per SM) kernels of
+    // the step; at the lowest priority the expansion of batch i+1 mostly ran AFTER step i and 0.25 ms of it were exposed
+    // (profiles/r2_diag_e2e_timeline.log); DCA_EXPAND_PRIO=low restores the old behaviour
+    const char* pe = getenv("DCA_EXPAND_PRIO");
+    DCA_CUDA_OK(cudaStreamCreateWithPriority(&hs.expand, cudaStreamNonBlocking, (pe && pe[0] == 'l') ? least : greatest));
     for (int k = 0; k < 2; ++k) {
       DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.h2d_done[k], cudaEventDisableTiming));
       DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.cnt_free[k], cudaEventDisableTiming));

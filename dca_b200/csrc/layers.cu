@@ -321,6 +321,7 @@ __global__ void expand_counts_kernel(const unsigned char* __restrict__ cnt, cons
 // dense) or 8 (the reference's float32 X + Y).  One block per row: the threads popcount their bitmap words, a block
 // scan gives every word the position of its first code in the row's nibble stream, then each thread expands its 32
 // genes (Y fp32, X normalised) with 128-bit stores.
+constexpr int kSparseMaxBytes = 8192;                    // bitmap bytes per row the kernel supports (65536 genes)
 template <typename XT>
 __global__ void __launch_bounds__(256)
 expand_sparse_kernel(const uint32_t* __restrict__ bitmap, const int64_t* __restrict__ nib_indptr,
@@ -328,74 +329,70 @@ expand_sparse_kernel(const uint32_t* __restrict__ bitmap, const int64_t* __restr
                      const float* __restrict__ mean, const float* __restrict__ inv_std, int use_sf, int use_log1p,
                      float* __restrict__ Yout, XT* __restrict__ Xout, float* __restrict__ sf_out,
                      const int64_t* __restrict__ ovf_indptr, const int2* __restrict__ ovf_entries) {
+  // One block per row.  Phase 1: thread t popcounts S consecutive bitmap bytes and records, per byte, the number of
+  // non-zero genes before it inside its own span; a block scan over the 256 span totals gives every span its base.
+  // Phase 2: thread = one bitmap byte = 8 consecutive genes, bytes taken in order b = tid, tid + 256, ... so that a
+  // warp writes 1 KB of Y and 512 B of X contiguously; the position of a byte's first code in the row's nibble stream
+  // is pre[b] + tbase[b / S].
+  __shared__ unsigned short pre[kSparseMaxBytes];
+  __shared__ int tbase[256];
   __shared__ int warp_tot[8];
-  __shared__ int s_base;
   const int r = blockIdx.x;
   if (r >= M) return;
-  const int words = (n + 31) / 32;                       // n % 8 == 0; the last word may be partial (upper bits zero)
-  const uint32_t* bm = bitmap + (int64_t)r * (n / 8) / 4;            // rows are n/8 bytes; n % 32 != 0 -> byte-addressed below
-  const unsigned char* bmb = reinterpret_cast<const unsigned char*>(bitmap) + (int64_t)r * (n / 8);
+  const int nbytes = n / 8;
+  const unsigned char* bmb = reinterpret_cast<const unsigned char*>(bitmap) + (int64_t)r * nbytes;
   const unsigned char* nib = nibbles + (nib_indptr[r] - nib_indptr[0]);
   const float s = sf_in ? sf_in[r] : 1.0f;
-  if (threadIdx.x == 0) { s_base = 0; if (sf_out) sf_out[r] = s; }
+  if (threadIdx.x == 0 && sf_out) sf_out[r] = s;
   const float inv_s = use_sf ? 1.0f / s : 1.0f;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  (void)bm;
+  const int S = (nbytes + 255) / 256;
+  int cnt = 0;
+  for (int k = 0; k < S; ++k) {
+    const int b = threadIdx.x * S + k;
+    if (b < nbytes) { pre[b] = (unsigned short)cnt; cnt += __popc((unsigned)bmb[b]); }
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
-  for (int w0 = 0; w0 < words; w0 += 256) {
-    const int w = w0 + threadIdx.x;
-    uint32_t bits = 0;
-    if (w < words) {
-      const int nb = min(4, n / 8 - w * 4);              // bytes of this word that exist
-      for (int k = 0; k < nb; ++k) bits |= (uint32_t)bmb[w * 4 + k] << (8 * k);
-    }
-    const int cnt = __popc(bits);
-    int incl = cnt;                                       // inclusive warp scan
+  int before = 0;
+  for (int k = 0; k < warp; ++k) before += warp_tot[k];
+  tbase[threadIdx.x] = before + incl - cnt;
+  __syncthreads();
+  for (int b = threadIdx.x; b < nbytes; b += 256) {
+    const unsigned bits = bmb[b];
+    int pos = (int)pre[b] + tbase[b / S];
+    const int c0 = b * 8;
+    float y[8], x[8];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    int before = s_base;
-    for (int k = 0; k < warp; ++k) before += warp_tot[k];
-    int pos = before + incl - cnt;                        // index of my first code in the row's nibble stream
-    if (w < words) {
-      const int c0 = w * 32;
-      const int ng = min(32, n - c0);
-      for (int q = 0; q < ng; q += 8) {                   // 8 genes at a time: two 128-bit stores of Y, one of X (bf16)
-        float y[8], x[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int c = c0 + q + k;
-          float yv = 0.f;
-          if ((bits >> (q + k)) & 1u) {
-            const uint32_t code = (nib[pos >> 1] >> ((pos & 1) * 4)) & 0xfu;
-            ++pos;
-            yv = (float)code;
-            if (ovf_indptr && code == 15u) yv = overflow_lookup(ovf_indptr, ovf_entries, r, c, yv);
-          }
-          y[k] = yv;
-          x[k] = normalise_count(yv, inv_s, use_log1p, mean, inv_std, c);
-        }
-        float* yo = Yout + (int64_t)r * n + c0 + q;
-        *reinterpret_cast<float4*>(yo) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(yo + 4) = make_float4(y[4], y[5], y[6], y[7]);
-        if (sizeof(XT) == 2) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(x[0], x[1]), p1 = __floats2bfloat162_rn(x[2], x[3]);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(x[4], x[5]), p3 = __floats2bfloat162_rn(x[6], x[7]);
-          uint4 o;
-          o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-          o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(Xout) + (int64_t)r * n + c0 + q) = o;
-        } else {
-          float* xo = reinterpret_cast<float*>(Xout) + (int64_t)r * n + c0 + q;
-          *reinterpret_cast<float4*>(xo) = make_float4(x[0], x[1], x[2], x[3]);
-          *reinterpret_cast<float4*>(xo + 4) = make_float4(x[4], x[5], x[6], x[7]);
-        }
+    for (int k = 0; k < 8; ++k) {
+      float yv = 0.f;
+      if ((bits >> k) & 1u) {
+        const unsigned code = (nib[pos >> 1] >> ((pos & 1) * 4)) & 0xfu;
+        ++pos;
+        yv = (float)code;
+        if (ovf_indptr && code == 15u) yv = overflow_lookup(ovf_indptr, ovf_entries, r, c0 + k, yv);
       }
+      y[k] = yv;
+      x[k] = normalise_count(yv, inv_s, use_log1p, mean, inv_std, c0 + k);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) { int t = s_base; for (int k = 0; k < 8; ++k) t += warp_tot[k]; s_base = t; }
-    __syncthreads();
+    float* yo = Yout + (int64_t)r * n + c0;
+    *reinterpret_cast<float4*>(yo) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(yo + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    if (sizeof(XT) == 2) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(x[0], x[1]), p1 = __floats2bfloat162_rn(x[2], x[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(x[4], x[5]), p3 = __floats2bfloat162_rn(x[6], x[7]);
+      uint4 o;
+      o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+      o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(Xout) + (int64_t)r * n + c0) = o;
+    } else {
+      float* xo = reinterpret_cast<float*>(Xout) + (int64_t)r * n + c0;
+      *reinterpret_cast<float4*>(xo) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(xo + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    }
   }
 }
 
@@ -407,6 +404,7 @@ int expand_sparse(const void* bitmap, const int64_t* nib_indptr, const void* nib
                   const float* mean, const float* inv_std, int use_sf, int use_log1p, float* Yout, void* Xout, int x_bf16,
                   float* sf_out, const int64_t* ovf_indptr, const void* ovf_entries, cudaStream_t s) {
   if (M <= 0) return DCA_OK;
+  if (n / 8 > kSparseMaxBytes) { set_error("expand_sparse: at most %d genes in the sparse format (got %d)", kSparseMaxBytes * 8, n); return DCA_ERR_UNSUPPORTED; }
   const int2* oe = ovf_indptr ? reinterpret_cast<const int2*>(ovf_entries) : nullptr;
   if (!oe) ovf_indptr = nullptr;
   if (x_bf16) expand_sparse_kernel<__nv_bfloat16><<<M, 256, 0, s>>>((const uint32_t*)bitmap, nib_indptr, (const unsigned char*)nibbles, sf_in, M, n, mean, inv_std, use_sf, use_log1p, Yout, (__nv_bfloat16*)Xout, sf_out, ovf_indptr, oe);

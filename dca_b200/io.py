@@ -239,6 +239,8 @@ def _choose_bits(per_row, n, g, batch):
 def _pack_sparse(C, batch):
     """NumPy statement of the sparse format (dca_stream_begin_sparse, include/dca_b200.h)."""
     n, g = C.shape
+    if g > 65536:
+        raise ValueError("the sparse format supports at most 65536 genes")
     nz = C != 0
     bitmap = np.packbits(nz, axis=1, bitorder="little")                    # [n, g/8]
     rows, cols = np.nonzero(nz)                                             # row-major: by row, then gene

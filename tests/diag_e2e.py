@@ -11,7 +11,7 @@ from dca_b200.hostmem import pin_near_gpu, gpu_local_cpus
 from bench import synth_on_device
 
 dev = torch.device("cuda:0"); torch.cuda.set_device(0)
-cells, genes, batch = 10000, 2000, 4096
+cells, genes, batch = int(os.environ.get("DIAG_CELLS", 10000)), int(os.environ.get("DIAG_GENES", 2000)), 4096
 X, Y, sf, zf, gmean, gstd = synth_on_device(cells, genes, dev, 1234)
 eng = DeviceEngine(genes, genes, (64, 32, 64), "zinb-conddisp", True, max_batch=batch, device=dev, seed=0)
 nb = 2
@@ -20,7 +20,7 @@ print("gpu-local cpus:", sorted(gpu_local_cpus(0) or [])[:8], "... affinity now:
 sf_h = pin_near_gpu(sf[: nb * batch].cpu(), 0)
 eng.set_input_transform(gmean, gstd, True, True)
 formats = {"u16": pin_near_gpu(counts.astype(np.uint16), 0),
-           "p8": dio.pack_counts(counts, 8, batch), "p4": dio.pack_counts(counts, 4, batch)}
+           "p8": dio.pack_counts(counts, 8, batch), "p4": dio.pack_counts(counts, 4, batch), "sp": dio.pack_counts(counts, "sparse", batch)}
 loss_h = pin_near_gpu(torch.zeros(64, dtype=torch.float32), 0)
 P = eng.n_params
 
@@ -64,7 +64,7 @@ def resident(k):
 
 print("mode DCA_STREAM_DIAG=%s" % os.environ.get("DCA_STREAM_DIAG", "0"))
 if os.environ.get("DCA_STREAM_DIAG") == "2":        # device-side timeline of a few steps (printed by the library)
-    for fmt in ("p4", "u16"):
+    for fmt in ("p4", "sp"):
         run(fmt, 5); print("timeline", fmt, flush=True); sys.stderr.flush()
         print("  -> %.3f ms/step" % run(fmt, 12, d2h=2)[0], flush=True)
     sys.exit(0)
