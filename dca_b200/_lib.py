@@ -101,6 +101,8 @@ PROTOTYPES = {
     "dca_write_text_matrix": (C.c_int, [C.c_char_p, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _i32, _i32]),
     "dca_count_escapes": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _vp, _i32]),
     "dca_pack_counts": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i32]),
+    "dca_sparse_counts": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i32]),
+    "dca_pack_sparse": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32]),
     "dca_launch_count": (C.c_int64, []),
     "dca_set_tunable": (C.c_int, [C.c_char_p, C.c_int64]),
 }

@@ -183,8 +183,88 @@ void pack_rows(const T* m, int64_t rows, int64_t cols, int64_t ld, int bits, uns
   });
 }
 
+// sparse format, pass 1: non-zero entries and entries >= 15 per row
+template <typename T>
+bool sparse_counts(const T* m, int64_t rows, int64_t cols, int64_t ld, int64_t* nnz, int64_t* esc, int threads) {
+  int bad = 0;
+  parallel_rows(rows, threads, [&](int64_t a, int64_t b) {
+    for (int64_t r = a; r < b; ++r) {
+      const T* row = m + r * ld; int64_t c = 0, e = 0; bool ok = true;
+      for (int64_t j = 0; j < cols; ++j) { double v; ok &= count_value(row[j], v); c += v != 0.0; e += v >= 15.0; }
+      nnz[r] = c; esc[r] = e;
+      if (!ok) bad = 1;
+    }
+  });
+  return bad == 0;
+}
+
+// sparse format, pass 2: bitmap (cols/8 bytes per row), 4-bit codes (row r from byte nib_indptr[r]), overflow entries
+template <typename T>
+void sparse_rows(const T* m, int64_t rows, int64_t cols, int64_t ld, unsigned char* bitmap, const int64_t* nib_indptr,
+                 unsigned char* nibbles, const int64_t* ovf_indptr, unsigned char* entries, int threads) {
+  const int64_t bm_bytes = cols / 8;
+  parallel_rows(rows, threads, [&](int64_t a, int64_t b) {
+    for (int64_t r = a; r < b; ++r) {
+      const T* row = m + r * ld; unsigned char* bm = bitmap + r * bm_bytes; unsigned char* nb = nibbles + nib_indptr[r];
+      int64_t k = 0, e = ovf_indptr[r];
+      for (int64_t j0 = 0; j0 < cols; j0 += 8) {
+        unsigned bits = 0;
+        for (int t = 0; t < 8; ++t) {
+          const double v = (double)row[j0 + t];
+          if (v == 0.0) continue;
+          bits |= 1u << t;
+          unsigned code = v >= 15.0 ? 15u : (unsigned)v;
+          if (v >= 15.0) { int32_t g = (int32_t)(j0 + t); float c = (float)v; memcpy(entries + 8 * e, &g, 4); memcpy(entries + 8 * e + 4, &c, 4); ++e; }
+          if (k & 1) nb[k >> 1] = (unsigned char)(nb[k >> 1] | (code << 4)); else nb[k >> 1] = (unsigned char)code;
+          ++k;
+        }
+        bm[j0 >> 3] = (unsigned char)bits;
+      }
+    }
+  });
+}
+
 }  // namespace
 }  // namespace dca
+
+// Sparse host format (dca_stream_begin_sparse), multi-threaded.  dca_sparse_counts: nnz[r] = non-zero entries of row r,
+// esc[r] = entries >= 15; the caller turns them into nib_indptr (bytes: cumsum((nnz + 1) / 2)) and ovf_indptr (cumsum(esc))
+// and calls dca_pack_sparse, which fills bitmap [rows x cols/8], nibbles and the overflow entries.
+extern "C" int dca_sparse_counts(const void* counts, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, int64_t* nnz,
+                                 int64_t* esc, int32_t threads) {
+  if (!counts || !nnz || !esc || rows < 0 || cols < 0 || ld < cols) { set_error("dca_sparse_counts: bad argument"); return DCA_ERR_BAD_ARG; }
+  if (threads <= 0) { threads = (int)std::thread::hardware_concurrency(); if (threads > 32) threads = 32; if (threads < 1) threads = 1; }
+  bool ok = false;
+  switch (dtype) {
+    case 0: ok = sparse_counts((const float*)counts, rows, cols, ld, nnz, esc, threads); break;
+    case 1: ok = sparse_counts((const double*)counts, rows, cols, ld, nnz, esc, threads); break;
+    case 2: ok = sparse_counts((const uint16_t*)counts, rows, cols, ld, nnz, esc, threads); break;
+    case 3: ok = sparse_counts((const int32_t*)counts, rows, cols, ld, nnz, esc, threads); break;
+    case 4: ok = sparse_counts((const int64_t*)counts, rows, cols, ld, nnz, esc, threads); break;
+    default: set_error("dca_sparse_counts: unknown dtype %d", dtype); return DCA_ERR_BAD_ARG;
+  }
+  if (!ok) { set_error("dca_sparse_counts: counts must be non-negative integers"); return DCA_ERR_BAD_ARG; }
+  return DCA_OK;
+}
+
+extern "C" int dca_pack_sparse(const void* counts, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, void* bitmap,
+                               const int64_t* nib_indptr, void* nibbles, const int64_t* ovf_indptr, void* entries, int32_t threads) {
+  if (!counts || !bitmap || !nib_indptr || !nibbles || !ovf_indptr || rows < 0 || cols < 0 || ld < cols || (ovf_indptr[rows] > 0 && !entries)) {
+    set_error("dca_pack_sparse: bad argument"); return DCA_ERR_BAD_ARG;
+  }
+  if (cols % 8 != 0) { set_error("dca_pack_sparse: the number of genes must be a multiple of 8"); return DCA_ERR_BAD_ARG; }
+  if (threads <= 0) { threads = (int)std::thread::hardware_concurrency(); if (threads > 32) threads = 32; if (threads < 1) threads = 1; }
+  unsigned char* bm = (unsigned char*)bitmap; unsigned char* nb = (unsigned char*)nibbles; unsigned char* e = (unsigned char*)entries;
+  switch (dtype) {
+    case 0: sparse_rows((const float*)counts, rows, cols, ld, bm, nib_indptr, nb, ovf_indptr, e, threads); break;
+    case 1: sparse_rows((const double*)counts, rows, cols, ld, bm, nib_indptr, nb, ovf_indptr, e, threads); break;
+    case 2: sparse_rows((const uint16_t*)counts, rows, cols, ld, bm, nib_indptr, nb, ovf_indptr, e, threads); break;
+    case 3: sparse_rows((const int32_t*)counts, rows, cols, ld, bm, nib_indptr, nb, ovf_indptr, e, threads); break;
+    case 4: sparse_rows((const int64_t*)counts, rows, cols, ld, bm, nib_indptr, nb, ovf_indptr, e, threads); break;
+    default: set_error("dca_pack_sparse: unknown dtype %d", dtype); return DCA_ERR_BAD_ARG;
+  }
+  return DCA_OK;
+}
 
 // dtype: 0 float32, 1 float64, 2 uint16, 3 int32, 4 int64.  per_row: int64 [3][rows] (escapes at 4 / 8 / 16 bits).
 extern "C" int dca_count_escapes(const void* counts, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, int64_t* per_row,

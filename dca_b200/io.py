@@ -236,6 +236,36 @@ def _choose_bits(per_row, n, g, batch):
     return best[1]
 
 
+def _pack_sparse_native(C, batch, threads=0):
+    """Multi-threaded packer of the library (dca_sparse_counts + dca_pack_sparse)."""
+    from . import _lib
+    lib = _lib.load()
+    if C.dtype not in _NATIVE_DTYPES:
+        C = C.astype(np.float64 if C.dtype.kind == "f" else np.int64)
+    C = np.ascontiguousarray(C)
+    n, g = C.shape
+    if g > 65536:
+        raise ValueError("the sparse format supports at most 65536 genes")
+    dt = _NATIVE_DTYPES[C.dtype]
+    nnz = np.zeros(n, dtype=np.int64); esc = np.zeros(n, dtype=np.int64)
+    st = lib.dca_sparse_counts(C.ctypes.data, dt, n, g, g, nnz.ctypes.data, esc.ctypes.data, int(threads))
+    if st != 0:
+        msg = lib.dca_last_error().decode("utf-8", "replace")
+        raise ValueError("counts must be non-negative integers" if "non-negative" in msg else msg)
+    nib_indptr = np.zeros(n + 1, dtype=np.int64); np.cumsum((nnz + 1) // 2, out=nib_indptr[1:])
+    indptr = np.zeros(n + 1, dtype=np.int64); np.cumsum(esc, out=indptr[1:])
+    if batch:
+        worst = max(int(nib_indptr[min(i + batch, n)] - nib_indptr[i]) for i in range(0, max(n, 1), batch)) if n else 0
+        if worst > batch * g // 4 + 64:
+            raise ValueError("more than 50 % non-zero entries in a batch: use a dense width (bits=4)")
+    bitmap = np.empty((n, g // 8), dtype=np.uint8)
+    nibbles = np.zeros(int(nib_indptr[-1]) + 16, dtype=np.uint8)
+    entries = np.empty(int(indptr[-1]), dtype=OVERFLOW_ENTRY)
+    _lib.check(lib.dca_pack_sparse(C.ctypes.data, dt, n, g, g, bitmap.ctypes.data, nib_indptr.ctypes.data, nibbles.ctypes.data,
+                                   indptr.ctypes.data, entries.ctypes.data if len(entries) else None, int(threads)), "dca_pack_sparse")
+    return PackedCounts(bitmap, 1, g, indptr, entries, nib_indptr, nibbles)
+
+
 def _pack_sparse(C, batch):
     """NumPy statement of the sparse format (dca_stream_begin_sparse, include/dca_b200.h)."""
     n, g = C.shape
@@ -286,13 +316,13 @@ def pack_counts(counts, bits="auto", batch=None, native=True, threads=0):
     if bits not in ("auto", "sparse", "dense") and bits not in (4, 8, 16):
         raise ValueError("bits must be 4, 8, 16, 'sparse', 'dense' (best dense width) or 'auto' (smallest of all)")
     if bits in ("sparse", "auto") and n > 0:
-        if C.size and (C.min() < 0 or np.any(C != np.floor(C))):
+        if not native and C.size and (C.min() < 0 or np.any(C != np.floor(C))):
             raise ValueError("counts must be non-negative integers")
         nnz = int(np.count_nonzero(C))
         # sparse: 1 bit per entry + 4 bits per non-zero (+ 8 B per count >= 15); dense 4-bit: 4 bits per entry
         if bits == "sparse" or (nnz < 0.45 * C.size and C.size / 8.0 + nnz / 2.0 < 0.8 * C.size / 2.0):
             try:
-                return _pack_sparse(C, batch)
+                return _pack_sparse_native(C, batch, threads) if native else _pack_sparse(C, batch)
             except ValueError:
                 if bits == "sparse":
                     raise

@@ -337,6 +337,14 @@ int dca_count_escapes(const void* counts, int32_t dtype, int64_t rows, int64_t c
 int dca_pack_counts(const void* counts, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, int32_t bits,
                     void* packed, const int64_t* indptr, void* entries, int32_t threads);
 
+/* Host-side packer of the sparse format (dca_stream_begin_sparse): dca_sparse_counts fills nnz[r] (non-zero entries of row r)
+ * and esc[r] (entries >= 15); with nib_indptr = cumsum((nnz + 1) / 2) (bytes) and ovf_indptr = cumsum(esc) dca_pack_sparse
+ * writes the bitmap [rows x cols/8], the 4-bit codes and the overflow entries.  Multi-threaded, no reference counterpart. */
+int dca_sparse_counts(const void* counts, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, int64_t* nnz, int64_t* esc,
+                      int32_t threads);
+int dca_pack_sparse(const void* counts, int32_t dtype, int64_t rows, int64_t cols, int64_t ld, void* bitmap,
+                    const int64_t* nib_indptr, void* nibbles, const int64_t* ovf_indptr, void* entries, int32_t threads);
+
 int64_t dca_launch_count(void);
 /* Launch tunables of the loss kernel (process-wide; set them BEFORE the first training step of an engine,
  * a captured step graph keeps the values it was recorded with): "loss_target_blocks",

@@ -242,11 +242,14 @@ def test_native_count_packer_equals_numpy_statement(dtype):
     C = rng.poisson(0.4, (300, 72)).astype(np.int64)
     C[3, 5] = 300; C[3, 6] = 15; C[10, 63] = 30000; C[299, 0] = 14; C[0, 1] = 255; C[0, 2] = 254; C[7, :] = 20
     C = C.astype(dtype)
-    for bits in (4, 8, 16, "auto"):
+    for bits in (4, 8, 16, "dense", "sparse", "auto"):
         a = io.pack_counts(C, bits, batch=64, native=True, threads=3)
         b = io.pack_counts(C, bits, batch=64, native=False)
         assert a.bits == b.bits and a.packed.dtype == b.packed.dtype
         assert np.array_equal(a.packed, b.packed) and np.array_equal(a.indptr, b.indptr) and np.array_equal(a.entries, b.entries)
+        if a.bits == 1:                                   # sparse: dca_sparse_counts + dca_pack_sparse
+            n = int(a.nib_indptr[-1])
+            assert np.array_equal(a.nib_indptr, b.nib_indptr) and np.array_equal(a.nibbles[:n], b.nibbles[:n])
         assert np.array_equal(io.unpack_counts(a), C.astype(np.float32))
     with pytest.raises(ValueError, match="non-negative integers"):
         io.pack_counts(np.where(C > 0, -1, 0).astype(np.int32) if np.issubdtype(dtype, np.integer) else C + 0.5)
