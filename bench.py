@@ -307,6 +307,9 @@ def main():
     if a.fused:
         from dca_b200 import _lib as _dl
         _dl.set_tunable("fused_heads", 1)
+    for kv in filter(None, os.environ.get("DCA_TUNABLES", "").split(",")):     # diagnosis only: name=value,...
+        from dca_b200 import _lib as _dl
+        _dl.set_tunable(kv.split("=")[0], int(kv.split("=")[1]))
     eng = DeviceEngine(genes, genes, HIDDEN, ae_type, True, max_batch=batch, x_dtype=a.x_dtype,
                        gemm_path=a.gemm_path, device=dev, seed=0)
     if world > 1:

@@ -22,6 +22,7 @@
 
 namespace dca {
 namespace tc {
+int g_gg_prefetch = 0;      // dca_set_tunable("gg_prefetch", 0 | 1)
 namespace gg {
 
 constexpr int kThreads = 256;
@@ -41,7 +42,7 @@ struct Params {
   int total_items;
   float* dW[3]; int64_t dW_ld; int dW_transposed;   // (a): transposed -> dW[f*ld + g] (Keras [64 x G]); else dW[g*ld + f]
   float* db[3];                                     // column sums of Z per head (COLSUM)
-  const __nv_bfloat16* Zp[3]; int64_t ldz;          // raw Z pointers: L2 prefetch of whole row segments ahead of the TMA boxes
+  const __nv_bfloat16* Zp[3]; int64_t ldz; int prefetch;   // raw Z pointers: L2 prefetch of whole row segments ahead of the TMA boxes
 };
 
 __device__ __forceinline__ void gg_prefetch_l2(const void* gptr, uint32_t bytes) {
@@ -65,9 +66,11 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
   uint8_t* s_ones = s_o + ((DO_B || (DO_A && !DO_B)) ? kOutBytes : 0);               // [16 x 64] bf16 ones (K-major B operand of the column sums)
   __shared__ uint64_t z_full[kZStages], z_empty[kZStages], h_full[2], h_empty[2], dh_full[2], dh_empty[2], dw_full, dw_empty;
   __shared__ uint32_t tmem_base_s;
+  __shared__ int s_unit;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
+    s_unit = -1;
     for (int i = 0; i < kZStages; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); mbar_init(&dh_full[i], 1); mbar_init(&dh_empty[i], 4); }
     mbar_init(&dw_full, 1); mbar_init(&dw_empty, 4);
@@ -99,60 +102,67 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    // A SWIZZLE_128B box is 128 rows x 128 bytes: on its own every box touches 128 DRAM pages for 128 bytes each
-    // (profiles/r2_ncu_k4_c3_raw.csv: 39 % of DRAM peak at 8 % issue utilisation).  The whole warp therefore prefetches
-    // the NEXT unit of work -- up to four gene blocks of one cell block, i.e. one contiguous segment of up to 1 KB per
-    // row -- into L2 with bulk prefetches (lane = row mod 32) while lane 0 issues the boxes of the current unit, which
-    // then hit L2.
-    {
+    if (lane == 0) {
       uint32_t zi = 0, hi = 0;
-      auto prefetch_unit = [&](int head, int cb, int g0, int g1) {            // genes [g0*128, g1*128) of cell block cb
-        const int c0 = g0 * 128, c1 = min(g1 * 128, p.G);
-        if (c1 <= c0) return;
-        const uint32_t bytes = (uint32_t)(c1 - c0) * 2u;
-        const __nv_bfloat16* zp = p.Zp[head];
-        for (int r = lane; r < 128; r += 32) {
-          const int row = cb * 128 + r;
-          if (row < p.B) gg_prefetch_l2(zp + (int64_t)row * p.ldz + c0, bytes);
-        }
-      };
+      int unit = 0;
       for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
         const Item x = decode(it);
         const CUtensorMap* mz = x.head == 0 ? &map_z0 : (x.head == 1 ? &map_z1 : &map_z2);
         for (int cb = x.cb0; cb < x.cb1; ++cb) {
-          if (DO_A && lane == 0) {
+          if (DO_A) {
             const uint32_t hs = hi & 1, hp = (hi >> 1) & 1; ++hi;
             mbar_wait(&h_empty[hs], hp ^ 1);
             mbar_expect_tx(&h_full[hs], kHBytes);
             tma_load_2d(s_h + hs * kHBytes, &map_h, 0, cb * 128, &h_full[hs]);
           }
-          for (int g4 = x.gb0; g4 < x.gb1; g4 += 4) {
-            // next unit in processing order: the following gene group of this cell block, else the first group of the next one
-            if (g4 + 4 < x.gb1) prefetch_unit(x.head, cb, g4 + 4, min(g4 + 8, x.gb1));
-            else if (cb + 1 < x.cb1) prefetch_unit(x.head, cb + 1, x.gb0, min(x.gb0 + 4, x.gb1));
-            if (lane == 0) {
-              for (int gb = g4; gb < min(g4 + 4, x.gb1); ++gb) {
-                const uint32_t st = zi % kZStages, ph = (zi / kZStages) & 1; ++zi;
-                mbar_wait(&z_empty[st], ph ^ 1);
-                uint8_t* dst = s_z + st * kStage;
-                mbar_expect_tx(&z_full[st], kStage);
-                tma_load_2d(dst, mz, gb * 128, cb * 128, &z_full[st]);
-                tma_load_2d(dst + kZBytes / 2, mz, gb * 128 + 64, cb * 128, &z_full[st]);
-                if (DO_B) {
-                  const CUtensorMap* mw = x.head == 0 ? &map_w0 : (x.head == 1 ? &map_w1 : &map_w2);
-                  if (DO_A) {      // head backward: W = Keras [64 x G] (K-major B): two [64 feats x 64 genes] boxes
-                    tma_load_2d(dst + kZBytes, mw, gb * 128, 0, &z_full[st]);
-                    tma_load_2d(dst + kZBytes + kWBytes / 2, mw, gb * 128 + 64, 0, &z_full[st]);
-                  } else {         // encoder forward: W = Keras [G x 64] (MN-major B): one [128 genes x 64 feats] box
-                    tma_load_2d(dst + kZBytes, mw, 0, gb * 128, &z_full[st]);
-                  }
-                }
+          for (int gb = x.gb0; gb < x.gb1; ++gb) {
+            if (((gb - x.gb0) & 3) == 0) *reinterpret_cast<volatile int*>(&s_unit) = unit++;      // progress mark for the prefetch warp
+            const uint32_t st = zi % kZStages, ph = (zi / kZStages) & 1; ++zi;
+            mbar_wait(&z_empty[st], ph ^ 1);
+            uint8_t* dst = s_z + st * kStage;
+            mbar_expect_tx(&z_full[st], kStage);
+            tma_load_2d(dst, mz, gb * 128, cb * 128, &z_full[st]);
+            tma_load_2d(dst + kZBytes / 2, mz, gb * 128 + 64, cb * 128, &z_full[st]);
+            if (DO_B) {
+              const CUtensorMap* mw = x.head == 0 ? &map_w0 : (x.head == 1 ? &map_w1 : &map_w2);
+              if (DO_A) {      // head backward: W = Keras [64 x G] (K-major B): two [64 feats x 64 genes] boxes
+                tma_load_2d(dst + kZBytes, mw, gb * 128, 0, &z_full[st]);
+                tma_load_2d(dst + kZBytes + kWBytes / 2, mw, gb * 128 + 64, 0, &z_full[st]);
+              } else {         // encoder forward: W = Keras [G x 64] (MN-major B): one [128 genes x 64 feats] box
+                tma_load_2d(dst + kZBytes, mw, 0, gb * 128, &z_full[st]);
               }
             }
-            __syncwarp();
           }
         }
       }
+    }
+  } else if (warp == 3 && p.prefetch) {
+    // ===================================================== L2 prefetch (optional, dca_set_tunable "gg_prefetch")
+    // A SWIZZLE_128B box is 128 rows x 128 bytes, i.e. every box touches 128 DRAM pages for 128 bytes each.  This warp
+    // walks the producer's sequence ONE unit ahead (unit = up to four gene blocks of one cell block = one contiguous
+    // segment of up to 1 KB per row) and prefetches the unit's row segments into L2 with bulk prefetches (lane = row
+    // mod 32), paced by the producer's progress mark in shared memory.
+    int unit = 0;
+    auto prefetch_unit = [&](int head, int cb, int g0, int g1) {              // genes [g0*128, g1*128) of cell block cb
+      const int c0 = g0 * 128, c1 = min(g1 * 128, p.G);
+      if (c1 <= c0) return;
+      const uint32_t bytes = (uint32_t)(c1 - c0) * 2u;
+      const __nv_bfloat16* zp = p.Zp[head];
+      for (int r = lane; r < 128; r += 32) {
+        const int row = cb * 128 + r;
+        if (row < p.B) gg_prefetch_l2(zp + (int64_t)row * p.ldz + c0, bytes);
+      }
+    };
+    for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
+      const Item x = decode(it);
+      for (int cb = x.cb0; cb < x.cb1; ++cb)
+        for (int g4 = x.gb0; g4 < x.gb1; g4 += 4, ++unit) {
+          if (unit > 0) {                                                      // unit 0 is not worth prefetching (its loads are already in flight)
+            long long spins = 0;
+            while (*reinterpret_cast<volatile int*>(&s_unit) < unit - 1) { __nanosleep(64); if (++spins > (1ll << 26)) break; }
+            prefetch_unit(x.head, cb, g4, min(g4 + 4, x.gb1));
+          }
+        }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
@@ -365,7 +375,7 @@ int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, 
   }
   p.total_items = p.gene_ranges * p.cell_splits * n_heads;
   for (int i = 0; i < 3; ++i) { p.dW[i] = dW ? dW[i] : nullptr; p.db[i] = db ? db[i] : nullptr; p.Zp[i] = Z[i < n_heads ? i : 0]; }
-  p.ldz = ldz;
+  p.ldz = ldz; p.prefetch = g_gg_prefetch;
   p.dW_ld = dW_ld; p.dW_transposed = dW_transposed;
   const int grid = p.total_items < sm_count ? p.total_items : sm_count;
 #define DCA_GG_LAUNCH(A, Bb, Cc)                                                                                       \

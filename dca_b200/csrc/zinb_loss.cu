@@ -14,6 +14,7 @@
 #include <cstdlib>
 
 namespace dca {
+namespace tc { extern int g_gg_prefetch; }
 
 namespace {
 
@@ -935,6 +936,7 @@ extern "C" int dca_set_tunable(const char* name, int64_t value) {
   else if (n == "fused_heads" && (value == 0 || value == 1)) g_fused_heads_default = (int)value;
   else if (n == "loss_branch_free" && (value == 0 || value == 1)) g_tune.branch_free = (int)value;
   else if (n == "loss_ring" && value >= 0 && value <= 2) g_tune.ring = (int)value;
+  else if (n == "gg_prefetch" && (value == 0 || value == 1)) tc::g_gg_prefetch = (int)value;
   else { set_error("dca_set_tunable: unknown name or value out of range (%s = %lld)", name, (long long)value); return DCA_ERR_BAD_ARG; }
   return DCA_OK;
 }
