@@ -329,15 +329,12 @@ def main():
     side = torch.cuda.Stream(dev)
     torch.cuda.set_stream(side)
 
-    prefetch = os.environ.get("DCA_BENCH_PREFETCH", "1") != "0"
-
     def step(i):
         rows = stream_idx[i * batch:(i + 1) * batch]
-        nxt = stream_idx[(i + 1) * batch:(i + 2) * batch] if (prefetch and i + 1 < total) else None   # gathered under this step
         if world > 1:
-            eng.train_step_allreduce(X, Y, sf, rows=rows, next_rows=nxt)     # head-gradient all-reduce overlaps the backward tail
+            eng.train_step_allreduce(X, Y, sf, rows=rows)     # head-gradient all-reduce overlaps the backward tail
         else:
-            eng.train_step(X, Y, sf, rows=rows, next_rows=nxt)
+            eng.train_step(X, Y, sf, rows=rows)
         eng.apply_update(lr, clip, gscale)
 
     def barrier():

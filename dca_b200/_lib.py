@@ -63,7 +63,6 @@ PROTOTYPES = {
     "dca_params_changed": (C.c_int, [_vp, _vp]),
     "dca_train_step": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
     "dca_train_step_phase": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp]),
-    "dca_set_next_batch": (C.c_int, [_vp, _vp, _i32]),
     "dca_grad_buckets": (C.c_int, [_vp, C.POINTER(_i64)]),
     "dca_comm_unique_id": (C.c_int, [_vp]),
     "dca_comm_init": (C.c_int, [_vp, _vp, _i32, _i32]),

@@ -308,9 +308,6 @@ Engine::~Engine() {
   comm_destroy();
   for (auto e : prof.ev) cudaEventDestroy(e);
   for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-  if (pre_stream) cudaStreamDestroy(pre_stream);
-  if (pre_fork) cudaEventDestroy(pre_fork);
-  if (pre_join) cudaEventDestroy(pre_join);
   if (hs.copy) cudaStreamDestroy(hs.copy);
   if (hs.expand) cudaStreamDestroy(hs.expand);
   for (int k = 0; k < 2; ++k) {

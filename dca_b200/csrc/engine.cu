@@ -180,8 +180,6 @@ int Engine::plan(const dca_config& c) {
   if (tc_enc) {
     o_da1b = take(2 * B * 64);
     o_xb = take(2 * B * (size_t)c.n_in);
-    o_xb2[0] = o_xb; o_xb2[1] = take(2 * B * (size_t)c.n_in);      // second buffer: gather of the next batch (dca_set_next_batch)
-    o_rowsnext = take(sizeof(int32_t) * B);
   }
   // double-buffered staging of raw uint16 counts streamed from the host + the input transform
   for (int k = 0; k < 2; ++k) { o_cnt[k] = take(sizeof(uint16_t) * B * (size_t)c.n_in); o_sfst[k] = take(sizeof(float) * B); }
@@ -256,9 +254,8 @@ int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, boo
     const bool can_gather = (ldx % (in_bf16 ? 8 : 4) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
     if (direct) { cur_xb = reinterpret_cast<const __nv_bfloat16*>(X); cur_ldxb = ldx; }
     else if (can_gather) {
-      __nv_bfloat16* xb = bf(o_xb2[xb_cur]);
-      if (!(training && step_use_pre)) DCA_TRY(gather_rows_bf16(X, in_bf16, ldx, rows, Bn, cfg.n_in, xb, s));   // else: gathered ahead
-      cur_xb = xb; cur_ldxb = cfg.n_in;
+      DCA_TRY(gather_rows_bf16(X, in_bf16, ldx, rows, Bn, cfg.n_in, bf(o_xb), s));
+      cur_xb = bf(o_xb); cur_ldxb = cfg.n_in;
     }
   }
   const bool fused = use_mid(Bn);
@@ -396,25 +393,6 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
   if (phase < 0 || phase > 3) { set_error("dca_train_step: phase must be 0, 1, 2 or 3"); return DCA_ERR_BAD_ARG; }
   if (!X || !Y) { set_error("dca_train_step: X and Y must not be NULL"); return DCA_ERR_BAD_ARG; }
   if (Bn <= 0 || Bn > cfg.max_batch) { set_error("dca_train_step: batch %d outside (0, max_batch=%d]", Bn, cfg.max_batch); return DCA_ERR_BAD_ARG; }
-  // ---- batch prefetch bookkeeping (dca_set_next_batch): is this batch already gathered, is a next one announced?
-  if (phase != 2) { step_use_pre = false; step_has_next = false; }       // (phase 2 continues the step phase 1 began)
-  if (tc_enc && !x_kind && phase != 2 && rows) {
-    if (pre.valid && pre.X == X && pre.rows == rows && pre.Bn == Bn) { step_use_pre = true; xb_cur = pre.buf; }
-    pre.valid = false;
-    if (next_rows && next_Bn > 0 && next_Bn <= cfg.max_batch && (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
-        s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
-      step_has_next = true;
-      if (!pre_stream) {
-        DCA_CUDA_OK(cudaStreamCreateWithFlags(&pre_stream, cudaStreamNonBlocking));
-        DCA_CUDA_OK(cudaEventCreateWithFlags(&pre_fork, cudaEventDisableTiming));
-        DCA_CUDA_OK(cudaEventCreateWithFlags(&pre_join, cudaEventDisableTiming));
-      }
-      DCA_CUDA_OK(cudaMemcpyAsync(base + o_rowsnext, next_rows, sizeof(int32_t) * (size_t)next_Bn, cudaMemcpyDeviceToDevice, s));
-      pre.X = X; pre.rows = next_rows; pre.Bn = next_Bn; pre.buf = xb_cur ^ 1; pre.valid = true;
-    }
-  }
-  if (phase != 2) { next_rows = nullptr; next_Bn = 0; }
-  const int variant = xb_cur | (step_use_pre ? 2 : 0) | (step_has_next ? 4 : 0);
   // the legacy default stream (handle 0) cannot be captured: stay on the direct path there
   if (!graphs_enabled || prof.on || s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread)
     return phase == 3 ? train_step_dp_body(X, ldx, Y, ldy, sf, rows, Bn, s) : train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, phase);
@@ -422,11 +400,10 @@ int Engine::train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, 
   // indices are copied into a fixed buffer so that the captured kernels read them from a stable address.
   StepGraph* g = nullptr;
   for (auto& c : graphs)
-    if (c.X == X && c.ldx == ldx && c.Y == Y && c.ldy == ldy && c.sf == sf && c.Bn == Bn && c.has_rows == (rows != nullptr) && c.phase == phase &&
-        c.variant == variant) { g = &c; break; }
+    if (c.X == X && c.ldx == ldx && c.Y == Y && c.ldy == ldy && c.sf == sf && c.Bn == Bn && c.has_rows == (rows != nullptr) && c.phase == phase) { g = &c; break; }
   if (!g) {
-    if (graphs.size() >= 32) { for (auto& c : graphs) if (c.exec) cudaGraphExecDestroy(c.exec); graphs.clear(); }
-    graphs.push_back(StepGraph{X, ldx, Y, ldy, sf, Bn, rows != nullptr, phase, variant, nullptr, 0, 0});
+    if (graphs.size() >= 16) { for (auto& c : graphs) if (c.exec) cudaGraphExecDestroy(c.exec); graphs.clear(); }
+    graphs.push_back(StepGraph{X, ldx, Y, ldy, sf, Bn, rows != nullptr, phase, nullptr, 0, 0});
     g = &graphs.back();
   }
   int32_t* rbuf = reinterpret_cast<int32_t*>(base + o_rowsbuf);
@@ -471,14 +448,6 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
   if (x_kind) return phase == 2 ? DCA_OK : x_train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s);   // whole step in phase 1
   const int G = cfg.n_out;
   float* dh = f(o_dh[0]); float* dh2 = f(o_dh[1]);
-  if (phase != 2 && step_has_next) {
-    // parallel branch: gather the NEXT batch's rows into the other bf16 buffer while this step computes
-    DCA_CUDA_OK(cudaEventRecord(pre_fork, s));
-    DCA_CUDA_OK(cudaStreamWaitEvent(pre_stream, pre_fork, 0));
-    DCA_TRY(gather_rows_bf16(X, x_override_bf16 ? 1 : (cfg.x_dtype == DCA_BF16), ldx, reinterpret_cast<const int32_t*>(base + o_rowsnext),
-                             pre.Bn, cfg.n_in, bf(o_xb2[xb_cur ^ 1]), pre_stream));
-    DCA_CUDA_OK(cudaEventRecord(pre_join, pre_stream));
-  }
   if (phase != 2) {
   DCA_CUDA_OK(cudaMemsetAsync(gp(0), 0, sizeof(float) * (size_t)(P + 2), s));
   bool any_pen = false;
@@ -557,8 +526,6 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
   }
   }  // !fuse
   }  // phase != 2
-  if (phase != 2 && step_has_next) DCA_CUDA_OK(cudaStreamWaitEvent(s, pre_join, 0));   // join the prefetch branch: it had the forward,
-                                                                                        // the loss and the head backward to hide under
   if (phase == 1) { mark(-1, s); return DCA_OK; }
   // ---- hidden stack backward
   mark(4, s);
@@ -876,12 +843,6 @@ extern "C" int dca_train_step_phase(dca_handle* h, const void* X, int64_t ldx, c
   DCA_NEED_HANDLE(h);
   if (phase != 1 && phase != 2) { set_error("dca_train_step_phase: phase must be 1 or 2"); return DCA_ERR_BAD_ARG; }
   return h->e.train_step(X, ldx, Y, ldy, sf, rows, batch, (cudaStream_t)stream, phase);
-}
-extern "C" int dca_set_next_batch(dca_handle* h, const int32_t* rows_next, int32_t batch) {
-  DCA_NEED_HANDLE(h);
-  if (rows_next && (batch <= 0 || batch > h->e.cfg.max_batch)) { set_error("dca_set_next_batch: batch %d outside (0, max_batch=%d]", batch, h->e.cfg.max_batch); return DCA_ERR_BAD_ARG; }
-  h->e.next_rows = rows_next; h->e.next_Bn = rows_next ? batch : 0;
-  return DCA_OK;
 }
 extern "C" int dca_grad_buckets(const dca_handle* h, int64_t* head_bucket_offset) {
   DCA_NEED_HANDLE(h);

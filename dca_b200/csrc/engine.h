@@ -37,7 +37,6 @@ struct Engine {
   // CUDA-graph replay of the training step (captured from the same launch sequence on the 2nd call with a key)
   struct StepGraph {
     const void* X; int64_t ldx; const void* Y; int64_t ldy; const void* sf; int Bn; int has_rows; int phase;
-    int variant;                 // xb_cur | use_pre << 1 | has_next << 2
     cudaGraphExec_t exec; long long launches; int seen;
   };
   std::vector<StepGraph> graphs;
@@ -88,14 +87,6 @@ struct Engine {
   int slot_head[3] = {0, -1, -1};          // packed head slot -> head index (0 mean, 1 dispersion, 2 pi)
   int slot_kind[3] = {0, 0, 0};
   size_t o_pbf = 0, o_h3b = 0, o_da1b = 0, o_xb = 0, o_dzb[3] = {0, 0, 0};
-  // batch prefetch (dca_set_next_batch): the row gather of the NEXT batch (X[rows] -> contiguous bf16) runs as a parallel
-  // branch of the current step's graph into the other of two buffers, so the next step finds its input ready
-  size_t o_xb2[2] = {0, 0}, o_rowsnext = 0;
-  int xb_cur = 0;                                   // buffer the current step reads
-  struct Pre { const void* X = nullptr; const int32_t* rows = nullptr; int Bn = 0; int buf = 0; bool valid = false; } pre;   // gathered ahead
-  const int32_t* next_rows = nullptr; int next_Bn = 0;      // announced for the coming dca_train_step (consumed by it)
-  cudaStream_t pre_stream = nullptr; cudaEvent_t pre_fork = nullptr, pre_join = nullptr;
-  bool step_use_pre = false, step_has_next = false;        // decided per dca_train_step call (part of the graph key)
   const __nv_bfloat16* cur_xb = nullptr; int64_t cur_ldxb = 0;   // bf16 batch input of the current step
   __nv_bfloat16* bf(size_t byte_off) const { return reinterpret_cast<__nv_bfloat16*>(base + byte_off); }
 

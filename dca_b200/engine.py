@@ -183,19 +183,10 @@ class DeviceEngine:
             raise ValueError("batch %d > max_batch %d" % (batch, self.max_batch))
         return int(batch)
 
-    def _announce(self, next_rows):
-        if next_rows is not None:
-            if next_rows.dtype != torch.int32 or not next_rows.is_contiguous():
-                raise ValueError("next_rows must be a contiguous int32 tensor")
-            check(self.lib.dca_set_next_batch(self.handle, next_rows.data_ptr(), next_rows.numel()), "dca_set_next_batch")
-
-    def train_step(self, X, Y, sf, rows=None, batch=None, phase=0, next_rows=None):
+    def train_step(self, X, Y, sf, rows=None, batch=None, phase=0):
         """Forward + loss + backward into ``self.grads`` (no update).  phase 1 / 2 run the two halves
-        (see dca_train_step_phase): after phase 1 ``self.grads[self.head_bucket:]`` is final.
-        next_rows: the row indices of the FOLLOWING batch (same X) -- gathered while this step computes."""
+        (see dca_train_step_phase): after phase 1 ``self.grads[self.head_bucket:]`` is final."""
         b = self._check_inputs(X, Y, sf, rows, batch)
-        if phase != 2:
-            self._announce(next_rows)
         if phase == 0:
             check(self.lib.dca_train_step(self.handle, _ptr(X), X.stride(0), _ptr(Y), Y.stride(0), _ptr(sf), _ptr(rows),
                                           b, self._stream()), "dca_train_step")
@@ -227,17 +218,16 @@ class DeviceEngine:
         """Sum all-reduce of the flat gradient buffer (+ loss slot, flag) over the engine's communicator."""
         check(self.lib.dca_allreduce(self.handle, self._stream()), "dca_allreduce")
 
-    def train_step_allreduce(self, X, Y, sf, rows=None, next_rows=None):
+    def train_step_allreduce(self, X, Y, sf, rows=None):
         """Data-parallel step: the all-reduce of the head-gradient bucket overlaps the hidden-stack backward.  With an
         engine communicator (comm_init) the whole sequence is one library call / one CUDA graph."""
         if getattr(self, "_comm", False):
             b = self._check_inputs(X, Y, sf, rows, None)
-            self._announce(next_rows)
             check(self.lib.dca_train_step_dp(self.handle, _ptr(X), X.stride(0), _ptr(Y), Y.stride(0), _ptr(sf), _ptr(rows),
                                              b, self._stream()), "dca_train_step_dp")
             return
         import torch.distributed as dist
-        self.train_step(X, Y, sf, rows=rows, phase=1, next_rows=next_rows)
+        self.train_step(X, Y, sf, rows=rows, phase=1)
         w1 = dist.all_reduce(self.grads[self.head_bucket:], async_op=True)
         self.train_step(X, Y, sf, rows=rows, phase=2)
         w2 = dist.all_reduce(self.grads[:self.head_bucket], async_op=True) if self.head_bucket > 0 else None

@@ -281,14 +281,12 @@ def _fit_loop(eng, network, Xd, Yd, sfd, n_tr, n_va, steps, batch_size, epochs, 
             np.random.shuffle(order)
         order_d = torch.from_numpy(order.astype(np.int32)).to(dev)
         eng.read_epoch_acc(reset=True)
-        batches = [order_d[s * batch_size: min((s + 1) * batch_size, n_tr)] for s in range(steps)]
         for s in range(steps):
-            rows = batches[s]
-            nxt = batches[s + 1] if s + 1 < steps else None          # its row gather runs under this step (dca_set_next_batch)
+            rows = order_d[s * batch_size: min((s + 1) * batch_size, n_tr)]
             if world > 1:
-                eng.train_step_allreduce(Xd, Yd, sfd, rows=rows, next_rows=nxt)     # NCCL all-reduce overlapped with the backward tail
+                eng.train_step_allreduce(Xd, Yd, sfd, rows=rows)     # NCCL all-reduce overlapped with the backward tail
             else:
-                eng.train_step(Xd, Yd, sfd, rows=rows, next_rows=nxt)
+                eng.train_step(Xd, Yd, sfd, rows=rows)
             eng.apply_update(ctl.lr, clip_grad, gscale)
         # validation pass: inference-mode BN over the held-out tail
         for s in range(n_tr, n_tr + n_va, batch_size):

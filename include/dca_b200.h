@@ -141,13 +141,6 @@ int dca_params_changed(dca_handle* h, void* stream);
 int dca_train_step(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy,
                    const float* sf, const int32_t* rows, int32_t batch, void* stream);
 
-/* Announce the rows of the batch AFTER the coming one: the next dca_train_step / _dp call then gathers X[rows_next] into a
- * second contiguous bf16 buffer as a parallel branch of its graph, and the call after it -- when it passes the same X and
- * the same rows_next pointer -- finds its input ready and skips its own gather (tcgen05 encoder path; ignored otherwise).
- * The index data must stay unchanged until that later step has been enqueued.  Keras has no counterpart (its input
- * pipeline is the NumPy slicing inside model.fit, dca/train.py:91-98).  NULL cancels. */
-int dca_set_next_batch(dca_handle* h, const int32_t* rows_next, int32_t batch);
-
 /* The same step in two halves, for overlapping the gradient all-reduce with the tail of the backward pass:
  * phase 1 = forward + loss + head backward (afterwards grads[head_bucket_offset : P+2] -- the head kernels and
  * biases, ~98 % of the parameters, plus the loss slot -- are final), phase 2 = hidden-stack / encoder backward

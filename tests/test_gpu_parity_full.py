@@ -423,35 +423,3 @@ def test_loss_kernel_variants_vs_oracle(ring, ae_type):
                 assert rel_err(dth.cpu().numpy(), ref["dtheta"]) < 3e-4
     finally:
         L.check(lib.dca_set_tunable(b"loss_ring", 1))
-
-
-def test_next_batch_prefetch_changes_nothing_but_the_schedule():
-    """dca_set_next_batch: the row gather of the following batch runs as a parallel branch of the current step's graph
-    into the second bf16 buffer.  Same losses / parameters as the plain sequence over direct call, capture and replays,
-    including a step whose announced batch is NOT the one that follows (the engine must then gather in-step)."""
-    from dca_b200.engine import DeviceEngine
-    N, G, B = 1500, 264, 256
-    Y = synth_counts(N, G, 61); X, sf = O.normalize_inputs(Y)
-    Xd, Yd, sfd = _t(X, torch.bfloat16), _t(Y), _t(sf)
-    order = torch.randperm(N, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)).int()
-    batches = [order[i * B:(i + 1) * B].contiguous() for i in range(5)]
-    side = torch.cuda.Stream(DEV)
-    losses = {}
-    for mode in ("plain", "prefetch"):
-        eng = DeviceEngine(G, G, (64, 32, 64), "zinb-conddisp", max_batch=B, seed=4, gemm_path="tcgen05", x_dtype="bfloat16")
-        ls = []
-        with torch.cuda.stream(side):
-            for i, rows in enumerate(batches):
-                nxt = None
-                if mode == "prefetch":
-                    nxt = batches[i + 1] if i + 1 < len(batches) else None
-                    if i == 2:
-                        nxt = batches[0]                          # a wrong announcement: step 3 must not use it
-                eng.train_step(Xd, Yd, sfd, rows=rows, next_rows=nxt)
-                eng.apply_update(1e-3, 5.0)
-                ls.append(eng.read_loss())
-        losses[mode] = (ls, eng.params.clone())
-        eng.close()
-    a, b = losses["plain"], losses["prefetch"]
-    np.testing.assert_allclose(b[0], a[0], rtol=2e-5)
-    assert (a[1] - b[1]).abs().max().item() <= 5e-3 * 1e-3 * 5 + 1e-6      # a few RMSprop steps of 1e-3 apart at most
