@@ -8,6 +8,7 @@
 // libdca_b200.so carries no link-time dependency on it and loads on boxes without NCCL.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <cstdlib>
 #include <cstring>
 #include "dca_internal.cuh"
 #include "engine.h"
@@ -107,19 +108,37 @@ int Engine::bn_allreduce(double* a, double* b, int n, cudaStream_t s) {
   return DCA_OK;
 }
 
-// phase 1 -> [comm stream: all-reduce(head bucket, loss slot, flag)] || phase 2 -> all-reduce(rest) -> join
+// phase 1 -> [comm stream: all-reduce of the head gradients] || phase 2 -> all-reduce(rest) -> join.
+// tcgen05 path with several heads: phase 1 itself launches the head backward per head and enqueues each head's all-reduce as
+// soon as that head's gradients are final (engine.cu), so only the loss slot / theta tail is left for the comm stream here.
 int Engine::train_step_dp_body(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows,
                                int Bn, cudaStream_t s) {
   const int64_t hb = x_kind ? 0 : head_W[0];
-  DCA_TRY(train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, 1));
+  const bool split = !x_kind && tc_heads && !fused_heads && n_slots > 1 && split_heads_enabled();
+  dp_split_heads = split;
+  const int st1 = train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, 1);
+  dp_split_heads = false;
+  DCA_TRY(st1);
   DCA_CUDA_OK(cudaEventRecord(ev_fork, s));
   DCA_CUDA_OK(cudaStreamWaitEvent(comm_stream, ev_fork, 0));
-  DCA_TRY(allreduce_range(hb, P + 2, comm_stream));
+  if (split) {
+    // what the per-head all-reduces have not covered: everything behind the last head tensor (theta, loss slot, flag)
+    int64_t tail = hb;
+    for (int k = 0; k < n_slots; ++k) { const int64_t e = head_b[slot_head[k]] + cfg.n_out; if (e > tail) tail = e; }
+    DCA_TRY(allreduce_range(tail, P + 2, comm_stream));
+  } else {
+    DCA_TRY(allreduce_range(hb, P + 2, comm_stream));
+  }
   DCA_CUDA_OK(cudaEventRecord(ev_join, comm_stream));
   DCA_TRY(train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, 2));
   DCA_TRY(allreduce_range(0, hb, s));
   DCA_CUDA_OK(cudaStreamWaitEvent(s, ev_join, 0));
   return DCA_OK;
+}
+
+bool Engine::split_heads_enabled() {
+  static const bool on = [] { const char* e = getenv("DCA_DP_SPLIT_HEADS"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 }  // namespace dca

@@ -505,6 +505,20 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
       Z[k] = bf(o_dzb[kk]); Wk[k] = bf(o_pbf) + head_W[slot_head[kk]];
       dWp[k] = gp(head_W[slot_head[kk]]); dbp[k] = gp(head_b[slot_head[kk]]);
     }
+    if (dp_split_heads && comm && n_slots > 1) {
+      // data-parallel step: one head-backward launch PER HEAD, each followed by the all-reduce of that head's kernel + bias
+      // gradients on the communicator stream -- two thirds of the gradient bytes travel under the remaining head-backward
+      // launches, the last third under the hidden-stack / encoder backward (comm.cu: train_step_dp_body)
+      for (int k = 0; k < n_slots; ++k) {
+        const __nv_bfloat16* Z1[3] = {Z[k], Z[k], Z[k]}; const __nv_bfloat16* W1[3] = {Wk[k], Wk[k], Wk[k]};
+        float* dW1[3] = {dWp[k], dWp[k], dWp[k]}; float* db1[3] = {dbp[k], dbp[k], dbp[k]};
+        DCA_TRY(tc::gene_gemm_tc(3, Z1, G, Bn, G, 1, bf(o_h3b), W1, dh, dW1, G, 1, db1, sm_count, s));
+        const int h = slot_head[k];
+        DCA_CUDA_OK(cudaEventRecord(ev_fork, s));
+        DCA_CUDA_OK(cudaStreamWaitEvent(comm_stream, ev_fork, 0));
+        DCA_TRY(allreduce_range(head_W[h], head_b[h] + G, comm_stream));
+      }
+    } else
     DCA_TRY(tc::gene_gemm_tc(3, Z, G, Bn, G, n_slots, bf(o_h3b), Wk, dh, dWp, G, 1, dbp, sm_count, s));
   } else
   for (int k = 0; k < 3; ++k) {

@@ -118,9 +118,11 @@ struct Engine {
 
   // data-parallel gradient exchange (comm.cu): NCCL communicator owned by the engine, resolved with dlopen
   void* comm = nullptr; int comm_world = 1, comm_rank = 0;
+  bool dp_split_heads = false;     // set around phase 1 of dca_train_step_dp: head backward per head + per-head all-reduce
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int comm_init(const void* id128, int rank, int world);
   int comm_destroy();
+  static bool split_heads_enabled();       // DCA_DP_SPLIT_HEADS=0 restores the single head-backward launch + one bucket
   int allreduce_range(int64_t lo, int64_t hi, cudaStream_t s);
   // sync_bn: sum the BatchNorm column sums (one or two double vectors) over the ranks; bn_rows(Bn) = rows behind the sums
   bool bn_synced() const { return cfg.sync_bn && comm && comm_world > 1; }

@@ -352,14 +352,23 @@ int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, 
   p.B = B; p.G = G; p.n_heads = n_heads;
   p.n_cb = cdiv(B, 128); p.n_gb = cdiv(G, 128);
   // Work decomposition: items = (head, gene range, cell range), processed by a persistent grid.
-  const int total_gb = p.n_gb * n_heads;
   if (do_a && do_b) {
-    // head backward: gene ranges limited by TMEM (kMaxGb accumulators); split cells to fill the SMs.  The (a)
-    // outputs leave by atomics, so few, fat items (one wave) are preferred.
-    int gpi = cdiv(total_gb, sm_count); if (gpi < 1) gpi = 1; if (gpi > kMaxGb) gpi = kMaxGb;
-    p.gb_per_item = gpi; p.gene_ranges = cdiv(p.n_gb, gpi);
-    int splits = sm_count / (p.gene_ranges * n_heads); if (splits < 1) splits = 1; if (splits > p.n_cb) splits = p.n_cb;
-    p.cb_per_item = cdiv(p.n_cb, splits); p.cell_splits = cdiv(p.n_cb, p.cb_per_item);
+    // head backward: gene ranges limited by TMEM (kMaxGb accumulators); cells split so that one wave of fat items fills the
+    // SMs.  Search the small space for the shortest makespan in tile units: rounds x (tiles per item + one tile-equivalent
+    // per cell block for the dH reduce-add the item issues + a flush / start-up term per gene block -- the (a) outputs
+    // leave by atomics, every extra cell split repeats the dW flush, every extra gene range the dH traffic).
+    int best_gpi = 1, best_splits = 1; long long best_cost = -1;
+    for (int gpi = 1; gpi <= kMaxGb; ++gpi) {
+      const int ranges = cdiv(p.n_gb, gpi) * n_heads;
+      for (int splits = 1; splits <= (p.n_cb < 8 ? p.n_cb : 8); ++splits) {
+        const int cbpi = cdiv(p.n_cb, splits), cs = cdiv(p.n_cb, cbpi);
+        const long long items = (long long)ranges * cs, rounds = (items + sm_count - 1) / sm_count;
+        const long long cost = rounds * ((long long)gpi * cbpi + cbpi + 2ll * gpi);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_gpi = gpi; best_splits = splits; }
+      }
+    }
+    p.gb_per_item = best_gpi; p.gene_ranges = cdiv(p.n_gb, best_gpi);
+    p.cb_per_item = cdiv(p.n_cb, best_splits); p.cell_splits = cdiv(p.n_cb, p.cb_per_item);
   } else if (do_a) {
     // encoder backward: outputs leave by TMA reduce-add, extra cell splits are cheap -> ~4 items per SM
     p.gb_per_item = 1; p.gene_ranges = p.n_gb;
