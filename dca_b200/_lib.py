@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libdca_b200.so")
 DCA_MAX_HIDDEN = 8
 DCA_NAME_LEN = 48
 
+ACTIVATION_IDS = {"relu": 0, "linear": 1, "elu": 2, "selu": 3, "tanh": 4, "sigmoid": 5, "hard_sigmoid": 6,
+                  "softplus": 7, "softsign": 8, "exponential": 9, "LeakyReLU": 10, "PReLU": 11}
 AE_TYPE_IDS = {"zinb-conddisp": 0, "zinb": 1, "nb-conddisp": 2, "nb": 3,
                # the remaining registry keys of dca/network.py:763-768: shape-general fp32 path (csrc/extra_types.cu)
                "poisson": 4, "normal": 5, "nb-shared": 6, "zinb-shared": 7, "zinb-elempi": 8, "nb-fork": 9, "zinb-fork": 10}
@@ -37,6 +39,8 @@ class Config(C.Structure):
         ("bn_momentum", C.c_float), ("bn_eps", C.c_float),
         ("rms_rho", C.c_float), ("rms_eps", C.c_float),
         ("elempi_shared", C.c_int32), ("sync_bn", C.c_int32),
+        ("activation", C.c_int32), ("input_dropout", C.c_float),
+        ("hidden_dropout", C.c_float * DCA_MAX_HIDDEN), ("dropout_seed", C.c_uint64),
     ]
 
 
@@ -88,6 +92,8 @@ PROTOTYPES = {
     "dca_zinb_loss_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f,
                                     _vp, _vp, _sz, _vp]),
     "dca_zinb_elem_host": (C.c_int, [_i32, _f, _f, _f, _f, _f, _f, C.POINTER(_f * 4)]),
+    "dca_dropout_mask_host": (C.c_int, [C.c_uint64, C.c_uint64, _i32, _i64, _f, _vp]),
+    "dca_activation_host": (C.c_int, [_i32, _f, _f, C.POINTER(_f * 2)]),
     "dca_dense_heads_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _vp, _i64, _vp]),
     "dca_tc_heads_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, C.POINTER(_i32 * 3), _vp, _vp, _vp, _vp, _i64, _vp]),

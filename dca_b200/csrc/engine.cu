@@ -56,6 +56,14 @@ int validate(const dca_config* c) {
   if (c->max_batch <= 0) { set_error("max_batch must be positive"); return DCA_ERR_BAD_ARG; }
   if (c->x_dtype != DCA_F32 && c->x_dtype != DCA_BF16) { set_error("x_dtype must be DCA_F32 or DCA_BF16"); return DCA_ERR_BAD_ARG; }
   if (c->gemm_path < 0 || c->gemm_path > 2) { set_error("unknown gemm_path %d", c->gemm_path); return DCA_ERR_BAD_ARG; }
+  if (c->activation < DCA_ACT_RELU || c->activation > DCA_ACT_PRELU) { set_error("unknown activation %d", c->activation); return DCA_ERR_BAD_ARG; }
+  if (c->activation == DCA_ACT_PRELU && c->ae_type >= DCA_AE_NB_FORK) {
+    // dca/network.py:711-712: the fork branches wrap the name in Activation(), which has no 'PReLU'
+    set_error("activation PReLU is not available for the fork types"); return DCA_ERR_UNSUPPORTED;
+  }
+  if (!(c->input_dropout >= 0.f && c->input_dropout < 1.f)) { set_error("input_dropout must be in [0, 1)"); return DCA_ERR_BAD_ARG; }
+  for (int i = 0; i < c->n_hidden; ++i)
+    if (!(c->hidden_dropout[i] >= 0.f && c->hidden_dropout[i] < 1.f)) { set_error("hidden_dropout[%d] must be in [0, 1)", i); return DCA_ERR_BAD_ARG; }
   return DCA_OK;
 }
 
@@ -102,6 +110,8 @@ int Engine::plan(const dca_config& c) {
       lay[i].mm = soff; add_tensor(states, soff, nm + "/bn_moving_mean", 1, h);
       lay[i].mv = soff; add_tensor(states, soff, nm + "/bn_moving_var", 1, h);
     }
+    if (c.activation == DCA_ACT_PRELU) { lay[i].alpha = off; add_tensor(params, off, nm + "_act/alpha", 1, h); }
+    lay[i].drop = c.hidden_dropout[i]; lay[i].id = i;
     prev = h;
     if (h > maxh) maxh = h;
   }
@@ -153,7 +163,10 @@ int Engine::plan(const dca_config& c) {
   loss_ws_bytes = loss_workspace_bytes((int)B, G);
   o_lossws = take(loss_ws_bytes);
   o_rowsbuf = take(sizeof(int32_t) * B);
-  mid_ok = !x_kind && mid_supported(c.hidden, L);
+  o_step = take(256);
+  if (c.activation == DCA_ACT_PRELU) o_actscr = take(sizeof(float) * B * (size_t)maxh);
+  if (c.input_dropout > 0.f) o_xdrop = take((c.x_dtype == DCA_BF16 ? sizeof(__nv_bfloat16) : sizeof(float)) * B * (size_t)c.n_in);
+  mid_ok = !x_kind && plain_hidden() && mid_supported(c.hidden, L);     // the one-launch hidden stack is relu-only, no dropout
   o_bar = take(256);
   o_midpart = take(sizeof(double) * mid_partial_doubles());
   // tcgen05 path (flagship shape): gene-wide layers with a 64-wide partner dimension
@@ -284,11 +297,8 @@ int Engine::forward(const void* X, int64_t ldx, const int32_t* rows, int Bn, boo
       } else {
         DCA_TRY(bn_infer_prepare(st(l.mm), st(l.mv), l.out, cfg.bn_eps, f(l.o_mean), f(l.o_inv), s));
       }
-      DCA_TRY(bn_relu_fwd(a, l.out, Bn, l.out, f(l.o_mean), f(l.o_inv), pp(l.beta), training ? f(l.o_xhat) : nullptr,
-                          f(l.o_h), (tc_heads && i == L - 1) ? bf(o_h3b) : nullptr, s));
-    } else {
-      DCA_TRY(bias_relu_fwd(a, l.out, Bn, l.out, f(l.o_h), (tc_heads && i == L - 1) ? bf(o_h3b) : nullptr, s));
     }
+    DCA_TRY(act_fwd(l, Bn, training, (tc_heads && i == L - 1) ? bf(o_h3b) : nullptr, s));
     hin = f(l.o_h); ldin = l.out; in_bf16 = 0; gather = nullptr;
   }
   if (fused) {
@@ -448,12 +458,21 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
   if (x_kind) return phase == 2 ? DCA_OK : x_train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s);   // whole step in phase 1
   const int G = cfg.n_out;
   float* dh = f(o_dh[0]); float* dh2 = f(o_dh[1]);
+  // input dropout: the network reads a masked, gathered copy of the batch (forward and encoder backward); Y keeps `rows`
+  const int32_t* xrows = rows;
+  if (cfg.input_dropout > 0.f) {
+    if (phase != 2) {
+      DCA_TRY(bump_step(s));
+      DCA_TRY(drop_input(X, x_override_bf16 ? 1 : (cfg.x_dtype == DCA_BF16), ldx, rows, Bn, s));
+    }
+    X = base + o_xdrop; ldx = cfg.n_in; xrows = nullptr;
+  } else if (phase != 2 && !plain_hidden()) DCA_TRY(bump_step(s));
   if (phase != 2) {
   DCA_CUDA_OK(cudaMemsetAsync(gp(0), 0, sizeof(float) * (size_t)(P + 2), s));
   bool any_pen = false;
   mark(0, s);
   DCA_TRY(penalty(s, any_pen));
-  DCA_TRY(forward(X, ldx, rows, Bn, true, s));
+  DCA_TRY(forward(X, ldx, xrows, Bn, true, s));
   mark(1, s);
   float* Mb = f(o_head[0]); float* Db = f(o_head[1]); float* Pb = f(o_head[2]);
   const float inv_n = 1.0f / ((float)Bn * (float)G);
@@ -555,7 +574,7 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
       DCA_TRY(tc::gene_gemm_tc(2, Z, cur_ldxb, Bn, cfg.n_in, 1, bf(o_da1b), nullptr, nullptr, dWp, l.out, 0, nullptr, sm_count, s));
     } else {
       GemmArgs g{};
-      g.A = X; g.lda = ldx; g.a_bf16 = x_override_bf16 ? 1 : (cfg.x_dtype == DCA_BF16); g.transA = 1; g.a_rows = rows;
+      g.A = X; g.lda = ldx; g.a_bf16 = x_override_bf16 ? 1 : (cfg.x_dtype == DCA_BF16); g.transA = 1; g.a_rows = xrows;
       g.B = dh2; g.ldb = l.out; g.transB = 0;
       g.C = gp(l.W); g.ldc = l.out; g.M = l.in; g.N = l.out; g.K = Bn; g.epilogue = EPI_ACCUM;
       DCA_TRY(gemm_auto(g, s));
@@ -563,7 +582,7 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
   } else
   for (int i = L - 1; i >= 0; --i) {
     Layer& l = lay[i];
-    DCA_TRY(relu_bwd(dh, f(l.o_h), l.out, Bn, l.out, s));
+    DCA_TRY(act_bwd(l, dh, Bn, s));
     if (cfg.batchnorm) {
       DCA_TRY(col_sums(dh, f(l.o_xhat), l.out, Bn, l.out, d(o_dsum), d(o_dprod), d(o_scratch), s));
       if (bn_synced()) {          // d beta is this rank's share (the gradient all-reduce sums it); the means are global
@@ -585,7 +604,7 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
     const void* ain = (i == 0) ? X : (const void*)f(lay[i - 1].o_h);
     GemmArgs g{};
     g.A = ain; g.lda = (i == 0) ? ldx : lay[i - 1].out; g.a_bf16 = (i == 0) ? (x_override_bf16 ? 1 : (cfg.x_dtype == DCA_BF16)) : 0;
-    g.transA = 1; g.a_rows = (i == 0) ? rows : nullptr;
+    g.transA = 1; g.a_rows = (i == 0) ? xrows : nullptr;
     g.B = dh; g.ldb = l.out; g.transB = 0;
     g.C = gp(l.W); g.ldc = l.out; g.M = l.in; g.N = l.out; g.K = Bn; g.epilogue = EPI_ACCUM;
     DCA_TRY(gemm_auto(g, s));

@@ -13,6 +13,8 @@ struct Layer {
   int64_t W = -1, b = -1, beta = -1;     // element offsets into params / grads
   int64_t mm = -1, mv = -1;              // element offsets into the BN state region
   size_t o_a = 0, o_xhat = 0, o_h = 0, o_mean = 0, o_inv = 0;   // byte offsets into the arena
+  int64_t alpha = -1;                    // PReLU slopes ("<layer>_act/alpha"), element offset into params / grads
+  float drop = 0.f; int id = 0;          // dropout rate after the activation; mask-stream id (dca_dropout_mask_host)
 };
 
 
@@ -80,6 +82,13 @@ struct Engine {
   bool mid_ok = false; size_t o_bar = 0, o_midpart = 0;
   bool use_mid(int Bn) const { return mid_ok && !bn_synced() && Bn <= mid::kMaxRows * mid::kMaxCtas; }
   void mid_params(mid::Params& p, int Bn, bool training);
+  // activations other than relu, PReLU slopes, dropout (activations.cu): per-layer hidden path only
+  size_t o_step = 0, o_actscr = 0, o_xdrop = 0;       // device step counter (mask stream), PReLU scratch, dropped input batch
+  bool plain_hidden() const;                          // relu and no dropout anywhere: the default model
+  int bump_step(cudaStream_t s);
+  int act_fwd(Layer& l, int Bn, bool training, __nv_bfloat16* hb, cudaStream_t s);
+  int act_bwd(Layer& l, float* dh, int Bn, cudaStream_t s);
+  int drop_input(const void* X, int in_bf16, int64_t ldx, const int32_t* rows, int Bn, cudaStream_t s);
   // tcgen05 path: flags + operand-layout shadows / bf16 activations in the arena
   bool tc_heads = false, tc_enc = false;
   bool fused_heads = false;       // flash_zinb.cu replaces K2 + K3 + K4 of the training step (zinb-conddisp only)

@@ -167,7 +167,8 @@ int Engine::x_plan_params(const dca_config& c, int64_t& off, int64_t& soff) {
   trunk_L = fork ? center + 1 : L;
   int prev = c.n_in;
   maxh = 1;
-  auto add_layer = [&](Layer& l, const std::string& nm, int in, int out, bool enc) {
+  auto add_layer = [&](Layer& l, const std::string& nm, int in, int out, bool enc, int id, float drop) {
+    l.id = id; l.drop = drop;
     l.in = in; l.out = out;
     l.W = off; x_add_tensor(params, off, nm + "/kernel", in, out);
     reg_items.push_back({l.W, (int64_t)in * out, enc});
@@ -177,15 +178,17 @@ int Engine::x_plan_params(const dca_config& c, int64_t& off, int64_t& soff) {
       l.mm = soff; x_add_tensor(states, soff, nm + "/bn_moving_mean", 1, out);
       l.mv = soff; x_add_tensor(states, soff, nm + "/bn_moving_var", 1, out);
     }
+    if (c.activation == DCA_ACT_PRELU) { l.alpha = off; x_add_tensor(params, off, nm + "_act/alpha", 1, out); }
     if (out > maxh) maxh = out;
   };
-  for (int i = 0; i < trunk_L; ++i) { add_layer(lay[i], x_layer_name(i, L), prev, c.hidden[i], i <= center); prev = c.hidden[i]; }
+  for (int i = 0; i < trunk_L; ++i) { add_layer(lay[i], x_layer_name(i, L), prev, c.hidden[i], i <= center, i, c.hidden_dropout[i]); prev = c.hidden[i]; }
   n_branch = 0;
   if (fork) {
     static const char* br[3] = {"mean", "disp", "pi"};
     n_branch = (t == DCA_AE_ZINB_FORK) ? 3 : 2;
     const std::string nm = x_layer_name(L - 1, L);
-    for (int b = 0; b < n_branch; ++b) add_layer(brlay[b], nm + "_last_" + br[b], prev, c.hidden[L - 1], false);
+    for (int b = 0; b < n_branch; ++b) add_layer(brlay[b], nm + "_last_" + br[b], prev, c.hidden[L - 1], false, DCA_MAX_HIDDEN + b,
+                                                c.hidden_dropout[L - 1]);
   }
   const int G = c.n_out;
   for (int k = 0; k < 3; ++k) { head_W[k] = head_b[k] = -1; head_N[k] = 0; head_K[k] = fork && k < n_branch ? c.hidden[L - 1] : prev; }
@@ -242,18 +245,14 @@ int Engine::x_layer_fwd(Layer& l, const void* hin, int64_t ldin, int in_bf16, co
     } else {
       DCA_TRY(bn_infer_prepare(st(l.mm), st(l.mv), l.out, cfg.bn_eps, f(l.o_mean), f(l.o_inv), s));
     }
-    DCA_TRY(bn_relu_fwd(a, l.out, Bn, l.out, f(l.o_mean), f(l.o_inv), pp(l.beta), training ? f(l.o_xhat) : nullptr, f(l.o_h),
-                        nullptr, s));
-  } else {
-    DCA_TRY(bias_relu_fwd(a, l.out, Bn, l.out, f(l.o_h), nullptr, s));
   }
-  return DCA_OK;
+  return act_fwd(l, Bn, training, nullptr, s);
 }
 
 // dh [Bn x l.out] (overwritten) -> parameter gradients of the layer; din (nullable) += or = dh * W^T
 int Engine::x_layer_bwd(Layer& l, float* dh, const void* hin, int64_t ldin, int in_bf16, const int32_t* gather, int Bn,
                         float* din, bool din_accumulate, cudaStream_t s) {
-  DCA_TRY(relu_bwd(dh, f(l.o_h), l.out, Bn, l.out, s));
+  DCA_TRY(act_bwd(l, dh, Bn, s));
   if (cfg.batchnorm) {
     DCA_TRY(col_sums(dh, f(l.o_xhat), l.out, Bn, l.out, d(o_dsum), d(o_dprod), d(o_scratch), s));
     if (bn_synced()) {
@@ -368,7 +367,14 @@ int Engine::x_train_step_body(const void* X, int64_t ldx, const float* Y, int64_
   bool any_pen = false;
   mark(0, s);
   DCA_TRY(x_penalty(s, any_pen));
-  DCA_TRY(x_forward(X, ldx, rows, Bn, true, s));
+  // input dropout: the network reads a masked, gathered copy of the batch; Y keeps `rows`
+  const int32_t* xrows = rows;
+  if (!plain_hidden()) DCA_TRY(bump_step(s));
+  if (cfg.input_dropout > 0.f) {
+    DCA_TRY(drop_input(X, cfg.x_dtype == DCA_BF16, ldx, rows, Bn, s));
+    X = base + o_xdrop; ldx = cfg.n_in; xrows = nullptr;
+  }
+  DCA_TRY(x_forward(X, ldx, xrows, Bn, true, s));
   mark(1, s);
   float* Mb = f(o_head[0]); float* Db = f(o_head[1]); float* Pb = f(o_head[2]);
   DCA_TRY(x_heads_forward(Bn, Mb, cond ? Db : nullptr, has_pi ? Pb : nullptr, nullptr, s));
@@ -454,7 +460,7 @@ int Engine::x_train_step_body(const void* X, int64_t ldx, const float* Y, int64_
   for (int i = trunk_L - 1; i >= 0; --i) {
     const void* ain = (i == 0) ? X : (const void*)f(lay[i - 1].o_h);
     DCA_TRY(x_layer_bwd(lay[i], dh, ain, (i == 0) ? ldx : lay[i - 1].out, (i == 0) ? (cfg.x_dtype == DCA_BF16) : 0,
-                        (i == 0) ? rows : nullptr, Bn, i > 0 ? dh2 : nullptr, false, s));
+                        (i == 0) ? xrows : nullptr, Bn, i > 0 ? dh2 : nullptr, false, s));
     float* t = dh; dh = dh2; dh2 = t;
   }
   mark(-1, s);

@@ -17,6 +17,7 @@
 // more tcgen05 product of the same tile with a constant ones operand (Z^T . 1, N = 16).
 //
 // Warp roles (256 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue.
+#include <cstdlib>
 #include "engine.h"
 #include "tc_common.cuh"
 
@@ -370,11 +371,22 @@ int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, 
     p.gb_per_item = best_gpi; p.gene_ranges = cdiv(p.n_gb, best_gpi);
     p.cb_per_item = cdiv(p.n_cb, best_splits); p.cell_splits = cdiv(p.n_cb, p.cb_per_item);
   } else if (do_a) {
-    // encoder backward: outputs leave by TMA reduce-add, extra cell splits are cheap -> ~4 items per SM
-    p.gb_per_item = 1; p.gene_ranges = p.n_gb;
-    int splits = cdiv(4 * sm_count, p.gene_ranges * n_heads); if (splits < 1) splits = 1; if (splits > p.n_cb) splits = p.n_cb;
-    while (splits > 1 && cdiv(p.n_cb, splits) < 4) --splits;          // >= 4 tiles per item
-    p.cb_per_item = cdiv(p.n_cb, splits); p.cell_splits = cdiv(p.n_cb, p.cb_per_item);
+    // encoder backward: the same search (per item: tiles + half a tile per cell block for the H tile it loads + the dW flush
+    // by TMA reduce-add per gene block); TMEM holds up to kMaxGb accumulators, so one H tile serves four gene blocks
+    int best_gpi = 1, best_splits = 1; long long best_cost = -1;
+    for (int gpi = 1; gpi <= kMaxGb; ++gpi) {
+      const int ranges = cdiv(p.n_gb, gpi) * n_heads;
+      for (int splits = 1; splits <= (p.n_cb < 8 ? p.n_cb : 8); ++splits) {
+        const int cbpi = cdiv(p.n_cb, splits), cs = cdiv(p.n_cb, cbpi);
+        const long long items = (long long)ranges * cs, rounds = (items + sm_count - 1) / sm_count;
+        const long long cost = rounds * (2ll * gpi * cbpi + cbpi + 4ll * gpi);      // in half tiles
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_gpi = gpi; best_splits = splits; }
+      }
+    }
+    if (getenv("DCA_GG_K5_OLD")) { best_gpi = 1; best_splits = cdiv(4 * sm_count, p.n_gb * n_heads); if (best_splits > p.n_cb) best_splits = p.n_cb;
+      while (best_splits > 1 && cdiv(p.n_cb, best_splits) < 4) --best_splits; }
+    p.gb_per_item = best_gpi; p.gene_ranges = cdiv(p.n_gb, best_gpi);
+    p.cb_per_item = cdiv(p.n_cb, best_splits); p.cell_splits = cdiv(p.n_cb, p.cb_per_item);
   } else {
     // encoder forward: one cell block per item, genes split so that there are ~4 items per SM
     p.cb_per_item = 1; p.cell_splits = p.n_cb;

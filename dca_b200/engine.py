@@ -30,7 +30,8 @@ class DeviceEngine:
                  x_dtype: str = "float32", ridge: float = 0.0, l1: float = 0.0, l2: float = 0.0,
                  l1_enc: float = 0.0, l2_enc: float = 0.0, gemm_path: str = "auto",
                  device: Optional[torch.device] = None, seed: Optional[int] = 0, sharedpi: bool = False,
-                 sync_bn: bool = False):
+                 sync_bn: bool = False, activation: str = "relu", hidden_dropout=0.0, input_dropout: float = 0.0,
+                 dropout_seed: Optional[int] = None):
         if ae_type not in _lib.AE_TYPE_IDS:
             raise NotImplementedError("ae_type %r is not on the accelerated path (supported: %s)"
                                       % (ae_type, sorted(_lib.AE_TYPE_IDS)))
@@ -56,6 +57,23 @@ class DeviceEngine:
         cfg.ridge, cfg.l1, cfg.l2, cfg.l1_enc, cfg.l2_enc = ridge, l1, l2, l1_enc, l2_enc
         cfg.elempi_shared = int(bool(sharedpi))          # zinb-elempi only (dca/network.py:425-427)
         cfg.sync_bn = int(bool(sync_bn))                 # BatchNorm over the global batch in data-parallel runs (comm_init)
+        # hidden activation + dropout (dca/network.py:98-99,129-138); anything but relu / rate 0 takes the per-layer hidden path
+        if activation not in _lib.ACTIVATION_IDS:
+            raise NotImplementedError("activation %r is not on the accelerated path (supported: %s)"
+                                      % (activation, sorted(_lib.ACTIVATION_IDS)))
+        cfg.activation = _lib.ACTIVATION_IDS[activation]
+        rates = list(hidden_dropout) if isinstance(hidden_dropout, (list, tuple)) else [hidden_dropout] * len(self.hidden)
+        if len(rates) != len(self.hidden):
+            raise ValueError("hidden_dropout needs one rate per hidden layer")
+        for i, r in enumerate(rates):
+            cfg.hidden_dropout[i] = float(r)
+        cfg.input_dropout = float(input_dropout)
+        self.activation, self.hidden_dropout, self.input_dropout = activation, [float(r) for r in rates], float(input_dropout)
+        if dropout_seed is None:                        # data-parallel replicas draw different masks
+            rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+            dropout_seed = (seed or 0) * 1000003 + 12345 + 7919 * rank
+        self.dropout_seed = int(dropout_seed) & (2 ** 64 - 1)
+        cfg.dropout_seed = self.dropout_seed
         cfg.bn_momentum, cfg.bn_eps = KERAS_DEFAULTS["bn_momentum"], KERAS_DEFAULTS["bn_eps"]
         cfg.rms_rho, cfg.rms_eps = KERAS_DEFAULTS["rms_rho"], KERAS_DEFAULTS["rms_eps"]
         self.cfg = cfg

@@ -80,10 +80,6 @@ class Autoencoder:
         if self.ae_type is None:
             raise NotImplementedError("autoencoder type %s is not on the B200-accelerated path"
                                       % type(self).__name__)
-        if any(d > 0.0 for d in self.hidden_dropout) or self.input_dropout > 0.0:
-            raise NotImplementedError("dropout > 0 is not on the accelerated path (reference default is 0)")
-        if self.activation != 'relu':
-            raise NotImplementedError("only activation='relu' is on the accelerated path")
         if self.init != 'glorot_uniform':
             raise NotImplementedError("only init='glorot_uniform' is on the accelerated path")
         if seed is not None:
@@ -94,7 +90,8 @@ class Autoencoder:
                                    ridge=self.ridge, l1=self.l1_coef, l2=self.l2_coef,
                                    l1_enc=self.l1_enc_coef, l2_enc=self.l2_enc_coef,
                                    gemm_path=self.gemm_path, seed=self._seed, sharedpi=self.sharedpi,
-                                   sync_bn=self.sync_bn)
+                                   sync_bn=self.sync_bn, activation=self.activation,
+                                   hidden_dropout=self.hidden_dropout, input_dropout=self.input_dropout)
         self.model = self.engine
         self.encoder = self.engine
         self.loss = self.ae_type

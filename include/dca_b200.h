@@ -56,6 +56,25 @@ typedef enum dca_ae_type {
   DCA_AE_ZINB_FORK = 10       /* 'zinb-fork'     ZINBForkAutoencoder          dca/network.py:553-661 */
 } dca_ae_type;
 
+/* Hidden-layer activation: Keras `Activation(name)` or, for the two names in `advanced_activations`
+ * (dca/network.py:41,132-135), the Keras layer of that name with its default arguments.  Anything but
+ * relu, and any dropout rate > 0, runs the per-layer hidden path (the one-launch hidden-stack kernel is
+ * relu-only). */
+typedef enum dca_activation {
+  DCA_ACT_RELU = 0,
+  DCA_ACT_LINEAR = 1,
+  DCA_ACT_ELU = 2,            /* alpha = 1 */
+  DCA_ACT_SELU = 3,
+  DCA_ACT_TANH = 4,
+  DCA_ACT_SIGMOID = 5,
+  DCA_ACT_HARD_SIGMOID = 6,   /* clip(0.2 x + 0.5, 0, 1) */
+  DCA_ACT_SOFTPLUS = 7,
+  DCA_ACT_SOFTSIGN = 8,
+  DCA_ACT_EXPONENTIAL = 9,
+  DCA_ACT_LEAKY_RELU = 10,    /* keras.layers.LeakyReLU(): alpha = 0.3 */
+  DCA_ACT_PRELU = 11          /* keras.layers.PReLU(): one trainable alpha per unit, zero-initialised ("<layer>_act/alpha") */
+} dca_activation;
+
 typedef enum dca_dtype { DCA_F32 = 0, DCA_BF16 = 1 } dca_dtype;
 
 typedef enum dca_gemm_path {
@@ -93,6 +112,10 @@ typedef struct dca_config {
   int32_t sync_bn;            /* data-parallel runs (dca_comm_init): BatchNorm statistics over the GLOBAL batch (sum all-reduce of
                                * the column sums, forward and backward) -- exactly the single-GPU model at the global batch size.
                                * 0 (default): per-rank batch statistics, no extra collective. */
+  int32_t activation;         /* dca_activation of every hidden layer (dca/network.py:58,129-135; CLI --activation); 0 = relu */
+  float input_dropout;        /* Dropout(rate) on the network input, training only (dca/network.py:98-99); 0 = off */
+  float hidden_dropout[DCA_MAX_HIDDEN];   /* Dropout(rate) after each hidden activation (dca/network.py:137-138) */
+  uint64_t dropout_seed;      /* stream of the counter-based mask generator (dca_dropout_mask_host reproduces a mask) */
 } dca_config;
 
 typedef struct dca_handle dca_handle;
@@ -264,6 +287,14 @@ int dca_zinb_loss_fwd(const float* Y, int64_t ldy, const int32_t* rows, const fl
  * branch-free zero branch and the NB branch computed from mu = m * sf with the MeanAct mask applied afterwards. */
 int dca_zinb_elem_host(int32_t ae_type, float y, float m, float sf, float d, float pi, float ridge,
                        float out[4]);
+
+/* HOST mirrors of the hidden-layer pieces the per-layer path adds (same source as the device code):
+ * dca_dropout_mask_host writes the keep mask (1 = kept) the device applies at training step `step` (1 for the first
+ * dca_train_step after dca_create) to elements [0, n) of `layer` (hidden layer index; -1 = the input; fork branches
+ * use DCA_MAX_HIDDEN + branch); kept values are scaled by 1 / (1 - rate) as keras.layers.Dropout does.
+ * dca_activation_host evaluates activation `act` (value and derivative; PReLU with slope `alpha`). */
+int dca_dropout_mask_host(uint64_t seed, uint64_t step, int32_t layer, int64_t n, float rate, uint8_t* keep);
+int dca_activation_host(int32_t act, float x, float alpha, float out[2]);
 
 /* Head Dense layers with fused output activations (dca/network.py:369-381, :38-39,
  * dca/layers.py:85): H (B x K float32, ld ldh) times the Keras-layout kernels (K x G) plus bias,

@@ -24,6 +24,30 @@ from .dca_oracle import KERAS_DEFAULTS, layer_names, head_names
 EPS = 1e-10
 
 
+def hidden_activation(name, x, alpha=None):
+    """Keras `Activation(name)` / `LeakyReLU()` / `PReLU()` as the reference applies them after every hidden layer
+    (dca/network.py:129-135), written with torch's own functions (independent of the engine's closed forms)."""
+    F = torch.nn.functional
+    if name == "relu": return torch.relu(x)
+    if name == "linear": return x
+    if name == "elu": return F.elu(x)
+    if name == "selu": return F.selu(x)
+    if name == "tanh": return torch.tanh(x)
+    if name == "sigmoid": return torch.sigmoid(x)
+    if name == "hard_sigmoid": return torch.clamp(0.2 * x + 0.5, 0.0, 1.0)
+    if name == "softplus": return F.softplus(x)
+    if name == "softsign": return F.softsign(x)
+    if name == "exponential": return torch.exp(x)
+    if name == "LeakyReLU": return F.leaky_relu(x, 0.3)
+    if name == "PReLU": return torch.relu(x) - alpha * torch.relu(-x)
+    raise ValueError(name)
+
+
+def apply_dropout(x, mask, rate):
+    """keras.layers.Dropout in training mode with the mask handed in: x * mask / (1 - rate)  (dca/network.py:98-99,137-138)."""
+    return x * mask.to(x.dtype).reshape(x.shape) / (1.0 - rate)
+
+
 def nb_elem(y, mu, theta):
     theta = torch.clamp(theta, max=1e6)                                   # dca/loss.py:85
     t1 = torch.lgamma(theta + EPS) + torch.lgamma(y + 1.0) - torch.lgamma(y + theta + EPS)   # :87
@@ -117,18 +141,20 @@ class TorchExtraNet:
     """float64 autograd statement of one training step of the extra types (the role TF autodiff plays in the reference);
     same parameter names as the engine.  TEST INFRASTRUCTURE ONLY."""
 
-    def __init__(self, params, hidden, ae_type, batchnorm=True, ridge=0.0, dtype=torch.float64):
+    def __init__(self, params, hidden, ae_type, batchnorm=True, ridge=0.0, dtype=torch.float64, activation="relu"):
         assert ae_type in EXTRA_TYPES
         self.hidden = tuple(hidden); self.ae_type = ae_type; self.batchnorm = batchnorm; self.ridge = ridge; self.dtype = dtype
+        self.activation = activation
+        self.masks = {}; self.rates = {}      # dropout: layer id (-1 input, i hidden, 8 + b fork branch) -> keep mask / rate
         self.names = layer_names(len(self.hidden)); self.center = len(self.hidden) // 2
         self.p = {k: torch.as_tensor(v).to(dtype).clone() for k, v in params.items()}
-        self.train_keys = [k for k in self.p if k.endswith(("/kernel", "/bias", "/bn_beta"))]
+        self.train_keys = [k for k in self.p if k.endswith(("/kernel", "/bias", "/bn_beta", "_act/alpha"))]
         for k in self.train_keys:
             self.p[k].requires_grad_(True)
         self.rms = {k: torch.zeros_like(self.p[k]) for k in self.train_keys}
         self.mom = KERAS_DEFAULTS["bn_momentum"]; self.bn_eps = KERAS_DEFAULTS["bn_eps"]
 
-    def _layer(self, h, nm, training, stats):
+    def _layer(self, h, nm, training, stats, lid=None):
         a = h @ self.p[nm + "/kernel"] + self.p[nm + "/bias"]
         pre = a
         if self.batchnorm:
@@ -138,19 +164,24 @@ class TorchExtraNet:
             else:
                 mean = self.p[nm + "/bn_moving_mean"]; var = self.p[nm + "/bn_moving_var"]
             pre = (a - mean) / torch.sqrt(var + self.bn_eps) + self.p[nm + "/bn_beta"]
-        return a, torch.relu(pre)
+        out = hidden_activation(self.activation, pre, self.p.get(nm + "_act/alpha"))
+        if training and lid in self.masks:
+            out = apply_dropout(out, self.masks[lid], self.rates[lid])
+        return a, out
 
     def forward(self, X, sf, training=True):
         stats = []
         h = X; latent = None
+        if training and -1 in self.masks:
+            h = apply_dropout(h, self.masks[-1], self.rates[-1])
         fork = FORK_BRANCHES.get(self.ae_type)
         branch = {}
         for i, nm in enumerate(self.names):
             if fork and i > self.center:
-                for br in fork:
-                    _, branch[br] = self._layer(h, "%s_last_%s" % (nm, br), training, stats)
+                for b, br in enumerate(fork):
+                    _, branch[br] = self._layer(h, "%s_last_%s" % (nm, br), training, stats, 8 + b)
                 continue
-            a, h = self._layer(h, nm, training, stats)
+            a, h = self._layer(h, nm, training, stats, i)
             if nm == "center":
                 latent = a
         hin = lambda br: branch.get(br, h)
@@ -211,12 +242,13 @@ class TorchRefNet:
     """Same parameter names / layouts as oracle.dca_oracle.OracleNet."""
 
     def __init__(self, params: Dict[str, "torch.Tensor"], hidden: Sequence[int], ae_type: str,
-                 batchnorm=True, ridge=0.0, dtype=torch.float32):
+                 batchnorm=True, ridge=0.0, dtype=torch.float32, activation="relu"):
         self.hidden = tuple(hidden); self.ae_type = ae_type; self.batchnorm = batchnorm
-        self.ridge = ridge; self.dtype = dtype
+        self.ridge = ridge; self.dtype = dtype; self.activation = activation
+        self.masks = {}; self.rates = {}      # dropout: layer id (-1 input, i hidden) -> keep mask / rate
         self.names = layer_names(len(self.hidden)); self.heads = head_names(ae_type)
         self.p = {k: torch.as_tensor(v).to(dtype).clone() for k, v in params.items()}
-        self.train_keys = [k for k in self.p if k.endswith(("/kernel", "/bias", "/bn_beta", "/theta"))]
+        self.train_keys = [k for k in self.p if k.endswith(("/kernel", "/bias", "/bn_beta", "/theta", "_act/alpha"))]
         for k in self.train_keys:
             self.p[k].requires_grad_(True)
         self.rms = {k: torch.zeros_like(self.p[k]) for k in self.train_keys}
@@ -224,8 +256,10 @@ class TorchRefNet:
 
     def forward(self, X, sf, training=True):
         h = X
+        if training and -1 in self.masks:
+            h = apply_dropout(h, self.masks[-1], self.rates[-1])
         stats = []
-        for nm in self.names:
+        for i, nm in enumerate(self.names):
             a = h @ self.p[nm + "/kernel"] + self.p[nm + "/bias"]
             if self.batchnorm:
                 if training:
@@ -234,7 +268,9 @@ class TorchRefNet:
                 else:
                     mean = self.p[nm + "/bn_moving_mean"]; var = self.p[nm + "/bn_moving_var"]
                 a = (a - mean) / torch.sqrt(var + self.bn_eps) + self.p[nm + "/bn_beta"]
-            h = torch.relu(a)
+            h = hidden_activation(self.activation, a, self.p.get(nm + "_act/alpha"))
+            if training and i in self.masks:
+                h = apply_dropout(h, self.masks[i], self.rates[i])
         z = {nm: h @ self.p[nm + "/kernel"] + self.p[nm + "/bias"] for nm in self.heads}
         m = torch.clamp(torch.exp(z["mean"]), 1e-5, 1e6)
         mu = m * sf.reshape(-1, 1)
