@@ -16,6 +16,11 @@ DCA_NAME_LEN = 48
 
 ACTIVATION_IDS = {"relu": 0, "linear": 1, "elu": 2, "selu": 3, "tanh": 4, "sigmoid": 5, "hard_sigmoid": 6,
                   "softplus": 7, "softsign": 8, "exponential": 9, "LeakyReLU": 10, "PReLU": 11}
+# keras.optimizers module attributes the reference's `opt.__dict__[optimizer]` resolves (dca/train.py:54-57): class names and
+# the lower-case aliases keras/optimizers.py defines; value = (dca_optimizer id, the class's default learning rate)
+OPTIMIZERS = {"RMSprop": (0, 1e-3), "SGD": (1, 1e-2), "Adagrad": (2, 1e-2), "Adadelta": (3, 1.0), "Adam": (4, 1e-3),
+              "Adamax": (5, 2e-3), "Nadam": (6, 2e-3)}
+OPTIMIZERS.update({k.lower(): v for k, v in list(OPTIMIZERS.items())})
 AE_TYPE_IDS = {"zinb-conddisp": 0, "zinb": 1, "nb-conddisp": 2, "nb": 3,
                # the remaining registry keys of dca/network.py:763-768: shape-general fp32 path (csrc/extra_types.cu)
                "poisson": 4, "normal": 5, "nb-shared": 6, "zinb-shared": 7, "zinb-elempi": 8, "nb-fork": 9, "zinb-fork": 10}
@@ -73,6 +78,8 @@ PROTOTYPES = {
     "dca_comm_destroy": (C.c_int, [_vp]),
     "dca_allreduce": (C.c_int, [_vp, _vp]),
     "dca_train_step_dp": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
+    "dca_set_optimizer": (C.c_int, [_vp, _i32, _vp]),
+    "dca_reset_optimizer": (C.c_int, [_vp, _vp]),
     "dca_apply_update": (C.c_int, [_vp, _f, _f, _f, _vp]),
     "dca_eval_step": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
     "dca_predict": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),

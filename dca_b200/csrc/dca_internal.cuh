@@ -90,6 +90,11 @@ int add_reg_grad(const float* w, float* g, int64_t n, float l1, float l2, cudaSt
 int reg_penalty(const float* w, int64_t n, float l1, float l2, double* acc, cudaStream_t s);
 int rmsprop_update(float* params, const float* grads, float* rms, int64_t n, float lr, float clip,
                    float rho, float eps, float grad_scale, __nv_bfloat16* shadow, float* loss_out, cudaStream_t s);
+// Keras 2.x update rules other than RMSprop (SGD, Adagrad, Adadelta, Adam, Adamax, Nadam); c[] are the per-step scalars
+// the host derives from the iteration count (bias corrections, Nadam's momentum schedule)
+struct OptScalars { int kind; float lr, clip, gs, c0, c1, c2, c3, c4; };
+int optimizer_update(float* params, const float* grads, float* s1, float* s2, int64_t n, OptScalars o, __nv_bfloat16* shadow,
+                     float* loss_out, cudaStream_t s);
 int glorot_fill(float* w, int64_t n, int fan_in, int fan_out, uint64_t seed, uint64_t stream_id, cudaStream_t s);
 int fill_value(float* p, int64_t n, float v, cudaStream_t s);
 int cast_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);

@@ -2,6 +2,7 @@
 // BatchNorm state, fixed workspace) and sequences the kernels of one training / validation /
 // predict batch.  Replaces what Keras Model.fit / Model.predict execute for
 // dca/train.py:91-98, dca/network.py:92-141,366-393 (see include/dca_b200.h per entry point).
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -139,6 +140,7 @@ int Engine::plan(const dca_config& c) {
   o_params = take(sizeof(float) * (size_t)P);
   o_grads = take(sizeof(float) * (size_t)(P + 2));
   o_rms = take(sizeof(float) * (size_t)P);
+  o_opt2 = take(sizeof(float) * (size_t)P);   // second accumulator of Adadelta / Adam / Adamax / Nadam (12 MB at 20k genes)
   o_state = take(sizeof(float) * (size_t)(S > 0 ? S : 1));
   o_acc = take(sizeof(double) * 8);          // epoch acc[4], loss_sum, penalty
   for (int i = 0; i < L; ++i) {
@@ -626,9 +628,34 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
 int Engine::apply_update(float lr, float clip, float grad_scale, cudaStream_t s) {
   mark(5, s);
   float* ring_slot = loss_ring ? loss_ring + (ring_pos++ % ring_n) : nullptr;
+  if (opt_kind != DCA_OPT_RMSPROP) {
+    // per-step scalars of keras/optimizers.py get_updates (t = iterations + 1), evaluated in double on the host
+    OptScalars o{}; o.kind = opt_kind; o.lr = lr; o.clip = clip; o.gs = grad_scale;
+    const double t = (double)(++opt_iter), b1 = 0.9, b2 = 0.999;
+    if (opt_kind == DCA_OPT_ADAM) o.c0 = (float)((double)lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t)));
+    else if (opt_kind == DCA_OPT_ADAMAX) o.c0 = (float)((double)lr / (1.0 - pow(b1, t)));
+    else if (opt_kind == DCA_OPT_NADAM) {
+      const double sd = 0.004;
+      const double mu_t = b1 * (1.0 - 0.5 * pow(0.96, t * sd)), mu_t1 = b1 * (1.0 - 0.5 * pow(0.96, (t + 1.0) * sd));
+      const double sched_new = nadam_sched * mu_t, sched_next = sched_new * mu_t1;
+      nadam_sched = sched_new;
+      o.c0 = (float)(1.0 / (1.0 - sched_new)); o.c1 = (float)(1.0 / (1.0 - sched_next)); o.c2 = (float)(1.0 / (1.0 - pow(b2, t)));
+      o.c3 = (float)mu_t; o.c4 = (float)mu_t1;
+    }
+    DCA_TRY(optimizer_update(pp(0), gp(0), f(o_rms), f(o_opt2), P, o, (tc_heads || tc_enc) ? bf(o_pbf) : nullptr, ring_slot, s));
+    mark(-1, s);
+    return DCA_OK;
+  }
   DCA_TRY(rmsprop_update(pp(0), gp(0), f(o_rms), P, lr, clip, cfg.rms_rho, cfg.rms_eps, grad_scale,
                          (tc_heads || tc_enc) ? bf(o_pbf) : nullptr, ring_slot, s));   // also refreshes the bf16 operand copy
   mark(-1, s);
+  return DCA_OK;
+}
+
+int Engine::reset_optimizer(cudaStream_t s) {
+  DCA_CUDA_OK(cudaMemsetAsync(f(o_rms), 0, sizeof(float) * (size_t)P, s));
+  DCA_CUDA_OK(cudaMemsetAsync(f(o_opt2), 0, sizeof(float) * (size_t)P, s));
+  opt_iter = 0; nadam_sched = 1.0;
   return DCA_OK;
 }
 
@@ -705,7 +732,7 @@ int Engine::refresh_shadows(cudaStream_t s) {
 
 int Engine::init_params(uint64_t seed, cudaStream_t s) {
   DCA_CUDA_OK(cudaMemsetAsync(pp(0), 0, sizeof(float) * (size_t)P, s));
-  DCA_CUDA_OK(cudaMemsetAsync(f(o_rms), 0, sizeof(float) * (size_t)P, s));
+  DCA_TRY(reset_optimizer(s));
   DCA_CUDA_OK(cudaMemsetAsync(gp(0), 0, sizeof(float) * (size_t)(P + 2), s));
   DCA_CUDA_OK(cudaMemsetAsync(d(o_acc), 0, sizeof(double) * 8, s));
   uint64_t sid = 0;
@@ -883,6 +910,18 @@ extern "C" int dca_grad_buckets(const dca_handle* h, int64_t* head_bucket_offset
   *head_bucket_offset = h->e.x_kind ? 0 : h->e.head_W[0];      // grads[offset : P+2] are final after phase 1
   return DCA_OK;
 }
+extern "C" int dca_set_optimizer(dca_handle* h, int32_t optimizer, void* stream) {
+  if (!h) { set_error("dca_set_optimizer: handle is NULL"); return DCA_ERR_BAD_ARG; }
+  if (optimizer < DCA_OPT_RMSPROP || optimizer > DCA_OPT_NADAM) { set_error("dca_set_optimizer: unknown optimizer %d", optimizer); return DCA_ERR_BAD_ARG; }
+  h->e.opt_kind = optimizer;
+  return h->e.reset_optimizer((cudaStream_t)stream);
+}
+
+extern "C" int dca_reset_optimizer(dca_handle* h, void* stream) {
+  if (!h) { set_error("dca_reset_optimizer: handle is NULL"); return DCA_ERR_BAD_ARG; }
+  return h->e.reset_optimizer((cudaStream_t)stream);
+}
+
 extern "C" int dca_apply_update(dca_handle* h, float lr, float clip, float grad_scale, void* stream) {
   DCA_NEED_HANDLE(h);
   return h->e.apply_update(lr, clip, grad_scale, (cudaStream_t)stream);

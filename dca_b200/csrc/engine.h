@@ -157,6 +157,9 @@ struct Engine {
   int train_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
                  cudaStream_t s, int phase = 0);
   int apply_update(float lr, float clip, float grad_scale, cudaStream_t s);
+  // optimizer of apply_update (dca_set_optimizer): Keras 2.x rules, state in o_rms (+ o_opt2), iteration count on the host
+  int opt_kind = DCA_OPT_RMSPROP; long long opt_iter = 0; double nadam_sched = 1.0; size_t o_opt2 = 0;
+  int reset_optimizer(cudaStream_t s);
   int eval_step(const void* X, int64_t ldx, const float* Y, int64_t ldy, const float* sf, const int32_t* rows, int Bn,
                 cudaStream_t s);
   int predict(const void* X, int64_t ldx, const float* sf, const int32_t* rows, int Bn, float* mean_out, float* disp_out,

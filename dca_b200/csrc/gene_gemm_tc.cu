@@ -17,7 +17,6 @@
 // more tcgen05 product of the same tile with a constant ones operand (Z^T . 1, N = 16).
 //
 // Warp roles (256 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue.
-#include <cstdlib>
 #include "engine.h"
 #include "tc_common.cuh"
 
@@ -383,8 +382,6 @@ int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, 
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_gpi = gpi; best_splits = splits; }
       }
     }
-    if (getenv("DCA_GG_K5_OLD")) { best_gpi = 1; best_splits = cdiv(4 * sm_count, p.n_gb * n_heads); if (best_splits > p.n_cb) best_splits = p.n_cb;
-      while (best_splits > 1 && cdiv(p.n_cb, best_splits) < 4) --best_splits; }
     p.gb_per_item = best_gpi; p.gene_ranges = cdiv(p.n_gb, best_gpi);
     p.cb_per_item = cdiv(p.n_cb, best_splits); p.cell_splits = cdiv(p.n_cb, p.cb_per_item);
   } else {

@@ -211,6 +211,54 @@ __global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ 
   if (shadow) shadow[i] = __float2bfloat16_rn(pn);          // bf16 operand copy for the tcgen05 kernels (same layout)
 }
 
+// keras/optimizers.py (Keras 2.x) get_updates of SGD / Adagrad / Adadelta / Adam / Adamax / Nadam, clipvalue first
+__global__ void optimizer_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s1,
+                                 float* __restrict__ s2, int64_t n, OptScalars o, __nv_bfloat16* __restrict__ shadow,
+                                 float* loss_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0 && loss_out) { *loss_out = g[n] * o.gs; __threadfence_system(); }
+  float gi = g[i] * o.gs;
+  if (o.clip > 0.f) gi = fminf(fmaxf(gi, -o.clip), o.clip);
+  const float eps = 1e-7f;
+  float pn = p[i];
+  switch (o.kind) {
+    case DCA_OPT_SGD: pn -= o.lr * gi; break;
+    case DCA_OPT_ADAGRAD: { const float a = s1[i] + gi * gi; s1[i] = a; pn -= o.lr * gi / (sqrtf(a) + eps); break; }
+    case DCA_OPT_ADADELTA: {
+      const float rho = 0.95f;
+      const float a = rho * s1[i] + (1.f - rho) * gi * gi; s1[i] = a;
+      const float d = s2[i];
+      const float u = gi * sqrtf(d + eps) / sqrtf(a + eps);
+      pn -= o.lr * u;
+      s2[i] = rho * d + (1.f - rho) * u * u;
+      break;
+    }
+    case DCA_OPT_ADAM: {          // c0 = lr * sqrt(1 - b2^t) / (1 - b1^t)
+      const float m = 0.9f * s1[i] + 0.1f * gi, v = 0.999f * s2[i] + 0.001f * gi * gi;
+      s1[i] = m; s2[i] = v;
+      pn -= o.c0 * m / (sqrtf(v) + eps);
+      break;
+    }
+    case DCA_OPT_ADAMAX: {        // c0 = lr / (1 - b1^t)
+      const float m = 0.9f * s1[i] + 0.1f * gi, u = fmaxf(0.999f * s2[i], fabsf(gi));
+      s1[i] = m; s2[i] = u;
+      pn -= o.c0 * m / (u + eps);
+      break;
+    }
+    case DCA_OPT_NADAM: {         // c0 = 1/(1 - m_schedule_new), c1 = 1/(1 - m_schedule_next), c2 = 1/(1 - b2^t), c3 = mu_t, c4 = mu_{t+1}
+      const float m = 0.9f * s1[i] + 0.1f * gi, v = 0.999f * s2[i] + 0.001f * gi * gi;
+      s1[i] = m; s2[i] = v;
+      const float mbar = (1.f - o.c3) * (gi * o.c0) + o.c4 * (m * o.c1);
+      pn -= o.lr * mbar / (sqrtf(v * o.c2) + eps);
+      break;
+    }
+    default: break;
+  }
+  p[i] = pn;
+  if (shadow) shadow[i] = __float2bfloat16_rn(pn);
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -515,6 +563,13 @@ int reg_penalty(const float* w, int64_t n, float l1, float l2, double* acc, cuda
 int rmsprop_update(float* params, const float* grads, float* rms, int64_t n, float lr, float clip, float rho,
                    float eps, float grad_scale, __nv_bfloat16* shadow, float* loss_out, cudaStream_t s) {
   rmsprop_kernel<<<blocks_for(n), 256, 0, s>>>(params, grads, rms, n, lr, clip, rho, eps, grad_scale, shadow, loss_out);
+  DCA_LAUNCH_CHECK();
+  return DCA_OK;
+}
+
+int optimizer_update(float* params, const float* grads, float* s1, float* s2, int64_t n, OptScalars o, __nv_bfloat16* shadow,
+                     float* loss_out, cudaStream_t s) {
+  optimizer_kernel<<<blocks_for(n), 256, 0, s>>>(params, grads, s1, s2, n, o, shadow, loss_out);
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }

@@ -179,7 +179,19 @@ class DeviceEngine:
         self.params_changed()
 
     def reset_optimizer(self):
-        self.rms.zero_()
+        """Clear the optimizer state (accumulators + iteration count) -- what compiling a fresh Keras optimizer does."""
+        check(self.lib.dca_reset_optimizer(self.handle, self._stream()), "dca_reset_optimizer")
+
+    def set_optimizer(self, name: str) -> float:
+        """Select the update rule of apply_update by its keras.optimizers name (dca/train.py:54-57); returns the Keras
+        default learning rate of that class (used when learning_rate is None)."""
+        if name not in _lib.OPTIMIZERS:
+            raise NotImplementedError("optimizer %r is not on the accelerated path (supported: %s)"
+                                      % (name, sorted(k for k in _lib.OPTIMIZERS if not k.islower())))
+        kind, default_lr = _lib.OPTIMIZERS[name]
+        check(self.lib.dca_set_optimizer(self.handle, kind, self._stream()), "dca_set_optimizer")
+        self.optimizer = name
+        return default_lr
 
     # ------------------------------------------------------------------ hot path
     def _check_inputs(self, X, Y, sf, rows, batch):

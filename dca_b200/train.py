@@ -87,8 +87,10 @@ def train(adata, network, output_dir=None, optimizer='RMSprop', learning_rate=No
     shuffle = kwds.pop('shuffle', True)
     if kwds:
         raise TypeError("train() got keyword arguments the accelerated fit loop does not implement: %s" % sorted(kwds))
-    if optimizer != 'RMSprop':
-        raise NotImplementedError("only the RMSprop optimizer is on the accelerated path (got %r)" % optimizer)
+    from . import _lib as _L
+    if optimizer not in _L.OPTIMIZERS:
+        raise NotImplementedError("optimizer %r is not on the accelerated path (supported: %s)"
+                                  % (optimizer, sorted(k for k in _L.OPTIMIZERS if not k.islower())))
     if tensorboard:
         raise NotImplementedError("tensorboard logging is not part of the accelerated path")
     if output_dir is not None:
@@ -121,6 +123,10 @@ def train(adata, network, output_dir=None, optimizer='RMSprop', learning_rate=No
     if stream == 'auto':
         free = torch.cuda.mem_get_info(dev)[0]
         stream = (tr_hi - tr_lo + va_hi - va_lo) * X.shape[1] * (4 + eng.params.element_size()) > 0.6 * free
+    # opt.__dict__[optimizer](clipvalue=clip_grad[, lr=learning_rate])                   (dca/train.py:54-57)
+    default_lr = eng.set_optimizer(optimizer)
+    if learning_rate is None:
+        learning_rate = default_lr
     if stream:
         return _fit_stream(eng, network, X, Yh, sf, (tr_lo, tr_hi), (va_lo, va_hi), batch_size, epochs, learning_rate, reduce_lr,
                            early_stop, clip_grad, world, rank, verbose, save_weights, output_dir, shuffle)
@@ -137,7 +143,7 @@ def train(adata, network, output_dir=None, optimizer='RMSprop', learning_rate=No
             eng.comm_init()          # gradient exchange inside the library: one CUDA graph per step (dca_train_step_dp)
     eng.reset_optimizer()
 
-    lr = KERAS_DEFAULTS["rms_lr"] if learning_rate is None else float(learning_rate)
+    lr = float(learning_rate)
     ctl = PlateauAndStop(lr, reduce_lr, early_stop, verbose)
     hist = History()
     if verbose:
@@ -236,7 +242,7 @@ def _fit_stream(eng, network, X, Yh, sf, tr, va, batch_size, epochs, learning_ra
         if torch.distributed.get_backend() == "nccl":
             eng.comm_init()
     eng.reset_optimizer()
-    lr = KERAS_DEFAULTS["rms_lr"] if learning_rate is None else float(learning_rate)
+    lr = float(learning_rate)
     ctl = PlateauAndStop(lr, reduce_lr, early_stop, verbose)
     hist = History()
     nb = (n_tr + batch_size - 1) // batch_size

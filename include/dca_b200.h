@@ -86,7 +86,7 @@ typedef enum dca_gemm_path {
 typedef enum dca_region_id {
   DCA_REGION_PARAMS = 0,      /* float[P]   trainable parameters, Keras layouts (see dca_param_info) */
   DCA_REGION_GRADS = 1,       /* float[P+2] gradient of the mean loss; [P] = batch loss, [P+1] = non-finite flag */
-  DCA_REGION_RMS = 2,         /* float[P]   RMSprop accumulator */
+  DCA_REGION_RMS = 2,         /* float[P]   first optimizer accumulator (RMSprop / Adagrad / Adadelta: mean square; Adam family: m) */
   DCA_REGION_BN_STATE = 3,    /* float[S]   BatchNorm moving_mean / moving_variance, see dca_state_info */
   DCA_REGION_EPOCH_ACC = 4    /* double[4]  {sum(loss*batch), sum(batch), sum(val_loss_elem), n_val_elem} */
 } dca_region_id;
@@ -187,7 +187,20 @@ int dca_allreduce(dca_handle* h, void* stream);
 int dca_train_step_dp(dca_handle* h, const void* X, int64_t ldx, const float* Y, int64_t ldy,
                       const float* sf, const int32_t* rows, int32_t batch, void* stream);
 
-/* clip(g*grad_scale, +-clip) -> RMSprop (rho, eps from config) -> parameters.
+/* Optimizer of dca_apply_update: `opt.__dict__[optimizer](clipvalue=clip_grad[, lr=learning_rate])` of dca/train.py:54-57
+ * (CLI --optimizer).  Every hyper-parameter except the learning rate and the clip value is the Keras 2.x default of that
+ * class (keras/optimizers.py -- a dependency of the reference, not vendored in it): SGD (no momentum), RMSprop (rho 0.9),
+ * Adagrad, Adadelta (rho 0.95), Adam / Adamax (beta 0.9 / 0.999), Nadam (schedule_decay 0.004); epsilon 1e-7, decay 0.
+ * dca_set_optimizer selects the rule and clears its state (accumulators, iteration count); dca_reset_optimizer only
+ * clears the state.  RMSprop is the default of a new handle. */
+typedef enum dca_optimizer {
+  DCA_OPT_RMSPROP = 0, DCA_OPT_SGD = 1, DCA_OPT_ADAGRAD = 2, DCA_OPT_ADADELTA = 3, DCA_OPT_ADAM = 4, DCA_OPT_ADAMAX = 5,
+  DCA_OPT_NADAM = 6
+} dca_optimizer;
+int dca_set_optimizer(dca_handle* h, int32_t optimizer, void* stream);
+int dca_reset_optimizer(dca_handle* h, void* stream);
+
+/* clip(g*grad_scale, +-clip) -> the selected optimizer (RMSprop unless dca_set_optimizer chose another) -> parameters.
  * Replaces keras RMSprop(clipvalue=clip_grad[, lr]) applied by model.fit: dca/train.py:54-57.
  * grad_scale = 1/world_size after a sum all-reduce of DCA_REGION_GRADS, else 1. */
 int dca_apply_update(dca_handle* h, float lr, float clip, float grad_scale, void* stream);

@@ -299,11 +299,52 @@ class TorchRefNet:
 
     @torch.no_grad()
     def _apply(self, grads, stats, lr, clip):
+        """Optimizer step.  self.optimizer (default 'RMSprop') names a keras.optimizers class; the rules restate
+        `get_updates` of Keras 2.x keras/optimizers.py (a dependency of the reference, pinned `keras>=2.0.8` in its
+        setup.py, not vendored) with every hyper-parameter but lr / clipvalue at the class default, epsilon = K.epsilon()
+        = 1e-7, decay 0 -- what `opt.__dict__[optimizer](clipvalue=clip_grad[, lr=...])` (dca/train.py:54-57) builds."""
+        kind = getattr(self, "optimizer", "RMSprop")
         rho = KERAS_DEFAULTS["rms_rho"]; eps = KERAS_DEFAULTS["rms_eps"]
+        if kind != "RMSprop":
+            if not hasattr(self, "opt2"):
+                self.opt2 = {k: torch.zeros_like(v) for k, v in self.rms.items()}; self.opt_t = 0; self.m_sched = 1.0
+            self.opt_t += 1
+            t = self.opt_t; b1, b2 = 0.9, 0.999
+            if kind == "Nadam":
+                mu_t = b1 * (1.0 - 0.5 * 0.96 ** (t * 0.004)); mu_t1 = b1 * (1.0 - 0.5 * 0.96 ** ((t + 1) * 0.004))
+                sched_new = self.m_sched * mu_t; sched_next = sched_new * mu_t1; self.m_sched = sched_new
         for k, g in grads.items():
             g = g.clamp(-clip, clip)
-            self.rms[k].mul_(rho).addcmul_(g, g, value=1.0 - rho)
-            self.p[k].sub_(lr * g / (self.rms[k].sqrt() + eps))
+            if kind == "RMSprop":
+                self.rms[k].mul_(rho).addcmul_(g, g, value=1.0 - rho)
+                self.p[k].sub_(lr * g / (self.rms[k].sqrt() + eps))
+                continue
+            a, b2s = self.rms[k], self.opt2[k]
+            if kind == "SGD":
+                self.p[k].sub_(lr * g)
+            elif kind == "Adagrad":
+                a.add_(g * g); self.p[k].sub_(lr * g / (a.sqrt() + eps))
+            elif kind == "Adadelta":
+                a.mul_(0.95).add_(0.05 * g * g)
+                upd = g * (b2s + eps).sqrt() / (a + eps).sqrt()
+                self.p[k].sub_(lr * upd)
+                b2s.mul_(0.95).add_(0.05 * upd * upd)
+            elif kind == "Adam":
+                lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+                a.mul_(b1).add_((1 - b1) * g); b2s.mul_(b2).add_((1 - b2) * g * g)
+                self.p[k].sub_(lr_t * a / (b2s.sqrt() + eps))
+            elif kind == "Adamax":
+                lr_t = lr / (1.0 - b1 ** t)
+                a.mul_(b1).add_((1 - b1) * g); torch.maximum(b2 * b2s, g.abs(), out=b2s)
+                self.p[k].sub_(lr_t * a / (b2s + eps))
+            elif kind == "Nadam":
+                gp = g / (1.0 - sched_new)
+                a.mul_(b1).add_((1 - b1) * g); mp = a / (1.0 - sched_next)
+                b2s.mul_(b2).add_((1 - b2) * g * g); vp = b2s / (1.0 - b2 ** t)
+                mbar = (1.0 - mu_t) * gp + mu_t1 * mp
+                self.p[k].sub_(lr * mbar / (vp.sqrt() + eps))
+            else:
+                raise ValueError(kind)
         for nm, mean, var in stats:
             self.p[nm + "/bn_moving_mean"].mul_(self.mom).add_((1 - self.mom) * mean)
             self.p[nm + "/bn_moving_var"].mul_(self.mom).add_((1 - self.mom) * var)
