@@ -62,6 +62,9 @@ def _check_grads(eng, og, batchnorm, tol, skip_hidden_bias=True):
         if skip_hidden_bias and name.endswith("/bias") and batchnorm and not name.startswith(("mean", "dispersion", "pi")):
             assert np.max(np.abs(got)) < 1e-5          # BatchNorm removes the Dense bias from the loss
             continue
+        if np.max(np.abs(ref)) < 1e-8:                 # structurally zero (e.g. a linear layer's beta in front of another BatchNorm)
+            assert np.max(np.abs(got)) < 1e-6, name
+            continue
         assert rel_err(got, ref, 2e-3) < tol, (name, rel_err(got, ref, 2e-3))
 
 
@@ -73,8 +76,8 @@ def test_activation_train_step_vs_autograd(activation, batchnorm):
     rows = np.random.default_rng(0).permutation(B + 16)[:B].astype(np.int32)
     p0 = _params(G, hidden, "zinb-conddisp", batchnorm, activation)
     if activation == "exponential":      # exp(.) hidden units drive the heads into their clips (mu 2e6, theta 1e-4), where the
-        for k in p0:                     # reference's own float32 formula is 2e-3 off its float64 value: stay inside
-            if k.endswith("/kernel"): p0[k] *= 0.2
+        for k in p0:                     # reference's own float32 formula is 1e-3 off its float64 value (the engine agrees
+            if k.endswith("/kernel"): p0[k] *= 0.05     # with the float32 evaluation to 1e-7 there): stay inside the clips
     net = TorchRefNet(p0, hidden, "zinb-conddisp", batchnorm, ridge=0.01, dtype=torch.float64, activation=activation)
     eng = _engine(G, hidden, "zinb-conddisp", batchnorm, B, p0, ridge=0.01, gemm_path="generic", activation=activation)
     eng.train_step(_t(X), _t(Y), _t(sf), rows=torch.as_tensor(rows).to(DEV))
