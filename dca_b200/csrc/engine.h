@@ -131,7 +131,7 @@ struct Engine {
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int comm_init(const void* id128, int rank, int world);
   int comm_destroy();
-  static bool split_heads_enabled();       // DCA_DP_SPLIT_HEADS=0 restores the single head-backward launch + one bucket
+  static bool split_heads_enabled();       // DCA_DP_SPLIT_HEADS=1: head backward per head + per-head all-reduce (opt-in)
   int allreduce_range(int64_t lo, int64_t hi, cudaStream_t s);
   // sync_bn: sum the BatchNorm column sums (one or two double vectors) over the ranks; bn_rows(Bn) = rows behind the sums
   bool bn_synced() const { return cfg.sync_bn && comm && comm_world > 1; }
