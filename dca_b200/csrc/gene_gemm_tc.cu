@@ -17,12 +17,16 @@
 // more tcgen05 product of the same tile with a constant ones operand (Z^T . 1, N = 16).
 //
 // Warp roles (256 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue.
+#include <cstdio>
+#include <vector>
 #include "engine.h"
 #include "tc_common.cuh"
 
 namespace dca {
 namespace tc {
 int g_gg_prefetch = 0;      // dca_set_tunable("gg_prefetch", 0 | 1)
+int g_gg_profile = 0;       // dca_set_tunable("gg_profile", 1): per-role wait-time counters, printed after every launch (diagnosis; DCA_GRAPH=0)
+int g_gg_flat = 1;          // dca_set_tunable("gg_flat", 0 | 1): flat unit partition of the backward kernels (every SM busy)
 namespace gg {
 
 constexpr int kThreads = 256;
@@ -40,6 +44,8 @@ struct Params {
   int gb_per_item, cb_per_item;
   int gene_ranges, cell_splits;   // per head
   int total_items;
+  unsigned long long* dbg;        // gg_profile: [grid][16] cycle counters (nullptr = off)
+  int flat, total_units;          // flat: units = (head, gene range, cell block) in that order, an equal contiguous run per CTA
   float* dW[3]; int64_t dW_ld; int dW_transposed;   // (a): transposed -> dW[f*ld + g] (Keras [64 x G]); else dW[g*ld + f]
   float* db[3];                                     // column sums of Z per head (COLSUM)
   const __nv_bfloat16* Zp[3]; int64_t ldz; int prefetch;   // raw Z pointers: L2 prefetch of whole row segments ahead of the TMA boxes
@@ -48,6 +54,13 @@ struct Params {
 __device__ __forceinline__ void gg_prefetch_l2(const void* gptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
 }
+
+// diagnosis: accumulate the cycles a single-thread role spends inside one wait / section into its counter slot
+#define GG_TIMED(slot, stmt)                                             \
+  do {                                                                   \
+    if (p.dbg) { const long long t0_ = clock64(); stmt; dbg_acc[slot] += (unsigned long long)(clock64() - t0_); } \
+    else { stmt; }                                                       \
+  } while (0)
 
 template <bool DO_A, bool DO_B, bool COLSUM>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -63,7 +76,9 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
   uint8_t* s_z = smem;                                          // [kZStages][Z | W]
   uint8_t* s_h = s_z + kZStages * kStage;                       // [2][H]
   uint8_t* s_o = s_h + (DO_A ? 2 * kHBytes : 0);                // staging for (b)
-  uint8_t* s_ones = s_o + ((DO_B || (DO_A && !DO_B)) ? kOutBytes : 0);               // [16 x 64] bf16 ones (K-major B operand of the column sums)
+  // COLSUM: a [128 cells x 64] bf16 tile of ones in H's layout -- the second N chunk of the dW product's B operand (N = 64 + 16):
+  // the 16 extra accumulator columns are the column sums of Z (every element equal, so the swizzle pattern does not matter)
+  uint8_t* s_ones = s_o + ((DO_B || (DO_A && !DO_B)) ? kOutBytes : 0);
   __shared__ uint64_t z_full[kZStages], z_empty[kZStages], h_full[2], h_empty[2], dh_full[2], dh_empty[2], dw_full, dw_empty;
   __shared__ uint32_t tmem_base_s;
   __shared__ int s_unit;
@@ -78,17 +93,17 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
     tma_prefetch_desc(&map_z0); tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_w0); tma_prefetch_desc(&map_o);
   }
   if (warp == 2) tmem_alloc(&tmem_base_s, kTmemCols);
-  if (COLSUM) {   // bf16 1.0 = 0x3F80; every element equal, so the swizzle pattern does not matter
-    for (int i = threadIdx.x; i < 2048 / 4; i += kThreads) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3F803F80u;
+  if (COLSUM) {   // bf16 1.0 = 0x3F80
+    for (int i = threadIdx.x; i < (int)kHBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3F803F80u;
     fence_proxy_async_smem();
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tm_dw = tmem;                 // kMaxGb x 64 columns
-  const uint32_t tm_dh = tmem + kMaxGb * 64;   // 2 x 64 columns
-  const uint32_t tm_cs = tm_dh + 2 * 64;       // kMaxGb x 16 columns: column sums (every column of a block is the same)
+  constexpr uint32_t kDwCols = COLSUM ? 80 : 64;   // per gene block: 64 dW columns (+ 16 column-sum columns)
+  const uint32_t tm_dw = tmem;                 // kMaxGb x kDwCols columns
+  const uint32_t tm_dh = tmem + kMaxGb * kDwCols;   // 2 x 64 columns
 
   struct Item { int head, gb0, gb1, cb0, cb1; };
   auto decode = [&](int it) {
@@ -99,42 +114,66 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
     x.cb0 = cs * p.cb_per_item; x.cb1 = min(p.n_cb, x.cb0 + p.cb_per_item);
     return x;
   };
+  // Item sequence of this CTA.  Strided: items blockIdx.x, +gridDim.x, ...  Flat: the CTA owns units [u0, u1) of the
+  // (head, gene range, cell block) order; an item is the part of ONE gene range inside that run, so that a CTA switches
+  // dW accumulators (and flushes them) at most (run length / n_cb) + 1 times and every SM gets the same number of tiles.
+  struct Cursor { int u, u1; };
+  auto first = [&]() {
+    Cursor c;
+    if (p.flat) { c.u = (int)((long long)blockIdx.x * p.total_units / gridDim.x); c.u1 = (int)((long long)(blockIdx.x + 1) * p.total_units / gridDim.x); }
+    else { c.u = blockIdx.x; c.u1 = p.total_items; }
+    return c;
+  };
+  auto next = [&](Cursor& c, Item& x) {
+    if (c.u >= c.u1) return false;
+    if (!p.flat) { x = decode(c.u); c.u += gridDim.x; return true; }
+    const int r = c.u / p.n_cb, cb0 = c.u % p.n_cb, n = min(p.n_cb - cb0, c.u1 - c.u);
+    const int gr = r % p.gene_ranges; x.head = r / p.gene_ranges;
+    x.gb0 = gr * p.gb_per_item; x.gb1 = min(p.n_gb, x.gb0 + p.gb_per_item);
+    x.cb0 = cb0; x.cb1 = cb0 + n; c.u += n;
+    return true;
+  };
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================== TMA producer (whole warp walks the loops, one elected lane issues)
+    const bool leader = elect_one();
+    {
+      unsigned long long dbg_acc[4] = {0, 0, 0, 0};          // 0 wait z_empty, 1 wait h_empty, 2 total
+      const long long t_begin = clock64();
       uint32_t zi = 0, hi = 0;
       int unit = 0;
-      for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
-        const Item x = decode(it);
+      Cursor cur = first(); Item x;
+      while (next(cur, x)) {
         const CUtensorMap* mz = x.head == 0 ? &map_z0 : (x.head == 1 ? &map_z1 : &map_z2);
         for (int cb = x.cb0; cb < x.cb1; ++cb) {
           if (DO_A) {
             const uint32_t hs = hi & 1, hp = (hi >> 1) & 1; ++hi;
-            mbar_wait(&h_empty[hs], hp ^ 1);
-            mbar_expect_tx(&h_full[hs], kHBytes);
-            tma_load_2d(s_h + hs * kHBytes, &map_h, 0, cb * 128, &h_full[hs]);
+            GG_TIMED(1, mbar_wait(&h_empty[hs], hp ^ 1));
+            if (leader) { mbar_expect_tx(&h_full[hs], kHBytes); tma_load_2d(s_h + hs * kHBytes, &map_h, 0, cb * 128, &h_full[hs]); }
           }
           for (int gb = x.gb0; gb < x.gb1; ++gb) {
-            if (((gb - x.gb0) & 3) == 0) *reinterpret_cast<volatile int*>(&s_unit) = unit++;      // progress mark for the prefetch warp
+            if (((gb - x.gb0) & 3) == 0) { if (leader) *reinterpret_cast<volatile int*>(&s_unit) = unit; ++unit; }      // progress mark for the prefetch warp
             const uint32_t st = zi % kZStages, ph = (zi / kZStages) & 1; ++zi;
-            mbar_wait(&z_empty[st], ph ^ 1);
+            GG_TIMED(0, mbar_wait(&z_empty[st], ph ^ 1));
             uint8_t* dst = s_z + st * kStage;
-            mbar_expect_tx(&z_full[st], kStage);
-            tma_load_2d(dst, mz, gb * 128, cb * 128, &z_full[st]);
-            tma_load_2d(dst + kZBytes / 2, mz, gb * 128 + 64, cb * 128, &z_full[st]);
-            if (DO_B) {
-              const CUtensorMap* mw = x.head == 0 ? &map_w0 : (x.head == 1 ? &map_w1 : &map_w2);
-              if (DO_A) {      // head backward: W = Keras [64 x G] (K-major B): two [64 feats x 64 genes] boxes
-                tma_load_2d(dst + kZBytes, mw, gb * 128, 0, &z_full[st]);
-                tma_load_2d(dst + kZBytes + kWBytes / 2, mw, gb * 128 + 64, 0, &z_full[st]);
-              } else {         // encoder forward: W = Keras [G x 64] (MN-major B): one [128 genes x 64 feats] box
-                tma_load_2d(dst + kZBytes, mw, 0, gb * 128, &z_full[st]);
+            if (leader) {
+              mbar_expect_tx(&z_full[st], kStage);
+              tma_load_2d(dst, mz, gb * 128, cb * 128, &z_full[st]);
+              tma_load_2d(dst + kZBytes / 2, mz, gb * 128 + 64, cb * 128, &z_full[st]);
+              if (DO_B) {
+                const CUtensorMap* mw = x.head == 0 ? &map_w0 : (x.head == 1 ? &map_w1 : &map_w2);
+                if (DO_A) {      // head backward: W = Keras [64 x G] (K-major B): two [64 feats x 64 genes] boxes
+                  tma_load_2d(dst + kZBytes, mw, gb * 128, 0, &z_full[st]);
+                  tma_load_2d(dst + kZBytes + kWBytes / 2, mw, gb * 128 + 64, 0, &z_full[st]);
+                } else {         // encoder forward: W = Keras [G x 64] (MN-major B): one [128 genes x 64 feats] box
+                  tma_load_2d(dst + kZBytes, mw, 0, gb * 128, &z_full[st]);
+                }
               }
             }
           }
         }
       }
+      if (p.dbg && leader) { dbg_acc[2] = (unsigned long long)(clock64() - t_begin); for (int i = 0; i < 3; ++i) p.dbg[blockIdx.x * 16 + i] = dbg_acc[i]; }
     }
   } else if (warp == 3 && p.prefetch) {
     // ===================================================== L2 prefetch (optional, dca_set_tunable "gg_prefetch")
@@ -153,8 +192,8 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
         if (row < p.B) gg_prefetch_l2(zp + (int64_t)row * p.ldz + c0, bytes);
       }
     };
-    for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
-      const Item x = decode(it);
+    Cursor cur = first(); Item x;
+    while (next(cur, x)) {
       for (int cb = x.cb0; cb < x.cb1; ++cb)
         for (int g4 = x.gb0; g4 < x.gb1; g4 += 4, ++unit) {
           if (unit > 0) {                                                      // unit 0 is not worth prefetching (its loads are already in flight)
@@ -166,21 +205,28 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    // The WHOLE warp walks the loops (so that smem addresses, descriptors and barrier phases are warp-uniform values the
+    // compiler keeps in uniform registers); only the tcgen05.mma / commit instructions are issued by one lane.  With the
+    // loops inside `if (lane == 0)` every descriptor went through a R2UR waterfall loop: ~75 cycles per MMA, 1800 per tile
+    // of the head backward (24 MMAs) -- the issuing thread, not HBM, bounded the kernel (gg_profile).
+    const bool leader = elect_one();
+    {
       constexpr uint32_t idesc_b = make_idesc_bf16(128, 64, 0, DO_A ? 0 : 1);   // Z K-major x W (K-major [64xG] | MN-major [Gx64])
-      constexpr uint32_t idesc_a = make_idesc_bf16(128, 64, 1, 1);     // Z MN-major x H MN-major
-      constexpr uint32_t idesc_c = make_idesc_bf16(128, 16, 1, 0);     // Z MN-major x ones K-major -> column sums
+      constexpr uint32_t idesc_a = make_idesc_bf16(128, kDwCols, 1, 1);     // Z MN-major x [H | ones] MN-major
       uint32_t zi = 0, hi = 0, di = 0, wi = 0;
-      for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++wi) {
-        const Item x = decode(it);
-        if (DO_A) { mbar_wait(&dw_empty, (wi & 1) ^ 1); tcgen05_fence_after(); }
+      unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 wait z_full, 1 wait h_full, 2 wait dh_empty, 3 wait dw_empty, 4 total, 5 tiles
+      const long long t_begin = clock64();
+      Cursor cur = first(); Item x;
+      for (; next(cur, x); ++wi) {
+        if (DO_A) { GG_TIMED(3, mbar_wait(&dw_empty, (wi & 1) ^ 1)); tcgen05_fence_after(); }
         for (int cb = x.cb0; cb < x.cb1; ++cb) {
           uint32_t hs = 0, ds = 0;
-          if (DO_A) { hs = hi & 1; const uint32_t hp = (hi >> 1) & 1; ++hi; mbar_wait(&h_full[hs], hp); }
-          if (DO_B) { ds = di & 1; const uint32_t dp = (di >> 1) & 1; ++di; mbar_wait(&dh_empty[ds], dp ^ 1); }
+          if (DO_A) { hs = hi & 1; const uint32_t hp = (hi >> 1) & 1; ++hi; GG_TIMED(1, mbar_wait(&h_full[hs], hp)); }
+          if (DO_B) { ds = di & 1; const uint32_t dp = (di >> 1) & 1; ++di; GG_TIMED(2, mbar_wait(&dh_empty[ds], dp ^ 1)); }
           for (int gb = x.gb0; gb < x.gb1; ++gb) {
             const uint32_t st = zi % kZStages, ph = (zi / kZStages) & 1; ++zi;
-            mbar_wait(&z_full[st], ph);
+            GG_TIMED(0, mbar_wait(&z_full[st], ph));
+            ++dbg_acc[5];
             tcgen05_fence_after();
             const uint32_t zb = smem_u32(s_z + st * kStage);
             if (DO_B) {
@@ -189,45 +235,48 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
               for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(tm_dh + ds * 64, make_smem_desc(zb + h * (kZBytes / 2) + k * 32, 0, 1024),
+                  if (leader) umma_bf16(tm_dh + ds * 64, make_smem_desc(zb + h * (kZBytes / 2) + k * 32, 0, 1024),
                             DO_A ? make_smem_desc(wb + h * (kWBytes / 2) + k * 32, 0, 1024)
                                  : make_smem_desc(wb + (h * 4 + k) * 2048, 0, 1024), idesc_b,
                             (gb > x.gb0 || h > 0 || k > 0) ? 1u : 0u);
             }
             if (DO_A) {
               const uint32_t hb = smem_u32(s_h + hs * kHBytes);
+              // COLSUM: N = 80 -- the B operand's second 64-element chunk (leading-dimension offset) is the ones tile, so the
+              // same MMA that forms dW also leaves db[g] = sum over the tile's cells of Z[cell][g] in 16 more columns
+              const uint32_t ones_off = smem_u32(s_ones) - hb;
 #pragma unroll
               for (int k = 0; k < 8; ++k)
-                umma_bf16(tm_dw + (gb - x.gb0) * 64, make_smem_desc(zb + k * 2048, kZBytes / 2, 1024),
-                          make_smem_desc(hb + k * 2048, 0, 1024), idesc_a, (cb > x.cb0 || k > 0) ? 1u : 0u);
-              if (COLSUM) {   // db[g] += sum over the tile's 128 cells of Z[cell][g]  (Z^T . 1 on the tensor core)
-                const uint32_t ob = smem_u32(s_ones);
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                  umma_bf16(tm_cs + (gb - x.gb0) * 16, make_smem_desc(zb + k * 2048, kZBytes / 2, 1024),
-                            make_smem_desc(ob + (k & 3) * 32, 0, 1024), idesc_c, (cb > x.cb0 || k > 0) ? 1u : 0u);
-              }
+                if (leader) umma_bf16(tm_dw + (gb - x.gb0) * kDwCols, make_smem_desc(zb + k * 2048, kZBytes / 2, 1024),
+                          make_smem_desc(hb + k * 2048, COLSUM ? ones_off : 0u, 1024), idesc_a, (cb > x.cb0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(&z_empty[st]);
+            if (leader) umma_commit(&z_empty[st]);
           }
-          if (DO_A) umma_commit(&h_empty[hs]);
-          if (DO_B) umma_commit(&dh_full[ds]);
+          if (DO_A) if (leader) umma_commit(&h_empty[hs]);
+          if (DO_B) if (leader) umma_commit(&dh_full[ds]);
         }
-        if (DO_A) umma_commit(&dw_full);
+        if (DO_A) if (leader) umma_commit(&dw_full);
       }
+      if (p.dbg && leader) { dbg_acc[4] = (unsigned long long)(clock64() - t_begin); for (int i = 0; i < 6; ++i) p.dbg[blockIdx.x * 16 + 4 + i] = dbg_acc[i]; }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================================================== epilogue
     const int quarter = warp & 3;
+    // ONE elected lane of warp 4 issues every TMA reduce-add and owns their bulk groups (commit / wait are per thread)
+    bool epi_leader = false;
+    if (warp == 4) epi_leader = elect_one();
     uint32_t di = 0, wi = 0;
-    for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++wi) {
-      const Item x = decode(it);
+    unsigned long long dbg_acc[6] = {0, 0, 0, 0, 0, 0};       // 0 wait dh_full, 1 dH flush, 2 wait dw_full, 3 dW flush, 4 total
+    const long long t_begin = clock64();
+    Cursor cur = first(); Item x;
+    for (; next(cur, x); ++wi) {
       if (DO_B) {
         for (int cb = x.cb0; cb < x.cb1; ++cb) {
           const uint32_t ds = di & 1, dp = (di >> 1) & 1; ++di;
-          mbar_wait(&dh_full[ds], dp);
+          GG_TIMED(0, mbar_wait(&dh_full[ds], dp));
+          const long long t_fl = clock64();
           tcgen05_fence_after();
-          if (warp == 4 && lane == 0) bulk_wait_read<0>();          // previous reduce has read the staging tiles
+          if (epi_leader) bulk_wait_read<0>();          // previous reduce has read the staging tiles
           named_barrier_sync(3, 128);
           const int row = quarter * 32 + lane;
 #pragma unroll
@@ -244,27 +293,29 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
           fence_proxy_async_smem();
           named_barrier_sync(3, 128);
           if (lane == 0) mbar_arrive(&dh_empty[ds]);
-          if (warp == 4 && lane == 0) {
+          if (epi_leader) {
             tma_reduce_add_2d(&map_o, 0, cb * 128, s_o);
             tma_reduce_add_2d(&map_o, 32, cb * 128, s_o + kOutBytes / 2);
             bulk_commit();
           }
+          dbg_acc[1] += (unsigned long long)(clock64() - t_fl);
         }
       }
       if (DO_A) {
-        mbar_wait(&dw_full, wi & 1);
+        GG_TIMED(2, mbar_wait(&dw_full, wi & 1));
+        const long long t_fw = clock64();
         tcgen05_fence_after();
         float* dst = p.dW[x.head];
         if (!DO_B && !p.dW_transposed) {
           // [128 genes x 64] accumulator == row-major block of dW[G x 64]: swizzled staging + TMA reduce-add
           for (int gb = x.gb0; gb < x.gb1; ++gb) {
-            if (warp == 4 && lane == 0) bulk_wait_read<0>();
+            if (epi_leader) bulk_wait_read<0>();
             named_barrier_sync(3, 128);
             const int row = quarter * 32 + lane;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               uint32_t v[32];
-              tmem_ld_32x32(tm_dw + ((uint32_t)(quarter * 32) << 16) + (gb - x.gb0) * 64 + c * 32, v);
+              tmem_ld_32x32(tm_dw + ((uint32_t)(quarter * 32) << 16) + (gb - x.gb0) * kDwCols + c * 32, v);
               tmem_ld_wait();
               uint8_t* tile = s_o + c * (kOutBytes / 2);
 #pragma unroll
@@ -273,7 +324,7 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
             }
             fence_proxy_async_smem();
             named_barrier_sync(3, 128);
-            if (warp == 4 && lane == 0) {
+            if (epi_leader) {
               tma_reduce_add_2d(&map_o, 0, gb * 128, s_o);
               tma_reduce_add_2d(&map_o, 32, gb * 128, s_o + kOutBytes / 2);
               bulk_commit();
@@ -284,14 +335,14 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
           const int g = gb * 128 + quarter * 32 + lane;
           if (COLSUM) {
             uint32_t v[32];
-            tmem_ld_32x32(tm_cs + ((uint32_t)(quarter * 32) << 16) + (gb - x.gb0) * 16, v);
+            tmem_ld_32x32(tm_dw + ((uint32_t)(quarter * 32) << 16) + (gb - x.gb0) * kDwCols + 64, v);
             tmem_ld_wait();
             if (g < p.G && p.db[x.head]) atomicAdd(p.db[x.head] + g, __uint_as_float(v[0]));
           }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32(tm_dw + ((uint32_t)(quarter * 32) << 16) + (gb - x.gb0) * 64 + c * 32, v);
+            tmem_ld_32x32(tm_dw + ((uint32_t)(quarter * 32) << 16) + (gb - x.gb0) * kDwCols + c * 32, v);
             tmem_ld_wait();
             if (g < p.G) {
 #pragma unroll
@@ -306,9 +357,11 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&dw_empty);
+        dbg_acc[3] += (unsigned long long)(clock64() - t_fw);
       }
     }
-    if (warp == 4 && lane == 0) bulk_wait<0>();
+    if (epi_leader) bulk_wait<0>();
+    if (p.dbg && epi_leader) { dbg_acc[4] = (unsigned long long)(clock64() - t_begin); for (int i = 0; i < 5; ++i) p.dbg[blockIdx.x * 16 + 10 + i] = dbg_acc[i]; }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -317,7 +370,7 @@ gene_gemm_kernel(const __grid_constant__ CUtensorMap map_z0, const __grid_consta
 
 template <bool DO_A, bool DO_B, bool COLSUM>
 constexpr uint32_t smem_bytes() {
-  return kZStages * (kZBytes + (DO_B ? kWBytes : 0)) + (DO_A ? 2 * kHBytes : 0) + kOutBytes + (COLSUM ? 2048 : 0) + 1024;
+  return kZStages * (kZBytes + (DO_B ? kWBytes : 0)) + (DO_A ? 2 * kHBytes : 0) + kOutBytes + (COLSUM ? kHBytes : 0) + 1024;
 }
 
 }  // namespace gg
@@ -392,8 +445,30 @@ int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, 
     p.gb_per_item = cdiv(p.n_gb, gsplits); p.gene_ranges = cdiv(p.n_gb, p.gb_per_item);
   }
   p.total_items = p.gene_ranges * p.cell_splits * n_heads;
+  if (do_a && g_gg_flat) {
+    // Flat partition (backward kernels): units = (head, gene range of gpi blocks, cell block); every CTA takes an equal
+    // contiguous run.  gpi by a small cost model in tile units per CTA: tiles + one per cell block (H tile / dH reduce-add)
+    // + two per gene block for each dW flush (one per gene range the run touches).
+    int best_gpi = 1; long long best_cost = -1;
+    for (int gpi = 1; gpi <= kMaxGb; ++gpi) {
+      const long long units = (long long)cdiv(p.n_gb, gpi) * n_heads * p.n_cb;
+      const long long ctas = units < sm_count ? units : sm_count, per = (units + ctas - 1) / ctas;
+      const long long cost = per * gpi + per + ((per + p.n_cb - 1) / p.n_cb + 1) * 2 * gpi;
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_gpi = gpi; }
+    }
+    p.flat = 1; p.gb_per_item = best_gpi; p.gene_ranges = cdiv(p.n_gb, best_gpi);
+    p.cb_per_item = p.n_cb; p.cell_splits = 1;
+    p.total_units = p.gene_ranges * n_heads * p.n_cb;
+    p.total_items = p.total_units;          // grid size below
+  }
   for (int i = 0; i < 3; ++i) { p.dW[i] = dW ? dW[i] : nullptr; p.db[i] = db ? db[i] : nullptr; p.Zp[i] = Z[i < n_heads ? i : 0]; }
-  p.ldz = ldz; p.prefetch = g_gg_prefetch;
+  p.ldz = ldz; p.prefetch = p.flat ? 0 : g_gg_prefetch;
+  if (g_gg_profile) {
+    static unsigned long long* dbg_buf = nullptr;
+    if (!dbg_buf) DCA_CUDA_OK(cudaMalloc(&dbg_buf, sizeof(unsigned long long) * 16 * 1024));
+    DCA_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, sizeof(unsigned long long) * 16 * 1024, s));
+    p.dbg = dbg_buf;
+  }
   p.dW_ld = dW_ld; p.dW_transposed = dW_transposed;
   const int grid = p.total_items < sm_count ? p.total_items : sm_count;
 #define DCA_GG_LAUNCH(A, Bb, Cc)                                                                                       \
@@ -409,6 +484,18 @@ int gene_gemm_tc(int mode, const __nv_bfloat16* const Z[3], int64_t ldz, int B, 
   else { set_error("gene_gemm_tc: bad mode %d", mode); return DCA_ERR_BAD_ARG; }
 #undef DCA_GG_LAUNCH
   DCA_LAUNCH_CHECK();
+  if (p.dbg) {          // diagnosis only: synchronises the stream
+    std::vector<unsigned long long> h((size_t)grid * 16);
+    DCA_CUDA_OK(cudaStreamSynchronize(s));
+    DCA_CUDA_OK(cudaMemcpy(h.data(), p.dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+    double a[16] = {0}; double mx_total = 0;
+    for (int b = 0; b < grid; ++b) { for (int i = 0; i < 16; ++i) a[i] += (double)h[(size_t)b * 16 + i] / grid; if ((double)h[(size_t)b * 16 + 8] > mx_total) mx_total = (double)h[(size_t)b * 16 + 8]; }
+    fprintf(stderr, "[gg_profile mode %d grid %d flat %d gpi %d] kcycles avg/CTA  producer: wait_z_empty %.0f wait_h_empty %.0f total %.0f | "
+                    "mma: wait_z_full %.0f wait_h_full %.0f wait_dh_empty %.0f wait_dw_empty %.0f total %.0f (max %.0f) tiles %.1f | "
+                    "epilogue: wait_dh_full %.0f dh_flush %.0f wait_dw_full %.0f dw_flush %.0f total %.0f\n",
+            mode, grid, p.flat, p.gb_per_item, a[0] / 1e3, a[1] / 1e3, a[2] / 1e3, a[4] / 1e3, a[5] / 1e3, a[6] / 1e3, a[7] / 1e3, a[8] / 1e3,
+            mx_total / 1e3, a[9], a[10] / 1e3, a[11] / 1e3, a[12] / 1e3, a[13] / 1e3, a[14] / 1e3);
+  }
   return DCA_OK;
 }
 

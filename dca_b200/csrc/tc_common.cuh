@@ -156,6 +156,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// one lane of the (converged) warp: the predicate the compiler recognises as single-lane, so that operands of the
+// instructions it guards move to uniform registers without a waterfall loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                              // c_format = F32

@@ -14,7 +14,7 @@
 #include <cstdlib>
 
 namespace dca {
-namespace tc { extern int g_gg_prefetch; }
+namespace tc { extern int g_gg_prefetch; extern int g_gg_flat; extern int g_gg_profile; }
 
 namespace {
 
@@ -937,6 +937,8 @@ extern "C" int dca_set_tunable(const char* name, int64_t value) {
   else if (n == "loss_branch_free" && (value == 0 || value == 1)) g_tune.branch_free = (int)value;
   else if (n == "loss_ring" && value >= 0 && value <= 2) g_tune.ring = (int)value;
   else if (n == "gg_prefetch" && (value == 0 || value == 1)) tc::g_gg_prefetch = (int)value;
+  else if (n == "gg_flat" && (value == 0 || value == 1)) tc::g_gg_flat = (int)value;
+  else if (n == "gg_profile" && (value == 0 || value == 1)) tc::g_gg_profile = (int)value;
   else { set_error("dca_set_tunable: unknown name or value out of range (%s = %lld)", name, (long long)value); return DCA_ERR_BAD_ARG; }
   return DCA_OK;
 }
