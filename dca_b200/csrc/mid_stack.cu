@@ -13,12 +13,14 @@
 //             previous layer; ends with da_0 (fp32 + bf16) for the first layer's weight gradient.
 #include "dca_internal.cuh"
 #include "mid_stack.h"
+#include <cstdio>
 #include <cstdlib>
 
 namespace dca {
 namespace mid {
 
 constexpr int kThreads = 256;
+#define MID_STAMP(i) do { if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[i] = clock64(); } while (0)
 constexpr int kGenWord = 32;       // generation counter lives 128 bytes after the arrival counter
 constexpr int kStripStride = kMaxW + 4;   // activation strips: rows 16-byte aligned (float4 broadcasts along k)
 typedef float Strip[kStripStride];        // lanes always differ in the COLUMN of a strip -> no bank conflicts
@@ -28,12 +30,14 @@ typedef float WRow[kMaxW + 1];            // weights: lanes differ in the ROW ->
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n, unsigned& gen) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    // release this CTA's writes (made visible to thread 0 by the block barrier) / acquire the others': an acq_rel fence at
+    // gpu scope is what the pattern needs; __threadfence() is the sequentially consistent MEMBAR.SC
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
     // bar[0] = arrival count, bar[kGenWord] = generation (separate 128-byte lines: pollers do not slow arrivals)
     const unsigned arrived = atomicAdd(&bar[0], 1u);
     if (arrived == n - 1) {
       bar[0] = 0;
-      __threadfence();
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
       atomicAdd(&bar[kGenWord], 1u);
     } else {
       // bounded: the kernels are launched cooperatively (co-residency is guaranteed by the driver), so a barrier that
@@ -51,7 +55,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n, unsigned
         }
       }
     }
-    __threadfence();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   ++gen;
   __syncthreads();
@@ -74,20 +78,40 @@ __device__ __forceinline__ void cta_col_sums(Strip* x, Strip* y, int rows, int w
   }
 }
 
-// tot[k][c] = sum over CTAs in a fixed order (deterministic).  Thread t owns pair t/2 and half t%2 of the
-// CTA axis: 32 independent, contiguous 8-byte loads in flight per thread, then one shuffle to join the halves.
+// tot[k][c] = sum over CTAs in a fixed order (deterministic).  A warp owns 16 of the 128 (stat, column) pairs; its lanes read
+// CONSECUTIVE CTAs of a pair (one coalesced 256-byte request per 32 CTAs -- the first version gave every thread its own
+// 256-byte run: 32 sectors per warp instruction, 9 k cycles per fold, gg_profile), then a shuffle tree joins the lanes.
 __device__ __forceinline__ void fold_partials(const double* partial, int n_ctas, int w, double* tot /* smem [2][kMaxW] */) {
-  const int pair = threadIdx.x >> 1, half = threadIdx.x & 1;       // 256 threads -> 128 pairs x 2 halves
-  const int c = pair & 63;
-  double v[32];
-  const double* src = partial + (size_t)pair * kMaxCtas + half * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kPairsPerWarp = 2 * kMaxW / (kThreads / 32), kPer = kMaxCtas / 32;
+  // every load first (64 independent 8-byte loads per thread, ONE round trip to L2), then the adds: written pair by pair
+  // the compiler emitted load-load-load-load-add-add-add-add per pair and the in-order issue serialised 16 round trips
+  double x[kPairsPerWarp][kPer];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = (c < w && half * 32 + i < n_ctas) ? src[i] : 0.0;
-  double s = 0.0;
+  for (int i = 0; i < kPairsPerWarp; ++i) {
+    const int pair = warp + i * (kThreads / 32), c = pair & (kMaxW - 1);
+    const double* src = partial + (size_t)pair * kMaxCtas;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) s += v[i];
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  if (half == 0) tot[pair] = s;
+    for (int j = 0; j < kPer; ++j) {
+      const int cta = j * 32 + lane;
+      x[i][j] = (c < w && cta < n_ctas) ? __ldcg(src + cta) : 0.0;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kPairsPerWarp; ++i) {
+    double sacc = x[i][0];
+#pragma unroll
+    for (int j = 1; j < kPer; ++j) sacc += x[i][j];
+    x[i][0] = sacc;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < kPairsPerWarp; ++i) x[i][0] += __shfl_xor_sync(0xffffffffu, x[i][0], o);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kPairsPerWarp; ++i) tot[warp + i * (kThreads / 32)] = x[i][0];
+  }
   __syncthreads();
 }
 
@@ -116,7 +140,8 @@ __device__ __forceinline__ void strip_gemm(Strip* in, WRow* Ws, const float* bia
 
 constexpr size_t kStripFloats = (size_t)(kMaxRows + 4) * kStripStride;
 constexpr size_t kWsFloats = (size_t)kMaxW * (kMaxW + 1);
-constexpr size_t kSmemBytes = sizeof(double) * (8 * kMaxW + 2 * kMaxW) + sizeof(float) * (2 * kStripFloats + kWsFloats + 2 * kMaxW) + 16;
+constexpr int kWSlots = DCA_MAX_HIDDEN - 1;      // forward: every inner kernel resident at once
+constexpr size_t kSmemBytes = sizeof(double) * (8 * kMaxW + 2 * kMaxW) + sizeof(float) * (2 * kStripFloats + kWSlots * kWsFloats + 2 * kMaxW) + 16;
 
 __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_mid[];
@@ -126,35 +151,73 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
   Strip* cur = reinterpret_cast<Strip*>(fbase);                       // current layer pre-activation / activation strip
   Strip* nxt = reinterpret_cast<Strip*>(fbase + kStripFloats);
   WRow* Ws = reinterpret_cast<WRow*>(fbase + 2 * kStripFloats);
-  float* s_mean = fbase + 2 * kStripFloats + kWsFloats;
+  float* s_mean = fbase + 2 * kStripFloats + kWSlots * kWsFloats;
   float* s_inv = s_mean + kMaxW;
   __shared__ unsigned s_gen;
   if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile unsigned*>(&p.bar[kGenWord]);
   __syncthreads();
   unsigned gen = s_gen;
+  MID_STAMP(0);
 
   const int row0 = blockIdx.x * p.rows_per_cta;
   const int rows = max(0, min(p.rows_per_cta, p.B - row0));
   for (int i = threadIdx.x; i < (int)kStripFloats; i += kThreads) { (&cur[0][0])[i] = 0.f; (&nxt[0][0])[i] = 0.f; }
-  for (int i = threadIdx.x; i < (int)kWsFloats; i += kThreads) (&Ws[0][0])[i] = 0.f;
   __syncthreads();
   // thread -> (column tc, row lane tr): no integer divisions in the element loops (widths <= 64)
   const int tc = threadIdx.x & 63, tr = threadIdx.x >> 6;
-  // load a_0 strip
-  if (tc < p.w[0])
-    for (int r = tr; r < rows; r += 4) cur[r][tc] = p.a0[(size_t)(row0 + r) * p.w[0] + tc];
+  // Prologue loads, ALL issued before the first dependent shared-memory store (in-order issue: a store that waits for its
+  // load blocks the loads behind it): the a_0 strip and every inner kernel (slot l - 1, zero-padded) -- the layer loop then
+  // never waits for a global load between two grid barriers.
+  constexpr int kRowIters = kMaxRows / 4, kKIters = kMaxW / 4;
+  float a0r[kRowIters];
+#pragma unroll
+  for (int i = 0; i < kRowIters; ++i) {
+    const int r = tr + 4 * i;
+    a0r[i] = (tc < p.w[0] && r < rows) ? p.a0[(size_t)(row0 + r) * p.w[0] + tc] : 0.f;
+  }
+  for (int l0 = 1; l0 < p.L; l0 += 2) {
+    float wr[2][kKIters];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const int l = l0 + d;
+      const int win = l < p.L ? p.w[l - 1] : 0, w = l < p.L ? p.w[l] : 0;
+#pragma unroll
+      for (int i = 0; i < kKIters; ++i) { const int k = tr + 4 * i; wr[d][i] = (k < win && tc < w) ? p.W[l][(size_t)k * w + tc] : 0.f; }
+    }
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      if (l0 + d >= p.L) break;
+      WRow* Wl = Ws + (size_t)(l0 + d - 1) * kMaxW;
+#pragma unroll
+      for (int i = 0; i < kKIters; ++i) Wl[tr + 4 * i][tc] = wr[d][i];
+    }
+  }
+  // CTA 0 updates the moving statistics: their old values are fetched here, not between the barriers
+  float mm_old[DCA_MAX_HIDDEN], mv_old[DCA_MAX_HIDDEN];
+#pragma unroll
+  for (int l = 0; l < DCA_MAX_HIDDEN; ++l) {
+    const bool mine = p.batchnorm && p.training && blockIdx.x == 0 && l < p.L && (int)threadIdx.x < p.w[l];
+    mm_old[l] = mine ? p.mm[l][threadIdx.x] : 0.f; mv_old[l] = mine ? p.mv[l][threadIdx.x] : 0.f;
+  }
+  float beta_r[DCA_MAX_HIDDEN];                 // this thread's column of every layer's beta (same reason)
+#pragma unroll
+  for (int l = 0; l < DCA_MAX_HIDDEN; ++l) beta_r[l] = (p.batchnorm && l < p.L && tc < p.w[l]) ? p.beta[l][tc] : 0.f;
+  if (tc < p.w[0]) {
+#pragma unroll
+    for (int i = 0; i < kRowIters; ++i) { const int r = tr + 4 * i; if (r < rows) cur[r][tc] = a0r[i]; }
+  }
   __syncthreads();
+  MID_STAMP(1);
   Strip* a = cur;
   Strip* o = nxt;
   for (int l = 0; l < p.L; ++l) {
     const int w = p.w[l];
     if (l > 0) {
       const int win = p.w[l - 1];
-      for (int k = tr; k < kMaxW; k += 4) Ws[k][tc] = (k < win && tc < w) ? p.W[l][(size_t)k * w + tc] : 0.f;
-      __syncthreads();
-      strip_gemm(a, Ws, p.b[l], rows, win, w, o);
+      strip_gemm(a, Ws + (size_t)(l - 1) * kMaxW, p.b[l], rows, win, w, o);
       __syncthreads();
       Strip* t = a; a = o; o = t;
+      MID_STAMP(2 + l * 5);
     }
     if (l == p.center && p.a_center && !(l == 0 && p.a_center == p.a0) && tc < w)
       for (int r = tr; r < rows; r += 4) p.a_center[(size_t)(row0 + r) * w + tc] = a[r][tc];
@@ -162,19 +225,31 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
       if (p.training) {
         double* part = p.partial + (size_t)(l & 1) * kMaxCtas * 2 * kMaxW;       // double-buffered across layers
         cta_col_sums(a, a, rows, w, part + blockIdx.x, red);
+        MID_STAMP(3 + l * 5);
         grid_barrier(p.bar, gridDim.x, gen);
+        MID_STAMP(4 + l * 5);
         fold_partials(part, gridDim.x, w, tot);
+        MID_STAMP(5 + l * 5);
         if (threadIdx.x < w) {
           const int c = threadIdx.x;
-          const double mu = tot[c] / (double)p.B;
-          double var = tot[kMaxW + c] / (double)p.B - mu * mu;      // biased batch variance
+          const double inv_b = 1.0 / (double)p.B;                    // (one division; B is a launch constant)
+          const double mu = tot[c] * inv_b;
+          double var = tot[kMaxW + c] * inv_b - mu * mu;             // biased batch variance
           if (var < 0.0) var = 0.0;
           s_mean[c] = (float)mu;
-          s_inv[c] = (float)(1.0 / sqrt(var + (double)p.eps));
+          // 1 / sqrt(var + eps): float rsqrt + one Newton step (2e-7 relative) instead of a double sqrt and division
+          const float vf = (float)(var + (double)p.eps);
+          float r = rsqrtf(vf);
+          r = r * (1.5f - 0.5f * vf * r * r);
+          s_inv[c] = r;
           if (blockIdx.x == 0) {
-            p.mean[l][c] = s_mean[c]; p.inv[l][c] = s_inv[c];
-            p.mm[l][c] = p.momentum * p.mm[l][c] + (1.0f - p.momentum) * (float)mu;
-            p.mv[l][c] = p.momentum * p.mv[l][c] + (1.0f - p.momentum) * (float)var;
+            p.mean[l][c] = s_mean[c]; p.inv[l][c] = r;
+#pragma unroll
+            for (int q = 0; q < DCA_MAX_HIDDEN; ++q)
+              if (q == l) {
+                p.mm[l][c] = p.momentum * mm_old[q] + (1.0f - p.momentum) * (float)mu;
+                p.mv[l][c] = p.momentum * mv_old[q] + (1.0f - p.momentum) * (float)var;
+              }
           }
         }
         __syncthreads();
@@ -186,7 +261,9 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
     const bool last = (l == p.L - 1);
     if (tc < w) {
       const float mean_c = p.batchnorm ? s_mean[tc] : 0.f, inv_c = p.batchnorm ? s_inv[tc] : 1.f;
-      const float beta_c = p.batchnorm ? p.beta[l][tc] : 0.f;
+      float beta_c = 0.f;
+#pragma unroll
+      for (int q = 0; q < DCA_MAX_HIDDEN; ++q) if (q == l) beta_c = beta_r[q];
       for (int r = tr; r < rows; r += 4) {
         const size_t gi = (size_t)(row0 + r) * w + tc;
         float v = a[r][tc];
@@ -202,7 +279,9 @@ __global__ void __launch_bounds__(kThreads, 1) mid_forward_kernel(const Params p
       }
     }
     __syncthreads();
+    MID_STAMP(6 + l * 5);
   }
+  MID_STAMP(31);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params p) {
@@ -217,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
   if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile unsigned*>(&p.bar[kGenWord]);
   __syncthreads();
   unsigned gen = s_gen;
+  MID_STAMP(0);
 
   const int row0 = blockIdx.x * p.rows_per_cta;
   const int rows = max(0, min(p.rows_per_cta, p.B - row0));
@@ -231,23 +311,39 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
       for (int r = tr; r < rows; r += 4) g[r][tc] = p.dh_last[(size_t)(row0 + r) * w + tc];
   }
   __syncthreads();
+  MID_STAMP(1);
   for (int l = p.L - 1; l >= 0; --l) {
     const int w = p.w[l];
-    // relu mask (+ load x_hat)
-    if (tc < w)
-      for (int r = tr; r < rows; r += 4) {
+    // relu mask (+ load x_hat): loads first, then the dependent shared-memory traffic
+    {
+      constexpr int kRowIters = kMaxRows / 4;
+      float hr[kRowIters], xr[kRowIters];
+#pragma unroll
+      for (int i = 0; i < kRowIters; ++i) {
+        const int r = tr + 4 * i;
+        const bool ok = tc < w && r < rows;
         const size_t gi = (size_t)(row0 + r) * w + tc;
-        const float hv = p.h[l][gi];
-        const float xv = p.batchnorm ? p.xhat[l][gi] : 0.f;
-        if (!(hv > 0.f)) g[r][tc] = 0.f;
-        xh[r][tc] = xv;
+        hr[i] = ok ? p.h[l][gi] : 0.f;
+        xr[i] = (ok && p.batchnorm) ? p.xhat[l][gi] : 0.f;
       }
+      if (tc < w) {
+#pragma unroll
+        for (int i = 0; i < kRowIters; ++i) {
+          const int r = tr + 4 * i;
+          if (r < rows) { if (!(hr[i] > 0.f)) g[r][tc] = 0.f; xh[r][tc] = xr[i]; }
+        }
+      }
+    }
     __syncthreads();
+    MID_STAMP(2 + (p.L - 1 - l) * 8);
     if (p.batchnorm) {
       double* part = p.partial + (size_t)(l & 1) * kMaxCtas * 2 * kMaxW;
       cta_col_sums(g, xh, rows, w, part + blockIdx.x, red);
+      MID_STAMP(3 + (p.L - 1 - l) * 8);
       grid_barrier(p.bar, gridDim.x, gen);
+      MID_STAMP(4 + (p.L - 1 - l) * 8);
       fold_partials(part, gridDim.x, w, tot);
+      MID_STAMP(5 + (p.L - 1 - l) * 8);
       if (blockIdx.x == 0 && threadIdx.x < w) p.gbeta[l][threadIdx.x] = (float)tot[threadIdx.x];   // d beta = sum(g)
       if (threadIdx.x < w) {
         s_mg[threadIdx.x] = (float)(tot[threadIdx.x] / (double)p.B);
@@ -271,6 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
       if (threadIdx.x < w) atomicAdd(&p.gb[l][threadIdx.x], (float)(red[0][c] + red[1][c] + red[2][c] + red[3][c]));
       __syncthreads();
     }
+    MID_STAMP(6 + (p.L - 1 - l) * 8);
     if (l == 0) {
       if (tc < w)
         for (int r = tr; r < rows; r += 4) {
@@ -282,9 +379,20 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
     }
     // ---- inner layer l >= 1: dW_l += h_{l-1}^T . da ;  dh_{l-1} = da . W_l^T
     const int win = p.w[l - 1];
-    if (tc < win)
-      for (int r = tr; r < rows; r += 4) xh[r][tc] = p.h[l - 1][(size_t)(row0 + r) * win + tc];
-    for (int k = tr; k < kMaxW; k += 4) Ws[k][tc] = (k < win && tc < w) ? p.W[l][(size_t)k * w + tc] : 0.f;
+    {
+      constexpr int kRowIters = kMaxRows / 4, kKIters = kMaxW / 4;
+      float hr[kRowIters], wr[kKIters];
+#pragma unroll
+      for (int i = 0; i < kRowIters; ++i) { const int r = tr + 4 * i; hr[i] = (tc < win && r < rows) ? p.h[l - 1][(size_t)(row0 + r) * win + tc] : 0.f; }
+#pragma unroll
+      for (int i = 0; i < kKIters; ++i) { const int k = tr + 4 * i; wr[i] = (k < win && tc < w) ? p.W[l][(size_t)k * w + tc] : 0.f; }
+      if (tc < win) {
+#pragma unroll
+        for (int i = 0; i < kRowIters; ++i) { const int r = tr + 4 * i; if (r < rows) xh[r][tc] = hr[i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < kKIters; ++i) Ws[tr + 4 * i][tc] = wr[i];
+    }
     __syncthreads();
     // dW[k][c] = sum_r h[r][k] * da[r][c]: thread = column c and a group of 4 consecutive k (128-bit broadcast of h)
     if (tc < w)
@@ -300,6 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
           if (k0 + j < win) atomicAdd(&p.gW[l][(size_t)(k0 + j) * w + tc], s[j]);
       }
     __syncthreads();
+    MID_STAMP(7 + (p.L - 1 - l) * 8);
     // dh_{l-1}[r][k] = sum_c da[r][c] * W[k][c]: thread = k (= tc), 4 rows at a time, c in groups of 4
     constexpr int kRowGroups = kMaxRows / 16;
     float dhv[kRowGroups][4];                                          // [row group][row in group]
@@ -334,7 +443,9 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
     if (tc < win)
       for (int r = tr; r < rows; r += 4) g[r][tc] = xh[r][tc];
     __syncthreads();
+    MID_STAMP(8 + (p.L - 1 - l) * 8);
   }
+  MID_STAMP(31);
 }
 
 }  // namespace mid
@@ -346,7 +457,7 @@ bool mid_supported(const int* widths, int L) {
 }
 
 static int mid_fill(mid::Params& p, int B) {
-  static const int rows_target = [] { const char* e = getenv("DCA_MID_ROWS"); int v = e ? atoi(e) : 64; return (v >= 16 && v <= mid::kMaxRows) ? v : 64; }();
+  static const int rows_target = [] { const char* e = getenv("DCA_MID_ROWS"); int v = e ? atoi(e) : 32; return (v >= 16 && v <= mid::kMaxRows) ? v : 32; }();
   int ctas = cdiv(B, rows_target);
   if (ctas > mid::kMaxCtas) ctas = mid::kMaxCtas;
   if ((long long)ctas * mid::kMaxRows < B) { set_error("mid_stack: batch %d exceeds %d rows", B, mid::kMaxRows * mid::kMaxCtas); return DCA_ERR_UNSUPPORTED; }
@@ -404,16 +515,40 @@ static int mid_launch(K kernel, mid::Params& p, cudaStream_t s) {
   return DCA_OK;
 }
 
+namespace tc { extern int g_gg_profile; }
+
+// gg_profile: phase timeline of CTA 0 (clock64 stamps), printed after the launch (synchronises; DCA_GRAPH=0)
+static int mid_profiled(const char* name, int (*launch)(mid::Params&, cudaStream_t), mid::Params& p, cudaStream_t s) {
+  static long long* dbg_buf = nullptr;
+  if (!dbg_buf) DCA_CUDA_OK(cudaMalloc(&dbg_buf, sizeof(long long) * 32));
+  DCA_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 32, s));
+  p.dbg = dbg_buf;
+  DCA_TRY(launch(p, s));
+  long long h[32];
+  DCA_CUDA_OK(cudaStreamSynchronize(s));
+  DCA_CUDA_OK(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+  fprintf(stderr, "[gg_profile %s ctas %d rows %d] cycles since start:", name, p.n_ctas, p.rows_per_cta);
+  for (int i = 1; i < 32; ++i) if (h[i]) fprintf(stderr, " s%d=%lld", i, h[i] - h[0]);
+  fprintf(stderr, "\n");
+  return DCA_OK;
+}
+static int mid_forward_launch(mid::Params& p, cudaStream_t s) { return mid_launch(mid::mid_forward_kernel, p, s); }
+static int mid_backward_launch(mid::Params& p, cudaStream_t s) { return mid_launch(mid::mid_backward_kernel, p, s); }
+
 int mid_forward(mid::Params& p, cudaStream_t s) {
   DCA_TRY(mid_fill(p, p.B));
   DCA_TRY(mid_attr());
-  return mid_launch(mid::mid_forward_kernel, p, s);
+  p.dbg = nullptr;
+  if (tc::g_gg_profile) return mid_profiled("mid_forward", mid_forward_launch, p, s);
+  return mid_forward_launch(p, s);
 }
 
 int mid_backward(mid::Params& p, cudaStream_t s) {
   DCA_TRY(mid_fill(p, p.B));
   DCA_TRY(mid_attr());
-  return mid_launch(mid::mid_backward_kernel, p, s);
+  p.dbg = nullptr;
+  if (tc::g_gg_profile) return mid_profiled("mid_backward", mid_backward_launch, p, s);
+  return mid_backward_launch(p, s);
 }
 
 }  // namespace dca

@@ -6,8 +6,8 @@ namespace dca {
 namespace mid {
 
 constexpr int kMaxW = 64;          // widest hidden layer handled by the fused kernels
-constexpr int kMaxCtas = 64;
-constexpr int kMaxRows = 64;       // rows per CTA strip  (=> batch <= 4096; larger batches use the per-layer kernels)
+constexpr int kMaxCtas = 128;      // co-resident CTAs (one per SM, cooperative launch)
+constexpr int kMaxRows = 64;       // rows per CTA strip  (=> batch <= 8192; larger batches use the per-layer kernels)
 
 struct Params {
   int L, B, training, batchnorm, center, rows_per_cta, n_ctas;
@@ -28,6 +28,7 @@ struct Params {
   double* partial;                    // [n_ctas][2][kMaxW] scratch per barrier round
   unsigned* bar;                      // {count, generation}
   float eps, momentum;
+  long long* dbg;                     // gg_profile: clock64 stamps of CTA 0 at the phase boundaries (nullptr = off)
 };
 
 }  // namespace mid
