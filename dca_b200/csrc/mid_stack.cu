@@ -123,6 +123,7 @@ __device__ __forceinline__ void strip_gemm(Strip* in, WRow* Ws, const float* bia
     const float bv = bias ? bias[c] : 0.f;
     for (int r0 = g * 4; r0 < rows; r0 += 16) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
       for (int k = 0; k < w_in; k += 4) {
         const float w0 = Ws[k][c], w1 = Ws[k + 1][c], w2 = Ws[k + 2][c], w3 = Ws[k + 3][c];   // rows >= w_in are zero
 #pragma unroll
@@ -304,6 +305,23 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
   for (int i = threadIdx.x; i < (int)kWsFloats; i += kThreads) (&Ws[0][0])[i] = 0.f;
   __syncthreads();
   const int tc = threadIdx.x & 63, tr = threadIdx.x >> 6;
+  // The saved activations of the layers visited LATER left L2 long ago (the loss kernel streamed 1.8 GB since the forward
+  // pass): ask for them now (one L2 prefetch per 128-byte line), so that the loads between the barriers are L2 hits.
+  if ((tc & 31) == 0) {
+    for (int l = p.L - 2; l >= 0; --l) {
+      const int w = p.w[l];
+      if (tc < w)
+        for (int r = tr; r < rows; r += 4) {
+          const size_t gi = (size_t)(row0 + r) * w + tc;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.h[l] + gi));
+          if (p.batchnorm) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.xhat[l] + gi));
+        }
+    }
+  }
+  for (int l = 1; l < p.L; ++l) {
+    const int n = p.w[l - 1] * p.w[l];
+    for (int i = threadIdx.x * 32; i < n; i += kThreads * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.W[l] + i));
+  }
   float* s_mg = reinterpret_cast<float*>(Ws);          // per-column means of the BN backward (Ws is free at that point)
   {
     const int w = p.w[p.L - 1];
@@ -394,18 +412,28 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
       for (int i = 0; i < kKIters; ++i) Ws[tr + 4 * i][tc] = wr[i];
     }
     __syncthreads();
+    MID_STAMP(24 + (p.L - 1 - l) * 3);
     // dW[k][c] = sum_r h[r][k] * da[r][c]: thread = column c and a group of 4 consecutive k (128-bit broadcast of h)
     if (tc < w)
       for (int k0 = tr * 4; k0 < win; k0 += 16) {
         float s[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = 0; r < rows; ++r) {
-          const float gv = g[r][tc];
-          const float4 hv = *reinterpret_cast<const float4*>(&xh[r][k0]);
-          s[0] = fmaf(hv.x, gv, s[0]); s[1] = fmaf(hv.y, gv, s[1]); s[2] = fmaf(hv.z, gv, s[2]); s[3] = fmaf(hv.w, gv, s[3]);
+        // four rows per trip, loads ahead of the FMAs (one row per trip exposed two shared-memory latencies per 4 FMAs: 37
+        // cycles per row, gg_profile); rows beyond `rows` are zero in both strips and the strip height is a multiple of 4
+        for (int r = 0; r < rows; r += 4) {
+          float gv[4]; float4 hv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { gv[j] = g[r + j][tc]; hv[j] = *reinterpret_cast<const float4*>(&xh[r + j][k0]); }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s[0] = fmaf(hv[j].x, gv[j], s[0]); s[1] = fmaf(hv[j].y, gv[j], s[1]);
+            s[2] = fmaf(hv[j].z, gv[j], s[2]); s[3] = fmaf(hv[j].w, gv[j], s[3]);
+          }
         }
+        if (k0 == tr * 4) MID_STAMP(25 + (p.L - 1 - l) * 3);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (k0 + j < win) atomicAdd(&p.gW[l][(size_t)(k0 + j) * w + tc], s[j]);
+        if (k0 == tr * 4) MID_STAMP(26 + (p.L - 1 - l) * 3);
       }
     __syncthreads();
     MID_STAMP(7 + (p.L - 1 - l) * 8);
@@ -418,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
         const int r0 = tr * 4 + q * 16;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         if (r0 < rows)
+#pragma unroll 4
           for (int c = 0; c < w; c += 4) {                             // padded columns of g / Ws are zero
             const float w0 = Ws[tc][c], w1 = Ws[tc][c + 1], w2 = Ws[tc][c + 2], w3 = Ws[tc][c + 3];
 #pragma unroll
