@@ -305,23 +305,6 @@ __global__ void __launch_bounds__(kThreads, 1) mid_backward_kernel(const Params 
   for (int i = threadIdx.x; i < (int)kWsFloats; i += kThreads) (&Ws[0][0])[i] = 0.f;
   __syncthreads();
   const int tc = threadIdx.x & 63, tr = threadIdx.x >> 6;
-  // The saved activations of the layers visited LATER left L2 long ago (the loss kernel streamed 1.8 GB since the forward
-  // pass): ask for them now (one L2 prefetch per 128-byte line), so that the loads between the barriers are L2 hits.
-  if ((tc & 31) == 0) {
-    for (int l = p.L - 2; l >= 0; --l) {
-      const int w = p.w[l];
-      if (tc < w)
-        for (int r = tr; r < rows; r += 4) {
-          const size_t gi = (size_t)(row0 + r) * w + tc;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.h[l] + gi));
-          if (p.batchnorm) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.xhat[l] + gi));
-        }
-    }
-  }
-  for (int l = 1; l < p.L; ++l) {
-    const int n = p.w[l - 1] * p.w[l];
-    for (int i = threadIdx.x * 32; i < n; i += kThreads * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.W[l] + i));
-  }
   float* s_mg = reinterpret_cast<float*>(Ws);          // per-column means of the BN backward (Ws is free at that point)
   {
     const int w = p.w[p.L - 1];
