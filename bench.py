@@ -390,7 +390,7 @@ def main():
                           " (not re-measured inside this run: ncu cannot run inside the timed process)"
     except Exception:
         pass
-    roofline = {"kernel": "zinb_loss_bwd_staged_kernel (phase loss_fwd_bwd: K3 + partial fold)", "bound": "hbm", "achieved": ach,
+    roofline = {"kernel": "zinb_loss_bwd_ring_kernel (phase loss_fwd_bwd: K3, the last block folds the partials)", "bound": "hbm", "achieved": ach,
                 "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": loss_bytes,

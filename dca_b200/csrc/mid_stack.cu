@@ -2,7 +2,7 @@
 // hidden activation, forward and backward, in ONE launch each (dca/network.py:124-139 for every hidden
 // layer: [Dense ->] BatchNormalization(center, no scale) -> relu).  The tensors are tiny (B x <=64), the
 // work is latency-bound, and training-mode BatchNorm needs full-batch column statistics before it can
-// normalise -- so the kernel runs as <= 64 co-resident CTAs that own a strip of rows each, keep the
+// normalise -- so the kernel runs as <= 128 co-resident CTAs that own a strip of rows each, keep the
 // strip in shared memory across layers, and meet at a grid-wide barrier once per BatchNorm layer.
 //
 //   forward : a_0 (given, bias included) -> BN/relu -> [Dense -> BN/relu]* -> h_last (fp32 + bf16)
