@@ -130,7 +130,13 @@ int Engine::train_step_dp_body(const void* X, int64_t ldx, const float* Y, int64
     DCA_TRY(allreduce_range(hb, P + 2, comm_stream));
   }
   DCA_CUDA_OK(cudaEventRecord(ev_join, comm_stream));
-  DCA_TRY(train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, 2));
+  // The persistent kernels of phase 2 take one CTA (and most of the shared memory) of EVERY SM; the collective's CTAs then
+  // only become resident when those retire and the "overlap" is a queue.  DCA_DP_RESERVE_SMS=n keeps n SMs free of them.
+  static const int reserve = [] { const char* e = getenv("DCA_DP_RESERVE_SMS"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 100 ? 100 : v); }();
+  dp_reserve_sms = reserve;
+  const int st2 = train_step_body(X, ldx, Y, ldy, sf, rows, Bn, s, 2);
+  dp_reserve_sms = 0;
+  DCA_TRY(st2);
   DCA_TRY(allreduce_range(0, hb, s));
   DCA_CUDA_OK(cudaStreamWaitEvent(s, ev_join, 0));
   return DCA_OK;

@@ -568,12 +568,13 @@ int Engine::train_step_body(const void* X, int64_t ldx, const float* Y, int64_t 
     mid::Params mp;
     mid_params(mp, Bn, true);
     mp.dh_last = dh; mp.da0 = dh2; mp.da0_bf16 = cur_xb ? bf(o_da1b) : nullptr;
+    mp.max_ctas = dp_reserve_sms ? (sm_count - dp_reserve_sms) : 0;
     DCA_TRY(mid_backward(mp, s));
     Layer& l = lay[0];
     if (cur_xb) {
       const __nv_bfloat16* Z[3] = {cur_xb, cur_xb, cur_xb};
       float* dWp[3] = {gp(l.W), gp(l.W), gp(l.W)};
-      DCA_TRY(tc::gene_gemm_tc(2, Z, cur_ldxb, Bn, cfg.n_in, 1, bf(o_da1b), nullptr, nullptr, dWp, l.out, 0, nullptr, sm_count, s));
+      DCA_TRY(tc::gene_gemm_tc(2, Z, cur_ldxb, Bn, cfg.n_in, 1, bf(o_da1b), nullptr, nullptr, dWp, l.out, 0, nullptr, sm_count - dp_reserve_sms, s));
     } else {
       GemmArgs g{};
       g.A = X; g.lda = ldx; g.a_bf16 = x_override_bf16 ? 1 : (cfg.x_dtype == DCA_BF16); g.transA = 1; g.a_rows = xrows;
@@ -715,7 +716,7 @@ int Engine::setup_tc() {
   int dev = 0;
   DCA_CUDA_OK(cudaGetDevice(&dev));
   DCA_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  if (mid_ok && !mid_device_ok()) mid_ok = false;   // grid-barrier kernels need a cooperative launch of <= 64 CTAs: else per-layer path
+  if (mid_ok && !mid_device_ok()) mid_ok = false;   // grid-barrier kernels need a cooperative launch of <= 128 CTAs: else per-layer path
   if (tc_heads || tc_enc) {
     int major = 0;
     DCA_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));

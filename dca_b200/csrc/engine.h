@@ -127,6 +127,7 @@ struct Engine {
 
   // data-parallel gradient exchange (comm.cu): NCCL communicator owned by the engine, resolved with dlopen
   void* comm = nullptr; int comm_world = 1, comm_rank = 0;
+  int dp_reserve_sms = 0;          // phase 2 of dca_train_step_dp: SMs the hidden-stack / encoder backward leave to the collective
   bool dp_split_heads = false;     // set around phase 1 of dca_train_step_dp: head backward per head + per-head all-reduce
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int comm_init(const void* id128, int rank, int world);

@@ -472,6 +472,7 @@ static int mid_fill(mid::Params& p, int B) {
   static const int rows_target = [] { const char* e = getenv("DCA_MID_ROWS"); int v = e ? atoi(e) : 32; return (v >= 16 && v <= mid::kMaxRows) ? v : 32; }();
   int ctas = cdiv(B, rows_target);
   if (ctas > mid::kMaxCtas) ctas = mid::kMaxCtas;
+  if (p.max_ctas > 0 && ctas > p.max_ctas) { ctas = p.max_ctas; if ((long long)ctas * mid::kMaxRows < B) ctas = cdiv(B, mid::kMaxRows); }
   if ((long long)ctas * mid::kMaxRows < B) { set_error("mid_stack: batch %d exceeds %d rows", B, mid::kMaxRows * mid::kMaxCtas); return DCA_ERR_UNSUPPORTED; }
   // spread rows evenly, at least 16 rows per CTA so tiny batches do not pay for 64 barriers participants
   int rpc = cdiv(B, ctas);

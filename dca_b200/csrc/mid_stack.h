@@ -11,6 +11,7 @@ constexpr int kMaxRows = 64;       // rows per CTA strip  (=> batch <= 8192; lar
 
 struct Params {
   int L, B, training, batchnorm, center, rows_per_cta, n_ctas;
+  int max_ctas;                       // 0: as many as the batch wants (<= kMaxCtas); else an upper bound (SMs left to a collective)
   int w[DCA_MAX_HIDDEN];
   const float* W[DCA_MAX_HIDDEN];      // W[i], i >= 1: [w[i-1] x w[i]] (Keras)
   const float* b[DCA_MAX_HIDDEN];
