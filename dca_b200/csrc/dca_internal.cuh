@@ -103,7 +103,7 @@ int expand_counts(const void* cnt, int bits, const float* sf_in, int M, int n, c
                   const void* ovf_entries, cudaStream_t s);
 int expand_sparse(const void* bitmap, const int64_t* nib_indptr, const void* nibbles, const float* sf_in, int M, int n,
                   const float* mean, const float* inv_std, int use_sf, int use_log1p, float* Yout, void* Xout, int x_bf16,
-                  float* sf_out, const int64_t* ovf_indptr, const void* ovf_entries, cudaStream_t s);
+                  float* sf_out, const int64_t* ovf_indptr, const void* ovf_entries, int max_row_nibble_bytes, cudaStream_t s);
 int gather_rows_bf16(const void* X, int x_bf16, int64_t ldx, const int32_t* rows, int M, int n, __nv_bfloat16* out,
                      cudaStream_t s);
 

@@ -1043,12 +1043,14 @@ int Engine::stream_prefetch(int64_t i, int b) {
   DCA_CUDA_OK(cudaStreamWaitEvent(hs.expand, hs.h2d_done[b], 0));
   DCA_CUDA_OK(cudaStreamWaitEvent(hs.expand, hs.step_done[b], 0));       // the step that read the expanded buffers b has finished
   const int x_bf16 = tc_enc ? 1 : (cfg.x_dtype == DCA_BF16);
+  int max_nib = 0;                       // longest nibble run of a row of this batch (host CSR): sizes the expansion's smem
+  if (sparse) for (int64_t r = r0; r < r0 + nb; ++r) { const int len = (int)(hs.nib_indptr[r + 1] - hs.nib_indptr[r]); if (len > max_nib) max_nib = len; }
   if (sparse)
     DCA_TRY(expand_sparse(base + o_cnt[b], reinterpret_cast<const int64_t*>(base + o_nibp[b]), base + o_nib[b],
                           hs.sf ? f(o_sfst[b]) : nullptr, (int)nb, cfg.n_in, tf_set == 2 ? f(o_gmean) : nullptr,
                           tf_set == 2 ? f(o_ginv) : nullptr, tf_use_sf && hs.sf, tf_use_log1p, f(o_sy[b]), base + o_sx[b], x_bf16,
                           f(o_ssf[b]), has_ovf ? reinterpret_cast<const int64_t*>(base + o_ovp[b]) : nullptr,
-                          has_ovf ? (const void*)(base + o_ove[b]) : nullptr, hs.expand));
+                          has_ovf ? (const void*)(base + o_ove[b]) : nullptr, max_nib, hs.expand));
   else
   DCA_TRY(expand_counts(base + o_cnt[b], hs.bits, hs.sf ? f(o_sfst[b]) : nullptr, (int)nb, cfg.n_in,
                         tf_set == 2 ? f(o_gmean) : nullptr, tf_set == 2 ? f(o_ginv) : nullptr, tf_use_sf && hs.sf,
