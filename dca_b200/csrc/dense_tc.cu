@@ -310,9 +310,11 @@ Engine::~Engine() {
   for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (hs.copy) cudaStreamDestroy(hs.copy);
   if (hs.expand) cudaStreamDestroy(hs.expand);
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 3; ++k) {
     if (hs.ready[k]) cudaEventDestroy(hs.ready[k]);
     if (hs.step_done[k]) cudaEventDestroy(hs.step_done[k]);
+  }
+  for (int k = 0; k < 2; ++k) {
     if (hs.h2d_done[k]) cudaEventDestroy(hs.h2d_done[k]);
     if (hs.cnt_free[k]) cudaEventDestroy(hs.cnt_free[k]);
   }

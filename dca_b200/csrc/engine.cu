@@ -205,7 +205,7 @@ int Engine::plan(const dca_config& c) {
   o_gmean = take(sizeof(float) * (size_t)c.n_in); o_ginv = take(sizeof(float) * (size_t)c.n_in);
   // staging for the host-buffer entry point
   const size_t xb = (c.x_dtype == DCA_BF16) ? 2 : 4;
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < kExpBufs; ++k) {
     o_sx[k] = take(xb * B * (size_t)c.n_in);
     o_sy[k] = take(sizeof(float) * B * (size_t)G);
     o_ssf[k] = take(sizeof(float) * B);
@@ -1010,7 +1010,8 @@ extern "C" int dca_engine_info(const dca_handle* h, int32_t info[8]) {
 // copy batch `i` of the host dataset into staging buffer `b` (copy stream) and expand it (counts -> Y fp32, X
 // normalised; low-priority expand stream): both overlap the training step of the previous batch, which works on the
 // other buffer pair, and the copy of batch i+1 does not wait for the expansion of batch i
-int Engine::stream_prefetch(int64_t i, int b) {
+// raw staging buffer b (packed counts as they arrive: two of them) and expanded buffer e (Y, X, sf of the batch: hs.exp_bufs)
+int Engine::stream_prefetch(int64_t i, int b, int e) {
   const int64_t r0 = i * hs.batch;
   const int64_t nb = (hs.n_rows - r0 < hs.batch) ? (hs.n_rows - r0) : hs.batch;
   const bool sparse = hs.bits == 1;
@@ -1041,24 +1042,24 @@ int Engine::stream_prefetch(int64_t i, int b) {
   if (hs.tl_base && hs.tl.size() < 400) hs.tl_mark(hs.copy);
   // expansion on its own low-priority stream: the next copy does not queue behind it, the step's kernels go first
   DCA_CUDA_OK(cudaStreamWaitEvent(hs.expand, hs.h2d_done[b], 0));
-  DCA_CUDA_OK(cudaStreamWaitEvent(hs.expand, hs.step_done[b], 0));       // the step that read the expanded buffers b has finished
+  DCA_CUDA_OK(cudaStreamWaitEvent(hs.expand, hs.step_done[e], 0));       // the step that read the expanded buffers b has finished
   const int x_bf16 = tc_enc ? 1 : (cfg.x_dtype == DCA_BF16);
   int max_nib = 0;                       // longest nibble run of a row of this batch (host CSR): sizes the expansion's smem
   if (sparse) for (int64_t r = r0; r < r0 + nb; ++r) { const int len = (int)(hs.nib_indptr[r + 1] - hs.nib_indptr[r]); if (len > max_nib) max_nib = len; }
   if (sparse)
     DCA_TRY(expand_sparse(base + o_cnt[b], reinterpret_cast<const int64_t*>(base + o_nibp[b]), base + o_nib[b],
                           hs.sf ? f(o_sfst[b]) : nullptr, (int)nb, cfg.n_in, tf_set == 2 ? f(o_gmean) : nullptr,
-                          tf_set == 2 ? f(o_ginv) : nullptr, tf_use_sf && hs.sf, tf_use_log1p, f(o_sy[b]), base + o_sx[b], x_bf16,
-                          f(o_ssf[b]), has_ovf ? reinterpret_cast<const int64_t*>(base + o_ovp[b]) : nullptr,
+                          tf_set == 2 ? f(o_ginv) : nullptr, tf_use_sf && hs.sf, tf_use_log1p, f(o_sy[e]), base + o_sx[e], x_bf16,
+                          f(o_ssf[e]), has_ovf ? reinterpret_cast<const int64_t*>(base + o_ovp[b]) : nullptr,
                           has_ovf ? (const void*)(base + o_ove[b]) : nullptr, max_nib, hs.expand));
   else
   DCA_TRY(expand_counts(base + o_cnt[b], hs.bits, hs.sf ? f(o_sfst[b]) : nullptr, (int)nb, cfg.n_in,
                         tf_set == 2 ? f(o_gmean) : nullptr, tf_set == 2 ? f(o_ginv) : nullptr, tf_use_sf && hs.sf,
-                        tf_use_log1p, f(o_sy[b]), base + o_sx[b], x_bf16, f(o_ssf[b]),
+                        tf_use_log1p, f(o_sy[e]), base + o_sx[e], x_bf16, f(o_ssf[e]),
                         has_ovf ? reinterpret_cast<const int64_t*>(base + o_ovp[b]) : nullptr,
                         has_ovf ? (const void*)(base + o_ove[b]) : nullptr, hs.expand));
   DCA_CUDA_OK(cudaEventRecord(hs.cnt_free[b], hs.expand));
-  DCA_CUDA_OK(cudaEventRecord(hs.ready[b], hs.expand));
+  DCA_CUDA_OK(cudaEventRecord(hs.ready[e], hs.expand));
   if (hs.tl_base && hs.tl.size() < 400) hs.tl_mark(hs.expand);
   hs.pref_idx = i;
   return DCA_OK;
@@ -1130,15 +1131,16 @@ extern "C" int dca_stream_begin_packed(dca_handle* h, const void* packed_host, i
     for (int k = 0; k < 2; ++k) {
       DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.h2d_done[k], cudaEventDisableTiming));
       DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.cnt_free[k], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < 3; ++k) {
       DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.ready[k], cudaEventDisableTiming));
       DCA_CUDA_OK(cudaEventCreateWithFlags(&hs.step_done[k], cudaEventDisableTiming));
     }
+    if (const char* eb = getenv("DCA_STREAM_BUFS")) hs.exp_bufs = (atoi(eb) == 2) ? 2 : 3;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  for (int k = 0; k < 2; ++k) {                                                   // both staging buffers start free
-    DCA_CUDA_OK(cudaEventRecord(hs.step_done[k], s));
-    DCA_CUDA_OK(cudaEventRecord(hs.cnt_free[k], s));
-  }
+  for (int k = 0; k < 2; ++k) DCA_CUDA_OK(cudaEventRecord(hs.cnt_free[k], s));     // every staging buffer starts free
+  for (int k = 0; k < 3; ++k) DCA_CUDA_OK(cudaEventRecord(hs.step_done[k], s));
   hs.counts = reinterpret_cast<const unsigned char*>(packed_host); hs.row_bytes = row_bytes; hs.bits = bits;
   hs.ovf_indptr = ovf_indptr_host; hs.ovf_entries = reinterpret_cast<const unsigned char*>(ovf_entries_host);
   hs.sf = sf_host; hs.n_rows = n_rows; hs.batch = batch;
@@ -1183,24 +1185,25 @@ extern "C" int dca_stream_step(dca_handle* h, int64_t i, int64_t next, void* str
     set_error("dca_stream_step: batch index out of range (%lld, next %lld)", (long long)i, (long long)next); return DCA_ERR_BAD_ARG;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const int b = (int)(hs.step_no & 1);
-  if (hs.pref_idx != i) DCA_TRY(e.stream_prefetch(i, b));           // not prefetched by the previous step: fetch now
+  const int b = (int)(hs.step_no & 1), xb = (int)(hs.step_no % hs.exp_bufs);
+  const int nb_raw = b ^ 1, nxb = (int)((hs.step_no + 1) % hs.exp_bufs);
+  if (hs.pref_idx != i) DCA_TRY(e.stream_prefetch(i, b, xb));       // not prefetched by the previous step: fetch now
   const int64_t r0 = i * hs.batch;
   const int nb = (int)((hs.n_rows - r0 < hs.batch) ? (hs.n_rows - r0) : hs.batch);
   ++hs.step_no;
   hs.pref_idx = -1;
-  if (next >= 0) DCA_TRY(e.stream_prefetch(next, b ^ 1));           // next batch: copy + expansion overlap this step
-  DCA_CUDA_OK(cudaStreamWaitEvent(s, hs.ready[b], 0));
+  if (next >= 0) DCA_TRY(e.stream_prefetch(next, nb_raw, nxb));     // next batch: copy + expansion overlap this step
+  DCA_CUDA_OK(cudaStreamWaitEvent(s, hs.ready[xb], 0));
   const bool tl_on = hs.tl_base && hs.tl.size() < 400;
   if (tl_on) hs.tl_mark(s);
   static const int diag = [] { const char* v = getenv("DCA_STREAM_DIAG"); return v ? atoi(v) : 0; }();
   int st = DCA_OK;
   if (diag != 1) {                                  // (1 = diagnosis: copies + expansion only)
     e.x_override_bf16 = e.tc_enc ? 1 : 0;           // the tcgen05 encoder reads the expanded bf16 batch in place
-    st = e.train_step(e.base + e.o_sx[b], e.cfg.n_in, e.f(e.o_sy[b]), e.cfg.n_out, e.f(e.o_ssf[b]), nullptr, nb, s, 0);
+    st = e.train_step(e.base + e.o_sx[xb], e.cfg.n_in, e.f(e.o_sy[xb]), e.cfg.n_out, e.f(e.o_ssf[xb]), nullptr, nb, s, 0);
     e.x_override_bf16 = 0;
   }
-  DCA_CUDA_OK(cudaEventRecord(hs.step_done[b], s));
+  DCA_CUDA_OK(cudaEventRecord(hs.step_done[xb], s));
   if (tl_on) hs.tl_mark(s);
   return st;
 }

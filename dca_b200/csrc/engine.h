@@ -33,7 +33,8 @@ struct Engine {
   size_t o_head[3] = {0, 0, 0}, o_dh[2] = {0, 0}, o_dsum = 0, o_dprod = 0, o_scratch = 0;
   size_t o_theta = 0, o_chain = 0, o_dtheta = 0, o_sfb = 0, o_lossws = 0, loss_ws_bytes = 0;
   size_t o_stage_x = 0, o_stage_y = 0, o_stage_sf = 0;       // == o_sx[0], o_sy[0], o_ssf[0]
-  size_t o_sx[2] = {0, 0}, o_sy[2] = {0, 0}, o_ssf[2] = {0, 0};  // double-buffered expanded batch (streaming path)
+  static constexpr int kExpBufs = 3;                           // expanded batches in flight (streaming path)
+  size_t o_sx[kExpBufs] = {0, 0, 0}, o_sy[kExpBufs] = {0, 0, 0}, o_ssf[kExpBufs] = {0, 0, 0};
   // head input of the current forward (set by forward())
   const void* head_in = nullptr; int64_t head_ld = 0; int head_bf16 = 0; const int32_t* head_rows = nullptr;
   // CUDA-graph replay of the training step (captured from the same launch sequence on the 2nd call with a key)
@@ -62,14 +63,15 @@ struct Engine {
     cudaStream_t expand = nullptr;                    // its expansion kernel (lowest priority: yields SMs to the step)
     cudaEvent_t h2d_done[2] = {nullptr, nullptr};     // copy stream: raw staging buffer b has arrived
     cudaEvent_t cnt_free[2] = {nullptr, nullptr};     // expand stream: raw staging buffer b has been consumed
-    cudaEvent_t ready[2] = {nullptr, nullptr};        // expand stream: batch in buffer b is expanded (Y, X, sf ready)
-    cudaEvent_t step_done[2] = {nullptr, nullptr};    // compute stream: the step that read buffer b has finished
+    cudaEvent_t ready[3] = {nullptr, nullptr, nullptr};        // expand stream: batch in expanded buffer e is ready (Y, X, sf)
+    cudaEvent_t step_done[3] = {nullptr, nullptr, nullptr};    // compute stream: the step that read expanded buffer e has finished
+    int exp_bufs = 3;                                 // 3: the expansion of batch k+1 may run under step k-1 (2: only after it)
     int64_t pref_idx = -1, step_no = 0; bool active = false;
     // DCA_STREAM_DIAG=2: device-side timeline (events) of the first steps, printed by dca_stream_end
     std::vector<cudaEvent_t> tl; cudaEvent_t tl_base = nullptr;
     void tl_mark(cudaStream_t st) { cudaEvent_t e; if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); tl.push_back(e); } }
   } hs;
-  int stream_prefetch(int64_t i, int buf);
+  int stream_prefetch(int64_t i, int raw_buf, int exp_buf);
   // optional phase timing
   struct Prof {
     bool on = false;
