@@ -169,14 +169,17 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
   // tile -> (head slot, n tile, m tile): m fastest so that consecutive CTAs share the weight tile in L2
   auto decode = [&](int t, int& hs, int& nt, int& mt) { mt = t % p.m_tiles; const int r = t / p.m_tiles; nt = r % p.n_tiles_per_head; hs = r / p.n_tiles_per_head; };
 
+  // Producer and MMA roles: the WHOLE warp walks the tile loop and one elected lane issues (gene_gemm_tc.cu: with the loop
+  // inside `if (lane == 0)` every TMA / MMA descriptor goes through a uniform-register waterfall loop)
   if (warp == 0) {
-    if (lane == 0) {
-      int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        int hs, nt, mt; decode(t, hs, nt, mt);
-        const int st = it % kStages; const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&empty_bar[st], ph ^ 1);
-        uint8_t* a = s_ab + (size_t)st * kStageBytes;
+    const bool leader = elect_one();
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      int hs, nt, mt; decode(t, hs, nt, mt);
+      const int st = it % kStages; const uint32_t ph = (it / kStages) & 1;
+      mbar_wait(&empty_bar[st], ph ^ 1);
+      uint8_t* a = s_ab + (size_t)st * kStageBytes;
+      if (leader) {
         mbar_expect_tx(&full_bar[st], kStageBytes);
         tma_load_2d(a, &map_h, 0, mt * BM, &full_bar[st]);
         // B = the head kernel in its Keras layout [64 k][G genes] (bf16 shadow): four 64-gene boxes, MN-major
@@ -186,16 +189,17 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 1);     // A = H K-major, B = W MN-major (genes contiguous)
-      int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const int st = it % kStages; const uint32_t ph = (it / kStages) & 1;
-        const int as = it % kAccStages; const uint32_t aph = (it / kAccStages) & 1;
-        mbar_wait(&tempty_bar[as], aph ^ 1);
-        mbar_wait(&full_bar[st], ph);
-        tcgen05_fence_after();
-        const uint32_t a0 = smem_u32(s_ab + (size_t)st * kStageBytes), b0 = a0 + kABytes;
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 1);     // A = H K-major, B = W MN-major (genes contiguous)
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int st = it % kStages; const uint32_t ph = (it / kStages) & 1;
+      const int as = it % kAccStages; const uint32_t aph = (it / kAccStages) & 1;
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      mbar_wait(&full_bar[st], ph);
+      tcgen05_fence_after();
+      const uint32_t a0 = smem_u32(s_ab + (size_t)st * kStageBytes), b0 = a0 + kABytes;
+      if (leader) {
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)
           umma_bf16(tmem + as * BN, make_smem_desc(a0 + k * 32, 0, 1024), make_smem_desc(b0 + k * 2048, kBBytes / 4, 1024), idesc, k > 0);
@@ -204,6 +208,7 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
       }
     }
   } else if (warp >= kEpiWarp0) {
+    const bool st_leader = elect_one();            // issues this warp's TMA stores and owns their bulk groups
     const int ew = warp - kEpiWarp0;               // 0..15
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
     const int cgrp = ew >> 2;                      // 64-column group of the tile
@@ -241,7 +246,7 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
         }
         if (!have[c]) continue;
         const int col0 = cgrp * 64 + c * 32;
-        if (lane == 0) bulk_wait_read<0>();                 // previous store has finished reading the staging tile
+        if (st_leader) bulk_wait_read<0>();                 // previous store has finished reading the staging tile
         __syncwarp();
         const float* bz = s_bias + ew * 64 + c * 32;
         auto emit = [&](auto act) {
@@ -259,13 +264,13 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
         else emit([](float z) { return act_sigmoid(z); });
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (st_leader) {
           tma_store_2d(mo, nt * BN + col0, mt * BM + quarter * 32, ob);
           bulk_commit();
         }
       }
     }
-    if (lane == 0) bulk_wait<0>();
+    if (st_leader) bulk_wait<0>();
   }
   tcgen05_fence_before();
   __syncthreads();

@@ -193,22 +193,45 @@ __global__ void reg_penalty_kernel(const float* __restrict__ w, int64_t n, float
   }
 }
 
+__device__ __forceinline__ float rmsprop_one(float p, float g, float& r, float lr, float clip, float rho, float eps, float gs) {
+  float gi = g * gs;
+  if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);       // clipvalue
+  r = rho * r + (1.0f - rho) * gi * gi;
+  return p - lr * gi / (sqrtf(r) + eps);                     // epsilon outside the sqrt (Keras RMSprop)
+}
+
+// four parameters per thread (128-bit loads / stores; the three regions are 256-byte aligned), scalar tail
 __global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ r, int64_t n,
                                float lr, float clip, float rho, float eps, float gs, __nv_bfloat16* __restrict__ shadow,
                                float* loss_out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (i == 0 && loss_out) {             // the step's (all-reduced) mean loss, mirrored into mapped HOST memory
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0 && loss_out) {             // the step's (all-reduced) mean loss, mirrored into mapped HOST memory
     *loss_out = g[n] * gs;              // grads[P] is the loss slot
     __threadfence_system();
   }
-  float gi = g[i] * gs;
-  if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);       // clipvalue
-  const float ri = rho * r[i] + (1.0f - rho) * gi * gi;
-  r[i] = ri;
-  const float pn = p[i] - lr * gi / (sqrtf(ri) + eps);      // epsilon outside the sqrt (Keras RMSprop)
-  p[i] = pn;
-  if (shadow) shadow[i] = __float2bfloat16_rn(pn);          // bf16 operand copy for the tcgen05 kernels (same layout)
+  const int64_t i = t * 4;
+  if (i >= n) return;
+  if (i + 3 < n) {
+    const float4 pv = *reinterpret_cast<const float4*>(p + i), gv = *reinterpret_cast<const float4*>(g + i);
+    float4 rv = *reinterpret_cast<const float4*>(r + i);
+    float4 o;
+    o.x = rmsprop_one(pv.x, gv.x, rv.x, lr, clip, rho, eps, gs); o.y = rmsprop_one(pv.y, gv.y, rv.y, lr, clip, rho, eps, gs);
+    o.z = rmsprop_one(pv.z, gv.z, rv.z, lr, clip, rho, eps, gs); o.w = rmsprop_one(pv.w, gv.w, rv.w, lr, clip, rho, eps, gs);
+    *reinterpret_cast<float4*>(r + i) = rv;
+    *reinterpret_cast<float4*>(p + i) = o;
+    if (shadow) {                        // bf16 operand copy for the tcgen05 kernels (same layout)
+      __nv_bfloat162 a = __floats2bfloat162_rn(o.x, o.y), b = __floats2bfloat162_rn(o.z, o.w);
+      uint2 w; w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(shadow + i) = w;
+    }
+  } else {
+    for (int64_t k = i; k < n; ++k) {
+      float rk = r[k];
+      const float pn = rmsprop_one(p[k], g[k], rk, lr, clip, rho, eps, gs);
+      r[k] = rk; p[k] = pn;
+      if (shadow) shadow[k] = __float2bfloat16_rn(pn);
+    }
+  }
 }
 
 // keras/optimizers.py (Keras 2.x) get_updates of SGD / Adagrad / Adadelta / Adam / Adamax / Nadam, clipvalue first
@@ -589,7 +612,7 @@ int reg_penalty(const float* w, int64_t n, float l1, float l2, double* acc, cuda
 
 int rmsprop_update(float* params, const float* grads, float* rms, int64_t n, float lr, float clip, float rho,
                    float eps, float grad_scale, __nv_bfloat16* shadow, float* loss_out, cudaStream_t s) {
-  rmsprop_kernel<<<blocks_for(n), 256, 0, s>>>(params, grads, rms, n, lr, clip, rho, eps, grad_scale, shadow, loss_out);
+  rmsprop_kernel<<<blocks_for((n + 3) / 4), 256, 0, s>>>(params, grads, rms, n, lr, clip, rho, eps, grad_scale, shadow, loss_out);
   DCA_LAUNCH_CHECK();
   return DCA_OK;
 }
