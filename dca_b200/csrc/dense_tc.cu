@@ -214,23 +214,36 @@ heads_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constan
     const int cgrp = ew >> 2;                      // 64-column group of the tile
     uint8_t* ob = s_out + (size_t)ew * kChunkBytes;
     int it = 0;
+    // bias / row scale of a tile are fetched one tile AHEAD into registers (the loads sat on the critical path of every tile:
+    // long_scoreboard was the top stall, profiles/r2_ncu_k2_final_raw.csv)
+    float nb0 = 0.f, nb1 = 0.f, nrs = 1.0f;
+    auto fetch = [&](int t) {
+      int hs, nt, mt; decode(t, hs, nt, mt);
+      const int g0 = nt * BN + cgrp * 64 + lane;
+      nb0 = (g0 < p.G) ? p.bias[hs][g0] : 0.f;
+      nb1 = (g0 + 32 < p.G) ? p.bias[hs][g0 + 32] : 0.f;
+      const int row = mt * BM + quarter * 32 + lane;
+      nrs = (p.row_scale && row < p.B) ? p.row_scale[row] : 1.0f;
+    };
+    if ((int)blockIdx.x < p.total_tiles) fetch(blockIdx.x);
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int hs, nt, mt; decode(t, hs, nt, mt);
       const int as = it % kAccStages; const uint32_t aph = (it / kAccStages) & 1;
       // bias of this warp's 64 columns -> its private smem slot (a block-wide barrier here cost 3 of every 12 stall cycles,
       // profiles/r2_ncu_k2_c3_raw.csv: the 16 warps drift by up to two tiles)
+      const float rs = nrs;
       {
         float* mine = s_bias + ew * 64;
-        const int g0 = nt * BN + cgrp * 64 + lane;
         __syncwarp();                                          // the previous tile's reads of the slot are done
-        mine[lane] = (g0 < p.G) ? p.bias[hs][g0] : 0.f;
-        mine[lane + 32] = (g0 + 32 < p.G) ? p.bias[hs][g0 + 32] : 0.f;
+        mine[lane] = nb0;
+        mine[lane + 32] = nb1;
         __syncwarp();
       }
+      if (t + (int)gridDim.x < p.total_tiles) fetch(t + gridDim.x);
       mbar_wait(&tfull_bar[as], aph);
       tcgen05_fence_after();
       const int row = mt * BM + quarter * 32 + lane;
-      const float rs = (p.row_scale && row < p.B) ? p.row_scale[row] : 1.0f;
+      (void)row;
       const int kind = p.kind[hs];
       const CUtensorMap* mo = hs == 0 ? &map_o0 : (hs == 1 ? &map_o1 : &map_o2);
       const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + cgrp * 64);
