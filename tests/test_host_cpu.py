@@ -308,3 +308,27 @@ def test_normalize_mutates_a_real_anndata_in_place(monkeypatch):
         # without filtering the zero-count cell is still dropped by normalize_per_cell, on the same object
         ad2 = cls(Y[:, keep_c].copy())
         assert io.normalize(ad2, filter_min_counts=False) is ad2 and ad2.X.shape == (49, 19) and ad2.raw.X.shape == (49, 19)
+
+
+def test_optimizer_names_follow_keras_module_attributes():
+    """`opt.__dict__[optimizer]` (dca/train.py:54-57) resolves the class names and the lower-case aliases keras/optimizers.py
+    defines; anything else (TFOptimizer, a typo) must be refused before any device work starts."""
+    from dca_b200 import _lib
+    from dca_b200.train import train
+    for name in ("RMSprop", "SGD", "Adagrad", "Adadelta", "Adam", "Adamax", "Nadam"):
+        assert _lib.OPTIMIZERS[name] == _lib.OPTIMIZERS[name.lower()]
+    assert _lib.OPTIMIZERS["RMSprop"] == (0, 1e-3) and _lib.OPTIMIZERS["Adadelta"][1] == 1.0 and _lib.OPTIMIZERS["Nadam"][1] == 2e-3
+    with pytest.raises(NotImplementedError):
+        train(None, None, optimizer="TFOptimizer")          # refused before adata / network are touched
+    with pytest.raises(TypeError):
+        train(None, None, callbacks=[])                     # model.fit keywords the fit loop does not implement
+
+
+def test_activation_names_cover_the_reference_choices():
+    """dca/hyper.py:32 samples ('relu', 'selu', 'elu', 'PReLU', 'linear', 'LeakyReLU'); network.py:41 lists the two advanced
+    activations; every one must map to a dca_activation id (softmax is the one Keras name that is refused)."""
+    from dca_b200 import _lib
+    for name in ("relu", "selu", "elu", "PReLU", "linear", "LeakyReLU", "tanh", "sigmoid", "softplus"):
+        assert name in _lib.ACTIVATION_IDS
+    assert "softmax" not in _lib.ACTIVATION_IDS
+    assert sorted(_lib.ACTIVATION_IDS.values()) == list(range(12))
