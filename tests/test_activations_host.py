@@ -83,3 +83,14 @@ def test_config_carries_activation_and_dropout_fields():
     assert lib.dca_arena_bytes(C.byref(cfg), C.byref(nbytes)) != 0
     cfg.hidden_dropout[1] = 0.0; cfg.activation = _lib.ACTIVATION_IDS["PReLU"]; cfg.ae_type = _lib.AE_TYPE_IDS["nb-fork"]
     assert lib.dca_arena_bytes(C.byref(cfg), C.byref(nbytes)) != 0         # Activation('PReLU') does not exist in Keras
+
+
+def test_dropout_mask_known_answers():
+    """Pins the mask generator (constants of the 64-bit mix, key derivation, 24-bit threshold): a run with the same
+    `random_state` must draw the same masks in a later version of the library.  Bit i of the word = keep flag of element i."""
+    lib = _lib.load()
+    kat = {(7, 1, 0, 0.5): 0xa072e29d8ef8d62c, (7, 1, -1, 0.25): 0x726fbf93e775fdbe, (12345678901234567, 3, 8, 0.8): 0x20340000460401}
+    for (seed, step, layer, rate), want in kat.items():
+        m = _mask(lib, seed, step, layer, 64, rate)
+        got = sum(int(b) << i for i, b in enumerate(m))
+        assert got == want, (seed, step, layer, rate, hex(got))
